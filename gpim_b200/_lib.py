@@ -1,0 +1,280 @@
+"""
+ctypes binding of libgpgrid.so (include/gpgrid.h) and the thin Engine wrapper the host code uses.
+
+There is deliberately NO fallback: if the shared library is missing, or no CUDA device is visible,
+every compute entry raises.  PyTorch is used only to own device memory and streams.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _build
+
+GPG_OK, GPG_EINVAL, GPG_ENOTPD, GPG_ECUDA = 0, 1, 2, 3
+GPG_F32, GPG_F64 = 0, 1
+KERNEL_IDS = {"RBF": 0, "Matern52": 1, "RationalQuadratic": 2}
+ACQ_IDS = {"cb": 0, "ei": 1, "poi": 2}
+OPT_GEMM_PATH, OPT_PREDICT_CHUNK = 1, 2
+
+_vp, _i32, _i64, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
+
+# name -> argtypes; every symbol include/gpgrid.h declares (tests check the export list against this)
+SIGNATURES = {
+    "gpg_version": ([], C.c_int),
+    "gpg_last_error": ([], C.c_char_p),
+    "gpg_create": ([_i32, C.POINTER(_vp)], C.c_int),
+    "gpg_destroy": ([_vp], C.c_int),
+    "gpg_set_option": ([_vp, _i32, C.c_longlong], C.c_int),
+    "gpg_launch_count": ([_vp], C.c_longlong),
+    "gpg_workspace_bytes": ([_vp], C.c_size_t),
+    "gpg_kmat": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _f64, _i32, _vp, _i64, _vp], C.c_int),
+    "gpg_cholesky": ([_vp, _i32, _vp, _i64, _i64, _vp, _vp], C.c_int),
+    "gpg_trtri": ([_vp, _i32, _vp, _i64, _i64, _vp, _i64, _vp], C.c_int),
+    "gpg_solve_vec": ([_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "gpg_factorize": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "gpg_predict": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp], C.c_int),
+    "gpg_predict_grid": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, C.POINTER(_i64), C.POINTER(_f64),
+                          _i64, _i64, _vp, _vp, _vp], C.c_int),
+    "gpg_nll_grad": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp, _vp], C.c_int),
+    "gpg_fit_adam": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _f64, _vp, C.POINTER(_f64), _i32, _f64,
+                      _vp, _vp, _vp, _vp], C.c_int),
+    "gpg_acq_sweep": ([_vp, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp],
+                      C.c_int),
+}
+
+_LIB = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load_library(build_if_missing=True):
+    """Loads (building if stale and nvcc is present) libgpgrid.so; raises if that is impossible."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if build_if_missing and _build.is_stale():
+        try:
+            _build.build()
+        except Exception as e:                       # noqa: BLE001
+            if not os.path.exists(path):
+                raise RuntimeError(f"libgpgrid.so is missing and could not be built: {e}") from e
+    if not os.path.exists(path):
+        raise RuntimeError("libgpgrid.so not found; run `python -m gpim_b200._build`")
+    lib = C.CDLL(path)
+    for name, (argtypes, restype) in SIGNATURES.items():
+        fn = getattr(lib, name)                       # AttributeError if the symbol is not exported
+        fn.argtypes = argtypes
+        fn.restype = restype
+    if lib.gpg_version() < 100:
+        raise RuntimeError("libgpgrid.so is older than this package")
+    _LIB = lib
+    return lib
+
+
+def _ptr(t):
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda:
+        raise ValueError("libgpgrid takes device pointers; got a CPU tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def _c(t):
+    """The C ABI assumes dense row-major arrays."""
+    return None if t is None else t.contiguous()
+
+
+def np_dtype(precision):
+    return np.float32 if precision == "single" else np.float64
+
+
+def torch_dtype(precision):
+    return torch.float32 if precision == "single" else torch.float64
+
+
+class Engine:
+    """One handle on one CUDA device.  All tensor arguments must live on that device."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError(
+                "gpim_b200 needs a CUDA device (B200, sm_100a): this engine has no CPU path. "
+                "The reference's use_gpu=False mode is reproduced numerically (same RNG stream), "
+                "not by running on the host.")
+        self.lib = load_library()
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        h = C.c_void_p()
+        self._check(self.lib.gpg_create(self.device.index, C.byref(h)))
+        self.h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.gpg_destroy(self.h)
+                self.h = None
+        except Exception:                             # noqa: BLE001
+            pass
+
+    # -- helpers ------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != GPG_OK:
+            msg = self.lib.gpg_last_error().decode()
+            if rc == GPG_EINVAL:
+                raise ValueError(msg)
+            raise RuntimeError(f"libgpgrid error {rc}: {msg}")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _dt(t):
+        if t.dtype == torch.float32:
+            return GPG_F32
+        if t.dtype == torch.float64:
+            return GPG_F64
+        raise TypeError(f"unsupported dtype {t.dtype}")
+
+    def set_option(self, key, value):
+        self._check(self.lib.gpg_set_option(self.h, key, int(value)))
+
+    def launch_count(self):
+        return int(self.lib.gpg_launch_count(self.h))
+
+    def empty(self, *shape, dtype):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    # -- entry points -------------------------------------------------------------------
+    def kmat(self, kernel_id, theta, X, Z=None, jitter=0.0, lower_only=False, out=None):
+        theta, X, Z = _c(theta), _c(X), _c(Z)
+        N, d = X.shape
+        P = N if Z is None else Z.shape[0]
+        if out is None:
+            out = self.empty(N, P, dtype=X.dtype)
+        self._check(self.lib.gpg_kmat(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), N, _ptr(Z), P,
+                                      float(jitter), int(lower_only), _ptr(out), out.stride(0), self._stream()))
+        return out
+
+    def cholesky_(self, A, info=None):
+        N = A.shape[0]
+        if info is None:
+            info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._check(self.lib.gpg_cholesky(self.h, self._dt(A), _ptr(A), N, A.stride(0), _ptr(info), self._stream()))
+        return A, info
+
+    def trtri(self, L, out=None):
+        N = L.shape[0]
+        if out is None:
+            out = self.empty(N, N, dtype=L.dtype)
+        self._check(self.lib.gpg_trtri(self.h, self._dt(L), _ptr(L), N, L.stride(0), _ptr(out), out.stride(0),
+                                       self._stream()))
+        return out
+
+    def solve_vec(self, L, Linv, y):
+        y = _c(y)
+        N = L.shape[0]
+        assert L.stride(0) == Linv.stride(0)
+        vhat, alpha = torch.empty_like(y), torch.empty_like(y)
+        scalars = self.empty(2, dtype=y.dtype)
+        self._check(self.lib.gpg_solve_vec(self.h, self._dt(L), _ptr(L), _ptr(Linv), N, L.stride(0), _ptr(y),
+                                           _ptr(vhat), _ptr(alpha), _ptr(scalars), self._stream()))
+        return vhat, alpha, scalars
+
+    def factorize(self, kernel_id, theta, X, y, jitter):
+        """-> dict(L, Linv, vhat, alpha, scalars, info); N x N buffers padded to ld % 64 == 0."""
+        theta, X, y = _c(theta), _c(X), _c(y)
+        N, d = X.shape
+        ld = (N + 63) // 64 * 64
+        L = self.empty(N, ld, dtype=X.dtype)
+        Linv = self.empty(N, ld, dtype=X.dtype)
+        vhat, alpha = torch.empty_like(y), torch.empty_like(y)
+        scalars = self.empty(2, dtype=y.dtype)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._check(self.lib.gpg_factorize(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), _ptr(y), N,
+                                           float(jitter), _ptr(L), _ptr(Linv), ld, _ptr(vhat), _ptr(alpha),
+                                           _ptr(scalars), _ptr(info), self._stream()))
+        return {"L": L, "Linv": Linv, "vhat": vhat, "alpha": alpha, "scalars": scalars, "info": info, "ld": ld}
+
+    def predict(self, kernel_id, theta, X, fac, Xs, mean=None, sd=None):
+        theta, X, Xs = _c(theta), _c(X), _c(Xs)
+        N, d = X.shape
+        M = Xs.shape[0]
+        if mean is None:
+            mean = self.empty(M, dtype=X.dtype)
+        if sd is None:
+            sd = self.empty(M, dtype=X.dtype)
+        self._check(self.lib.gpg_predict(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), N, _ptr(fac["Linv"]),
+                                         fac["ld"], _ptr(fac["alpha"]), _ptr(Xs), M, _ptr(mean), _ptr(sd),
+                                         self._stream()))
+        return mean, sd
+
+    def predict_grid(self, kernel_id, theta, X, fac, dims, step, j0, M, mean=None, sd=None):
+        theta, X = _c(theta), _c(X)
+        N, d = X.shape
+        if mean is None:
+            mean = self.empty(M, dtype=X.dtype)
+        if sd is None:
+            sd = self.empty(M, dtype=X.dtype)
+        dims_c = (_i64 * d)(*[int(v) for v in dims])
+        step_c = (_f64 * d)(*[float(v) for v in step])
+        self._check(self.lib.gpg_predict_grid(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), N,
+                                              _ptr(fac["Linv"]), fac["ld"], _ptr(fac["alpha"]), dims_c, step_c,
+                                              int(j0), int(M), _ptr(mean), _ptr(sd), self._stream()))
+        return mean, sd
+
+    def nll_grad(self, kernel_id, theta, X, y, jitter):
+        theta, X, y = _c(theta), _c(X), _c(y)
+        N, d = X.shape
+        nll = self.empty(1, dtype=X.dtype)
+        grad = self.empty(3 + d, dtype=X.dtype)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._check(self.lib.gpg_nll_grad(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), _ptr(y), N,
+                                          float(jitter), _ptr(nll), _ptr(grad), _ptr(info), self._stream()))
+        return nll, grad, info
+
+    def fit_adam(self, kernel_id, X, y, jitter, u, bounds, n_ls, iters, lr):
+        """u (device, in/out) layout {variance, noise, scale_mixture, lengthscale[n_ls]}.
+        Returns (traj [iters, 4+d], theta [3+d], info)."""
+        X, y = _c(X), _c(y)
+        assert u.is_contiguous()
+        N, d = X.shape
+        traj = self.empty(max(iters, 1), 4 + d, dtype=X.dtype)
+        theta = self.empty(3 + d, dtype=X.dtype)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        b = (_f64 * len(bounds))(*[float(v) for v in bounds])
+        self._check(self.lib.gpg_fit_adam(self.h, self._dt(X), kernel_id, d, n_ls, _ptr(X), _ptr(y), N, float(jitter),
+                                          _ptr(u), b, int(iters), float(lr), _ptr(traj), _ptr(theta), _ptr(info),
+                                          self._stream()))
+        return traj[:iters], theta, info
+
+    def acq_sweep(self, acq_id, mean, sd, k, mu_best=0.0, xi=0.01, alpha=0.0, beta=1.0, mask=None, want_acq=False):
+        mean, sd, mask = _c(mean), _c(sd), _c(mask)
+        M = mean.numel()
+        k = int(min(k, M))
+        vals = self.empty(k, dtype=mean.dtype)
+        idx = torch.empty(k, dtype=torch.int64, device=self.device)
+        count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        acq = self.empty(M, dtype=mean.dtype) if want_acq else None
+        self._check(self.lib.gpg_acq_sweep(self.h, self._dt(mean), acq_id, _ptr(mean), _ptr(sd), _ptr(mask), M,
+                                           float(mu_best), float(xi), float(alpha), float(beta), k, _ptr(vals),
+                                           _ptr(idx), _ptr(count), _ptr(acq), self._stream()))
+        return vals, idx, count, acq
+
+
+_ENGINES = {}
+
+
+def get_engine(device=None):
+    """Process-wide engine per device (the reference is single-threaded with global state too, gpr.py:103-113)."""
+    if not torch.cuda.is_available():
+        return Engine(device)                         # raises with the explanatory message
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index or 0
+    if idx not in _ENGINES:
+        _ENGINES[idx] = Engine(idx)
+    return _ENGINES[idx]

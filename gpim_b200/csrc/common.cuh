@@ -1,0 +1,146 @@
+// common.cuh -- handle, error plumbing and the covariance-function math shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+#include <string>
+#include "../../include/gpgrid.h"
+
+#define GPG_MAX_D 4
+
+struct gpg_handle_s {
+    int device = 0;
+    int sm_count = 148;
+    long long launches = 0;
+    int opt_gemm_path = 0;
+    long long opt_predict_chunk = 0;
+    void *ws = nullptr;          // grow-only device workspace
+    size_t ws_bytes = 0;
+};
+
+void gpg_set_error(const char *fmt, ...);
+// returns pointer into the handle workspace, growing it if needed (synchronises on growth)
+int gpg_ws_reserve(gpg_handle_s *h, size_t bytes, void **out);
+
+#define GPG_CUDA_CHECK(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            gpg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return GPG_ECUDA;                                                             \
+        }                                                                                 \
+    } while (0)
+
+#define GPG_LAUNCH_CHECK(h)                                                               \
+    do {                                                                                  \
+        (h)->launches++;                                                                  \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            gpg_set_error("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return GPG_ECUDA;                                                             \
+        }                                                                                 \
+    } while (0)
+
+#define GPG_REQUIRE(cond, msg)                                                            \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            gpg_set_error("%s:%d invalid argument: %s", __FILE__, __LINE__, msg);         \
+            return GPG_EINVAL;                                                            \
+        }                                                                                 \
+    } while (0)
+
+#define GPG_TRY(expr)                                                                     \
+    do {                                                                                  \
+        int _rc = (expr);                                                                 \
+        if (_rc != GPG_OK) return _rc;                                                    \
+    } while (0)
+
+static inline size_t gpg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// Covariance functions.  r2 is the squared lengthscale-scaled distance computed by DIRECT
+// DIFFERENCE (the reference expands X2 - 2XZ^T + Z2, pyro Isotropy._square_scaled_dist; the
+// direct form is what keeps fp32 within tolerance).
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Theta {
+    T variance, noise, alpha;
+    T inv_ls[GPG_MAX_D];
+};
+
+template <typename T, int D>
+__device__ __forceinline__ Theta<T> load_theta(const T *__restrict__ theta) {
+    Theta<T> t;
+    t.variance = theta[0];
+    t.noise = theta[1];
+    t.alpha = theta[2];
+#pragma unroll
+    for (int k = 0; k < D; ++k) t.inv_ls[k] = T(1) / theta[3 + k];
+    return t;
+}
+
+__device__ __forceinline__ float gpg_exp(float x) { return expf(x); }
+__device__ __forceinline__ double gpg_exp(double x) { return exp(x); }
+__device__ __forceinline__ float gpg_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double gpg_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float gpg_log(float x) { return logf(x); }
+__device__ __forceinline__ double gpg_log(double x) { return log(x); }
+__device__ __forceinline__ float gpg_pow(float x, float y) { return powf(x, y); }
+__device__ __forceinline__ double gpg_pow(double x, double y) { return pow(x, y); }
+
+// k(r2) for kernel KID.  Matern52 follows pyro's _torch_sqrt(r2 + 1e-12).
+template <typename T, int KID>
+__device__ __forceinline__ T cov_from_r2(T r2, const Theta<T> &t) {
+    if (KID == GPG_RBF) {
+        return t.variance * gpg_exp(T(-0.5) * r2);
+    } else if (KID == GPG_MATERN52) {
+        T r = gpg_sqrt(r2 + T(1e-12));
+        T s = T(2.23606797749978969641) * r;
+        return t.variance * (T(1) + s + (T(5) / T(3)) * r * r) * gpg_exp(-s);
+    } else {
+        T base = T(1) + (T(0.5) / t.alpha) * r2;
+        return t.variance * gpg_pow(base, -t.alpha);
+    }
+}
+
+template <typename T, int D>
+__device__ __forceinline__ T scaled_r2(const T *__restrict__ x, const T *__restrict__ z, const Theta<T> &t) {
+    T r2 = T(0);
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        T dlt = (x[k] - z[k]) * t.inv_ls[k];
+        r2 += dlt * dlt;
+    }
+    return r2;
+}
+
+// dispatch helpers ------------------------------------------------------------------------
+#define GPG_DISPATCH_D(d, ...)                                       \
+    switch (d) {                                                     \
+        case 1: { constexpr int D = 1; __VA_ARGS__; } break;         \
+        case 2: { constexpr int D = 2; __VA_ARGS__; } break;         \
+        case 3: { constexpr int D = 3; __VA_ARGS__; } break;         \
+        case 4: { constexpr int D = 4; __VA_ARGS__; } break;         \
+        default: gpg_set_error("input dimension %d not in 1..4", d); return GPG_EINVAL; \
+    }
+
+#define GPG_DISPATCH_KID(kid, ...)                                                  \
+    switch (kid) {                                                                  \
+        case GPG_RBF: { constexpr int KID = GPG_RBF; __VA_ARGS__; } break;          \
+        case GPG_MATERN52: { constexpr int KID = GPG_MATERN52; __VA_ARGS__; } break;\
+        case GPG_RATQUAD: { constexpr int KID = GPG_RATQUAD; __VA_ARGS__; } break;  \
+        default: gpg_set_error("unknown kernel id %d", kid); return GPG_EINVAL;     \
+    }
+
+template <typename T> __device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <typename T> __device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}

@@ -1,0 +1,206 @@
+// gemm_simt.cuh -- register-tiled SIMT GEMM used by every dense step when the tcgen05 path does
+// not apply (fp64 everywhere; fp32 for small problems):
+//     C[m][n] (+)= alpha * sum_k Aop(m,k) * Bop(n,k)
+// with Aop(m,k) = a_kmajor ? A[m*lda+k] : A[k*lda+m] and the same for B, per-tile triangular
+// k-ranges (so the structural zeros of L / L^-1 are skipped at tile granularity), an optional
+// lower-tiles-only sweep (SYRK) and a fused column-sum-of-squares epilogue (predictive variance:
+// diag(K*^T K^-1 K*) = colsum((L^-1 K*)^2), util.conditional's W.pow(2).sum(-1)).
+#pragma once
+#include "common.cuh"
+
+enum { GEMM_KB_NONE = 0, GEMM_KB_N0 = 1, GEMM_KB_MAXMN = 2 };
+enum { GEMM_KE_NONE = 0, GEMM_KE_M = 1, GEMM_KE_N = 2 };
+enum { GEMM_TILES_ALL = 0, GEMM_TILES_LOWER = 1 };
+enum { GEMM_EPI_STORE = 0, GEMM_EPI_COLSUMSQ = 1 };
+
+template <typename T> struct GemmArgs {
+    const T *A = nullptr;
+    const T *B = nullptr;
+    T *C = nullptr;
+    int64_t lda = 0, ldb = 0, ldc = 0;
+    int M = 0, N = 0, K = 0;
+    int a_kmajor = 1, b_kmajor = 1;
+    int kb_mode = GEMM_KB_NONE, ke_mode = GEMM_KE_NONE, tile_mode = GEMM_TILES_ALL, epi = GEMM_EPI_STORE;
+    T alpha = T(1), beta = T(0);
+    int64_t strideA = 0, strideB = 0, strideC = 0;
+    int batch = 1;
+    T *part = nullptr;       // COLSUMSQ: part[tile_m * ldpart + n]
+    int64_t ldpart = 0;
+};
+
+template <typename T> struct GemmCfg;
+template <> struct GemmCfg<float> { static constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8; };
+template <> struct GemmCfg<double> { static constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs<T> g) {
+    using C = GemmCfg<T>;
+    constexpr int BM = C::BM, BN = C::BN, BK = C::BK, TM = C::TM, TN = C::TN;
+    constexpr int TMH = TM / 2, TNH = TN / 2;
+    constexpr int NT = 256;
+    constexpr int ELA = BM * BK / NT, ELB = BN * BK / NT;
+    constexpr int LDS_A = BM + 4, LDS_B = BN + 4;
+    __shared__ __align__(16) T As[BK * LDS_A];
+    __shared__ __align__(16) T Bs[BK * LDS_B];
+
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    if (g.tile_mode == GEMM_TILES_LOWER && n0 > m0 + BM - 1) return;
+    const T *A = g.A + (int64_t)blockIdx.z * g.strideA;
+    const T *B = g.B + (int64_t)blockIdx.z * g.strideB;
+    T *Cp = g.C + (int64_t)blockIdx.z * g.strideC;
+
+    int kb = 0, ke = g.K;
+    if (g.kb_mode == GEMM_KB_N0) kb = n0;
+    else if (g.kb_mode == GEMM_KB_MAXMN) kb = max(m0, n0);
+    if (g.ke_mode == GEMM_KE_M) ke = min(g.K, m0 + BM);
+    else if (g.ke_mode == GEMM_KE_N) ke = min(g.K, n0 + BN);
+    kb = (kb / BK) * BK;
+
+    const int t = threadIdx.x;
+    const int tx = t % (BN / TN), ty = t / (BN / TN);
+
+    T acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+
+    T ra[ELA], rb[ELB];
+
+    auto load_a = [&](int k0) {
+        if (g.a_kmajor) {
+            constexpr int TPR = BK / ELA;
+            const int r = t / TPR, ko = (t % TPR) * ELA;
+            const int m = m0 + r;
+            const T *src = A + (int64_t)m * g.lda + k0 + ko;
+#pragma unroll
+            for (int e = 0; e < ELA; ++e) ra[e] = (m < g.M && k0 + ko + e < ke) ? src[e] : T(0);
+        } else {
+            constexpr int TPK = BM / ELA;
+            const int k = k0 + t / TPK, mo = (t % TPK) * ELA;
+            const T *src = A + (int64_t)k * g.lda + m0 + mo;
+#pragma unroll
+            for (int e = 0; e < ELA; ++e) ra[e] = (k < ke && m0 + mo + e < g.M) ? src[e] : T(0);
+        }
+    };
+    auto load_b = [&](int k0) {
+        if (g.b_kmajor) {
+            constexpr int TPR = BK / ELB;
+            const int r = t / TPR, ko = (t % TPR) * ELB;
+            const int n = n0 + r;
+            const T *src = B + (int64_t)n * g.ldb + k0 + ko;
+#pragma unroll
+            for (int e = 0; e < ELB; ++e) rb[e] = (n < g.N && k0 + ko + e < ke) ? src[e] : T(0);
+        } else {
+            constexpr int TPK = BN / ELB;
+            const int k = k0 + t / TPK, no = (t % TPK) * ELB;
+            const T *src = B + (int64_t)k * g.ldb + n0 + no;
+#pragma unroll
+            for (int e = 0; e < ELB; ++e) rb[e] = (k < ke && n0 + no + e < g.N) ? src[e] : T(0);
+        }
+    };
+    auto store_smem = [&]() {
+        if (g.a_kmajor) {
+            constexpr int TPR = BK / ELA;
+            const int r = t / TPR, ko = (t % TPR) * ELA;
+#pragma unroll
+            for (int e = 0; e < ELA; ++e) As[(ko + e) * LDS_A + r] = ra[e];
+        } else {
+            constexpr int TPK = BM / ELA;
+            const int k = t / TPK, mo = (t % TPK) * ELA;
+#pragma unroll
+            for (int e = 0; e < ELA; ++e) As[k * LDS_A + mo + e] = ra[e];
+        }
+        if (g.b_kmajor) {
+            constexpr int TPR = BK / ELB;
+            const int r = t / TPR, ko = (t % TPR) * ELB;
+#pragma unroll
+            for (int e = 0; e < ELB; ++e) Bs[(ko + e) * LDS_B + r] = rb[e];
+        } else {
+            constexpr int TPK = BN / ELB;
+            const int k = t / TPK, no = (t % TPK) * ELB;
+#pragma unroll
+            for (int e = 0; e < ELB; ++e) Bs[k * LDS_B + no + e] = rb[e];
+        }
+    };
+
+    if (kb < ke) {
+        load_a(kb);
+        load_b(kb);
+    }
+    for (int k0 = kb; k0 < ke; k0 += BK) {
+        __syncthreads();
+        store_smem();
+        __syncthreads();
+        if (k0 + BK < ke) {
+            load_a(k0 + BK);
+            load_b(k0 + BK);
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            T a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TMH; ++i) {
+                a[i] = As[kk * LDS_A + ty * TMH + i];
+                a[TMH + i] = As[kk * LDS_A + BM / 2 + ty * TMH + i];
+            }
+#pragma unroll
+            for (int j = 0; j < TNH; ++j) {
+                b[j] = Bs[kk * LDS_B + tx * TNH + j];
+                b[TNH + j] = Bs[kk * LDS_B + BN / 2 + tx * TNH + j];
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+
+    if (g.epi == GEMM_EPI_STORE) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            const int m = m0 + (i < TMH ? ty * TMH + i : BM / 2 + ty * TMH + (i - TMH));
+            if (m >= g.M) continue;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = n0 + (j < TNH ? tx * TNH + j : BN / 2 + tx * TNH + (j - TNH));
+                if (n >= g.N) continue;
+                T *dst = Cp + (int64_t)m * g.ldc + n;
+                T v = g.alpha * acc[i][j];
+                if (g.beta != T(0)) v += g.beta * *dst;
+                *dst = v;
+            }
+        }
+    } else {
+        // column sums of squares over this tile's rows -> part[tile_m][n]
+        __syncthreads();
+        T *red = As;   // (BM/TM) x BN values fit: 16 x 128 <= BK * LDS_A
+        static_assert((BM / TM) * BN <= BK * LDS_A, "reduction scratch too small");
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            T s = T(0);
+#pragma unroll
+            for (int i = 0; i < TM; ++i) s = fma(acc[i][j], acc[i][j], s);
+            const int nl = (j < TNH ? tx * TNH + j : BN / 2 + tx * TNH + (j - TNH));
+            red[ty * BN + nl] = s;
+        }
+        __syncthreads();
+        for (int nl = t; nl < BN; nl += NT) {
+            T s = T(0);
+#pragma unroll
+            for (int r = 0; r < BM / TM; ++r) s += red[r * BN + nl];
+            if (n0 + nl < g.N)
+                g.part[(int64_t)blockIdx.z * g.strideC + (int64_t)blockIdx.y * g.ldpart + n0 + nl] = s;
+        }
+    }
+}
+
+template <typename T>
+static int gemm_simt(gpg_handle_s *h, const GemmArgs<T> &g, cudaStream_t stream) {
+    using C = GemmCfg<T>;
+    if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return GPG_OK;
+    dim3 grid((g.N + C::BN - 1) / C::BN, (g.M + C::BM - 1) / C::BM, g.batch);
+    gemm_simt_kernel<T><<<grid, 256, 0, stream>>>(g);
+    GPG_LAUNCH_CHECK(h);
+    return GPG_OK;
+}

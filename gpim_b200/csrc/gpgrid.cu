@@ -1,0 +1,559 @@
+// gpgrid.cu -- extern "C" entry points of libgpgrid.so (see include/gpgrid.h) and the drivers
+// that sequence the kernels of kmat.cuh / factor.cuh / train.cuh / acq.cuh / gemm_*.cuh.
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "kmat.cuh"
+#include "factor.cuh"
+#include "train.cuh"
+#include "acq.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// errors, handle, workspace
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void gpg_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int gpg_ws_reserve(gpg_handle_s *h, size_t bytes, void **out) {
+    if (bytes > h->ws_bytes) {
+        GPG_CUDA_CHECK(cudaDeviceSynchronize());
+        if (h->ws) GPG_CUDA_CHECK(cudaFree(h->ws));
+        h->ws = nullptr;
+        h->ws_bytes = 0;
+        const size_t want = gpg_align_up(bytes + bytes / 8, 1 << 20);
+        GPG_CUDA_CHECK(cudaMalloc(&h->ws, want));
+        h->ws_bytes = want;
+    }
+    *out = h->ws;
+    return GPG_OK;
+}
+
+struct Bump {            // carve a reserved workspace into aligned pieces
+    unsigned char *base;
+    size_t off = 0;
+    explicit Bump(void *b) : base(reinterpret_cast<unsigned char *>(b)) {}
+    template <typename U> U *take(size_t count) {
+        off = gpg_align_up(off, 1024);
+        U *p = reinterpret_cast<U *>(base + off);
+        off += count * sizeof(U);
+        return p;
+    }
+};
+static size_t bump_size(std::initializer_list<size_t> parts) {
+    size_t off = 0;
+    for (size_t p : parts) off = gpg_align_up(off, 1024) + p;
+    return off + 1024;
+}
+
+extern "C" int gpg_version(void) { return GPG_VERSION; }
+extern "C" const char *gpg_last_error(void) { return g_err; }
+
+extern "C" int gpg_create(int device, gpg_handle_t *out) {
+    GPG_REQUIRE(out != nullptr, "out is NULL");
+    int count = 0;
+    GPG_CUDA_CHECK(cudaGetDeviceCount(&count));
+    GPG_REQUIRE(device >= 0 && device < count, "device index out of range");
+    GPG_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GPG_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        gpg_set_error("libgpgrid is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+        return GPG_ECUDA;
+    }
+    gpg_handle_s *h = new gpg_handle_s();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return GPG_OK;
+}
+
+extern "C" int gpg_destroy(gpg_handle_t h) {
+    if (!h) return GPG_OK;
+    if (h->ws) cudaFree(h->ws);
+    delete h;
+    return GPG_OK;
+}
+
+extern "C" int gpg_set_option(gpg_handle_t h, int key, long long value) {
+    GPG_REQUIRE(h != nullptr, "handle is NULL");
+    switch (key) {
+        case GPG_OPT_GEMM_PATH: GPG_REQUIRE(value >= 0 && value <= 2, "gemm path 0..2"); h->opt_gemm_path = (int)value; break;
+        case GPG_OPT_PREDICT_CHUNK: GPG_REQUIRE(value >= 0, "chunk >= 0"); h->opt_predict_chunk = value; break;
+        default: gpg_set_error("unknown option %d", key); return GPG_EINVAL;
+    }
+    return GPG_OK;
+}
+
+extern "C" long long gpg_launch_count(gpg_handle_t h) { return h ? h->launches : -1; }
+extern "C" size_t gpg_workspace_bytes(gpg_handle_t h) { return h ? h->ws_bytes : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// GEMM dispatch: tcgen05 split-fp16 path for large fp32 problems, SIMT otherwise
+// ---------------------------------------------------------------------------------------------
+template <> int gemm_dispatch<double>(gpg_handle_s *h, const GemmArgs<double> &g, cudaStream_t stream) {
+    return gemm_simt<double>(h, g, stream);
+}
+template <> int gemm_dispatch<float>(gpg_handle_s *h, const GemmArgs<float> &g, cudaStream_t stream) {
+    return gemm_simt<float>(h, g, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 / K2
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int kmat_launch(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, int64_t N, const T *Z,
+                       int64_t P, double jitter, int lower_only, T *out, int64_t ld, cudaStream_t stream) {
+    const int sym = (Z == nullptr);
+    if (sym) { Z = X; P = N; }
+    if (N <= 0 || P <= 0) return GPG_OK;
+    dim3 block(64, 4);
+    dim3 grid((unsigned)((P + 255) / 256), (unsigned)((N + 15) / 16));
+    GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, kmat_kernel<T, KID, D><<<grid, block, 0, stream>>>(
+                                                       theta, X, N, Z, P, sym, (T)jitter, sym ? lower_only : 0, out, ld)));
+    GPG_LAUNCH_CHECK(h);
+    return GPG_OK;
+}
+
+extern "C" int gpg_kmat(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X, int64_t N,
+                        const void *Z, int64_t P, double jitter, int lower_only, void *out, int64_t ld, void *stream) {
+    GPG_REQUIRE(h && theta && X && out, "NULL argument");
+    GPG_REQUIRE(N >= 0 && (Z == nullptr || P >= 0), "negative size");
+    GPG_REQUIRE(ld >= (Z ? P : N), "ld smaller than row length");
+    GPG_REQUIRE((int64_t)((N + 15) / 16) < 65536, "N too large for one launch");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return kmat_launch<float>(h, kernel_id, d, (const float *)theta, (const float *)X, N, (const float *)Z, P, jitter,
+                                  lower_only, (float *)out, ld, s);
+    if (dtype == GPG_F64)
+        return kmat_launch<double>(h, kernel_id, d, (const double *)theta, (const double *)X, N, (const double *)Z, P,
+                                   jitter, lower_only, (double *)out, ld, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3, trtri, K7a
+// ---------------------------------------------------------------------------------------------
+template <typename T> static int cholesky_entry(gpg_handle_s *h, T *A, int64_t N, int64_t ld, int32_t *info, cudaStream_t s) {
+    constexpr int NB = GemmCfg<T>::BN;
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, bump_size({NB * NB * sizeof(T)}), &ws));
+    Bump b(ws);
+    return cholesky_blocked<T>(h, A, N, ld, info, 1, b.take<T>(NB * NB), s);
+}
+
+extern "C" int gpg_cholesky(gpg_handle_t h, int dtype, void *A, int64_t N, int64_t ld, int32_t *info, void *stream) {
+    GPG_REQUIRE(h && A && info, "NULL argument");
+    GPG_REQUIRE(N >= 0 && ld >= N, "bad size");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (N == 0) return GPG_OK;
+    if (dtype == GPG_F32) return cholesky_entry<float>(h, (float *)A, N, ld, info, s);
+    if (dtype == GPG_F64) return cholesky_entry<double>(h, (double *)A, N, ld, info, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+template <typename T>
+static int trtri_entry(gpg_handle_s *h, const T *L, int64_t N, int64_t ld, T *Linv, int64_t ldi, cudaStream_t s) {
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)N * ld * sizeof(T)}), &ws));
+    Bump b(ws);
+    return trtri_blocked<T>(h, L, N, ld, Linv, ldi, b.take<T>((size_t)N * ld), s);
+}
+
+extern "C" int gpg_trtri(gpg_handle_t h, int dtype, const void *L, int64_t N, int64_t ld, void *Linv, int64_t ldinv,
+                         void *stream) {
+    GPG_REQUIRE(h && L && Linv && L != Linv, "NULL or aliased argument");
+    GPG_REQUIRE(N >= 0 && ld >= N && ldinv >= N, "bad size");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (N == 0) return GPG_OK;
+    if (dtype == GPG_F32) return trtri_entry<float>(h, (const float *)L, N, ld, (float *)Linv, ldinv, s);
+    if (dtype == GPG_F64) return trtri_entry<double>(h, (const double *)L, N, ld, (double *)Linv, ldinv, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+template <typename T>
+static int solve_entry(gpg_handle_s *h, const T *L, const T *Linv, int64_t N, int64_t ld, const T *y, T *vhat, T *alpha,
+                       T *scalars, cudaStream_t s) {
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, bump_size({2 * (size_t)N * sizeof(T)}), &ws));
+    Bump b(ws);
+    return solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, scalars, b.take<T>(2 * N), s);
+}
+
+extern "C" int gpg_solve_vec(gpg_handle_t h, int dtype, const void *L, const void *Linv, int64_t N, int64_t ld,
+                             const void *y, void *vhat_out, void *alpha_out, void *scalars_out, void *stream) {
+    GPG_REQUIRE(h && L && Linv && y && vhat_out && alpha_out, "NULL argument");
+    GPG_REQUIRE(N > 0 && ld >= N, "bad size");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return solve_entry<float>(h, (const float *)L, (const float *)Linv, N, ld, (const float *)y, (float *)vhat_out,
+                                  (float *)alpha_out, (float *)scalars_out, s);
+    if (dtype == GPG_F64)
+        return solve_entry<double>(h, (const double *)L, (const double *)Linv, N, ld, (const double *)y,
+                                   (double *)vhat_out, (double *)alpha_out, (double *)scalars_out, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+// K1 + K3 + trtri + K7a.  tmp (N*ld), dinv, vec scratch come from the caller-provided bump.
+template <typename T>
+static int factorize_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
+                          double jitter, T *L, T *Linv, int64_t ld, T *vhat, T *alpha, T *scalars, int32_t *info,
+                          int reset_info, T *tmp, T *dinv, T *vscratch, cudaStream_t s) {
+    GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, nullptr, N, jitter, 1, L, ld, s));
+    GPG_TRY(cholesky_blocked<T>(h, L, N, ld, info, reset_info, dinv, s));
+    GPG_TRY(trtri_blocked<T>(h, L, N, ld, Linv, ld, tmp, s));
+    GPG_TRY(solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, scalars, vscratch, s));
+    return GPG_OK;
+}
+
+template <typename T>
+static int factorize_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
+                           double jitter, T *L, T *Linv, int64_t ld, T *vhat, T *alpha, T *scalars, int32_t *info,
+                           cudaStream_t s) {
+    constexpr int NB = GemmCfg<T>::BN;
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)N * ld * sizeof(T), NB * NB * sizeof(T), 2 * (size_t)N * sizeof(T)}), &ws));
+    Bump b(ws);
+    T *tmp = b.take<T>((size_t)N * ld);
+    T *dinv = b.take<T>(NB * NB);
+    T *vs = b.take<T>(2 * N);
+    return factorize_core<T>(h, kernel_id, d, theta, X, y, N, jitter, L, Linv, ld, vhat, alpha, scalars, info, 1, tmp,
+                             dinv, vs, s);
+}
+
+extern "C" int gpg_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X,
+                             const void *y, int64_t N, double jitter, void *L, void *Linv, int64_t ld, void *vhat_out,
+                             void *alpha_out, void *scalars_out, int32_t *info, void *stream) {
+    GPG_REQUIRE(h && theta && X && y && L && Linv && vhat_out && alpha_out && info, "NULL argument");
+    GPG_REQUIRE(N > 0 && ld >= N, "bad size");
+    GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return factorize_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, (const float *)y, N, jitter,
+                                      (float *)L, (float *)Linv, ld, (float *)vhat_out, (float *)alpha_out,
+                                      (float *)scalars_out, info, s);
+    if (dtype == GPG_F64)
+        return factorize_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, (const double *)y, N,
+                                       jitter, (double *)L, (double *)Linv, ld, (double *)vhat_out, (double *)alpha_out,
+                                       (double *)scalars_out, info, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 + K4 + K5: predict
+// ---------------------------------------------------------------------------------------------
+template <typename T, int D>
+static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T *X, int64_t N, const T *Linv, int64_t ld,
+                        const T *alpha, TestPoints<T, D> tp, int64_t M, T *mean, T *sd, cudaStream_t s) {
+    using C = GemmCfg<T>;
+    const int64_t ldk = gpg_align_up((size_t)N, 64);
+    int64_t chunk = h->opt_predict_chunk;
+    if (chunk <= 0) {
+        chunk = 8192;
+        while (chunk > 512 && chunk * ldk * (int64_t)sizeof(T) > (int64_t)768 << 20) chunk /= 2;
+    }
+    chunk = std::min<int64_t>(chunk, gpg_align_up((size_t)M, 128));
+    const int tiles_m = (int)((N + C::BM - 1) / C::BM);
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)chunk * ldk * sizeof(T), (size_t)tiles_m * chunk * sizeof(T)}), &ws));
+    Bump b(ws);
+    T *Ks = b.take<T>((size_t)chunk * ldk);
+    T *part = b.take<T>((size_t)tiles_m * chunk);
+    for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+        const int64_t mc = std::min<int64_t>(chunk, M - c0);
+        TestPoints<T, D> tpc = tp;
+        if (tpc.Xs) tpc.Xs += c0 * D; else tpc.j0 += c0;
+        const unsigned gk = (unsigned)((mc + 7) / 8);
+        GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<T, KID, D, false><<<gk, 256, 0, s>>>(
+                                        theta, X, N, tpc, mc, alpha, Ks, ldk, nullptr, nullptr, 0, 1.0f, mean + c0));
+        GPG_LAUNCH_CHECK(h);
+        GemmArgs<T> g;           // colsum((Linv Ks^T)^2): C[i][j] = sum_k Linv[i][k] Ks[j][k], k <= i
+        g.A = Linv; g.lda = ld; g.a_kmajor = 1;
+        g.B = Ks; g.ldb = ldk; g.b_kmajor = 1;
+        g.M = (int)N; g.N = (int)mc; g.K = (int)N;
+        g.ke_mode = GEMM_KE_M;
+        g.epi = GEMM_EPI_COLSUMSQ;
+        g.part = part; g.ldpart = chunk;
+        GPG_TRY(gemm_simt<T>(h, g, s));
+        predict_finalize_kernel<T, D><<<(unsigned)((mc + 255) / 256), 256, 0, s>>>(theta, part, tiles_m, chunk, tpc, mc,
+                                                                                   T(1), sd + c0);
+        GPG_LAUNCH_CHECK(h);
+    }
+    return GPG_OK;
+}
+
+template <typename T>
+static int predict_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, int64_t N, const T *Linv,
+                         int64_t ld, const T *alpha, const T *Xs, const int64_t *dims, const double *step, int64_t j0,
+                         int64_t M, T *mean, T *sd, cudaStream_t s) {
+    if (M == 0) return GPG_OK;
+    GPG_DISPATCH_D(d, {
+        TestPoints<T, D> tp;
+        tp.Xs = Xs;
+        tp.j0 = j0;
+        for (int k = 0; k < GPG_MAX_D; ++k) {
+            tp.dims[k] = (dims && k < D) ? dims[k] : 1;
+            tp.step[k] = (step && k < D) ? (T)step[k] : T(1);
+        }
+        return predict_core<T, D>(h, kernel_id, theta, X, N, Linv, ld, alpha, tp, M, mean, sd, s);
+    });
+    return GPG_OK;
+}
+
+extern "C" int gpg_predict(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X, int64_t N,
+                           const void *Linv, int64_t ld, const void *alpha, const void *Xs, int64_t M, void *mean_out,
+                           void *sd_out, void *stream) {
+    GPG_REQUIRE(h && theta && X && Linv && alpha && mean_out && sd_out, "NULL argument");
+    GPG_REQUIRE(M == 0 || Xs != nullptr, "Xs is NULL");
+    GPG_REQUIRE(N > 0 && M >= 0 && ld >= N, "bad size");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return predict_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, N, (const float *)Linv, ld,
+                                    (const float *)alpha, (const float *)Xs, nullptr, nullptr, 0, M, (float *)mean_out,
+                                    (float *)sd_out, s);
+    if (dtype == GPG_F64)
+        return predict_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, N, (const double *)Linv,
+                                     ld, (const double *)alpha, (const double *)Xs, nullptr, nullptr, 0, M,
+                                     (double *)mean_out, (double *)sd_out, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+extern "C" int gpg_predict_grid(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X,
+                                int64_t N, const void *Linv, int64_t ld, const void *alpha, const int64_t *dims_host,
+                                const double *step_host, int64_t j0, int64_t M, void *mean_out, void *sd_out,
+                                void *stream) {
+    GPG_REQUIRE(h && theta && X && Linv && alpha && mean_out && sd_out && dims_host && step_host, "NULL argument");
+    GPG_REQUIRE(N > 0 && M >= 0 && ld >= N && j0 >= 0, "bad size");
+    GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
+    int64_t total = 1;
+    for (int k = 0; k < d; ++k) { GPG_REQUIRE(dims_host[k] > 0, "grid dims must be positive"); total *= dims_host[k]; }
+    GPG_REQUIRE(j0 + M <= total, "grid tile exceeds the grid");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return predict_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, N, (const float *)Linv, ld,
+                                    (const float *)alpha, nullptr, dims_host, step_host, j0, M, (float *)mean_out,
+                                    (float *)sd_out, s);
+    if (dtype == GPG_F64)
+        return predict_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, N, (const double *)Linv,
+                                     ld, (const double *)alpha, nullptr, dims_host, step_host, j0, M, (double *)mean_out,
+                                     (double *)sd_out, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7: nll + gradient, Adam loop
+// ---------------------------------------------------------------------------------------------
+struct TrainBufs {
+    void *L, *Linv, *Kinv, *dinv, *vs, *vhat, *alpha, *scalars, *grad, *nll, *theta;
+    double *partial;
+    FitState *st;
+    int64_t ld;
+    int nblocks;
+};
+
+template <typename T> static size_t train_ws_bytes(int64_t N, int64_t ld) {
+    constexpr int NB = GemmCfg<T>::BN;
+    const size_t nn = (size_t)N * ld * sizeof(T);
+    const size_t nb = (size_t)((N + 7) / 8);
+    return bump_size({nn, nn, nn, NB * NB * sizeof(T), 2 * (size_t)N * sizeof(T), (size_t)N * sizeof(T),
+                      (size_t)N * sizeof(T), 2 * sizeof(T), GPG_MAX_P * sizeof(T), sizeof(T), GPG_MAX_P * sizeof(T),
+                      nb * GPG_MAX_P * sizeof(double), sizeof(FitState)});
+}
+
+template <typename T> static TrainBufs train_carve(void *ws, int64_t N, int64_t ld) {
+    constexpr int NB = GemmCfg<T>::BN;
+    Bump b(ws);
+    TrainBufs t;
+    t.ld = ld;
+    t.L = b.take<T>((size_t)N * ld);
+    t.Linv = b.take<T>((size_t)N * ld);
+    t.Kinv = b.take<T>((size_t)N * ld);
+    t.dinv = b.take<T>(NB * NB);
+    t.vs = b.take<T>(2 * N);
+    t.vhat = b.take<T>(N);
+    t.alpha = b.take<T>(N);
+    t.scalars = b.take<T>(2);
+    t.grad = b.take<T>(GPG_MAX_P);
+    t.nll = b.take<T>(1);
+    t.theta = b.take<T>(GPG_MAX_P);
+    t.nblocks = (int)((N + 7) / 8);
+    t.partial = b.take<double>((size_t)t.nblocks * GPG_MAX_P);
+    t.st = b.take<FitState>(1);
+    return t;
+}
+
+// one evaluation of nll and d nll / d theta at the theta stored in `theta`
+template <typename T>
+static int nll_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
+                         double jitter, const TrainBufs &tb, T *nll_out, T *grad_out, int32_t *info, int reset_info,
+                         cudaStream_t s) {
+    T *L = (T *)tb.L, *Linv = (T *)tb.Linv, *Kinv = (T *)tb.Kinv;
+    GPG_TRY(factorize_core<T>(h, kernel_id, d, theta, X, y, N, jitter, L, Linv, tb.ld, (T *)tb.vhat, (T *)tb.alpha,
+                              (T *)tb.scalars, info, reset_info, Kinv, (T *)tb.dinv, (T *)tb.vs, s));
+    GemmArgs<T> g;               // Kinv = Linv^T Linv on lower tiles: sum_k Linv[k][i] Linv[k][j], k >= max(i,j)
+    g.A = Linv; g.lda = tb.ld; g.a_kmajor = 0;
+    g.B = Linv; g.ldb = tb.ld; g.b_kmajor = 0;
+    g.C = Kinv; g.ldc = tb.ld;
+    g.M = (int)N; g.N = (int)N; g.K = (int)N;
+    g.kb_mode = GEMM_KB_MAXMN;
+    g.tile_mode = GEMM_TILES_LOWER;
+    GPG_TRY(gemm_dispatch<T>(h, g, s));
+    GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, grad_partial_kernel<T, KID, D><<<tb.nblocks, 256, 0, s>>>(
+                                                       theta, X, (const T *)tb.alpha, Kinv, tb.ld, N, tb.partial)));
+    GPG_LAUNCH_CHECK(h);
+    const double hl = 0.5 * (double)N * 1.8378770664093454835606594728112;   // N/2 log(2 pi)
+    grad_finish_kernel<T><<<1, 256, 0, s>>>(tb.partial, tb.nblocks, 3 + d, (const T *)tb.scalars, hl, grad_out, nll_out);
+    GPG_LAUNCH_CHECK(h);
+    return GPG_OK;
+}
+
+template <typename T>
+static int nll_grad_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
+                          double jitter, T *nll_out, T *grad_out, int32_t *info, cudaStream_t s) {
+    const int64_t ld = gpg_align_up((size_t)N, 64);
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, train_ws_bytes<T>(N, ld), &ws));
+    TrainBufs tb = train_carve<T>(ws, N, ld);
+    return nll_grad_core<T>(h, kernel_id, d, theta, X, y, N, jitter, tb, nll_out, grad_out, info, 1, s);
+}
+
+extern "C" int gpg_nll_grad(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X,
+                            const void *y, int64_t N, double jitter, void *nll_out, void *grad_out, int32_t *info,
+                            void *stream) {
+    GPG_REQUIRE(h && theta && X && y && nll_out && grad_out && info, "NULL argument");
+    GPG_REQUIRE(N > 0, "bad size");
+    GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return nll_grad_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, (const float *)y, N, jitter,
+                                     (float *)nll_out, (float *)grad_out, info, s);
+    if (dtype == GPG_F64)
+        return nll_grad_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, (const double *)y, N,
+                                      jitter, (double *)nll_out, (double *)grad_out, info, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+template <typename T>
+static int fit_entry(gpg_handle_s *h, int kernel_id, int d, int n_ls, const T *X, const T *y, int64_t N, double jitter,
+                     T *u, const double *bounds, int iters, double lr, T *traj, T *theta_out, int32_t *info,
+                     cudaStream_t s) {
+    const int64_t ld = gpg_align_up((size_t)N, 64);
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, train_ws_bytes<T>(N, ld), &ws));
+    TrainBufs tb = train_carve<T>(ws, N, ld);
+    FitCfg c;
+    memset(&c, 0, sizeof(c));
+    c.d = d; c.n_ls = n_ls; c.is_rq = (kernel_id == GPG_RATQUAD);
+    c.var_lo = bounds[0]; c.var_hi = bounds[1];
+    for (int k = 0; k < n_ls; ++k) { c.ls_lo[k] = bounds[2 + k]; c.ls_hi[k] = bounds[2 + n_ls + k]; }
+    c.lr = lr; c.beta1 = 0.9; c.beta2 = 0.999; c.eps = 1e-8;
+    T *theta = (T *)tb.theta;
+    adam_step_kernel<T><<<1, 32, 0, s>>>(0, c, u, tb.st, nullptr, nullptr, theta, nullptr);
+    GPG_LAUNCH_CHECK(h);
+    // info keeps the FIRST failing pivot over all iterations (reset once, atomicCAS afterwards)
+    GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
+    for (int it = 0; it < iters; ++it) {
+        GPG_TRY(nll_grad_core<T>(h, kernel_id, d, theta, X, y, N, jitter, tb, (T *)tb.nll, (T *)tb.grad, info, 0, s));
+        adam_step_kernel<T><<<1, 32, 0, s>>>(1, c, u, tb.st, (const T *)tb.grad, (const T *)tb.nll, theta,
+                                             traj ? traj + (size_t)it * (4 + d) : nullptr);
+        GPG_LAUNCH_CHECK(h);
+    }
+    if (theta_out) GPG_CUDA_CHECK(cudaMemcpyAsync(theta_out, theta, (3 + d) * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    return GPG_OK;
+}
+
+extern "C" int gpg_fit_adam(gpg_handle_t h, int dtype, int kernel_id, int d, int n_ls, const void *X, const void *y,
+                            int64_t N, double jitter, void *u, const double *bounds_host, int iters, double lr,
+                            void *traj_out, void *theta_out, int32_t *info, void *stream) {
+    GPG_REQUIRE(h && X && y && u && bounds_host && info, "NULL argument");
+    GPG_REQUIRE(N > 0 && iters >= 0, "bad size");
+    GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
+    GPG_REQUIRE(n_ls == 1 || n_ls == d, "n_ls must be 1 or d");
+    GPG_REQUIRE(kernel_id >= 0 && kernel_id <= 2, "unknown kernel id");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return fit_entry<float>(h, kernel_id, d, n_ls, (const float *)X, (const float *)y, N, jitter, (float *)u,
+                                bounds_host, iters, lr, (float *)traj_out, (float *)theta_out, info, s);
+    if (dtype == GPG_F64)
+        return fit_entry<double>(h, kernel_id, d, n_ls, (const double *)X, (const double *)y, N, jitter, (double *)u,
+                                 bounds_host, iters, lr, (double *)traj_out, (double *)theta_out, info, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: acquisition sweep + top-k
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int acq_entry(gpg_handle_s *h, int acq_id, const T *mean, const T *sd, const T *mask, int64_t M, double mu_best,
+                     double xi, double alpha, double beta, int k, T *topk_val, int64_t *topk_idx, int32_t *count,
+                     T *acq_out, cudaStream_t s) {
+    constexpr int CH = 2048;
+    const int64_t nblk0 = (M + CH - 1) / CH;
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)M * sizeof(Cand<T>), (size_t)(nblk0 * k + CH) * sizeof(Cand<T>),
+                                         (size_t)(nblk0 * k + CH) * sizeof(Cand<T>)}), &ws));
+    Bump b(ws);
+    Cand<T> *cand = b.take<Cand<T>>(M);
+    Cand<T> *bufA = b.take<Cand<T>>(nblk0 * k + CH);
+    Cand<T> *bufB = b.take<Cand<T>>(nblk0 * k + CH);
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPG_CUDA_CHECK(cudaFuncSetAttribute(topk_round_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            CH * (int)sizeof(Cand<T>)));
+        attr_set = true;
+    }
+    acq_eval_kernel<T><<<(unsigned)((M + 255) / 256), 256, 0, s>>>(acq_id, mean, sd, mask, M, mu_best, xi, alpha, beta,
+                                                                   acq_out, cand);
+    GPG_LAUNCH_CHECK(h);
+    const Cand<T> *in = cand;
+    int64_t n = M;
+    Cand<T> *out = bufA;
+    while (true) {
+        const int64_t nblk = (n + CH - 1) / CH;
+        topk_round_kernel<T><<<(unsigned)nblk, 1024, CH * sizeof(Cand<T>), s>>>(in, n, k, out);
+        GPG_LAUNCH_CHECK(h);
+        if (nblk == 1) break;
+        in = out;
+        n = nblk * k;
+        out = (out == bufA) ? bufB : bufA;
+    }
+    topk_emit_kernel<T><<<1, 256, 0, s>>>(out, k, topk_val, topk_idx, count);
+    GPG_LAUNCH_CHECK(h);
+    return GPG_OK;
+}
+
+extern "C" int gpg_acq_sweep(gpg_handle_t h, int dtype, int acq_id, const void *mean, const void *sd, const void *mask,
+                             int64_t M, double mu_best, double xi, double alpha, double beta, int k, void *topk_val,
+                             int64_t *topk_idx, int32_t *count_out, void *acq_out, void *stream) {
+    GPG_REQUIRE(h && mean && sd && topk_val && topk_idx && count_out, "NULL argument");
+    GPG_REQUIRE(M > 0, "M must be positive");
+    GPG_REQUIRE(k >= 1 && k <= 1024, "k must be in 1..1024");
+    GPG_REQUIRE(acq_id >= 0 && acq_id <= 2, "unknown acquisition id");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return acq_entry<float>(h, acq_id, (const float *)mean, (const float *)sd, (const float *)mask, M, mu_best, xi,
+                                alpha, beta, k, (float *)topk_val, topk_idx, count_out, (float *)acq_out, s);
+    if (dtype == GPG_F64)
+        return acq_entry<double>(h, acq_id, (const double *)mean, (const double *)sd, (const double *)mask, M, mu_best, xi,
+                                 alpha, beta, k, (double *)topk_val, topk_idx, count_out, (double *)acq_out, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}

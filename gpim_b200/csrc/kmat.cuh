@@ -1,0 +1,161 @@
+// kmat.cuh -- K1 (symmetric K(X,X) + diag) and K2 (cross-kernel rows for a tile of test points,
+// fused with the predictive mean row-reduction).  Both are HBM-write-bound: one FMA chain + one
+// exp per 4-byte store, 128-bit stores, coordinates re-read through L1/L2.
+#pragma once
+#include "common.cuh"
+
+// Where test-point coordinates come from: an (M, d) array, or the analytic np.mgrid layout.
+template <typename T, int D> struct TestPoints {
+    const T *Xs;            // nullptr -> analytic grid
+    int64_t dims[GPG_MAX_D];
+    T step[GPG_MAX_D];
+    int64_t j0;
+    __device__ __forceinline__ void load(int64_t j, T *z) const {
+        if (Xs) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) z[k] = Xs[j * D + k];
+        } else {
+            int64_t f = j0 + j;
+#pragma unroll
+            for (int k = D - 1; k >= 0; --k) {
+                z[k] = T(f % dims[k]) * step[k];
+                f /= dims[k];
+            }
+        }
+    }
+};
+
+template <typename T> struct Vec4 { T v[4]; };
+
+template <typename T> __device__ __forceinline__ void store4(T *dst, const T *v, bool vec_ok, int n_valid) {
+    if (vec_ok && n_valid == 4) {
+        if (sizeof(T) == 4) {
+            *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(v);
+        } else {
+            reinterpret_cast<double2 *>(dst)[0] = reinterpret_cast<const double2 *>(v)[0];
+            reinterpret_cast<double2 *>(dst)[1] = reinterpret_cast<const double2 *>(v)[1];
+        }
+    } else {
+        for (int e = 0; e < n_valid; ++e) dst[e] = v[e];
+    }
+}
+
+// out[i*ld + j] = k(X_i, Z_j) (+ diag_add on i == j when sym).  Block: 64 x 4 threads, each
+// thread 4 rows x 4 consecutive columns -> tile of 16 rows x 256 columns.
+template <typename T, int KID, int D>
+__global__ void __launch_bounds__(256) kmat_kernel(const T *__restrict__ theta, const T *__restrict__ X, int64_t N,
+                                                   const T *__restrict__ Z, int64_t P, int sym, T jitter,
+                                                   int lower_only, T *__restrict__ out, int64_t ld) {
+    const int64_t j = ((int64_t)blockIdx.x * 64 + threadIdx.x) * 4;
+    const int64_t i0 = ((int64_t)blockIdx.y * 4 + threadIdx.y) * 4;
+    if (lower_only && (int64_t)blockIdx.x * 256 > (int64_t)blockIdx.y * 16 + 15) return;
+    if (j >= P) return;
+    const Theta<T> th = load_theta<T, D>(theta);
+    const T diag_add = sym ? th.noise + jitter : T(0);
+    T z[4][D];
+    const int nv = (int)min((int64_t)4, P - j);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int k = 0; k < D; ++k) z[c][k] = (c < nv) ? Z[(j + c) * D + k] : T(0);
+    const bool vec_ok = ((ld % 4) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t i = i0 + r;
+        if (i >= N) break;
+        T x[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k] = X[i * D + k];
+        T v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            v[c] = cov_from_r2<T, KID>(scaled_r2<T, D>(x, z[c], th), th);
+            if (sym && i == j + c) v[c] += diag_add;
+        }
+        store4(out + i * ld + j, v, vec_ok, nv);
+    }
+}
+
+// K2: rows of the cross-kernel for test points j in [0, mc): Ks[j*ldk + i] = k(Xs_j, X_i), and
+// mean[j] = sum_i Ks[j][i] * alpha[i].  One warp per test point, lanes sweep i four at a time.
+// Test points with a NaN coordinate get a zero row (so the variance GEMM stays finite) and
+// mean = NaN.  SPLIT: additionally/instead emit fp16 hi/lo operands scaled by `scale`
+// (tensor-core path, see gemm_tc.cuh); then Ks is not written.
+template <typename T, int KID, int D, bool SPLIT>
+__global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ theta, const T *__restrict__ X, int64_t N,
+                                                          TestPoints<T, D> tp, int64_t mc, const T *__restrict__ alpha,
+                                                          T *__restrict__ Ks, int64_t ldk,
+                                                          __half *__restrict__ Khi, __half *__restrict__ Klo, int64_t ldh,
+                                                          float scale, T *__restrict__ mean) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= mc) return;
+    const Theta<T> th = load_theta<T, D>(theta);
+    T z[D];
+    tp.load(j, z);
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < D; ++k) bad |= (z[k] != z[k]);
+    double acc = 0.0;
+    const bool vec_ok = ((ldk % 4) == 0);
+    // row padding [N, ldk) (and [N, ldh)) is zero-filled so K-tiles may over-read it
+    const int64_t width = SPLIT ? ldh : ldk;
+    for (int64_t i = (int64_t)lane * 4; i < width; i += 128) {
+        T v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            T val = T(0);
+            if (i + c < N && !bad) {
+                T x[D];
+#pragma unroll
+                for (int k = 0; k < D; ++k) x[k] = X[(i + c) * D + k];
+                val = cov_from_r2<T, KID>(scaled_r2<T, D>(z, x, th), th);
+                acc += (double)val * (double)alpha[i + c];
+            }
+            v[c] = val;
+        }
+        const int nvalid = (int)min((int64_t)4, width - i);
+        if (SPLIT) {
+            __half hi[4], lo[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float s = (float)v[c] * scale;
+                hi[c] = __float2half_rn(s);
+                lo[c] = __float2half_rn(s - __half2float(hi[c]));
+            }
+            if (nvalid == 4 && (ldh % 4) == 0) {
+                *reinterpret_cast<uint2 *>(Khi + j * ldh + i) = *reinterpret_cast<uint2 *>(hi);
+                *reinterpret_cast<uint2 *>(Klo + j * ldh + i) = *reinterpret_cast<uint2 *>(lo);
+            } else {
+                for (int c = 0; c < nvalid; ++c) {
+                    Khi[j * ldh + i + c] = hi[c];
+                    Klo[j * ldh + i + c] = lo[c];
+                }
+            }
+        } else {
+            store4(Ks + j * ldk + i, v, vec_ok && ((reinterpret_cast<uintptr_t>(Ks) & 15) == 0), nvalid);
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) mean[j] = bad ? T(NAN) : (T)acc;
+}
+
+// K5: sd = sqrt(max(v - sum_tiles part[t][j], 0) + noise); NaN coordinates -> NaN.
+template <typename T, int D>
+__global__ void predict_finalize_kernel(const T *__restrict__ theta, const T *__restrict__ part, int ntiles, int64_t ldpart,
+                                        TestPoints<T, D> tp, int64_t mc, T inv_scale2, T *__restrict__ sd) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= mc) return;
+    double s = 0.0;
+    for (int t = 0; t < ntiles; ++t) s += (double)part[(int64_t)t * ldpart + j];
+    s *= (double)inv_scale2;
+    T z[D];
+    tp.load(j, z);
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < D; ++k) bad |= (z[k] != z[k]);
+    const double v = (double)theta[0], noise = (double)theta[1];
+    double var = v - s;
+    var = (var > 0.0 ? var : 0.0) + noise;
+    sd[j] = bad ? T(NAN) : (T)sqrt(var);
+}

@@ -1,0 +1,182 @@
+// train.cuh -- K7: marginal-likelihood gradient and the on-device Adam loop
+// (reconstructor.train, gpr.py:170-217).  One iteration = kmat -> cholesky -> trtri -> solves ->
+// Kinv = Linv^T Linv -> fused gradient reduction -> Adam step, all enqueued without host syncs.
+#pragma once
+#include "common.cuh"
+
+#define GPG_MAX_P (3 + GPG_MAX_D)
+
+struct FitState {               // lives in device workspace, double regardless of dtype
+    double m[GPG_MAX_P], v[GPG_MAX_P];
+    double dtheta_du[GPG_MAX_P];
+    int step;
+};
+
+struct FitCfg {
+    int d, n_ls, is_rq;
+    double var_lo, var_hi, ls_lo[GPG_MAX_D], ls_hi[GPG_MAX_D];
+    double lr, beta1, beta2, eps;
+    double half_n_log2pi;
+};
+
+// torch.distributions SigmoidTransform uses a clipped sigmoid (finfo.tiny .. 1 - finfo.eps)
+template <typename T> __device__ __forceinline__ void interval_fwd(T u, double lo, double hi, T &val, double &dval) {
+    const T tiny = sizeof(T) == 4 ? T(1.17549435e-38f) : T(2.2250738585072014e-308);
+    const T eps = sizeof(T) == 4 ? T(1.1920929e-07f) : T(2.220446049250313e-16);
+    T s = T(1) / (T(1) + gpg_exp(-u));
+    bool clipped = false;
+    if (s < tiny) { s = tiny; clipped = true; }
+    if (s > T(1) - eps) { s = T(1) - eps; clipped = true; }
+    const T scale = (T)(hi - lo);
+    val = (T)lo + scale * s;
+    dval = clipped ? 0.0 : (double)(scale * s * (T(1) - s));
+}
+
+// u -> theta (+ d theta / d u).  u layout: {variance, noise, scale_mixture, lengthscale[n_ls]}.
+template <typename T>
+__device__ void constrain_params(const T *u, const FitCfg &c, T *theta, double *dtheta_du) {
+    T val; double dv;
+    interval_fwd<T>(u[0], c.var_lo, c.var_hi, val, dv);
+    theta[0] = val; dtheta_du[0] = dv;
+    theta[1] = gpg_exp(u[1]); dtheta_du[1] = (double)theta[1];
+    theta[2] = c.is_rq ? gpg_exp(u[2]) : T(1); dtheta_du[2] = c.is_rq ? (double)theta[2] : 0.0;
+    for (int k = 0; k < c.n_ls; ++k) {
+        interval_fwd<T>(u[3 + k], c.ls_lo[k], c.ls_hi[k], val, dv);
+        dtheta_du[3 + k] = dv;
+        if (c.n_ls == 1) { for (int q = 0; q < c.d; ++q) theta[3 + q] = val; }
+        else theta[3 + k] = val;
+    }
+}
+
+// 0.5 * sum_ij G_ij dA_ij/dtheta_p over the lower triangle, G = Kinv - alpha alpha^T.
+// One warp per row i; partial[block][3+D] in double.  Reads Kinv's lower triangle once.
+template <typename T, int KID, int D>
+__global__ void __launch_bounds__(256) grad_partial_kernel(const T *__restrict__ theta, const T *__restrict__ X,
+                                                           const T *__restrict__ alpha, const T *__restrict__ Kinv,
+                                                           int64_t ld, int64_t N, double *__restrict__ partial) {
+    constexpr int P = 3 + D;
+    __shared__ double red[8][P];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 8 + w;
+    double g[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) g[p] = 0.0;
+    if (i < N) {
+        const Theta<T> th = load_theta<T, D>(theta);
+        T x[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k] = X[i * D + k];
+        const T ai = alpha[i];
+        for (int64_t j = lane; j <= i; j += 32) {
+            const double G = (double)Kinv[i * ld + j] - (double)ai * (double)alpha[j];
+            const double wgt = (j < i) ? 1.0 : 0.5;
+            T q[D];
+            T r2 = T(0);
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                T dlt = (x[k] - X[j * D + k]) * th.inv_ls[k];
+                q[k] = dlt * dlt;
+                r2 += q[k];
+            }
+            T dv, dl_common, da = T(0);     // dA/dv, factor such that dA/dl_k = dl_common * q_k / l_k
+            if (KID == GPG_RBF) {
+                const T e = gpg_exp(T(-0.5) * r2);
+                dv = e;
+                dl_common = th.variance * e;
+            } else if (KID == GPG_MATERN52) {
+                const T r = gpg_sqrt(r2 + T(1e-12));
+                const T s = T(2.23606797749978969641) * r;
+                const T e = gpg_exp(-s);
+                dv = (T(1) + s + (T(5) / T(3)) * r * r) * e;
+                dl_common = th.variance * e * (T(5) / T(3)) * (T(1) + s);
+            } else {
+                const T base = T(1) + (T(0.5) / th.alpha) * r2;
+                const T kb = gpg_pow(base, -th.alpha);
+                dv = kb;
+                dl_common = th.variance * kb / base;
+                da = th.variance * kb * (-gpg_log(base) + r2 / (T(2) * th.alpha * base));
+            }
+            const double gw = G * wgt;
+            g[0] += gw * (double)dv;
+            if (j == i) g[1] += gw;
+            g[2] += gw * (double)da;
+#pragma unroll
+            for (int k = 0; k < D; ++k) g[3 + k] += gw * (double)(dl_common * q[k] * th.inv_ls[k]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const double s = warp_sum(g[p]);
+        if (lane == 0) red[w][p] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < P) {
+        double s = 0.0;
+        for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
+        partial[(int64_t)blockIdx.x * P + threadIdx.x] = s;
+    }
+}
+
+// Sums the partials into grad_theta (constrained-theta layout, dtype T) and nll.
+template <typename T>
+__global__ void __launch_bounds__(256) grad_finish_kernel(const double *__restrict__ partial, int nblocks, int P,
+                                                          const T *__restrict__ scalars, double half_n_log2pi,
+                                                          T *__restrict__ grad_out, T *__restrict__ nll_out) {
+    __shared__ double red[8];
+    for (int p = 0; p < P; ++p) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += 256) s += partial[(int64_t)b * P + p];
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0;
+            for (int w = 0; w < 8; ++w) tot += red[w];
+            grad_out[p] = (T)tot;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && nll_out) nll_out[0] = (T)((double)scalars[0] + (double)scalars[1] + half_n_log2pi);
+}
+
+// mode 0: theta = constrain(u) (start of a train() call: fresh Adam state).
+// mode 1: chain rule, one torch.optim.Adam step on u, re-constrain, record {theta, loss}.
+template <typename T>
+__global__ void adam_step_kernel(int mode, FitCfg c, T *__restrict__ u, FitState *__restrict__ st,
+                                 const T *__restrict__ grad_theta, const T *__restrict__ nll, T *__restrict__ theta,
+                                 T *__restrict__ traj_row) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int P = 3 + c.n_ls;
+    if (mode == 0) {
+        for (int p = 0; p < GPG_MAX_P; ++p) { st->m[p] = 0.0; st->v[p] = 0.0; }
+        st->step = 0;
+        constrain_params<T>(u, c, theta, st->dtheta_du);
+        return;
+    }
+    st->step += 1;
+    const double bc1 = 1.0 - pow(c.beta1, (double)st->step);
+    const double bc2 = 1.0 - pow(c.beta2, (double)st->step);
+    const double step_size = c.lr / bc1;
+    const double bc2_sqrt = sqrt(bc2);
+    for (int p = 0; p < P; ++p) {
+        if (p == 2 && !c.is_rq) continue;
+        double gth;
+        if (p >= 3 && c.n_ls == 1) {
+            gth = 0.0;
+            for (int q = 0; q < c.d; ++q) gth += (double)grad_theta[3 + q];
+        } else gth = (double)grad_theta[p];
+        const T g = (T)(gth * st->dtheta_du[p]);
+        // state kept in double but rounded through T so fp32 runs follow torch's fp32 state
+        T m = (T)st->m[p], v = (T)st->v[p];
+        m = m + (T)(1.0 - c.beta1) * (g - m);                       // exp_avg.lerp_(grad, 1 - beta1)
+        v = v * (T)c.beta2 + ((T)(1.0 - c.beta2) * g) * g;          // mul_(beta2).addcmul_(g, g, 1 - beta2)
+        const T denom = gpg_sqrt(v) / (T)bc2_sqrt + (T)c.eps;
+        u[p] = u[p] + ((T)(-step_size) * m) / denom;                // addcdiv_(exp_avg, denom, -step_size)
+        st->m[p] = (double)m; st->v[p] = (double)v;
+    }
+    constrain_params<T>(u, c, theta, st->dtheta_du);
+    if (traj_row) {
+        for (int p = 0; p < 3 + c.d; ++p) traj_row[p] = theta[p];
+        traj_row[3 + c.d] = nll[0];
+    }
+}

@@ -1,0 +1,163 @@
+"""
+Grid / data-layout utilities of the hot path: the host-side boundary that fixes the (n, c) row
+layout the CUDA kernels consume.  Mirrors the data half of the reference's gpim/gprutils.py
+(:23-383) by name, argument meaning and error behaviour; plotting helpers (:385-938) are out of
+scope.  NumPy-2 safe (the reference calls the removed np.product at :49,54,82).
+"""
+import numpy as np
+import torch
+
+
+def _torch_dtype(kwargs):
+    return torch.float32 if kwargs.get("precision", "double") == "single" else torch.float64
+
+
+def _rows(X):
+    X = np.asarray(X)
+    return X.reshape(X.shape[0], -1).T
+
+
+def prepare_training_data(X, y=None, vector_valued=False, **kwargs):
+    """(c, *dims) coordinates and (*dims) observations -> torch (n, c) and (n,), NaN rows dropped
+    (gprutils.py:23-59)."""
+    dt = _torch_dtype(kwargs)
+    Xr = _rows(X)
+    Xr = torch.from_numpy(np.ascontiguousarray(Xr[~np.isnan(Xr).any(axis=1)])).to(dt)
+    if y is None:
+        return Xr, y
+    y = np.asarray(y)
+    if vector_valued:
+        yr = y.reshape(-1, y.shape[-1])
+        yr = yr[~np.isnan(yr).any(axis=1)]
+    else:
+        yr = y.reshape(-1)
+        yr = yr[~np.isnan(yr)]
+    return Xr, torch.from_numpy(np.ascontiguousarray(yr)).to(dt)
+
+
+def prepare_test_data(X, **kwargs):
+    """(c, *dims) -> torch (prod(dims), c); NaN rows are KEPT (gprutils.py:62-85)."""
+    return torch.from_numpy(np.ascontiguousarray(_rows(X))).to(_torch_dtype(kwargs))
+
+
+def get_full_grid(R, extent=None, dense_x=1.):
+    """np.mgrid coordinates for a 2D-4D array (gprutils.py:108-172).  With `extent`
+    ([[lo, hi], ...]) the step along each axis is dense_x / (size // (hi - lo)) as in the
+    reference's 2-D branch (its 3-D/4-D extent branches unpack incorrectly, :147,164; here all
+    dimensionalities follow the 2-D rule)."""
+    R = np.asarray(R)
+    if not 2 <= R.ndim <= 4:
+        raise NotImplementedError("Currently works only for 2D-4D sets")
+    dense_x = np.float64(dense_x)
+    if extent:
+        sl = []
+        for e, (lo, hi) in zip(R.shape, extent):
+            sl.append(slice(lo, hi, dense_x / (e // (hi - lo))))
+    else:
+        sl = [slice(0, e, dense_x) for e in R.shape]
+    return np.array(np.mgrid[tuple(sl)])
+
+
+def get_sparse_grid(R, extent=None):
+    """Grid coordinates with NaN where R is NaN (gprutils.py:175-210).  3-D data whose last
+    z-slice is fully observed is treated as whole-spectrum sparsity: an (x, y) position with any
+    NaN loses all of its z coordinates."""
+    R = np.asarray(R)
+    if not np.isnan(R).any():
+        raise NotImplementedError("Missing values in sparse data must be represented as NaNs")
+    X = get_full_grid(R, extent).astype(np.float64)
+    if R.ndim == 2 or (R.ndim == 3 and np.isnan(R[..., -1]).any()):
+        flat = X.reshape(X.shape[0], -1)
+        flat[:, np.isnan(R.reshape(-1))] = np.nan
+        return flat.reshape(X.shape)
+    if R.ndim == 3:
+        e1, e2, e3 = R.shape
+        X3 = X.reshape(3, e1 * e2, e3)
+        X3[:, np.isnan(R.reshape(e1 * e2, e3)).any(axis=1)] = np.nan
+        return X3.reshape(3, e1, e2, e3)
+    raise NotImplementedError("Currently supports only 2D and 3D sets with sparsity in xy and xyz dims")
+
+
+def get_grid_indices(R, dense_x=1.):
+    """(X_full, X_sparse) for 2D / 3D arrays (gprutils.py:88-105; the reference passes dense_x in
+    the `extent` slot at :103 -- here it reaches dense_x)."""
+    if np.ndim(R) > 3:
+        raise NotImplementedError("Currently supports only 2D and 3D arrays")
+    return get_full_grid(R, dense_x=np.float64(dense_x)), get_sparse_grid(R)
+
+
+def to_constrained_interval(state_dict, lscale, amp):
+    """Unconstrained lengthscale / variance of a kernel state dict -> their intervals
+    (gprutils.py:213-241; the reference reads the misspelt key 'lenghtscale_map_unconstrained',
+    both spellings are accepted here)."""
+    from torch.distributions import constraints, transform_to
+    sd = state_dict() if callable(state_dict) else state_dict
+    l_ = sd.get("lenghtscale_map_unconstrained", sd.get("lengthscale_map_unconstrained"))
+    a_ = sd["variance_map_unconstrained"]
+    l_int = constraints.interval(torch.as_tensor(lscale[0], dtype=l_.dtype), torch.as_tensor(lscale[1], dtype=l_.dtype))
+    a_int = constraints.interval(torch.as_tensor(amp[0], dtype=a_.dtype), torch.as_tensor(amp[1], dtype=a_.dtype))
+    return transform_to(l_int)(l_), transform_to(a_int)(a_)
+
+
+def _bernoulli_indices(n, prob):
+    """The reference draws n sequential pyro Bernoulli samples after pyro.set_rng_seed(0)
+    (gprutils.py:299-301), i.e. torch.bernoulli on the CPU generator seeded with 0."""
+    torch.manual_seed(0)
+    np.random.seed(0)
+    p = torch.tensor(float(prob))
+    return [i for i in range(n) if torch.bernoulli(p) == 1]
+
+
+def corrupt_image2d(X_true, R_true, prob, replace_w_zeros):
+    """Knock out a fraction of a 2-D image (gprutils.py:269-311)."""
+    e1, e2 = R_true.shape
+    if np.isnan(R_true).any():
+        X = X_true.copy().reshape(2, e1 * e2)
+        X[:, np.isnan(R_true.reshape(-1))] = np.nan
+        return X.reshape(2, e1, e2), R_true
+    idx = _bernoulli_indices(e1 * e2, prob)
+    R = R_true.copy().reshape(-1)
+    R[idx] = np.nan
+    X = X_true.astype(np.float64).reshape(2, -1)
+    X[:, idx] = np.nan
+    X, R = X.reshape(2, e1, e2), R.reshape(e1, e2)
+    if replace_w_zeros:
+        X, R = np.nan_to_num(X), np.nan_to_num(R)
+    return X, R
+
+
+def corrupt_image3d(X_true, R_true, prob, replace_w_zeros):
+    """Remove whole spectra at random (x, y) positions (gprutils.py:314-359)."""
+    e1, e2, e3 = R_true.shape
+    if np.isnan(R_true).any():
+        X = X_true.copy().reshape(3, e1 * e2, e3)
+        X[:, np.isnan(R_true.reshape(e1 * e2, e3)).any(axis=1)] = np.nan
+        return X.reshape(3, e1, e2, e3), R_true
+    idx = _bernoulli_indices(e1 * e2, prob)
+    R = R_true.copy().reshape(e1 * e2, e3)
+    R[idx, :] = np.nan
+    X = X_true.astype(np.float64).reshape(3, e1 * e2, e3)
+    X[:, idx, :] = np.nan
+    X, R = X.reshape(3, e1, e2, e3), R.reshape(e1, e2, e3)
+    if replace_w_zeros:
+        X, R = np.nan_to_num(X), np.nan_to_num(R)
+    return X, R
+
+
+def corrupt_data_xy(X_true, R_true, prob=0.5, replace_w_zeros=False):
+    """Dispatch on dimensionality (gprutils.py:244-266)."""
+    if np.ndim(R_true) == 2:
+        return corrupt_image2d(X_true, R_true, prob, replace_w_zeros)
+    if np.ndim(R_true) == 3:
+        return corrupt_image3d(X_true, R_true, prob, replace_w_zeros)
+    raise NotImplementedError("Currently supports only 2D and 3D sets")
+
+
+def open_edge_points(R, R_true, s=6):
+    """Reveal every s-th measurement along the frame edges (gprutils.py:362-382)."""
+    e1, e2 = R_true.shape[:2]
+    R[0, ::s] = R_true[0, ::s]
+    R[::s, 0] = R_true[::s, 0]
+    R[e1 - 1, s:e2 - s:s] = R_true[e1 - 1, s:e2 - s:s]
+    R[s::s, e2 - 1] = R_true[s::s, e2 - 1]
+    return R

@@ -1,0 +1,143 @@
+/*
+ * gpgrid.h -- C ABI of libgpgrid.so: the B200 (sm_100a) exact-GP-on-grids engine that sits under
+ * the gpim.reconstructor / gpim.boptimizer Python API.
+ *
+ * The reference (ziatdinovmax/GPim) has no FFI: its boundary to the arithmetic is the Python
+ * object protocol of pyro.contrib.gp.models.GPRegression.  Each entry point below names the
+ * reference call site whose arithmetic it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer argument is a DEVICE pointer owned by the caller (torch tensor data_ptr())
+ *     unless its name ends in _host; the library never frees or retains caller memory;
+ *   - matrices are row-major with an explicit leading dimension (in elements);
+ *   - work is enqueued on the cudaStream_t passed as `stream` (void* here so the header needs
+ *     no CUDA include); calls do not synchronise unless documented;
+ *   - dtype selects the arithmetic type of ALL floating-point buffers of the call
+ *     (GPG_F32 = float, GPG_F64 = double), mirroring precision="single"/"double"
+ *     (gpim/gpreg/gpr.py:92-99);
+ *   - return value: GPG_OK, or an error code with text in gpg_last_error();
+ *   - theta (constrained hyper-parameters) is a device array of dtype, length 3 + d:
+ *       theta[0] variance, theta[1] noise, theta[2] scale_mixture (RationalQuadratic only),
+ *       theta[3 + k] lengthscale of input dimension k (an isotropic kernel repeats its value);
+ *   - thread-compatible: a handle must not be used from two host threads at once.
+ */
+#ifndef GPGRID_H
+#define GPGRID_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPG_VERSION 100
+
+enum { GPG_OK = 0, GPG_EINVAL = 1, GPG_ENOTPD = 2, GPG_ECUDA = 3 };
+enum { GPG_F32 = 0, GPG_F64 = 1 };
+/* kernel book of gpim/kernels/pyro_kernels.py:58-68 */
+enum { GPG_RBF = 0, GPG_MATERN52 = 1, GPG_RATQUAD = 2 };
+/* gpim/gpbayes/acqfunc.py:11-92 */
+enum { GPG_ACQ_CB = 0, GPG_ACQ_EI = 1, GPG_ACQ_POI = 2 };
+/* gpg_set_option keys */
+enum {
+    GPG_OPT_GEMM_PATH = 1,      /* 0 auto (tcgen05 for f32 when large enough), 1 SIMT only, 2 force tcgen05 */
+    GPG_OPT_PREDICT_CHUNK = 2   /* test points per internal tile of gpg_predict (0 = auto) */
+};
+
+typedef struct gpg_handle_s *gpg_handle_t;
+
+int gpg_version(void);
+const char *gpg_last_error(void);
+int gpg_create(int device, gpg_handle_t *out);
+int gpg_destroy(gpg_handle_t h);
+int gpg_set_option(gpg_handle_t h, int key, long long value);
+/* number of kernel launches this handle has enqueued since creation (bench.py gpu_launches) */
+long long gpg_launch_count(gpg_handle_t h);
+/* bytes of device workspace currently owned by the handle */
+size_t gpg_workspace_bytes(gpg_handle_t h);
+
+/* K1/K2 -- kernel-matrix assembly.  Replaces Pyro Isotropy.forward reached from
+ * gpim/gpreg/gpr.py:192,248 (kernel(X), kernel(X, Xnew)) with the kernels configured at
+ * gpim/kernels/pyro_kernels.py:58-68.
+ * out[i*ld + j] = k_theta(X_i, Z_j) for i < N, j < P;  Z == NULL means Z = X, P = N and
+ * (theta.noise + jitter) is added on the diagonal (GPRegression.model: Kff.view(-1)[::N+1] += ...).
+ * lower_only != 0 (Z == NULL only) skips tiles strictly above the diagonal. */
+int gpg_kmat(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
+             const void *X, int64_t N, const void *Z, int64_t P, double jitter, int lower_only,
+             void *out, int64_t ld, void *stream);
+
+/* K3 -- in-place blocked Cholesky of the lower triangle of A (torch.linalg.cholesky inside
+ * GPRegression.model / .forward, reached from gpr.py:192,248).  The strict upper triangle is
+ * not referenced and is left unspecified.  *info (device int32) receives 0, or 1 + the index of
+ * the first non-positive pivot; no host synchronisation. */
+int gpg_cholesky(gpg_handle_t h, int dtype, void *A, int64_t N, int64_t ld, int32_t *info, void *stream);
+
+/* Linv = L^-1 (lower; strict upper triangle of Linv is written as zero).  L and Linv must not alias. */
+int gpg_trtri(gpg_handle_t h, int dtype, const void *L, int64_t N, int64_t ld,
+              void *Linv, int64_t ldinv, void *stream);
+
+/* K7a -- vhat = L^-1 y, alpha = L^-T vhat, logdet = sum_i log L_ii  (MultivariateNormal.log_prob
+ * in GPRegression.model, gpr.py:192; the y column of util.conditional's pack, gpr.py:248).
+ * Uses Linv with residual correction against L.  scalars_out (dtype[2]): {0.5*|vhat|^2, logdet}. */
+int gpg_solve_vec(gpg_handle_t h, int dtype, const void *L, const void *Linv, int64_t N, int64_t ld,
+                  const void *y, void *vhat_out, void *alpha_out, void *scalars_out, void *stream);
+
+/* K1+K3+trtri+K7a in one call: the factor cache {L, Linv, alpha, vhat} for fixed theta.
+ * Replaces the kernel(X)+cholesky that GPRegression.forward redoes on every predict (gpr.py:248). */
+int gpg_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
+                  const void *X, const void *y, int64_t N, double jitter,
+                  void *L, void *Linv, int64_t ld, void *vhat_out, void *alpha_out,
+                  void *scalars_out, int32_t *info, void *stream);
+
+/* K2+K4+K5 -- predictive mean and standard deviation at M test points, tiled over M internally
+ * (never materialises the N x M cross-kernel).  Replaces util.conditional + the noise add and
+ * sqrt at gpr.py:248-250:  mean = K*^T alpha,  sd = sqrt(max(v - colsum((Linv K*)^2), 0) + noise).
+ * Rows of Xs that contain NaN give NaN outputs (acqfunc.py:57-59 relies on it). */
+int gpg_predict(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
+                const void *X, int64_t N, const void *Linv, int64_t ld, const void *alpha,
+                const void *Xs, int64_t M, void *mean_out, void *sd_out, void *stream);
+
+/* Analytic grid variant: Xs is not read; test point j has coordinates unravel(j0 + j, dims)*step
+ * (np.mgrid layout of gprutils.get_full_grid, gprutils.py:136).  dims_host/step_host: host arrays [d]. */
+int gpg_predict_grid(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
+                     const void *X, int64_t N, const void *Linv, int64_t ld, const void *alpha,
+                     const int64_t *dims_host, const double *step_host, int64_t j0, int64_t M,
+                     void *mean_out, void *sd_out, void *stream);
+
+/* K7 -- negative log marginal likelihood and its gradient w.r.t. the constrained theta
+ * (Trace_ELBO.differentiable_loss + backward at gpr.py:192-193, minus the constant Uniform
+ * log-priors).  nll_out: dtype[1]; grad_out: dtype[3 + d] in theta layout. */
+int gpg_nll_grad(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
+                 const void *X, const void *y, int64_t N, double jitter,
+                 void *nll_out, void *grad_out, int32_t *info, void *stream);
+
+/* Whole training loop on the device (reconstructor.train, gpr.py:170-217): `iters` Adam steps
+ * (torch.optim.Adam defaults) on the unconstrained parameters, constrained values recorded after
+ * each step, no host synchronisation.
+ *   u        dtype[3 + n_ls] in/out: unconstrained {variance, noise, scale_mixture, lengthscale[n_ls]}
+ *            variance, lengthscale: sigmoid onto [lo, hi] (interval constraint); noise,
+ *            scale_mixture: exp (positive constraint)
+ *   bounds_host  double[2 + 2*n_ls]: {var_lo, var_hi, ls_lo[n_ls], ls_hi[n_ls]}
+ *   n_ls     1 (isotropic) or d (ARD)
+ *   traj_out dtype[iters * (4 + d)]: per iteration {theta[0..3+d), loss}
+ *   theta_out dtype[3 + d]: constrained theta after the last step */
+int gpg_fit_adam(gpg_handle_t h, int dtype, int kernel_id, int d, int n_ls,
+                 const void *X, const void *y, int64_t N, double jitter,
+                 void *u, const double *bounds_host, int iters, double lr,
+                 void *traj_out, void *theta_out, int32_t *info, void *stream);
+
+/* K6 -- acquisition sweep + top-k (acqfunc.py:11-92, boptim.py:303-315).
+ *   acq_id CB: alpha*mean + beta*sd;  EI: imp*Phi(z) + sd*phi(z), imp = mean - mu_best - xi,
+ *   z = imp/sd;  POI: Phi(z).   mask (nullable, dtype[M]): multiplied in, NaN entries excluded.
+ *   topk_val dtype[k], topk_idx int64[k]: descending value, ties by descending flat index
+ *   (the reversed ascending argsort of boptim.py:304-306); unmasked NaNs rank first, as there.
+ *   count_out int32[1]: number of valid entries written (< k only when masked).  acq_out nullable. */
+int gpg_acq_sweep(gpg_handle_t h, int dtype, int acq_id, const void *mean, const void *sd,
+                  const void *mask, int64_t M, double mu_best, double xi, double alpha, double beta,
+                  int k, void *topk_val, int64_t *topk_idx, int32_t *count_out, void *acq_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPGRID_H */

@@ -1,0 +1,326 @@
+"""
+GPU parity tests (-m gpu): every C-ABI entry point of libgpgrid.so against the CPU oracle
+(oracle/gp_oracle.py) on the same seeded inputs.  Tolerances: fp64 ~1e-9 (different summation
+order only); fp32 mean 1e-4 / sd 1e-3 in the inf-norm relative sense of BASELINE.json
+(||a - b||_inf / ||b||_inf), measured against the fp64 oracle.
+"""
+import numpy as np
+import pytest
+import torch
+from scipy.stats import norm
+
+import workloads as W
+from oracle import gp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ["RBF", "Matern52", "RationalQuadratic"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from gpim_b200._lib import get_engine
+    return get_engine()
+
+
+def relinf(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def make_theta(d, dtype, variance=0.7, noise=0.05, alpha=1.3, ls=(2.0, 3.0, 4.0, 5.0)):
+    return torch.tensor([variance, noise, alpha, *ls[:d]], dtype=dtype)
+
+
+def rand_points(n, d, seed, scale=20.0):
+    rng = np.random.RandomState(seed)
+    return rng.rand(n, d) * scale
+
+
+def spiral_problem(n):
+    R = W.spiral_scan(n)
+    Xs = O.sparse_grid(R)
+    X, y = O.training_rows(Xs, R)
+    return R, X, y
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("d", [2, 3, 4])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-5)])
+def test_kmat_matches_oracle(eng, kernel, d, dtype, tol):
+    from gpim_b200._lib import KERNEL_IDS
+    X = rand_points(333, d, 0)
+    Z = rand_points(257, d, 1)
+    th = make_theta(d, dtype)
+    ref_cross = O.kernel_matrix(kernel, torch.tensor(X), torch.tensor(Z), th[0].double(), th[3:].double(), th[2].double())
+    ref_sym = O.kernel_matrix(kernel, torch.tensor(X), torch.tensor(X), th[0].double(), th[3:].double(), th[2].double())
+    ref_sym = ref_sym + (th[1].double() + 1e-5) * torch.eye(len(X), dtype=torch.float64)
+    Xd = torch.tensor(X, dtype=dtype).cuda()
+    Zd = torch.tensor(Z, dtype=dtype).cuda()
+    got_cross = eng.kmat(KERNEL_IDS[kernel], th.cuda(), Xd, Zd).cpu()
+    got_sym = eng.kmat(KERNEL_IDS[kernel], th.cuda(), Xd, None, jitter=1e-5).cpu()
+    assert relinf(got_cross, ref_cross) < tol
+    assert relinf(got_sym, ref_sym) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 5e-4)])
+@pytest.mark.parametrize("n", [1, 37, 128, 300, 777])
+def test_cholesky_trtri_solve(eng, dtype, tol, n):
+    rng = np.random.RandomState(n)
+    B = rng.randn(n, n)
+    A = B @ B.T / n + np.eye(n) * 0.5
+    ref_L = np.linalg.cholesky(A)
+    Ad = torch.tensor(A, dtype=dtype).cuda()
+    L, info = eng.cholesky_(Ad.clone())
+    assert int(info.item()) == 0
+    Lh = torch.tril(L).cpu().double().numpy()
+    assert relinf(Lh, ref_L) < tol
+    Linv = eng.trtri(L)
+    Lih = Linv.cpu().double().numpy()
+    assert np.all(np.triu(Lih, 1) == 0)
+    assert relinf(Lih @ ref_L, np.eye(n)) < tol * 10
+    y = rng.randn(n)
+    vhat, alpha, scal = eng.solve_vec(L, Linv, torch.tensor(y, dtype=dtype).cuda())
+    ref_v = np.linalg.solve(ref_L, y)
+    ref_a = np.linalg.solve(A, y)
+    assert relinf(vhat.cpu(), ref_v) < tol * 10
+    assert relinf(alpha.cpu(), ref_a) < tol * 10
+    sc = scal.cpu().double().numpy()
+    assert abs(sc[0] - 0.5 * ref_v @ ref_v) < tol * 10 * max(1.0, abs(0.5 * ref_v @ ref_v))
+    assert abs(sc[1] - np.log(np.diag(ref_L)).sum()) < tol * 10 * max(1.0, n)
+
+
+def test_cholesky_reports_first_bad_pivot(eng):
+    n = 200
+    A = np.eye(n)
+    A[150, 150] = -1.0
+    _, info = eng.cholesky_(torch.tensor(A).cuda())
+    assert int(info.item()) == 151
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_predict_fixed_theta_matches_oracle(eng, kernel, precision):
+    """C1-shaped problem (32x32 blob, N=615, M=1024) + NaN test rows, fixed theta."""
+    from gpim_b200._lib import KERNEL_IDS
+    dtype = torch.float64 if precision == "double" else torch.float32
+    R = W.dummy_blob()
+    X, y = O.training_rows(O.sparse_grid(R), R)
+    Xs = O.to_rows(O.sparse_grid(R))            # contains NaN rows, like predict(X_sparse) in EI
+    v, l, noise = 0.5, [12.0, 9.0], 1e-3
+    good = ~np.isnan(Xs).any(axis=1)
+    ref_mean, ref_sd, _ = O.predict_fixed_theta(kernel, X, y, Xs[good], v, l, noise, jitter=1e-5, scale_mixture=1.3)
+    th = torch.tensor([v, noise, 1.3, *l], dtype=dtype).cuda()
+    Xd, yd = torch.tensor(X, dtype=dtype).cuda(), torch.tensor(y, dtype=dtype).cuda()
+    fac = eng.factorize(KERNEL_IDS[kernel], th, Xd, yd, 1e-5)
+    assert int(fac["info"].item()) == 0
+    mean, sd = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, torch.tensor(Xs, dtype=dtype).cuda())
+    mean, sd = mean.cpu().numpy(), sd.cpu().numpy()
+    assert np.isnan(mean[~good]).all() and np.isnan(sd[~good]).all()
+    tol_m, tol_s = (1e-8, 1e-8) if precision == "double" else (1e-4, 1e-3)
+    assert relinf(mean[good], ref_mean) < tol_m
+    assert relinf(sd[good], ref_sd) < tol_s
+
+
+@pytest.mark.parametrize("precision,tol_m,tol_s", [("double", 1e-8, 1e-8), ("single", 1e-4, 1e-3)])
+def test_predict_spiral_and_grid_variant(eng, precision, tol_m, tol_s):
+    """C2-shaped problem at 96x96 (spiral, RBF): array test points == analytic grid test points == oracle."""
+    from gpim_b200._lib import KERNEL_IDS
+    dtype = torch.float64 if precision == "double" else torch.float32
+    n = 96
+    R, X, y = spiral_problem(n)
+    ft = W.FIXED_THETA
+    Xfull = O.to_rows(O.full_grid(R))
+    ref_mean, ref_sd, _ = O.predict_fixed_theta("RBF", X, y, Xfull, ft["variance"], [ft["lengthscale"]] * 2,
+                                                ft["noise"], jitter=ft["jitter"])
+    th = torch.tensor([ft["variance"], ft["noise"], 1.0, ft["lengthscale"], ft["lengthscale"]], dtype=dtype).cuda()
+    Xd, yd = torch.tensor(X, dtype=dtype).cuda(), torch.tensor(y, dtype=dtype).cuda()
+    fac = eng.factorize(KERNEL_IDS["RBF"], th, Xd, yd, ft["jitter"])
+    m1, s1 = eng.predict(KERNEL_IDS["RBF"], th, Xd, fac, torch.tensor(Xfull, dtype=dtype).cuda())
+    m2, s2 = eng.predict_grid(KERNEL_IDS["RBF"], th, Xd, fac, [n, n], [1.0, 1.0], 0, n * n)
+    assert relinf(m1.cpu(), ref_mean) < tol_m and relinf(s1.cpu(), ref_sd) < tol_s
+    assert torch.equal(m1, m2) and torch.equal(s1, s2)
+    # a tile of the grid (what one rank of the multi-GPU shard computes)
+    j0, mt = 1000, 3000
+    m3, s3 = eng.predict_grid(KERNEL_IDS["RBF"], th, Xd, fac, [n, n], [1.0, 1.0], j0, mt)
+    assert relinf(m3.cpu(), ref_mean[j0:j0 + mt]) < tol_m and relinf(s3.cpu(), ref_sd[j0:j0 + mt]) < tol_s
+
+
+def test_predict_3d_matern(eng):
+    """C3-shaped (hyperspectral, Matern52, d=3) at 16x16x8, fp32 vs fp64 oracle."""
+    from gpim_b200._lib import KERNEL_IDS
+    R = W.hyperspectral((16, 16, 8))
+    X, y = O.training_rows(O.sparse_grid(R), R)
+    Xfull = O.to_rows(O.full_grid(R))
+    v, l, noise = 0.4, [3.0, 3.0, 8.0], 5e-3
+    ref_mean, ref_sd, _ = O.predict_fixed_theta("Matern52", X, y, Xfull, v, l, noise)
+    th = torch.tensor([v, noise, 1.0, *l], dtype=torch.float32).cuda()
+    Xd, yd = torch.tensor(X, dtype=torch.float32).cuda(), torch.tensor(y, dtype=torch.float32).cuda()
+    fac = eng.factorize(KERNEL_IDS["Matern52"], th, Xd, yd, 1e-5)
+    m, s = eng.predict_grid(KERNEL_IDS["Matern52"], th, Xd, fac, list(R.shape), [1.0] * 3, 0, R.size)
+    assert relinf(m.cpu(), ref_mean) < 1e-4 and relinf(s.cpu(), ref_sd) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------
+def _torch_nll(kernel, X, y, theta, jitter):
+    v, n, a, l = theta[0], theta[1], theta[2], theta[3:]
+    K = O.kernel_matrix(kernel, X, X, v, l, a) + (jitter + n) * torch.eye(len(X), dtype=X.dtype)
+    L = torch.linalg.cholesky(K)
+    al = torch.linalg.solve_triangular(L, y.unsqueeze(1), upper=False)
+    return 0.5 * (al ** 2).sum() + L.diagonal().log().sum() + 0.5 * len(X) * np.log(2 * np.pi)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("d,n", [(2, 150), (3, 421)])
+def test_nll_grad_matches_autograd(eng, kernel, d, n):
+    from gpim_b200._lib import KERNEL_IDS
+    X = torch.tensor(rand_points(n, d, 3, scale=10.0))
+    y = torch.sin(X.sum(1)) + 0.1 * torch.tensor(np.random.RandomState(4).randn(n))
+    theta = make_theta(d, torch.float64, variance=0.9, noise=0.02).requires_grad_(True)
+    ref = _torch_nll(kernel, X, y, theta, 1e-6)
+    ref.backward()
+    nll, grad, info = eng.nll_grad(KERNEL_IDS[kernel], theta.detach().cuda(), X.cuda(), y.cuda(), 1e-6)
+    assert int(info.item()) == 0
+    assert abs(nll.item() - ref.item()) < 1e-8 * max(1.0, abs(ref.item()))
+    g_ref = theta.grad.numpy().copy()
+    if kernel != "RationalQuadratic":
+        g_ref[2] = 0.0
+    np.testing.assert_allclose(grad.cpu().numpy(), g_ref, rtol=1e-7, atol=1e-8)
+
+
+@pytest.mark.parametrize("kernel,iso", [("RBF", False), ("Matern52", False), ("RationalQuadratic", False), ("RBF", True)])
+def test_fit_adam_trajectory_matches_oracle(kernel, iso):
+    """reconstructor.train vs OracleGP.train, fp64, 25 iterations: per-iteration hyper-parameters."""
+    import gpim_b200 as gpim
+    R = W.dummy_blob(20, 200)
+    Xs, Xf = O.sparse_grid(R), O.full_grid(R)
+    ora = O.OracleGP(Xs, R, Xf, kernel=kernel, learning_rate=0.1, iterations=25, isotropic=iso)
+    ora.train()
+    rec = gpim.reconstructor(Xs, R, Xf, kernel=kernel, learning_rate=0.1, iterations=25, verbose=0, isotropic=iso)
+    rec.train()
+    np.testing.assert_allclose(np.array(rec.hyperparams["variance"]), np.array(ora.amp_all), rtol=1e-7)
+    np.testing.assert_allclose(np.array(rec.hyperparams["noise"]), np.array(ora.noise_all), rtol=1e-7)
+    np.testing.assert_allclose(np.array(rec.hyperparams["lengthscale"]), np.array(ora.lscales), rtol=1e-7)
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "Matern52"])
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_reconstructor_run_like_reference_test(kernel, precision):
+    """test/test_gpreg.py:24-36 through the native path, plus values against the oracle."""
+    import gpim_b200 as gpim
+    np.random.seed(0)
+    xx, yy = np.meshgrid(np.arange(0, 100, 5), np.arange(0, 100, 5))
+    R = np.exp(-((xx - 25) ** 2 + (yy - 50) ** 2) / 300)
+    for _ in range(200):
+        R[np.random.randint(R.shape[0]), np.random.randint(R.shape[1])] = np.nan
+    X, X_true = gpim.utils.get_sparse_grid(R), gpim.utils.get_full_grid(R)
+    mean, sd, hp = gpim.reconstructor(X, R, X_true, kernel=kernel, learning_rate=0.1, iterations=2,
+                                      use_gpu=False, verbose=False, precision=precision).run()
+    assert mean.shape == sd.shape == R.shape
+    assert not np.isnan(mean).any() and not np.isnan(sd).any()
+    om, osd, ohp = O.OracleGP(X, R, X_true, kernel=kernel, learning_rate=0.1, iterations=2, precision=precision).run()
+    tol_m, tol_s = (1e-8, 1e-8) if precision == "double" else (1e-4, 1e-3)
+    assert relinf(mean, om) < tol_m and relinf(sd, osd) < tol_s
+    np.testing.assert_allclose(hp["noise"], ohp["noise"], rtol=1e-6 if precision == "double" else 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("acq", ["cb", "ei", "poi"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("M,k", [(625, 100), (16384, 100), (100000, 1000), (50, 100)])
+def test_acq_sweep_and_topk(eng, acq, dtype, M, k):
+    from gpim_b200._lib import ACQ_IDS
+    rng = np.random.RandomState(M)
+    mean = rng.randn(M).astype(np.float64)
+    sd = np.abs(rng.randn(M)) + 0.01
+    mean[::7] = mean[3]                     # ties
+    sd[::7] = sd[3]
+    md, sdd = torch.tensor(mean, dtype=dtype).cuda(), torch.tensor(sd, dtype=dtype).cuda()
+    mh, sh = md.cpu().double().numpy(), sdd.cpu().double().numpy()
+    mu_best, xi = 0.3, 0.01
+    if acq == "cb":
+        ref = 0.5 * mh + 2.0 * sh
+    else:
+        z = (mh - mu_best - xi) / sh
+        ref = (mh - mu_best - xi) * norm.cdf(z) + sh * norm.pdf(z) if acq == "ei" else norm.cdf(z)
+    vals, idx, count, out = eng.acq_sweep(ACQ_IDS[acq], md, sdd, k, mu_best=mu_best, xi=xi, alpha=0.5, beta=2.0,
+                                          want_acq=True)
+    out = out.cpu().double().numpy()
+    # EI cancels like 1/z^2 in its far tail and fp32 underflows there: absolute floor relative to max|ref|
+    np.testing.assert_allclose(out, ref, rtol=1e-9 if dtype == torch.float64 else 2e-5,
+                               atol=(1e-13 if dtype == torch.float64 else 1e-7) * np.abs(ref).max())
+    kk = min(k, M)
+    assert int(count.item()) == kk
+    # ranking must equal the reference's reversed ascending argsort of the SAME values (stable ties)
+    order = np.argsort(out, kind="stable")[::-1][:kk]
+    np.testing.assert_array_equal(idx.cpu().numpy(), order)
+    np.testing.assert_array_equal(vals.cpu().double().numpy(), out[order])
+
+
+def test_acq_sweep_mask(eng):
+    from gpim_b200._lib import ACQ_IDS
+    rng = np.random.RandomState(0)
+    M = 5000
+    mean, sd = rng.randn(M), np.abs(rng.randn(M)) + 0.1
+    mask = np.ones(M)
+    mask[rng.rand(M) < 0.99] = np.nan        # ~50 valid entries < k
+    vals, idx, count, _ = eng.acq_sweep(ACQ_IDS["cb"], torch.tensor(mean).cuda(), torch.tensor(sd).cuda(), 100,
+                                        alpha=1.0, beta=1.0, mask=torch.tensor(mask).cuda())
+    n = int(count.item())
+    acq = mask * (mean + sd)
+    order = np.argsort(acq, kind="stable")
+    valid = order[~np.isnan(acq[order])][::-1]
+    assert n == len(valid)
+    np.testing.assert_array_equal(idx.cpu().numpy()[:n], valid[:n])
+
+
+# ---------------------------------------------------------------------------------------------
+def _boptim_setup():
+    def trial_func(idx, x0=5, y0=10, fwhm=4.5):
+        return np.exp(-4 * np.log(2) * ((idx[0] - x0) ** 2 + (idx[1] - y0) ** 2) / fwhm ** 2)
+    np.random.seed(0)
+    x = np.arange(0, 25, 1.0)
+    y = x[:, np.newaxis]
+    Z = trial_func([y, x])
+    idx = np.random.randint(0, Z.shape[0], size=(2, 5))
+    Zs = np.ones_like(Z) * np.nan
+    Zs[idx[0], idx[1]] = Z[idx[0], idx[1]]
+    return trial_func, Zs
+
+
+@pytest.mark.parametrize("acqf", ["ei", "poi", "cb"])
+def test_boptimizer_reproduces_reference_golden(acqf, golden_dir, tmp_path):
+    """test/test_boptim.py:42-58 verbatim, through the CUDA path (fp64 default)."""
+    import os
+    import gpim
+    trial_func, Z_sparse = _boptim_setup()
+    X_full = gpim.utils.get_full_grid(Z_sparse)
+    X_sparse = gpim.utils.get_sparse_grid(Z_sparse)
+    expected = np.load(os.path.join(golden_dir, f"ref_test_{acqf}.npy"))
+    bo = gpim.boptimizer(X_sparse, Z_sparse, X_full, trial_func, acquisition_function=acqf, exploration_steps=20,
+                         use_gpu=False, verbose=0, filename=str(tmp_path / "bo"))
+    bo.run()
+    np.testing.assert_allclose(bo.target_func_vals[-1], expected)
+
+
+def test_boptimizer_custom_acquisition_and_mask(tmp_path):
+    """Custom callables keep working (boptim.py:296-298) and agree with the built-in device path."""
+    import gpim
+    trial_func, Z_sparse = _boptim_setup()
+    X_full, X_sparse = gpim.utils.get_full_grid(Z_sparse), gpim.utils.get_sparse_grid(Z_sparse)
+
+    def my_cb(gpmodel, X_full, X_sparse):
+        mean, sd = gpmodel.predict(X_full, verbose=0)
+        return 0 * mean + 1 * sd, (mean, sd)
+    mask = np.ones_like(Z_sparse)
+    mask[:3, :] = np.nan
+    runs = []
+    for fn in (my_cb, "cb"):
+        bo = gpim.boptimizer(X_sparse, Z_sparse, X_full, trial_func, acquisition_function=fn, exploration_steps=3,
+                             gp_iterations=50, verbose=0, mask=mask, filename=str(tmp_path / "bo"))
+        bo.run()
+        runs.append(bo.indices_all)
+        assert all(p[0] >= 3 for p in bo.indices_all)
+    assert runs[0] == runs[1]
