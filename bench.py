@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""
+bench.py -- the headline benchmark of the exact-GP-on-grids hot path (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|h512|c3|c5]
+
+A "step" is ONE pass of the hot path over one dense grid: everything the reference's
+reconstructor.predict does per call (gpr.py:248): K(X,X) assembly, Cholesky of K + (noise+jitter) I,
+the triangular solves, K(X*,X), the diagonal predictive variance and the mean, for all M points
+of X_full.  Metric: predicted grid points per second (mean + sd), whole job.
+
+* `value`  : inputs (X, y, theta, X_full rows) already resident in HBM, outputs left in HBM.
+* `e2e`    : the same pass through the reference-facing API gpim.reconstructor (host numpy
+             arrays in, numpy arrays out; host<->device copies inside the timed region).
+* `roofline`: the dominant kernel (the Linv x K* product with the fused column-sum-of-squares
+             epilogue), CUDA-event bracketed inside libgpgrid.so on the launching stream.
+* `cpu_baseline` / `--impl reference`: oracle/gp_oracle.py (the CPU restatement of the
+             reference's Pyro path -- pyro-ppl is not installable here) timed on the
+             host cores on a bounded sample of the same workload.
+
+N > 1 (torchrun, one rank per GPU): weak scaling -- the dense grid gets N times more rows (step
+1/N), rank 0 factorises, one NCCL broadcast of {Linv, alpha}, every rank predicts its row tile,
+one all-gather of (mean, sd).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import workloads as W  # noqa: E402
+
+METRIC = "predicted grid points/sec (mean+sd)"
+UNIT = "points/s"
+
+
+# ---------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------
+def make_workload(name, dense=1):
+    """-> dict(R, kernel, theta(list), d, label).  `dense` multiplies the number of X_full rows."""
+    ft = W.FIXED_THETA
+    if name in ("c2", "h512", "c5", "c1k"):
+        n = {"c2": 256, "h512": 512, "c5": 1024, "c1k": 128}[name]
+        R = W.spiral_scan(n)
+        theta = [ft["variance"], ft["noise"], 1.0, ft["lengthscale"], ft["lengthscale"]]
+        kern = "RBF"
+        label = f"2D {n}x{n} sparse spiral scan, RBF, fixed theta"
+    elif name == "c3":
+        R = W.hyperspectral((64, 64, 16))
+        theta = [ft["variance"], ft["noise"], 1.0, ft["lengthscale"], ft["lengthscale"], ft["lengthscale_z"]]
+        kern = "Matern52"
+        label = "3D 64x64x16 hyperspectral, Matern52, fixed theta"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    sl = [slice(0, R.shape[0], 1.0 / dense)] + [slice(0, e, 1.0) for e in R.shape[1:]]
+    Xfull = np.array(np.mgrid[tuple(sl)])                     # gprutils.get_full_grid layout (c, *dims)
+    return {"name": name, "R": R, "kernel": kern, "theta": theta, "d": R.ndim, "label": label,
+            "Xfull": Xfull, "jitter": ft["jitter"]}
+
+
+def rows_of(Xgrid):
+    return Xgrid.reshape(Xgrid.shape[0], -1).T
+
+
+def train_rows(R):
+    """(N, d) coordinates and (N,) values of the observed pixels (product-side layout helper)."""
+    from gpim_b200 import gprutils
+    X, y = gprutils.prepare_training_data(gprutils.get_sparse_grid(R), R)
+    return X.numpy(), y.numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:                                    # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            # "under load" = samples at or above half the peak power seen
+            thr = 0.5 * max(pw)
+            load = [s for s, p in zip(sm, pw) if p >= thr] or sm
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(pw)))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on the host cores, bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_predict_sample(wl, m_sample, dtype_name="f32"):
+    """One reference-style predict on the host: full factorisation (K, Cholesky) + K*, TRSM and
+    reductions on `m_sample` grid points; whole-grid time extrapolated linearly in M for the
+    per-point stages.  Returns (points_per_s, seconds_measured, stage dict)."""
+    import torch
+    from oracle import gp_oracle as O
+    X, y = train_rows(wl["R"])
+    Xs = rows_of(wl["Xfull"])
+    M = Xs.shape[0]
+    sel = np.linspace(0, M - 1, m_sample).astype(np.int64)
+    th = wl["theta"]
+    dt = torch.float32 if dtype_name == "f32" else torch.float64
+    t0 = time.perf_counter()
+    _, _, st = O.predict_fixed_theta(wl["kernel"], X, y, Xs[sel], th[0], th[3:], th[1], jitter=wl["jitter"], dtype=dt,
+                                     scale_mixture=th[2])
+    wall = time.perf_counter() - t0
+    t_fact = st["kmat"] + st["cholesky"]
+    t_pts = st["kcross"] + st["trsm"] + st["reduce"]
+    t_full = t_fact + t_pts * (M / m_sample)
+    return M / t_full, wall, st
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    wl = make_workload(args.workload, dense=args.gpus)
+    M = rows_of(wl["Xfull"]).shape[0]
+    m_sample = args.cpu_sample
+    for _ in range(min(args.warmup, 1)):
+        cpu_predict_sample(wl, m_sample, args.cpu_dtype)
+    vals, walls = [], []
+    for _ in range(args.steps):
+        v, wall, st = cpu_predict_sample(wl, m_sample, args.cpu_dtype)
+        vals.append(v); walls.append(wall)
+    value = float(np.mean(vals))
+    N = int((~np.isnan(wl["R"])).sum())
+    sample = (f"full K assembly + Cholesky (N={N}) and K*/TRSM/reduce on {m_sample} of {M} grid points per step, "
+              f"per-point stages scaled by M/{m_sample}; torch {torch.__version__} CPU {args.cpu_dtype}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * M / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.cpu_dtype, "data": "synthetic",
+            "config": bench_config(wl, args.gpus, N, M),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample, "measured_s_per_step": float(np.mean(walls))},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(wl, gpus, N, M):
+    return {"workload": wl["label"], "name": wl["name"], "N_train": N, "M_grid": M, "kernel": wl["kernel"],
+            "theta": {"variance": wl["theta"][0], "noise": wl["theta"][1], "lengthscale": wl["theta"][3:],
+                      "jitter": wl["jitter"]},
+            "sharding": "1 GPU" if gpus == 1 else f"X_full row tiles over {gpus} GPUs, 1 broadcast {{Linv,alpha}} + 1 all-gather",
+            "l2_policy": "inputs larger than L2: every step rewrites and rereads K/L/Linv (N x N fp32 each) and the "
+                         "K* tiles; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------
+# the CUDA arm
+# ---------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    from gpim_b200 import _lib, sharded
+    from gpim_b200._lib import KERNEL_IDS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the host baseline)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = _lib.get_engine(local)
+    dev = eng.device
+
+    wl = make_workload(args.workload, dense=world)
+    X, y = train_rows(wl["R"])
+    Xs = rows_of(wl["Xfull"])
+    N, M, d = X.shape[0], Xs.shape[0], X.shape[1]
+    kid = KERNEL_IDS[wl["kernel"]]
+    dt = torch.float32
+    th = torch.tensor(wl["theta"], dtype=dt, device=dev)
+    Xd = torch.tensor(X, dtype=dt, device=dev)
+    yd = torch.tensor(y, dtype=dt, device=dev)
+    Xsd = torch.tensor(Xs, dtype=dt, device=dev)
+    fac = eng.alloc_factor(N, dt)
+    lo, hi = sharded.tile_bounds(M, world, rank)
+    mean_t = torch.empty(hi - lo, dtype=dt, device=dev)
+    sd_t = torch.empty(hi - lo, dtype=dt, device=dev)
+
+    def step():
+        if rank == 0:
+            eng.factorize(kid, th, Xd, yd, wl["jitter"], out=fac)
+        if world > 1:
+            sharded.broadcast_factor(fac, 0)
+        eng.predict(kid, th, Xd, fac, Xsd[lo:hi], mean=mean_t, sd=sd_t)
+        if world > 1:
+            return sharded.gather_tiles(mean_t, M), sharded.gather_tiles(sd_t, M)
+        return mean_t, sd_t
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    eng.set_option(_lib.OPT_STAGE_TIMING, 1)
+    eng.stage_times()
+    launches0 = eng.launch_count()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    stages = eng.stage_times()
+    eng.set_option(_lib.OPT_STAGE_TIMING, 0)
+    clk = clocks.stop() if clocks else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    assert bool(torch.isfinite(out[0]).all()) and bool(torch.isfinite(out[1]).all()), "non-finite prediction"
+    ms_per_step = ms / args.steps
+    value = M / (ms_per_step * 1e-3)
+
+    # ---- end to end through the reference-facing API (host arrays in / out), all ranks idle but 0 at N>1
+    e2e = None
+    if world == 1:
+        e2e = run_e2e(args, wl, eng)
+    else:
+        e2e = run_e2e_sharded(args, wl, eng, world, rank)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:                                        # noqa: BLE001
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (dense 16-bit tensor rate, kernel timed inside a long step)" \
+        if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    pg_ms, pg_n = stages["pgemm"]
+    m_local = hi - lo
+    flops_per_step = float(N) * float(N) * float(m_local)    # N^2 FLOP per predicted point
+    achieved = flops_per_step * args.steps / (pg_ms * 1e-3) / 1e12 if pg_ms > 0 else 0.0
+    km_ms, km_n = stages["kmat"]
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    kmat_gbps = (4.0 * N * N / 2 + 8.0 * d * N) * km_n / (km_ms * 1e-3) / 1e9 if km_ms > 0 else 0.0
+    ch_ms, ch_n = stages["cholesky"]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(wl, world, N, M),
+        "roofline": {"kernel": "predict GEMM Linv x K* + colsumsq epilogue (stage pgemm)", "bound": "tensor",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                     "traffic": None, "launches": pg_n, "avg_launch_ms": pg_ms / max(pg_n, 1),
+                     "algorithmic_flops_per_launch": flops_per_step * args.steps / max(pg_n, 1),
+                     "peak_source": peak_src},
+        "stages_ms_per_step": {k: v[0] / args.steps for k, v in stages.items() if v[1]},
+        "kmat_assembly": {"bound": "hbm", "achieved": kmat_gbps, "peak": hbm, "unit": "GB/s", "frac": kmat_gbps / hbm,
+                          "note": "lower-triangle tiles only: 2 N^2 + 8 d N bytes per launch"},
+        "cholesky_tflops": (N ** 3 / 3.0) * ch_n / (ch_ms * 1e-3) / 1e12 if ch_ms > 0 else None,
+        "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        import torch as _t
+        _t.set_num_threads(os.cpu_count() or 1)
+        v, wall, st = cpu_predict_sample(wl, args.cpu_sample, args.cpu_dtype)
+        line["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
+            "sample": f"oracle predict (K + Cholesky at N={N}, K*/TRSM/reduce on {args.cpu_sample} of {M} points, "
+                      f"per-point stages scaled to M), {args.cpu_dtype}, {wall:.1f} s measured",
+            "stages_s": st}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, wl, eng):
+    """gpim.reconstructor: swap the training set in (host -> device), predict over X_full given as
+    a host numpy grid, results back as numpy arrays.  Factor cache invalidated every step, as the
+    reference refactorises on every predict (gpr.py:248)."""
+    import torch
+    import gpim_b200 as gpim
+    R = wl["R"]
+    Xsp = gpim.utils.get_sparse_grid(R)
+    rec = gpim.reconstructor(Xsp, R, wl["Xfull"], kernel=wl["kernel"], iterations=0, verbose=0, precision="single",
+                             jitter=wl["jitter"], lengthscale=[[1.0] * R.ndim, [20.0] * R.ndim])
+    th = wl["theta"]
+    rec.model.set_theta(th[0], th[3:], th[1], th[2])
+    Xh = rec.X.cpu().pin_memory()
+    yh = rec.y.cpu().pin_memory()
+    Xfull = wl["Xfull"]
+
+    def step():
+        rec.model.X = Xh
+        rec.model.y = yh
+        return rec.predict(Xfull, verbose=0)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        mean, sd = step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    M = mean.size
+    h2d = Xh.numel() * 4 + yh.numel() * 4 + M * R.ndim * 4
+    return {"value": M / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * M * 4),
+            "ms_per_step": dt * 1e3, "api": "gpim.reconstructor.predict(X_full) after model.X/.y swap (host numpy in/out)"}
+
+
+def run_e2e_sharded(args, wl, eng, world, rank):
+    """N > 1: host rows in, every rank copies its tile to the device, sharded predict, rank 0 reads
+    the gathered result back to the host."""
+    import torch
+    import torch.distributed as dist
+    from gpim_b200 import sharded
+    from gpim_b200._lib import KERNEL_IDS
+    dev = eng.device
+    dt = torch.float32
+    X, y = train_rows(wl["R"])
+    Xs = rows_of(wl["Xfull"])
+    N, M = X.shape[0], Xs.shape[0]
+    kid = KERNEL_IDS[wl["kernel"]]
+    Xh = torch.tensor(X, dtype=dt).pin_memory()
+    yh = torch.tensor(y, dtype=dt).pin_memory()
+    lo, hi = sharded.tile_bounds(M, world, rank)
+    Xsh = torch.tensor(Xs[lo:hi], dtype=dt).pin_memory()
+    th = torch.tensor(wl["theta"], dtype=dt, device=dev)
+    fac = eng.alloc_factor(N, dt)
+
+    def step():
+        Xd = Xh.to(dev, non_blocking=True)
+        yd = yh.to(dev, non_blocking=True)
+        Xsd = Xsh.to(dev, non_blocking=True)
+        if rank == 0:
+            eng.factorize(kid, th, Xd, yd, wl["jitter"], out=fac)
+        sharded.broadcast_factor(fac, 0)
+        m, s = eng.predict(kid, th, Xd, fac, Xsd)
+        m, s = sharded.gather_tiles(m, M), sharded.gather_tiles(s, M)
+        if rank == 0:
+            return m.cpu().numpy(), s.cpu().numpy()
+        return None
+
+    for _ in range(2):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    sec = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+    sec = float(sec.item())
+    h2d = (Xh.numel() + yh.numel()) * 4 * world + M * Xs.shape[1] * 4
+    return {"value": M / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * M * 4),
+            "ms_per_step": sec * 1e3, "api": "sharded.predict: pinned host rows -> per-rank tiles -> gathered numpy on rank 0"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--cpu-sample", type=int, default=1024, dest="cpu_sample")
+    ap.add_argument("--cpu-dtype", default="f32", choices=["f32", "f64"], dest="cpu_dtype")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "cuda" and world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            # convenience: relaunch under torchrun
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

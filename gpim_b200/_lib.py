@@ -16,7 +16,8 @@ GPG_OK, GPG_EINVAL, GPG_ENOTPD, GPG_ECUDA = 0, 1, 2, 3
 GPG_F32, GPG_F64 = 0, 1
 KERNEL_IDS = {"RBF": 0, "Matern52": 1, "RationalQuadratic": 2}
 ACQ_IDS = {"cb": 0, "ei": 1, "poi": 2}
-OPT_GEMM_PATH, OPT_PREDICT_CHUNK = 1, 2
+OPT_GEMM_PATH, OPT_PREDICT_CHUNK, OPT_STAGE_TIMING = 1, 2, 3
+STAGES = ("kmat", "cholesky", "trtri", "solve", "kcross", "pgemm", "pfinal", "grad", "acq")
 
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
 
@@ -29,6 +30,7 @@ SIGNATURES = {
     "gpg_set_option": ([_vp, _i32, C.c_longlong], C.c_int),
     "gpg_launch_count": ([_vp], C.c_longlong),
     "gpg_workspace_bytes": ([_vp], C.c_size_t),
+    "gpg_stage_times": ([_vp, C.POINTER(_f64), C.POINTER(C.c_longlong)], C.c_int),
     "gpg_kmat": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _f64, _i32, _vp, _i64, _vp], C.c_int),
     "gpg_cholesky": ([_vp, _i32, _vp, _i64, _i64, _vp, _vp], C.c_int),
     "gpg_trtri": ([_vp, _i32, _vp, _i64, _i64, _vp, _i64, _vp], C.c_int),
@@ -147,6 +149,13 @@ class Engine:
     def launch_count(self):
         return int(self.lib.gpg_launch_count(self.h))
 
+    def stage_times(self):
+        """{stage: (device_ms, n_brackets)} since the last call; needs set_option(OPT_STAGE_TIMING, 1)."""
+        ms = (_f64 * len(STAGES))()
+        n = (C.c_longlong * len(STAGES))()
+        self._check(self.lib.gpg_stage_times(self.h, ms, n))
+        return {name: (ms[i], int(n[i])) for i, name in enumerate(STAGES)}
+
     def empty(self, *shape, dtype):
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
@@ -186,20 +195,25 @@ class Engine:
                                            _ptr(vhat), _ptr(alpha), _ptr(scalars), self._stream()))
         return vhat, alpha, scalars
 
-    def factorize(self, kernel_id, theta, X, y, jitter):
+    def alloc_factor(self, N, dtype, with_L=True):
+        """Empty factor cache (what a non-factorising rank receives by broadcast, sharded.py)."""
+        ld = (N + 63) // 64 * 64
+        return {"L": self.empty(N, ld, dtype=dtype) if with_L else None,
+                "Linv": self.empty(N, ld, dtype=dtype),
+                "vhat": self.empty(N, dtype=dtype), "alpha": self.empty(N, dtype=dtype),
+                "scalars": self.empty(2, dtype=dtype),
+                "info": torch.zeros(1, dtype=torch.int32, device=self.device), "ld": ld}
+
+    def factorize(self, kernel_id, theta, X, y, jitter, out=None):
         """-> dict(L, Linv, vhat, alpha, scalars, info); N x N buffers padded to ld % 64 == 0."""
         theta, X, y = _c(theta), _c(X), _c(y)
         N, d = X.shape
-        ld = (N + 63) // 64 * 64
-        L = self.empty(N, ld, dtype=X.dtype)
-        Linv = self.empty(N, ld, dtype=X.dtype)
-        vhat, alpha = torch.empty_like(y), torch.empty_like(y)
-        scalars = self.empty(2, dtype=y.dtype)
-        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        fac = out if out is not None else self.alloc_factor(N, X.dtype)
+        L, Linv, vhat, alpha, scalars, info, ld = (fac[k] for k in ("L", "Linv", "vhat", "alpha", "scalars", "info", "ld"))
         self._check(self.lib.gpg_factorize(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), _ptr(y), N,
                                            float(jitter), _ptr(L), _ptr(Linv), ld, _ptr(vhat), _ptr(alpha),
                                            _ptr(scalars), _ptr(info), self._stream()))
-        return {"L": L, "Linv": Linv, "vhat": vhat, "alpha": alpha, "scalars": scalars, "info": info, "ld": ld}
+        return fac
 
     def predict(self, kernel_id, theta, X, fac, Xs, mean=None, sd=None):
         theta, X, Xs = _c(theta), _c(X), _c(Xs)

@@ -11,14 +11,41 @@
 
 #define GPG_MAX_D 4
 
+#include <vector>
+
+struct gpg_stage_span { int stage; cudaEvent_t beg, end; };
+
 struct gpg_handle_s {
     int device = 0;
     int sm_count = 148;
     long long launches = 0;
     int opt_gemm_path = 0;
     long long opt_predict_chunk = 0;
+    int opt_stage_timing = 0;
     void *ws = nullptr;          // grow-only device workspace
     size_t ws_bytes = 0;
+    std::vector<gpg_stage_span> spans;       // recorded while opt_stage_timing != 0
+    std::vector<cudaEvent_t> event_pool;
+};
+
+// CUDA-event bracket around the launches of one stage (bench.py roofline: average device time of
+// the dominant kernel measured on the launching stream).  No-ops unless GPG_OPT_STAGE_TIMING is set.
+struct StageTimer {
+    gpg_handle_s *h;
+    cudaStream_t s;
+    cudaEvent_t end = nullptr;
+    StageTimer(gpg_handle_s *h_, int stage, cudaStream_t s_) : h(h_), s(s_) {
+        if (!h->opt_stage_timing) return;
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i) {
+            if (!h->event_pool.empty()) { ev[i] = h->event_pool.back(); h->event_pool.pop_back(); }
+            else if (cudaEventCreate(&ev[i]) != cudaSuccess) return;
+        }
+        cudaEventRecord(ev[0], s);
+        end = ev[1];
+        h->spans.push_back({stage, ev[0], ev[1]});
+    }
+    ~StageTimer() { if (end) cudaEventRecord(end, s); }
 };
 
 void gpg_set_error(const char *fmt, ...);

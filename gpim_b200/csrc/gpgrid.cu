@@ -80,6 +80,8 @@ extern "C" int gpg_create(int device, gpg_handle_t *out) {
 extern "C" int gpg_destroy(gpg_handle_t h) {
     if (!h) return GPG_OK;
     if (h->ws) cudaFree(h->ws);
+    for (auto &sp : h->spans) { cudaEventDestroy(sp.beg); cudaEventDestroy(sp.end); }
+    for (auto &e : h->event_pool) cudaEventDestroy(e);
     delete h;
     return GPG_OK;
 }
@@ -89,8 +91,26 @@ extern "C" int gpg_set_option(gpg_handle_t h, int key, long long value) {
     switch (key) {
         case GPG_OPT_GEMM_PATH: GPG_REQUIRE(value >= 0 && value <= 2, "gemm path 0..2"); h->opt_gemm_path = (int)value; break;
         case GPG_OPT_PREDICT_CHUNK: GPG_REQUIRE(value >= 0, "chunk >= 0"); h->opt_predict_chunk = value; break;
+        case GPG_OPT_STAGE_TIMING: h->opt_stage_timing = value != 0; break;
         default: gpg_set_error("unknown option %d", key); return GPG_EINVAL;
     }
+    return GPG_OK;
+}
+
+extern "C" int gpg_stage_times(gpg_handle_t h, double *ms_host, long long *spans_host) {
+    GPG_REQUIRE(h && ms_host && spans_host, "NULL argument");
+    GPG_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int i = 0; i < GPG_ST_COUNT; ++i) { ms_host[i] = 0.0; spans_host[i] = 0; }
+    for (auto &sp : h->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.beg, sp.end) == cudaSuccess && sp.stage >= 0 && sp.stage < GPG_ST_COUNT) {
+            ms_host[sp.stage] += ms;
+            spans_host[sp.stage] += 1;
+        }
+        h->event_pool.push_back(sp.beg);
+        h->event_pool.push_back(sp.end);
+    }
+    h->spans.clear();
     return GPG_OK;
 }
 
@@ -212,10 +232,10 @@ template <typename T>
 static int factorize_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
                           double jitter, T *L, T *Linv, int64_t ld, T *vhat, T *alpha, T *scalars, int32_t *info,
                           int reset_info, T *tmp, T *dinv, T *vscratch, cudaStream_t s) {
-    GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, nullptr, N, jitter, 1, L, ld, s));
-    GPG_TRY(cholesky_blocked<T>(h, L, N, ld, info, reset_info, dinv, s));
-    GPG_TRY(trtri_blocked<T>(h, L, N, ld, Linv, ld, tmp, s));
-    GPG_TRY(solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, scalars, vscratch, s));
+    { StageTimer st(h, GPG_ST_KMAT, s); GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, nullptr, N, jitter, 1, L, ld, s)); }
+    { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, L, N, ld, info, reset_info, dinv, s)); }
+    { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, L, N, ld, Linv, ld, tmp, s)); }
+    { StageTimer st(h, GPG_ST_SOLVE, s); GPG_TRY(solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, scalars, vscratch, s)); }
     return GPG_OK;
 }
 
@@ -278,9 +298,12 @@ static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T 
         TestPoints<T, D> tpc = tp;
         if (tpc.Xs) tpc.Xs += c0 * D; else tpc.j0 += c0;
         const unsigned gk = (unsigned)((mc + 7) / 8);
-        GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<T, KID, D, false><<<gk, 256, 0, s>>>(
-                                        theta, X, N, tpc, mc, alpha, Ks, ldk, nullptr, nullptr, 0, 1.0f, mean + c0));
-        GPG_LAUNCH_CHECK(h);
+        {
+            StageTimer st(h, GPG_ST_KCROSS, s);
+            GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<T, KID, D, false><<<gk, 256, 0, s>>>(
+                                            theta, X, N, tpc, mc, alpha, Ks, ldk, nullptr, nullptr, 0, 1.0f, mean + c0));
+            GPG_LAUNCH_CHECK(h);
+        }
         GemmArgs<T> g;           // colsum((Linv Ks^T)^2): C[i][j] = sum_k Linv[i][k] Ks[j][k], k <= i
         g.A = Linv; g.lda = ld; g.a_kmajor = 1;
         g.B = Ks; g.ldb = ldk; g.b_kmajor = 1;
@@ -288,7 +311,8 @@ static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T 
         g.ke_mode = GEMM_KE_M;
         g.epi = GEMM_EPI_COLSUMSQ;
         g.part = part; g.ldpart = chunk;
-        GPG_TRY(gemm_simt<T>(h, g, s));
+        { StageTimer st(h, GPG_ST_PGEMM, s); GPG_TRY(gemm_simt<T>(h, g, s)); }
+        StageTimer st(h, GPG_ST_PFINAL, s);
         predict_finalize_kernel<T, D><<<(unsigned)((mc + 255) / 256), 256, 0, s>>>(theta, part, tiles_m, chunk, tpc, mc,
                                                                                    T(1), sd + c0);
         GPG_LAUNCH_CHECK(h);
@@ -406,6 +430,7 @@ static int nll_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, 
     T *L = (T *)tb.L, *Linv = (T *)tb.Linv, *Kinv = (T *)tb.Kinv;
     GPG_TRY(factorize_core<T>(h, kernel_id, d, theta, X, y, N, jitter, L, Linv, tb.ld, (T *)tb.vhat, (T *)tb.alpha,
                               (T *)tb.scalars, info, reset_info, Kinv, (T *)tb.dinv, (T *)tb.vs, s));
+    StageTimer st(h, GPG_ST_GRAD, s);
     GemmArgs<T> g;               // Kinv = Linv^T Linv on lower tiles: sum_k Linv[k][i] Linv[k][j], k >= max(i,j)
     g.A = Linv; g.lda = tb.ld; g.a_kmajor = 0;
     g.B = Linv; g.ldb = tb.ld; g.b_kmajor = 0;
@@ -520,6 +545,7 @@ static int acq_entry(gpg_handle_s *h, int acq_id, const T *mean, const T *sd, co
                                             CH * (int)sizeof(Cand<T>)));
         attr_set = true;
     }
+    StageTimer st(h, GPG_ST_ACQ, s);
     acq_eval_kernel<T><<<(unsigned)((M + 255) / 256), 256, 0, s>>>(acq_id, mean, sd, mask, M, mu_best, xi, alpha, beta,
                                                                    acq_out, cand);
     GPG_LAUNCH_CHECK(h);

@@ -42,7 +42,21 @@ enum { GPG_ACQ_CB = 0, GPG_ACQ_EI = 1, GPG_ACQ_POI = 2 };
 /* gpg_set_option keys */
 enum {
     GPG_OPT_GEMM_PATH = 1,      /* 0 auto (tcgen05 for f32 when large enough), 1 SIMT only, 2 force tcgen05 */
-    GPG_OPT_PREDICT_CHUNK = 2   /* test points per internal tile of gpg_predict (0 = auto) */
+    GPG_OPT_PREDICT_CHUNK = 2,  /* test points per internal tile of gpg_predict (0 = auto) */
+    GPG_OPT_STAGE_TIMING = 3    /* != 0: bracket every stage with CUDA events, read by gpg_stage_times */
+};
+/* stages reported by gpg_stage_times */
+enum {
+    GPG_ST_KMAT = 0,        /* K(X,X) assembly */
+    GPG_ST_CHOLESKY = 1,
+    GPG_ST_TRTRI = 2,
+    GPG_ST_SOLVE = 3,       /* vector solves + logdet */
+    GPG_ST_KCROSS = 4,      /* K(X*,X) tile assembly + predictive mean */
+    GPG_ST_PGEMM = 5,       /* Linv K* with the fused column-sum-of-squares epilogue */
+    GPG_ST_PFINAL = 6,      /* sd epilogue */
+    GPG_ST_GRAD = 7,        /* Kinv + gradient reduction + Adam step */
+    GPG_ST_ACQ = 8,
+    GPG_ST_COUNT = 9
 };
 
 typedef struct gpg_handle_s *gpg_handle_t;
@@ -56,6 +70,10 @@ int gpg_set_option(gpg_handle_t h, int key, long long value);
 long long gpg_launch_count(gpg_handle_t h);
 /* bytes of device workspace currently owned by the handle */
 size_t gpg_workspace_bytes(gpg_handle_t h);
+/* Synchronises the device, then adds up the CUDA-event spans recorded since the last call:
+ * ms_host[GPG_ST_COUNT] device milliseconds per stage, spans_host[GPG_ST_COUNT] number of
+ * brackets per stage (host arrays).  Clears the record. */
+int gpg_stage_times(gpg_handle_t h, double *ms_host, long long *spans_host);
 
 /* K1/K2 -- kernel-matrix assembly.  Replaces Pyro Isotropy.forward reached from
  * gpim/gpreg/gpr.py:192,248 (kernel(X), kernel(X, Xnew)) with the kernels configured at

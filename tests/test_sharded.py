@@ -1,0 +1,51 @@
+"""Host-side logic of the multi-GPU shard (gpim_b200/sharded.py) on the gloo backend, world_size 2,
+CPU tensors, with a stand-in tile predictor (the CUDA engine is not needed for the plumbing)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gpim_b200 import sharded
+
+
+def test_tile_bounds_partition_exactly():
+    for M in (0, 1, 7, 64, 65537):
+        for world in (1, 2, 3, 8):
+            edges = [sharded.tile_bounds(M, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == M
+            for (a, b), (c, d) in zip(edges, edges[1:]):
+                assert b == c and b - a >= d - c >= 0 and (b - a) - (d - c) <= 1
+
+
+def _worker(rank, world, port, M, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    N = 5
+    Xs = torch.arange(M * 2, dtype=torch.float64).reshape(M, 2)
+
+    def factorize():
+        return {"Linv": torch.full((N, N), 3.0, dtype=torch.float64), "alpha": torch.arange(N, dtype=torch.float64)}
+
+    def alloc():
+        return {"Linv": torch.zeros(N, N, dtype=torch.float64), "alpha": torch.zeros(N, dtype=torch.float64)}
+
+    def tile(fac, X):
+        # depends on the broadcast factor AND on the tile rows
+        return X[:, 0] * fac["Linv"][0, 0] + fac["alpha"].sum(), X[:, 1] + fac["Linv"].sum()
+
+    mean, sd = sharded.predict_sharded(factorize, alloc, tile, Xs)
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), np.stack([mean.numpy(), sd.numpy()]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("M", [64, 37])
+def test_sharded_predict_world2_gloo(tmp_path, M):
+    port = 29600 + (os.getpid() + M) % 300
+    mp.spawn(_worker, args=(2, port, M, str(tmp_path)), nprocs=2, join=True)
+    Xs = np.arange(M * 2, dtype=np.float64).reshape(M, 2)
+    want = np.stack([Xs[:, 0] * 3.0 + 10.0, Xs[:, 1] + 75.0])
+    for r in range(2):
+        np.testing.assert_array_equal(np.load(tmp_path / f"r{r}.npy"), want)
