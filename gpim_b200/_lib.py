@@ -31,14 +31,16 @@ SIGNATURES = {
     "gpg_launch_count": ([_vp], C.c_longlong),
     "gpg_workspace_bytes": ([_vp], C.c_size_t),
     "gpg_stage_times": ([_vp, C.POINTER(_f64), C.POINTER(C.c_longlong)], C.c_int),
+    "gpg_gemm_nt_f32": ([_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _f64, _vp], C.c_int),
     "gpg_kmat": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _f64, _i32, _vp, _i64, _vp], C.c_int),
     "gpg_cholesky": ([_vp, _i32, _vp, _i64, _i64, _vp, _vp], C.c_int),
     "gpg_trtri": ([_vp, _i32, _vp, _i64, _i64, _vp, _i64, _vp], C.c_int),
     "gpg_solve_vec": ([_vp, _i32, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp], C.c_int),
-    "gpg_factorize": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp], C.c_int),
-    "gpg_predict": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp], C.c_int),
-    "gpg_predict_grid": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, C.POINTER(_i64), C.POINTER(_f64),
-                          _i64, _i64, _vp, _vp, _vp], C.c_int),
+    "gpg_factorize": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                       _vp], C.c_int),
+    "gpg_predict": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp], C.c_int),
+    "gpg_predict_grid": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, C.POINTER(_i64),
+                          C.POINTER(_f64), _i64, _i64, _vp, _vp, _vp], C.c_int),
     "gpg_nll_grad": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp, _vp], C.c_int),
     "gpg_fit_adam": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _f64, _vp, C.POINTER(_f64), _i32, _f64,
                       _vp, _vp, _vp, _vp], C.c_int),
@@ -160,6 +162,23 @@ class Engine:
         return torch.empty(*shape, dtype=dtype, device=self.device)
 
     # -- entry points -------------------------------------------------------------------
+    def gemm_nt(self, A, B, C=None, alpha=1.0, beta=0.0, scale_a=None, scale_b=None):
+        """C = alpha * A @ B.T + beta * C on the split-fp16 tcgen05 kernel (f32 row-major)."""
+        assert A.dtype == torch.float32 and B.dtype == torch.float32 and A.stride(1) == 1 and B.stride(1) == 1
+        M, K = A.shape
+        N = B.shape[0]
+        if C is None:
+            C = self.empty(M, N, dtype=torch.float32)
+
+        def pow2_scale(t):
+            m = float(t.abs().max().item()) or 1.0
+            return 2.0 ** np.floor(np.log2(16384.0 / m))
+        sa = pow2_scale(A) if scale_a is None else scale_a
+        sb = pow2_scale(B) if scale_b is None else scale_b
+        self._check(self.lib.gpg_gemm_nt_f32(self.h, _ptr(A), A.stride(0), _ptr(B), B.stride(0), _ptr(C), C.stride(0),
+                                             M, N, K, float(alpha), float(beta), float(sa), float(sb), self._stream()))
+        return C
+
     def kmat(self, kernel_id, theta, X, Z=None, jitter=0.0, lower_only=False, out=None):
         theta, X, Z = _c(theta), _c(X), _c(Z)
         N, d = X.shape
@@ -198,8 +217,12 @@ class Engine:
     def alloc_factor(self, N, dtype, with_L=True):
         """Empty factor cache (what a non-factorising rank receives by broadcast, sharded.py)."""
         ld = (N + 63) // 64 * 64
+        f32 = dtype == torch.float32
         return {"L": self.empty(N, ld, dtype=dtype) if with_L else None,
                 "Linv": self.empty(N, ld, dtype=dtype),
+                # tensor-core form of Linv (fp16 hi plane, lo plane) + operand scales; f32 only
+                "wsplit": torch.empty(2, N, ld, dtype=torch.float16, device=self.device) if f32 else None,
+                "scales": torch.zeros(4, dtype=torch.float32, device=self.device) if f32 else None,
                 "vhat": self.empty(N, dtype=dtype), "alpha": self.empty(N, dtype=dtype),
                 "scalars": self.empty(2, dtype=dtype),
                 "info": torch.zeros(1, dtype=torch.int32, device=self.device), "ld": ld}
@@ -212,7 +235,8 @@ class Engine:
         L, Linv, vhat, alpha, scalars, info, ld = (fac[k] for k in ("L", "Linv", "vhat", "alpha", "scalars", "info", "ld"))
         self._check(self.lib.gpg_factorize(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), _ptr(y), N,
                                            float(jitter), _ptr(L), _ptr(Linv), ld, _ptr(vhat), _ptr(alpha),
-                                           _ptr(scalars), _ptr(info), self._stream()))
+                                           _ptr(scalars), _ptr(info), _ptr(fac.get("wsplit")), _ptr(fac.get("scales")),
+                                           self._stream()))
         return fac
 
     def predict(self, kernel_id, theta, X, fac, Xs, mean=None, sd=None):
@@ -224,8 +248,8 @@ class Engine:
         if sd is None:
             sd = self.empty(M, dtype=X.dtype)
         self._check(self.lib.gpg_predict(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), N, _ptr(fac["Linv"]),
-                                         fac["ld"], _ptr(fac["alpha"]), _ptr(Xs), M, _ptr(mean), _ptr(sd),
-                                         self._stream()))
+                                         fac["ld"], _ptr(fac["alpha"]), _ptr(fac.get("wsplit")), _ptr(fac.get("scales")),
+                                         _ptr(Xs), M, _ptr(mean), _ptr(sd), self._stream()))
         return mean, sd
 
     def predict_grid(self, kernel_id, theta, X, fac, dims, step, j0, M, mean=None, sd=None):
@@ -238,7 +262,8 @@ class Engine:
         dims_c = (_i64 * d)(*[int(v) for v in dims])
         step_c = (_f64 * d)(*[float(v) for v in step])
         self._check(self.lib.gpg_predict_grid(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), N,
-                                              _ptr(fac["Linv"]), fac["ld"], _ptr(fac["alpha"]), dims_c, step_c,
+                                              _ptr(fac["Linv"]), fac["ld"], _ptr(fac["alpha"]),
+                                              _ptr(fac.get("wsplit")), _ptr(fac.get("scales")), dims_c, step_c,
                                               int(j0), int(M), _ptr(mean), _ptr(sd), self._stream()))
         return mean, sd
 

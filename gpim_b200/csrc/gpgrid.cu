@@ -2,6 +2,7 @@
 // that sequence the kernels of kmat.cuh / factor.cuh / train.cuh / acq.cuh / gemm_*.cuh.
 #include <cstdarg>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -128,6 +129,47 @@ template <> int gemm_dispatch<float>(gpg_handle_s *h, const GemmArgs<float> &g, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// fp32-faithful tensor-core GEMM as a stand-alone entry (unit tests, and callers that want the
+// split-fp16 tcgen05 kernel on their own matrices):  C = alpha * A B^T + beta * C
+// ---------------------------------------------------------------------------------------------
+__global__ void set_scales_kernel(float sa, float sb, float *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = sa; out[1] = sb; out[2] = 1.0f / (sa * sb); out[3] = 1.0f; }
+}
+
+extern "C" int gpg_gemm_nt_f32(gpg_handle_t h, const float *A, int64_t lda, const float *B, int64_t ldb, float *C,
+                               int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, double beta, double scale_a,
+                               double scale_b, void *stream) {
+    GPG_REQUIRE(h && A && B && C, "NULL argument");
+    GPG_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldb >= K && ldc >= N, "bad size");
+    GPG_REQUIRE(scale_a > 0 && scale_b > 0, "scales must be positive");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t ldk = gpg_align_up((size_t)K, 64);
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)M * ldk * 2, (size_t)M * ldk * 2, (size_t)N * ldk * 2, (size_t)N * ldk * 2,
+                                         64, 64}), &ws));
+    Bump b(ws);
+    __half *Ahi = b.take<__half>((size_t)M * ldk), *Alo = b.take<__half>((size_t)M * ldk);
+    __half *Bhi = b.take<__half>((size_t)N * ldk), *Blo = b.take<__half>((size_t)N * ldk);
+    float *scales = b.take<float>(16);
+    int *counter = b.take<int>(16);
+    set_scales_kernel<<<1, 32, 0, s>>>((float)scale_a, (float)scale_b, scales);
+    GPG_LAUNCH_CHECK(h);
+    GPG_TRY(tc::split_matrix(h, A, lda, M, K, scales, Ahi, Alo, ldk, 0, s));
+    GPG_TRY(tc::split_matrix(h, B, ldb, N, K, scales + 1, Bhi, Blo, ldk, 0, s));
+    tc::Launch g;
+    memset(&g.p, 0, sizeof(g.p));
+    g.A.hi = Ahi; g.A.lo = Alo; g.A.rows = M; g.A.cols = K; g.A.ld = ldk;
+    g.B.hi = Bhi; g.B.lo = Blo; g.B.rows = N; g.B.cols = K; g.B.ld = ldk;
+    g.p.M = (int)M; g.p.N = (int)N; g.p.K = (int)K; g.p.batch = 1;
+    g.p.epi = tc::EPI_STORE;
+    g.p.scale_inv = scales + 2;
+    g.p.C = C; g.p.ldc = ldc;
+    g.p.alpha = (float)alpha; g.p.beta = (float)beta;
+    g.p.tile_counter = counter;
+    return tc::launch(h, g, s);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K1 / K2
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -227,6 +269,25 @@ extern "C" int gpg_solve_vec(gpg_handle_t h, int dtype, const void *L, const voi
     return GPG_EINVAL;
 }
 
+// Power-of-two operand scales of the split-fp16 tensor-core path, from rigorous magnitude bounds:
+//   |K*_ij| <= variance;   |Linv_ij| <= ||L^-1||_2 = lambda_min(K)^-1/2 <= (noise + jitter)^-1/2
+// (K = K_f + (noise + jitter) I with K_f positive semi-definite).  Scaled magnitudes stay <= 2^14.
+// scales: {s_K, s_W, 1 / (s_K s_W), reserved}
+template <typename T>
+__global__ void predict_scales_kernel(const T *__restrict__ theta, float jitter, float *__restrict__ scales) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float v = fmaxf((float)theta[0], 1e-30f);
+    const float nz = fmaxf((float)theta[1] + jitter, 1e-30f);
+    int ek = (int)floorf(log2f(16384.0f / v));
+    int ew = (int)floorf(log2f(16384.0f * sqrtf(nz)));
+    ek = max(-40, min(40, ek));
+    ew = max(-40, min(40, ew));
+    scales[0] = exp2f((float)ek);
+    scales[1] = exp2f((float)ew);
+    scales[2] = exp2f((float)(-ek - ew));
+    scales[3] = 0.f;
+}
+
 // K1 + K3 + trtri + K7a.  tmp (N*ld), dinv, vec scratch come from the caller-provided bump.
 template <typename T>
 static int factorize_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
@@ -256,15 +317,27 @@ static int factorize_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta
 
 extern "C" int gpg_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X,
                              const void *y, int64_t N, double jitter, void *L, void *Linv, int64_t ld, void *vhat_out,
-                             void *alpha_out, void *scalars_out, int32_t *info, void *stream) {
+                             void *alpha_out, void *scalars_out, int32_t *info, void *wsplit_out, float *scales_out,
+                             void *stream) {
     GPG_REQUIRE(h && theta && X && y && L && Linv && vhat_out && alpha_out && info, "NULL argument");
     GPG_REQUIRE(N > 0 && ld >= N, "bad size");
     GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
+    GPG_REQUIRE((wsplit_out == nullptr) == (scales_out == nullptr), "wsplit_out and scales_out go together");
+    GPG_REQUIRE(wsplit_out == nullptr || (dtype == GPG_F32 && ld % 8 == 0), "the split factor needs f32 and ld % 8 == 0");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (dtype == GPG_F32)
-        return factorize_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, (const float *)y, N, jitter,
-                                      (float *)L, (float *)Linv, ld, (float *)vhat_out, (float *)alpha_out,
-                                      (float *)scalars_out, info, s);
+    if (dtype == GPG_F32) {
+        GPG_TRY(factorize_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, (const float *)y, N, jitter,
+                                       (float *)L, (float *)Linv, ld, (float *)vhat_out, (float *)alpha_out,
+                                       (float *)scalars_out, info, s));
+        if (wsplit_out) {
+            StageTimer st(h, GPG_ST_TRTRI, s);
+            predict_scales_kernel<float><<<1, 32, 0, s>>>((const float *)theta, (float)jitter, scales_out);
+            GPG_LAUNCH_CHECK(h);
+            __half *whi = (__half *)wsplit_out, *wlo = whi + (size_t)N * ld;
+            GPG_TRY(tc::split_matrix(h, (const float *)Linv, ld, N, N, scales_out + 1, whi, wlo, ld, 1, s));
+        }
+        return GPG_OK;
+    }
     if (dtype == GPG_F64)
         return factorize_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, (const double *)y, N,
                                        jitter, (double *)L, (double *)Linv, ld, (double *)vhat_out, (double *)alpha_out,
@@ -301,7 +374,7 @@ static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T 
         {
             StageTimer st(h, GPG_ST_KCROSS, s);
             GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<T, KID, D, false><<<gk, 256, 0, s>>>(
-                                            theta, X, N, tpc, mc, alpha, Ks, ldk, nullptr, nullptr, 0, 1.0f, mean + c0));
+                                            theta, X, N, tpc, mc, alpha, Ks, ldk, nullptr, nullptr, 0, nullptr, mean + c0));
             GPG_LAUNCH_CHECK(h);
         }
         GemmArgs<T> g;           // colsum((Linv Ks^T)^2): C[i][j] = sum_k Linv[i][k] Ks[j][k], k <= i
@@ -320,9 +393,81 @@ static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T 
     return GPG_OK;
 }
 
+// fp32 tensor-core path: K* tiles are generated directly as fp16 hi/lo operands, the variance
+// reduction runs in the epilogue of the tcgen05 GEMM (test points on the TMEM lanes).
+template <int D>
+static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, const float *X, int64_t N,
+                           const __half *Whi, const __half *Wlo, int64_t ldh, const float *scales, const float *alpha,
+                           TestPoints<float, D> tp, int64_t M, float *mean, float *sd, cudaStream_t s) {
+    int64_t chunk = h->opt_predict_chunk;
+    if (chunk <= 0) {
+        chunk = 8192;
+        while (chunk > 1024 && chunk * ldh * 4 > (int64_t)1 << 30) chunk /= 2;
+    }
+    chunk = gpg_align_up((size_t)std::min<int64_t>(chunk, gpg_align_up((size_t)M, 128)), 128);
+    const int tiles_n = (int)((N + tc::BN - 1) / tc::BN);
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)chunk * ldh * 2, (size_t)chunk * ldh * 2,
+                                         (size_t)tiles_n * chunk * sizeof(float), 64}), &ws));
+    Bump b(ws);
+    __half *Khi = b.take<__half>((size_t)chunk * ldh);
+    __half *Klo = b.take<__half>((size_t)chunk * ldh);
+    float *part = b.take<float>((size_t)tiles_n * chunk);
+    int *counter = b.take<int>(16);
+    // A-operand groups sized to stay L2-resident while the n-blocks sweep over them
+    const int m_group = (int)std::max<int64_t>(1, ((int64_t)64 << 20) / (tc::BM * ldh * 4));
+    for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+        const int64_t mc = std::min<int64_t>(chunk, M - c0);
+        TestPoints<float, D> tpc = tp;
+        if (tpc.Xs) tpc.Xs += c0 * D; else tpc.j0 += c0;
+        {
+            StageTimer st(h, GPG_ST_KCROSS, s);
+            GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<float, KID, D, true><<<(unsigned)((mc + 7) / 8), 256, 0, s>>>(
+                                            theta, X, N, tpc, mc, alpha, nullptr, 0, Khi, Klo, ldh, scales, mean + c0));
+            GPG_LAUNCH_CHECK(h);
+        }
+        {
+            StageTimer st(h, GPG_ST_PGEMM, s);
+            tc::Launch g;
+            memset(&g.p, 0, sizeof(g.p));
+            g.A.hi = Khi; g.A.lo = Klo; g.A.rows = mc; g.A.cols = N; g.A.ld = ldh;
+            g.B.hi = Whi; g.B.lo = Wlo; g.B.rows = N; g.B.cols = N; g.B.ld = ldh;
+            g.p.M = (int)mc; g.p.N = (int)N; g.p.K = (int)N; g.p.batch = 1;
+            g.p.m_group = m_group;
+            g.p.ke_mode = GEMM_KE_N;
+            g.p.epi = tc::EPI_ROWSUMSQ;
+            g.p.scale_inv = scales + 2;
+            g.p.part = part; g.p.ldpart = chunk;
+            g.p.tile_counter = counter;
+            GPG_TRY(tc::launch(h, g, s));
+        }
+        StageTimer st(h, GPG_ST_PFINAL, s);
+        predict_finalize_kernel<float, D><<<(unsigned)((mc + 255) / 256), 256, 0, s>>>(theta, part, tiles_n, chunk, tpc, mc,
+                                                                                       1.0f, sd + c0);
+        GPG_LAUNCH_CHECK(h);
+    }
+    return GPG_OK;
+}
+
+template <typename T, int D>
+static int predict_route(gpg_handle_s *h, int kernel_id, const T *theta, const T *X, int64_t N, const T *Linv, int64_t ld,
+                         const T *alpha, const void *wsplit, const float *scales, TestPoints<T, D> tp, int64_t M, T *mean,
+                         T *sd, cudaStream_t s) {
+    if constexpr (std::is_same<T, float>::value) {
+        const bool want_tc = wsplit != nullptr && h->opt_gemm_path != 1 && (h->opt_gemm_path == 2 || N >= 1024);
+        if (want_tc) {
+            const __half *whi = (const __half *)wsplit;
+            return predict_core_tc<D>(h, kernel_id, theta, X, N, whi, whi + (size_t)N * ld, ld, scales, alpha, tp, M, mean,
+                                      sd, s);
+        }
+    }
+    return predict_core<T, D>(h, kernel_id, theta, X, N, Linv, ld, alpha, tp, M, mean, sd, s);
+}
+
 template <typename T>
 static int predict_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, int64_t N, const T *Linv,
-                         int64_t ld, const T *alpha, const T *Xs, const int64_t *dims, const double *step, int64_t j0,
+                         int64_t ld, const T *alpha, const void *wsplit, const float *scales, const T *Xs,
+                         const int64_t *dims, const double *step, int64_t j0,
                          int64_t M, T *mean, T *sd, cudaStream_t s) {
     if (M == 0) return GPG_OK;
     GPG_DISPATCH_D(d, {
@@ -333,32 +478,33 @@ static int predict_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, 
             tp.dims[k] = (dims && k < D) ? dims[k] : 1;
             tp.step[k] = (step && k < D) ? (T)step[k] : T(1);
         }
-        return predict_core<T, D>(h, kernel_id, theta, X, N, Linv, ld, alpha, tp, M, mean, sd, s);
+        return predict_route<T, D>(h, kernel_id, theta, X, N, Linv, ld, alpha, wsplit, scales, tp, M, mean, sd, s);
     });
     return GPG_OK;
 }
 
 extern "C" int gpg_predict(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X, int64_t N,
-                           const void *Linv, int64_t ld, const void *alpha, const void *Xs, int64_t M, void *mean_out,
-                           void *sd_out, void *stream) {
+                           const void *Linv, int64_t ld, const void *alpha, const void *wsplit, const float *scales,
+                           const void *Xs, int64_t M, void *mean_out, void *sd_out, void *stream) {
     GPG_REQUIRE(h && theta && X && Linv && alpha && mean_out && sd_out, "NULL argument");
     GPG_REQUIRE(M == 0 || Xs != nullptr, "Xs is NULL");
     GPG_REQUIRE(N > 0 && M >= 0 && ld >= N, "bad size");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == GPG_F32)
         return predict_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, N, (const float *)Linv, ld,
-                                    (const float *)alpha, (const float *)Xs, nullptr, nullptr, 0, M, (float *)mean_out,
-                                    (float *)sd_out, s);
+                                    (const float *)alpha, wsplit, scales, (const float *)Xs, nullptr, nullptr, 0, M,
+                                    (float *)mean_out, (float *)sd_out, s);
     if (dtype == GPG_F64)
         return predict_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, N, (const double *)Linv,
-                                     ld, (const double *)alpha, (const double *)Xs, nullptr, nullptr, 0, M,
+                                     ld, (const double *)alpha, nullptr, nullptr, (const double *)Xs, nullptr, nullptr, 0, M,
                                      (double *)mean_out, (double *)sd_out, s);
     gpg_set_error("unknown dtype %d", dtype);
     return GPG_EINVAL;
 }
 
 extern "C" int gpg_predict_grid(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X,
-                                int64_t N, const void *Linv, int64_t ld, const void *alpha, const int64_t *dims_host,
+                                int64_t N, const void *Linv, int64_t ld, const void *alpha, const void *wsplit,
+                                const float *scales, const int64_t *dims_host,
                                 const double *step_host, int64_t j0, int64_t M, void *mean_out, void *sd_out,
                                 void *stream) {
     GPG_REQUIRE(h && theta && X && Linv && alpha && mean_out && sd_out && dims_host && step_host, "NULL argument");
@@ -370,12 +516,12 @@ extern "C" int gpg_predict_grid(gpg_handle_t h, int dtype, int kernel_id, int d,
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == GPG_F32)
         return predict_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, N, (const float *)Linv, ld,
-                                    (const float *)alpha, nullptr, dims_host, step_host, j0, M, (float *)mean_out,
-                                    (float *)sd_out, s);
+                                    (const float *)alpha, wsplit, scales, nullptr, dims_host, step_host, j0, M,
+                                    (float *)mean_out, (float *)sd_out, s);
     if (dtype == GPG_F64)
         return predict_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, N, (const double *)Linv,
-                                     ld, (const double *)alpha, nullptr, dims_host, step_host, j0, M, (double *)mean_out,
-                                     (double *)sd_out, s);
+                                     ld, (const double *)alpha, nullptr, nullptr, nullptr, dims_host, step_host, j0, M,
+                                     (double *)mean_out, (double *)sd_out, s);
     gpg_set_error("unknown dtype %d", dtype);
     return GPG_EINVAL;
 }

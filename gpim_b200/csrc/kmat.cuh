@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                                                           TestPoints<T, D> tp, int64_t mc, const T *__restrict__ alpha,
                                                           T *__restrict__ Ks, int64_t ldk,
                                                           __half *__restrict__ Khi, __half *__restrict__ Klo, int64_t ldh,
-                                                          float scale, T *__restrict__ mean) {
+                                                          const float *__restrict__ scale_ptr, T *__restrict__ mean) {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (j >= mc) return;
@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
 #pragma unroll
     for (int k = 0; k < D; ++k) bad |= (z[k] != z[k]);
     double acc = 0.0;
+    const float scale = SPLIT ? *scale_ptr : 1.0f;
     const bool vec_ok = ((ldk % 4) == 0);
     // row padding [N, ldk) (and [N, ldh)) is zero-filled so K-tiles may over-read it
     const int64_t width = SPLIT ? ldh : ldk;

@@ -23,8 +23,9 @@ def tile_bounds(M, world, rank):
 
 def broadcast_factor(fac, src=0, group=None):
     """Broadcast the tensors of a factor cache in place (every rank passes same-shaped buffers)."""
-    for key in ("Linv", "alpha"):
-        dist.broadcast(fac[key], src=src, group=group)
+    for key in ("Linv", "alpha", "wsplit", "scales"):
+        if fac.get(key) is not None:
+            dist.broadcast(fac[key], src=src, group=group)
     return fac
 
 

@@ -75,6 +75,14 @@ size_t gpg_workspace_bytes(gpg_handle_t h);
  * brackets per stage (host arrays).  Clears the record. */
 int gpg_stage_times(gpg_handle_t h, double *ms_host, long long *spans_host);
 
+/* The engine's tensor-core GEMM on caller matrices (f32, row-major): C = alpha * A B^T + beta * C with
+ * A [M x K], B [N x K].  Operands are split into fp16 hi/lo planes after multiplication by the
+ * power-of-two scale_a / scale_b (choose them so that scale * max|x| <= 2^15) and multiplied as
+ * Ahi Bhi + Ahi Blo + Alo Bhi on tcgen05 with fp32 accumulation in TMEM. */
+int gpg_gemm_nt_f32(gpg_handle_t h, const float *A, int64_t lda, const float *B, int64_t ldb, float *C,
+                    int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, double beta,
+                    double scale_a, double scale_b, void *stream);
+
 /* K1/K2 -- kernel-matrix assembly.  Replaces Pyro Isotropy.forward reached from
  * gpim/gpreg/gpr.py:192,248 (kernel(X), kernel(X, Xnew)) with the kernels configured at
  * gpim/kernels/pyro_kernels.py:58-68.
@@ -102,11 +110,14 @@ int gpg_solve_vec(gpg_handle_t h, int dtype, const void *L, const void *Linv, in
                   const void *y, void *vhat_out, void *alpha_out, void *scalars_out, void *stream);
 
 /* K1+K3+trtri+K7a in one call: the factor cache {L, Linv, alpha, vhat} for fixed theta.
- * Replaces the kernel(X)+cholesky that GPRegression.forward redoes on every predict (gpr.py:248). */
+ * Replaces the kernel(X)+cholesky that GPRegression.forward redoes on every predict (gpr.py:248).
+ * wsplit_out / scales_out (both NULL or both set; f32 only): the tensor-core form of Linv --
+ * 2*N*ld fp16 values (hi plane then lo plane, power-of-two scaled) and float[4] operand scales --
+ * which gpg_predict needs to run on the tcgen05 path (without them it runs the SIMT kernels). */
 int gpg_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
                   const void *X, const void *y, int64_t N, double jitter,
                   void *L, void *Linv, int64_t ld, void *vhat_out, void *alpha_out,
-                  void *scalars_out, int32_t *info, void *stream);
+                  void *scalars_out, int32_t *info, void *wsplit_out, float *scales_out, void *stream);
 
 /* K2+K4+K5 -- predictive mean and standard deviation at M test points, tiled over M internally
  * (never materialises the N x M cross-kernel).  Replaces util.conditional + the noise add and
@@ -114,12 +125,14 @@ int gpg_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *t
  * Rows of Xs that contain NaN give NaN outputs (acqfunc.py:57-59 relies on it). */
 int gpg_predict(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
                 const void *X, int64_t N, const void *Linv, int64_t ld, const void *alpha,
+                const void *wsplit, const float *scales,
                 const void *Xs, int64_t M, void *mean_out, void *sd_out, void *stream);
 
 /* Analytic grid variant: Xs is not read; test point j has coordinates unravel(j0 + j, dims)*step
  * (np.mgrid layout of gprutils.get_full_grid, gprutils.py:136).  dims_host/step_host: host arrays [d]. */
 int gpg_predict_grid(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
                      const void *X, int64_t N, const void *Linv, int64_t ld, const void *alpha,
+                     const void *wsplit, const float *scales,
                      const int64_t *dims_host, const double *step_host, int64_t j0, int64_t M,
                      void *mean_out, void *sd_out, void *stream);
 
