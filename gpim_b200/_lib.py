@@ -222,7 +222,7 @@ class Engine:
                 "Linv": self.empty(N, ld, dtype=dtype),
                 # tensor-core form of Linv (fp16 hi plane, lo plane) + operand scales; f32 only
                 "wsplit": torch.empty(2, N, ld, dtype=torch.float16, device=self.device) if f32 else None,
-                "scales": torch.zeros(4, dtype=torch.float32, device=self.device) if f32 else None,
+                "scales": torch.zeros(16, dtype=torch.float32, device=self.device) if f32 else None,
                 "vhat": self.empty(N, dtype=dtype), "alpha": self.empty(N, dtype=dtype),
                 "scalars": self.empty(2, dtype=dtype),
                 "info": torch.zeros(1, dtype=torch.int32, device=self.device), "ld": ld}

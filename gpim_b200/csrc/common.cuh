@@ -24,6 +24,8 @@ struct gpg_handle_s {
     int opt_stage_timing = 0;
     void *ws = nullptr;          // grow-only device workspace
     size_t ws_bytes = 0;
+    int *tc_counters = nullptr;              // pool of zeroed tile counters for the persistent GEMM
+    int tc_counter_pos = 0;
     std::vector<gpg_stage_span> spans;       // recorded while opt_stage_timing != 0
     std::vector<cudaEvent_t> event_pool;
 };
@@ -49,6 +51,8 @@ struct StageTimer {
 };
 
 void gpg_set_error(const char *fmt, ...);
+// next zeroed tile counter of the handle's pool (re-zeroed stream-ordered when it wraps)
+int gpg_tc_counter(gpg_handle_s *h, cudaStream_t stream, int **out);
 // returns pointer into the handle workspace, growing it if needed (synchronises on growth)
 int gpg_ws_reserve(gpg_handle_s *h, size_t bytes, void **out);
 

@@ -12,71 +12,258 @@
 template <typename T> int gemm_dispatch(gpg_handle_s *h, const GemmArgs<T> &g, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
-// diagonal block: Cholesky + inverse in shared memory.  grid = 1 CTA (potf2) or one CTA per
-// diagonal block (inverse-only mode, used by trtri).  S, W: NB x (NB+1).
+// diagonal block: Cholesky + inverse of one NB x NB block in shared memory, blocked by 32.
+// grid = 1 CTA (potf2 inside the blocked Cholesky) or one CTA per diagonal block (inverse-only
+// mode, level 0 of trtri).  S: the block / its factor, W: the inverse, both NB x (NB+1).
+//   factor   per 32-column panel: (1) warp 0 factors the 32 x 32 diagonal sub-block in registers
+//            (lane = row, warp shuffles broadcast the pivot column), (2) one thread per row solves
+//            the panel below against it, (3) all threads apply the rank-32 update to the rest;
+//   inverse  32 x 32 diagonal sub-blocks by forward substitution (lane = column), then recursive
+//            doubling W21 = -W22 (L21 W11) with the products held in registers between barriers.
+// Optional fp16 hi/lo emission (f32 only) of the factor block (Lh/Ll) and of the inverse block,
+// plain (Wh/Wl) and transposed (WTh/WTl), for the tensor-core GEMMs that follow.
 // ---------------------------------------------------------------------------------------------
+struct DiagEmit {
+    __half *Lh = nullptr, *Ll = nullptr;        // factor block at [j0+i][j0+k]
+    __half *Wh = nullptr, *Wl = nullptr;        // inverse block at [j0+i][j0+k]
+    __half *WTh = nullptr, *WTl = nullptr;      // inverse block transposed at [j0+k][j0+i]
+    int64_t lds = 0;
+    const float *scale_L = nullptr, *scale_W = nullptr;
+};
+
+__device__ __forceinline__ void emit_split(__half *hi, __half *lo, int64_t off, float v) {
+    const __half h = __float2half_rn(v);
+    hi[off] = h;
+    lo[off] = __float2half_rn(v - __half2float(h));
+}
+
+// 256 threads as a 16 x 16 grid; thread (ty, tx) accumulates out(ty + 16 a, tx + 16 b), a < TI, b < TJ:
+//   out(i, j) += sum_{k < K} A[i * lds + k] * (B_KMAJOR ? B[j * lds + k] : B[k * lds + j])
+// The strided assignment makes every shared-memory read either a broadcast or conflict-free.
+template <typename T, int TI, int TJ, bool B_KMAJOR>
+__device__ __forceinline__ void smem_mm(const T *__restrict__ A, const T *__restrict__ B, int lds, int K,
+                                        T (&acc)[TI][TJ], int ty, int tx) {
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        T a[TI], b[TJ];
+#pragma unroll
+        for (int i = 0; i < TI; ++i) a[i] = A[(ty + 16 * i) * lds + k];
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) b[j] = B_KMAJOR ? B[(tx + 16 * j) * lds + k] : B[k * lds + tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < TI; ++i)
+#pragma unroll
+            for (int j = 0; j < TJ; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+}
+
+// inverse of the 32 x 32 lower-triangular block at S[b0.., b0..] into W[b0.., b0..]; one warp, lane = column
+template <typename T>
+__device__ __forceinline__ void invert_tri32(const T *__restrict__ S, T *__restrict__ W, int lds, int b0, int lane) {
+    T x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        T s0 = (i == lane) ? T(1) : T(0), s1 = T(0);
+#pragma unroll
+        for (int k = 0; k + 1 < i; k += 2) {
+            s0 -= S[(b0 + i) * lds + b0 + k] * x[k];
+            s1 -= S[(b0 + i) * lds + b0 + k + 1] * x[k + 1];
+        }
+        if (i & 1) s0 -= S[(b0 + i) * lds + b0 + i - 1] * x[i - 1];
+        x[i] = (s0 + s1) / S[(b0 + i) * lds + b0 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) W[(b0 + i) * lds + b0 + lane] = x[i];
+}
+
 template <typename T, int NB>
 __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int64_t ld, int64_t N, int64_t j0_first,
                                                          int do_factor, T *__restrict__ inv_out, int64_t ld_inv,
                                                          int64_t inv_block_stride, int dense_out,
-                                                         int32_t *__restrict__ info) {
+                                                         int32_t *__restrict__ info, DiagEmit em) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *S = reinterpret_cast<T *>(smem_raw);
-    T *W = S + NB * (NB + 1);
     constexpr int LDS = NB + 1;
-    const int t = threadIdx.x;
+    constexpr int NSUB = NB / 32;
+    constexpr unsigned FULL = 0xffffffffu;
+    T *S = reinterpret_cast<T *>(smem_raw);
+    T *W = S + NB * LDS;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int tx = t & 15, ty = t >> 4;
     const int64_t j0 = j0_first + (int64_t)blockIdx.x * NB;
     const int nb = (int)min((int64_t)NB, N - j0);
     T *Ab = A + j0 * ld + j0;
     for (int idx = t; idx < NB * NB; idx += 256) {
         const int i = idx / NB, k = idx % NB;
-        T v = (i == k) ? T(1) : T(0);
+        T v = (i == k) ? T(1) : T(0);                 // identity padding of a ragged last block
         if (i < nb && k <= i) v = Ab[(int64_t)i * ld + k];
         S[i * LDS + k] = v;
+        W[i * LDS + k] = T(0);
     }
     __syncthreads();
     if (do_factor) {
-        const int tx = t & 15, ty = t >> 4;
-        for (int j = 0; j < nb; ++j) {
+        for (int p = 0; p < NSUB; ++p) {
+            const int c0 = p * 32;
+            if (warp == 0) {                          // 32 x 32 diagonal sub-block in registers, lane = row
+                T row[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) row[k] = S[(c0 + lane) * LDS + c0 + k];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const T djj = __shfl_sync(FULL, row[j], j);
+                    if (lane == 0 && !(djj > T(0)) && c0 + j < nb) atomicCAS(info, 0, (int32_t)(j0 + c0 + j + 1));
+                    const T ljj = gpg_sqrt(djj);
+                    T lij = row[j] * (T(1) / ljj);
+                    if (lane == j) lij = ljj;
+                    row[j] = lij;
+#pragma unroll
+                    for (int k = j + 1; k < 32; ++k) {
+                        const T lkj = __shfl_sync(FULL, lij, k);
+                        row[k] -= lij * lkj;          // meaningful for lane >= k only
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (k <= lane) S[(c0 + lane) * LDS + c0 + k] = row[k];
+                __syncwarp();
+                invert_tri32<T>(S, W, LDS, c0, lane);  // needed by the panel below and by the block inverse
+            }
             __syncthreads();
-            const T d = S[j * LDS + j];
-            if (!(d > T(0)) && t == 0) atomicCAS(info, 0, (int32_t)(j0 + j + 1));
-            const T ljj = gpg_sqrt(d);
-            const T inv = T(1) / ljj;
-            __syncthreads();
-            for (int i = j + 1 + t; i < nb; i += 256) S[i * LDS + j] *= inv;
-            if (t == 0) S[j * LDS + j] = ljj;
-            __syncthreads();
-            for (int i = j + 1 + ty; i < nb; i += 16) {
-                const T lij = S[i * LDS + j];
-                for (int k = j + 1 + tx; k <= i; k += 16) S[i * LDS + k] -= lij * S[k * LDS + j];
+            const int base = c0 + 32;
+            if (base < NB) {
+                // panel: A21 <- A21 W11^T, 32 rows per chunk, accumulate everything before overwriting
+                constexpr int MAXCH = NSUB - 1;
+                T pacc[MAXCH > 0 ? MAXCH : 1][2][2];
+                const int nch = (NB - base) / 32;
+#pragma unroll
+                for (int ch = 0; ch < MAXCH; ++ch) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) pacc[ch][i][j] = T(0);
+                    if (ch < nch)
+                        smem_mm<T, 2, 2, true>(S + (base + 32 * ch) * LDS + c0, W + c0 * LDS + c0, LDS, 32, pacc[ch], ty, tx);
+                }
+                __syncthreads();
+#pragma unroll
+                for (int ch = 0; ch < MAXCH; ++ch)
+                    if (ch < nch)
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                                S[(base + 32 * ch + ty + 16 * i) * LDS + c0 + tx + 16 * j] = pacc[ch][i][j];
+                __syncthreads();
+                // trailing lower triangle: S[i][k] -= sum_m S[i][c0+m] S[k][c0+m], 64 x 64 chunks
+                const int R = NB - base;
+                for (int ib = 0; ib < R; ib += 64) {
+                    for (int kb = 0; kb <= ib; kb += 64) {
+                        T uacc[4][4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) uacc[i][j] = T(0);
+                        // rows beyond NB are never touched: clamp the chunk with the guards below
+                        if (ib + 64 <= R && kb + 64 <= R) {
+                            smem_mm<T, 4, 4, true>(S + (base + ib) * LDS + c0, S + (base + kb) * LDS + c0, LDS, 32, uacc, ty, tx);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int gi = base + ib + ty + 16 * i, gk = base + kb + tx + 16 * j;
+                                    if (gk <= gi) S[gi * LDS + gk] -= uacc[i][j];
+                                }
+                        } else {                      // ragged 32-wide edge chunk
+                            T eacc[2][2];
+                            for (int si = 0; si < 64 && ib + si < R; si += 32)
+                                for (int sk = 0; sk < 64 && kb + sk < R && kb + sk <= ib + si; sk += 32) {
+#pragma unroll
+                                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                        for (int j = 0; j < 2; ++j) eacc[i][j] = T(0);
+                                    smem_mm<T, 2, 2, true>(S + (base + ib + si) * LDS + c0, S + (base + kb + sk) * LDS + c0, LDS,
+                                                           32, eacc, ty, tx);
+#pragma unroll
+                                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                                        for (int j = 0; j < 2; ++j) {
+                                            const int gi = base + ib + si + ty + 16 * i, gk = base + kb + sk + tx + 16 * j;
+                                            if (gk <= gi) S[gi * LDS + gk] -= eacc[i][j];
+                                        }
+                                }
+                        }
+                    }
+                }
+                __syncthreads();
             }
         }
-        __syncthreads();
         for (int idx = t; idx < nb * nb; idx += 256) {
             const int i = idx / nb, k = idx % nb;
             if (k <= i) Ab[(int64_t)i * ld + k] = S[i * LDS + k];
         }
+    } else {
+        if (warp < NSUB) invert_tri32<T>(S, W, LDS, warp * 32, lane);
+        __syncthreads();
     }
-    // inverse of the lower-triangular block, one thread per column
-    if (t < NB) {
-        const int c = t;
-        for (int i = 0; i < NB; ++i) {
-            T s = T(0);
-            if (i >= c) {
-                s = (i == c) ? T(1) : T(0);
-                for (int k = c; k < i; ++k) s -= S[i * LDS + k] * W[k * LDS + c];
-                s /= S[i * LDS + i];
-            }
-            W[i * LDS + c] = s;
+    // recursive doubling inside the block: W21 = -W22 (L21 W11); the upper triangles of S and W are zero,
+    // so the products are plain dense ones
+    if (NB >= 64) {
+        for (int s0 = 0; s0 < NB; s0 += 64) {        // hb = 32
+            T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
+            smem_mm<T, 2, 2, false>(S + (s0 + 32) * LDS + s0, W + s0 * LDS + s0, LDS, 32, acc, ty, tx);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) W[(s0 + 32 + ty + 16 * i) * LDS + s0 + tx + 16 * j] = acc[i][j];
+            __syncthreads();
+            T acc2[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
+            smem_mm<T, 2, 2, false>(W + (s0 + 32) * LDS + s0 + 32, W + (s0 + 32) * LDS + s0, LDS, 32, acc2, ty, tx);
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) W[(s0 + 32 + ty + 16 * i) * LDS + s0 + tx + 16 * j] = -acc2[i][j];
+            __syncthreads();
         }
     }
-    __syncthreads();
-    T *out = inv_out + (int64_t)blockIdx.x * inv_block_stride;
+    if (NB >= 128) {                                  // hb = 64
+        T acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+        smem_mm<T, 4, 4, false>(S + 64 * LDS, W, LDS, 64, acc, ty, tx);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) W[(64 + ty + 16 * i) * LDS + tx + 16 * j] = acc[i][j];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+        smem_mm<T, 4, 4, false>(W + 64 * LDS + 64, W + 64 * LDS, LDS, 64, acc, ty, tx);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) W[(64 + ty + 16 * i) * LDS + tx + 16 * j] = -acc[i][j];
+        __syncthreads();
+    }
+    static_assert(NB == 64 || NB == 128, "diag_block_kernel handles NB = 64 or 128");
+    T *out = inv_out ? inv_out + (int64_t)blockIdx.x * inv_block_stride : nullptr;
+    const float sL = em.scale_L ? *em.scale_L : 1.0f, sW = em.scale_W ? *em.scale_W : 1.0f;
     for (int idx = t; idx < NB * NB; idx += 256) {
         const int i = idx / NB, k = idx % NB;
+        const bool inside = (i < nb && k < nb);
         // dense NB x NB scratch block, or in-place block of Linv (guard the ragged last block)
-        if (dense_out || (i < nb && k < nb)) out[(int64_t)i * ld_inv + k] = W[i * LDS + k];
+        if (out && (dense_out || inside)) out[(int64_t)i * ld_inv + k] = W[i * LDS + k];
+        if (sizeof(T) == 4 && inside) {
+            if (em.Lh) emit_split(em.Lh, em.Ll, (j0 + i) * em.lds + j0 + k, (k <= i) ? (float)S[i * LDS + k] * sL : 0.f);
+            if (em.Wh) emit_split(em.Wh, em.Wl, (j0 + i) * em.lds + j0 + k, (float)W[i * LDS + k] * sW);
+            if (em.WTh) emit_split(em.WTh, em.WTl, (j0 + k) * em.lds + j0 + i, (float)W[i * LDS + k] * sW);
+        }
     }
 }
 
@@ -95,7 +282,8 @@ static int cholesky_blocked(gpg_handle_s *h, T *A, int64_t N, int64_t ld, int32_
     if (reset_info) GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
     for (int64_t j0 = 0; j0 < N; j0 += NB) {
         const int64_t nb = std::min<int64_t>(NB, N - j0);
-        diag_block_kernel<T, NB><<<1, 256, diag_block_smem<T, NB>(), stream>>>(A, ld, N, j0, 1, dinv, NB, 0, 1, info);
+        diag_block_kernel<T, NB><<<1, 256, diag_block_smem<T, NB>(), stream>>>(A, ld, N, j0, 1, dinv, NB, 0, 1, info,
+                                                                               DiagEmit());
         GPG_LAUNCH_CHECK(h);
         const int64_t rows = N - j0 - nb;
         if (rows <= 0) break;
@@ -136,7 +324,7 @@ static int trtri_blocked(gpg_handle_s *h, const T *L, int64_t N, int64_t ld, T *
     GPG_CUDA_CHECK(cudaMemset2DAsync(Linv, ldi * sizeof(T), 0, N * sizeof(T), N, stream));
     const int nblk = (int)((N + NB - 1) / NB);
     diag_block_kernel<T, NB><<<nblk, 256, diag_block_smem<T, NB>(), stream>>>(
-        const_cast<T *>(L), ld, N, 0, 0, Linv, ldi, (int64_t)NB * (ldi + 1), 0, nullptr);
+        const_cast<T *>(L), ld, N, 0, 0, Linv, ldi, (int64_t)NB * (ldi + 1), 0, nullptr, DiagEmit());
     GPG_LAUNCH_CHECK(h);
     for (int64_t b = NB; b < N; b *= 2) {
         const int64_t npairs_full = N / (2 * b);                   // pairs whose second block is complete

@@ -26,6 +26,11 @@ template <typename T> struct GemmArgs {
     int batch = 1;
     T *part = nullptr;       // COLSUMSQ: part[tile_m * ldpart + n]
     int64_t ldpart = 0;
+    // STORE, f32 only: also emit the fp16 hi/lo split of the stored value times *split_scale at
+    // [m * ld_split + n] (operand of a following tensor-core GEMM, see gemm_tc.cuh)
+    __half *split_hi = nullptr, *split_lo = nullptr;
+    int64_t ld_split = 0;
+    const float *split_scale = nullptr;
 };
 
 template <typename T> struct GemmCfg;
@@ -157,6 +162,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs<T> g) {
     }
 
     if (g.epi == GEMM_EPI_STORE) {
+        const float sscale = (sizeof(T) == 4 && g.split_hi) ? *g.split_scale : 0.f;
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
             const int m = m0 + (i < TMH ? ty * TMH + i : BM / 2 + ty * TMH + (i - TMH));
@@ -169,6 +175,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs<T> g) {
                 T v = g.alpha * acc[i][j];
                 if (g.beta != T(0)) v += g.beta * *dst;
                 *dst = v;
+                if (sizeof(T) == 4 && g.split_hi) {
+                    const float sv = (float)v * sscale;
+                    const __half hh = __float2half_rn(sv);
+                    g.split_hi[(int64_t)m * g.ld_split + n] = hh;
+                    g.split_lo[(int64_t)m * g.ld_split + n] = __float2half_rn(sv - __half2float(hh));
+                }
             }
         }
     } else {

@@ -60,9 +60,10 @@ struct Params {
     // STORE
     float *C; long long ldc; long long c_bs;      // batch b adds c_bs elements
     float alpha, beta;
-    __half *S_hi, *S_lo; long long lds; long long s_bs; int s_transposed;
-    const float *scale_out;      // device scalar multiplied into the emitted split
-    int *tile_counter;           // zeroed before launch
+    __half *S_hi, *S_lo; long long lds; long long s_bs;      // split of the result at [m][n]
+    __half *T_hi, *T_lo; long long ldt; long long t_bs;      // split of the result at [n][m] (transposed)
+    const float *scale_out;      // device scalar multiplied into the emitted splits
+    int *tile_counter;           // zero before launch
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -283,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         int slot = 0; uint32_t sphase = 0;
         int buf = 0; uint32_t bphase = 0;
         const float sinv = *p.scale_inv;
-        const float sout = (p.epi == EPI_STORE && p.S_hi && p.scale_out) ? *p.scale_out : 1.0f;
+        const float sout = (p.epi == EPI_STORE && (p.S_hi || p.T_hi) && p.scale_out) ? *p.scale_out : 1.0f;
         while (true) {
             mbar_wait(BAR(8 + slot), sphase);
             const int t = sched_tile[slot];
@@ -320,6 +321,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 float *Cb = p.C ? p.C + (long long)ti.batch * p.c_bs : nullptr;
                 __half *Sh = p.S_hi ? p.S_hi + (long long)ti.batch * p.s_bs : nullptr;
                 __half *Sl = p.S_lo ? p.S_lo + (long long)ti.batch * p.s_bs : nullptr;
+                __half *Th = p.T_hi ? p.T_hi + (long long)ti.batch * p.t_bs : nullptr;
+                __half *Tl = p.T_lo ? p.T_lo + (long long)ti.batch * p.t_bs : nullptr;
                 const float a_eff = p.alpha * sinv;
 #pragma unroll 1
                 for (int c = 0; c < BN; c += 32) {
@@ -356,15 +359,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                         } else if (p.beta != 0.f) {
                             // no fp32 destination: beta is meaningless; ignored
                         }
-                        if (Sh) {
+                        if (Sh || Th) {
+#pragma unroll 4
                             for (int i = 0; i < 32; ++i) {
                                 if (nbase + i < p.N) {
                                     __half hi, lo;
                                     split_fp16(v[i] * sout, hi, lo);
-                                    const long long off = p.s_transposed ? (long long)(nbase + i) * p.lds + m
-                                                                         : (long long)m * p.lds + nbase + i;
-                                    Sh[off] = hi;
-                                    Sl[off] = lo;
+                                    if (Sh) {
+                                        const long long off = (long long)m * p.lds + nbase + i;
+                                        Sh[off] = hi;
+                                        Sl[off] = lo;
+                                    }
+                                    if (Th) {
+                                        const long long off = (long long)(nbase + i) * p.ldt + m;
+                                        Th[off] = hi;
+                                        Tl[off] = lo;
+                                    }
                                 }
                             }
                         }
@@ -446,7 +456,7 @@ inline int launch(gpg_handle_s *h, Launch &L, cudaStream_t stream) {
     GPG_TRY(make_tensor_map(&mAlo, L.A.lo, L.A.rows, L.A.cols, L.A.ld, BM));
     GPG_TRY(make_tensor_map(&mBhi, L.B.hi, L.B.rows, L.B.cols, L.B.ld, BN));
     GPG_TRY(make_tensor_map(&mBlo, L.B.lo, L.B.rows, L.B.cols, L.B.ld, BN));
-    GPG_CUDA_CHECK(cudaMemsetAsync(p.tile_counter, 0, sizeof(int), stream));
+    GPG_TRY(gpg_tc_counter(h, stream, &p.tile_counter));
     const long long total = (long long)p.tiles_m * p.tiles_n * p.batch;
     const int grid = (int)std::min<long long>(total, h->sm_count);
     gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mAhi, mAlo, mBhi, mBlo, p);

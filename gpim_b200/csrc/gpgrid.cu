@@ -10,6 +10,7 @@
 #include "gemm_tc.cuh"
 #include "kmat.cuh"
 #include "factor.cuh"
+#include "factor_tc.cuh"
 #include "train.cuh"
 #include "acq.cuh"
 
@@ -36,6 +37,20 @@ int gpg_ws_reserve(gpg_handle_s *h, size_t bytes, void **out) {
         h->ws_bytes = want;
     }
     *out = h->ws;
+    return GPG_OK;
+}
+
+int gpg_tc_counter(gpg_handle_s *h, cudaStream_t stream, int **out) {
+    constexpr int POOL = 8192;
+    if (!h->tc_counters) {
+        GPG_CUDA_CHECK(cudaMalloc(&h->tc_counters, POOL * sizeof(int)));
+        h->tc_counter_pos = POOL;
+    }
+    if (h->tc_counter_pos >= POOL) {
+        GPG_CUDA_CHECK(cudaMemsetAsync(h->tc_counters, 0, POOL * sizeof(int), stream));
+        h->tc_counter_pos = 0;
+    }
+    *out = h->tc_counters + h->tc_counter_pos++;
     return GPG_OK;
 }
 
@@ -81,6 +96,7 @@ extern "C" int gpg_create(int device, gpg_handle_t *out) {
 extern "C" int gpg_destroy(gpg_handle_t h) {
     if (!h) return GPG_OK;
     if (h->ws) cudaFree(h->ws);
+    if (h->tc_counters) cudaFree(h->tc_counters);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.beg); cudaEventDestroy(sp.end); }
     for (auto &e : h->event_pool) cudaEventDestroy(e);
     delete h;
@@ -151,7 +167,6 @@ extern "C" int gpg_gemm_nt_f32(gpg_handle_t h, const float *A, int64_t lda, cons
     __half *Ahi = b.take<__half>((size_t)M * ldk), *Alo = b.take<__half>((size_t)M * ldk);
     __half *Bhi = b.take<__half>((size_t)N * ldk), *Blo = b.take<__half>((size_t)N * ldk);
     float *scales = b.take<float>(16);
-    int *counter = b.take<int>(16);
     set_scales_kernel<<<1, 32, 0, s>>>((float)scale_a, (float)scale_b, scales);
     GPG_LAUNCH_CHECK(h);
     GPG_TRY(tc::split_matrix(h, A, lda, M, K, scales, Ahi, Alo, ldk, 0, s));
@@ -165,7 +180,6 @@ extern "C" int gpg_gemm_nt_f32(gpg_handle_t h, const float *A, int64_t lda, cons
     g.p.scale_inv = scales + 2;
     g.p.C = C; g.p.ldc = ldc;
     g.p.alpha = (float)alpha; g.p.beta = (float)beta;
-    g.p.tile_counter = counter;
     return tc::launch(h, g, s);
 }
 
@@ -208,6 +222,20 @@ extern "C" int gpg_kmat(gpg_handle_t h, int dtype, int kernel_id, int d, const v
 // ---------------------------------------------------------------------------------------------
 template <typename T> static int cholesky_entry(gpg_handle_s *h, T *A, int64_t N, int64_t ld, int32_t *info, cudaStream_t s) {
     constexpr int NB = GemmCfg<T>::BN;
+    StageTimer st(h, GPG_ST_CHOLESKY, s);
+    if constexpr (std::is_same<T, float>::value) {
+        if ((ld % 8) == 0 && h->opt_gemm_path != 1 && (h->opt_gemm_path == 2 || N >= 1024)) {
+            void *ws;
+            GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)N * ld * 4, NB * NB * sizeof(T), SC_COUNT * sizeof(float)}), &ws));
+            Bump b(ws);
+            TcPlanes Ls(b.take<unsigned char>((size_t)N * ld * 4), N, ld);
+            float *dinv = b.take<float>(NB * NB);
+            float *scales = b.take<float>(SC_COUNT);
+            scales_from_diag_kernel<<<1, 256, 0, s>>>(A, ld, N, scales);
+            GPG_LAUNCH_CHECK(h);
+            return cholesky_blocked_tc(h, A, N, ld, info, 1, dinv, Ls, scales, s);
+        }
+    }
     void *ws;
     GPG_TRY(gpg_ws_reserve(h, bump_size({NB * NB * sizeof(T)}), &ws));
     Bump b(ws);
@@ -269,50 +297,83 @@ extern "C" int gpg_solve_vec(gpg_handle_t h, int dtype, const void *L, const voi
     return GPG_EINVAL;
 }
 
-// Power-of-two operand scales of the split-fp16 tensor-core path, from rigorous magnitude bounds:
-//   |K*_ij| <= variance;   |Linv_ij| <= ||L^-1||_2 = lambda_min(K)^-1/2 <= (noise + jitter)^-1/2
-// (K = K_f + (noise + jitter) I with K_f positive semi-definite).  Scaled magnitudes stay <= 2^14.
-// scales: {s_K, s_W, 1 / (s_K s_W), reserved}
-template <typename T>
-__global__ void predict_scales_kernel(const T *__restrict__ theta, float jitter, float *__restrict__ scales) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const float v = fmaxf((float)theta[0], 1e-30f);
-    const float nz = fmaxf((float)theta[1] + jitter, 1e-30f);
-    int ek = (int)floorf(log2f(16384.0f / v));
-    int ew = (int)floorf(log2f(16384.0f * sqrtf(nz)));
-    ek = max(-40, min(40, ek));
-    ew = max(-40, min(40, ew));
-    scales[0] = exp2f((float)ek);
-    scales[1] = exp2f((float)ew);
-    scales[2] = exp2f((float)(-ek - ew));
-    scales[3] = 0.f;
+// Scratch of one factorisation.  SIMT path: tmp (N x ld of T).  Tensor-core path (f32): the three
+// fp16 plane pairs Ls / WTs / TTs of factor_tc.cuh (the fourth, Ws, is caller memory: it is part
+// of the factor cache gpg_predict consumes).
+template <typename T> struct FactorWs {
+    T *tmp = nullptr, *dinv = nullptr, *vs = nullptr;
+    void *planes = nullptr;           // 3 x (2 N ld halves) when the tensor-core path is possible
+};
+
+static bool tc_factor_wanted(const gpg_handle_s *h, int64_t N, int64_t ld, const void *wsplit) {
+    return wsplit != nullptr && (ld % 8) == 0 && h->opt_gemm_path != 1 && (h->opt_gemm_path == 2 || N >= 1024);
 }
 
-// K1 + K3 + trtri + K7a.  tmp (N*ld), dinv, vec scratch come from the caller-provided bump.
+template <typename T> static size_t factor_ws_bytes(const gpg_handle_s *h, int64_t N, int64_t ld, const void *wsplit) {
+    constexpr int NB = GemmCfg<T>::BN;
+    const bool tcp = std::is_same<T, float>::value && tc_factor_wanted(h, N, ld, wsplit);
+    const size_t big = tcp ? 3 * (size_t)N * ld * 4 : (size_t)N * ld * sizeof(T);
+    return bump_size({big, NB * NB * sizeof(T), 2 * (size_t)N * sizeof(T)});
+}
+
+template <typename T> static FactorWs<T> factor_ws_carve(const gpg_handle_s *h, Bump &b, int64_t N, int64_t ld, const void *wsplit) {
+    constexpr int NB = GemmCfg<T>::BN;
+    const bool tcp = std::is_same<T, float>::value && tc_factor_wanted(h, N, ld, wsplit);
+    FactorWs<T> w;
+    if (tcp) w.planes = b.take<unsigned char>(3 * (size_t)N * ld * 4);
+    else w.tmp = b.take<T>((size_t)N * ld);
+    w.dinv = b.take<T>(NB * NB);
+    w.vs = b.take<T>(2 * N);
+    return w;
+}
+
+// K1 + K3 + trtri + K7a: the factor cache for the theta stored on the device.
+// wsplit / scales (f32, nullable together): tensor-core form of Linv for gpg_predict.
 template <typename T>
 static int factorize_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
                           double jitter, T *L, T *Linv, int64_t ld, T *vhat, T *alpha, T *scalars, int32_t *info,
-                          int reset_info, T *tmp, T *dinv, T *vscratch, cudaStream_t s) {
+                          int reset_info, const FactorWs<T> &w, void *wsplit, float *scales, cudaStream_t s) {
     { StageTimer st(h, GPG_ST_KMAT, s); GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, nullptr, N, jitter, 1, L, ld, s)); }
-    { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, L, N, ld, info, reset_info, dinv, s)); }
-    { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, L, N, ld, Linv, ld, tmp, s)); }
-    { StageTimer st(h, GPG_ST_SOLVE, s); GPG_TRY(solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, scalars, vscratch, s)); }
+    bool done = false;
+    if constexpr (std::is_same<T, float>::value) {
+        if (wsplit) {
+            scales_from_theta_kernel<float><<<1, 32, 0, s>>>(theta, (float)jitter, (float)N, scales);
+            GPG_LAUNCH_CHECK(h);
+        }
+        if (w.planes) {
+            const size_t pl = (size_t)N * ld * 4;
+            TcPlanes Ls(w.planes, N, ld), WTs((unsigned char *)w.planes + pl, N, ld), TTs((unsigned char *)w.planes + 2 * pl, N, ld);
+            TcPlanes Ws(wsplit, N, ld);
+            { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked_tc(h, L, N, ld, info, reset_info, w.dinv, Ls, scales, s)); }
+            { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_tc(h, L, N, ld, Linv, Ls, Ws, WTs, TTs, scales, s)); }
+            done = true;
+        }
+    }
+    if (!done) {
+        { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, L, N, ld, info, reset_info, w.dinv, s)); }
+        { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, L, N, ld, Linv, ld, w.tmp, s)); }
+        if constexpr (std::is_same<T, float>::value) {
+            if (wsplit) {
+                StageTimer st(h, GPG_ST_TRTRI, s);
+                TcPlanes Ws(wsplit, N, ld);
+                GPG_TRY(tc::split_matrix(h, Linv, ld, N, N, scales + SC_W, Ws.hi, Ws.lo, ld, 1, s));
+            }
+        }
+    }
+    { StageTimer st(h, GPG_ST_SOLVE, s); GPG_TRY(solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, scalars, w.vs, s)); }
     return GPG_OK;
 }
 
 template <typename T>
 static int factorize_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
                            double jitter, T *L, T *Linv, int64_t ld, T *vhat, T *alpha, T *scalars, int32_t *info,
-                           cudaStream_t s) {
-    constexpr int NB = GemmCfg<T>::BN;
+                           void *wsplit, float *scales, cudaStream_t s) {
     void *ws;
-    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)N * ld * sizeof(T), NB * NB * sizeof(T), 2 * (size_t)N * sizeof(T)}), &ws));
+    GPG_TRY(gpg_ws_reserve(h, factor_ws_bytes<T>(h, N, ld, wsplit), &ws));
     Bump b(ws);
-    T *tmp = b.take<T>((size_t)N * ld);
-    T *dinv = b.take<T>(NB * NB);
-    T *vs = b.take<T>(2 * N);
-    return factorize_core<T>(h, kernel_id, d, theta, X, y, N, jitter, L, Linv, ld, vhat, alpha, scalars, info, 1, tmp,
-                             dinv, vs, s);
+    FactorWs<T> w = factor_ws_carve<T>(h, b, N, ld, wsplit);
+    return factorize_core<T>(h, kernel_id, d, theta, X, y, N, jitter, L, Linv, ld, vhat, alpha, scalars, info, 1, w,
+                             wsplit, scales, s);
 }
 
 extern "C" int gpg_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X,
@@ -325,23 +386,14 @@ extern "C" int gpg_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, co
     GPG_REQUIRE((wsplit_out == nullptr) == (scales_out == nullptr), "wsplit_out and scales_out go together");
     GPG_REQUIRE(wsplit_out == nullptr || (dtype == GPG_F32 && ld % 8 == 0), "the split factor needs f32 and ld % 8 == 0");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (dtype == GPG_F32) {
-        GPG_TRY(factorize_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, (const float *)y, N, jitter,
-                                       (float *)L, (float *)Linv, ld, (float *)vhat_out, (float *)alpha_out,
-                                       (float *)scalars_out, info, s));
-        if (wsplit_out) {
-            StageTimer st(h, GPG_ST_TRTRI, s);
-            predict_scales_kernel<float><<<1, 32, 0, s>>>((const float *)theta, (float)jitter, scales_out);
-            GPG_LAUNCH_CHECK(h);
-            __half *whi = (__half *)wsplit_out, *wlo = whi + (size_t)N * ld;
-            GPG_TRY(tc::split_matrix(h, (const float *)Linv, ld, N, N, scales_out + 1, whi, wlo, ld, 1, s));
-        }
-        return GPG_OK;
-    }
+    if (dtype == GPG_F32)
+        return factorize_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, (const float *)y, N, jitter,
+                                      (float *)L, (float *)Linv, ld, (float *)vhat_out, (float *)alpha_out,
+                                      (float *)scalars_out, info, wsplit_out, scales_out, s);
     if (dtype == GPG_F64)
         return factorize_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, (const double *)y, N,
                                        jitter, (double *)L, (double *)Linv, ld, (double *)vhat_out, (double *)alpha_out,
-                                       (double *)scalars_out, info, s);
+                                       (double *)scalars_out, info, nullptr, nullptr, s);
     gpg_set_error("unknown dtype %d", dtype);
     return GPG_EINVAL;
 }
@@ -413,7 +465,6 @@ static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, c
     __half *Khi = b.take<__half>((size_t)chunk * ldh);
     __half *Klo = b.take<__half>((size_t)chunk * ldh);
     float *part = b.take<float>((size_t)tiles_n * chunk);
-    int *counter = b.take<int>(16);
     // A-operand groups sized to stay L2-resident while the n-blocks sweep over them
     const int m_group = (int)std::max<int64_t>(1, ((int64_t)64 << 20) / (tc::BM * ldh * 4));
     for (int64_t c0 = 0; c0 < M; c0 += chunk) {
@@ -438,7 +489,6 @@ static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, c
             g.p.epi = tc::EPI_ROWSUMSQ;
             g.p.scale_inv = scales + 2;
             g.p.part = part; g.p.ldpart = chunk;
-            g.p.tile_counter = counter;
             GPG_TRY(tc::launch(h, g, s));
         }
         StageTimer st(h, GPG_ST_PFINAL, s);
@@ -531,29 +581,48 @@ extern "C" int gpg_predict_grid(gpg_handle_t h, int dtype, int kernel_id, int d,
 // ---------------------------------------------------------------------------------------------
 struct TrainBufs {
     void *L, *Linv, *Kinv, *dinv, *vs, *vhat, *alpha, *scalars, *grad, *nll, *theta;
+    void *planes;            // tensor-core path: Ls | WTs | TTs (Kinv aliases TTs, which is dead by then)
+    void *wsplit;            // tensor-core path: Ws
+    float *scales;
     double *partial;
     FitState *st;
     int64_t ld;
     int nblocks;
 };
 
-template <typename T> static size_t train_ws_bytes(int64_t N, int64_t ld) {
+template <typename T> static bool train_uses_tc(const gpg_handle_s *h, int64_t N, int64_t ld) {
+    return std::is_same<T, float>::value && tc_factor_wanted(h, N, ld, (const void *)1);
+}
+
+template <typename T> static size_t train_ws_bytes(const gpg_handle_s *h, int64_t N, int64_t ld) {
     constexpr int NB = GemmCfg<T>::BN;
     const size_t nn = (size_t)N * ld * sizeof(T);
     const size_t nb = (size_t)((N + 7) / 8);
-    return bump_size({nn, nn, nn, NB * NB * sizeof(T), 2 * (size_t)N * sizeof(T), (size_t)N * sizeof(T),
+    const bool tcp = train_uses_tc<T>(h, N, ld);
+    // L, Linv + (SIMT: Kinv | TC: 3 plane pairs + Ws)
+    return bump_size({nn, nn, tcp ? 4 * nn : nn, NB * NB * sizeof(T), 2 * (size_t)N * sizeof(T), (size_t)N * sizeof(T),
                       (size_t)N * sizeof(T), 2 * sizeof(T), GPG_MAX_P * sizeof(T), sizeof(T), GPG_MAX_P * sizeof(T),
-                      nb * GPG_MAX_P * sizeof(double), sizeof(FitState)});
+                      SC_COUNT * sizeof(float), nb * GPG_MAX_P * sizeof(double), sizeof(FitState)});
 }
 
-template <typename T> static TrainBufs train_carve(void *ws, int64_t N, int64_t ld) {
+template <typename T> static TrainBufs train_carve(const gpg_handle_s *h, void *ws, int64_t N, int64_t ld) {
     constexpr int NB = GemmCfg<T>::BN;
     Bump b(ws);
     TrainBufs t;
     t.ld = ld;
     t.L = b.take<T>((size_t)N * ld);
     t.Linv = b.take<T>((size_t)N * ld);
-    t.Kinv = b.take<T>((size_t)N * ld);
+    if (train_uses_tc<T>(h, N, ld)) {
+        const size_t pl = (size_t)N * ld * 4;
+        unsigned char *big = b.take<unsigned char>(4 * pl);
+        t.planes = big;
+        t.wsplit = big + 3 * pl;
+        t.Kinv = big + 2 * pl;
+    } else {
+        t.planes = nullptr;
+        t.wsplit = nullptr;
+        t.Kinv = b.take<T>((size_t)N * ld);
+    }
     t.dinv = b.take<T>(NB * NB);
     t.vs = b.take<T>(2 * N);
     t.vhat = b.take<T>(N);
@@ -562,6 +631,7 @@ template <typename T> static TrainBufs train_carve(void *ws, int64_t N, int64_t 
     t.grad = b.take<T>(GPG_MAX_P);
     t.nll = b.take<T>(1);
     t.theta = b.take<T>(GPG_MAX_P);
+    t.scales = b.take<float>(SC_COUNT);
     t.nblocks = (int)((N + 7) / 8);
     t.partial = b.take<double>((size_t)t.nblocks * GPG_MAX_P);
     t.st = b.take<FitState>(1);
@@ -574,17 +644,32 @@ static int nll_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, 
                          double jitter, const TrainBufs &tb, T *nll_out, T *grad_out, int32_t *info, int reset_info,
                          cudaStream_t s) {
     T *L = (T *)tb.L, *Linv = (T *)tb.Linv, *Kinv = (T *)tb.Kinv;
+    FactorWs<T> w;
+    w.planes = tb.planes;
+    w.tmp = tb.planes ? nullptr : Kinv;          // SIMT trtri scratch; Kinv is overwritten afterwards
+    w.dinv = (T *)tb.dinv;
+    w.vs = (T *)tb.vs;
     GPG_TRY(factorize_core<T>(h, kernel_id, d, theta, X, y, N, jitter, L, Linv, tb.ld, (T *)tb.vhat, (T *)tb.alpha,
-                              (T *)tb.scalars, info, reset_info, Kinv, (T *)tb.dinv, (T *)tb.vs, s));
+                              (T *)tb.scalars, info, reset_info, w, tb.wsplit, tb.scales, s));
     StageTimer st(h, GPG_ST_GRAD, s);
-    GemmArgs<T> g;               // Kinv = Linv^T Linv on lower tiles: sum_k Linv[k][i] Linv[k][j], k >= max(i,j)
-    g.A = Linv; g.lda = tb.ld; g.a_kmajor = 0;
-    g.B = Linv; g.ldb = tb.ld; g.b_kmajor = 0;
-    g.C = Kinv; g.ldc = tb.ld;
-    g.M = (int)N; g.N = (int)N; g.K = (int)N;
-    g.kb_mode = GEMM_KB_MAXMN;
-    g.tile_mode = GEMM_TILES_LOWER;
-    GPG_TRY(gemm_dispatch<T>(h, g, s));
+    bool done = false;
+    if constexpr (std::is_same<T, float>::value) {
+        if (tb.planes) {             // Kinv = Linv^T Linv on tcgen05 from the transposed split of Linv
+            TcPlanes WTs((unsigned char *)tb.planes + (size_t)N * tb.ld * 4, N, tb.ld);
+            GPG_TRY(kinv_tc(h, N, tb.ld, WTs, Kinv, tb.scales, s));
+            done = true;
+        }
+    }
+    if (!done) {
+        GemmArgs<T> g;           // Kinv = Linv^T Linv on lower tiles: sum_k Linv[k][i] Linv[k][j], k >= max(i,j)
+        g.A = Linv; g.lda = tb.ld; g.a_kmajor = 0;
+        g.B = Linv; g.ldb = tb.ld; g.b_kmajor = 0;
+        g.C = Kinv; g.ldc = tb.ld;
+        g.M = (int)N; g.N = (int)N; g.K = (int)N;
+        g.kb_mode = GEMM_KB_MAXMN;
+        g.tile_mode = GEMM_TILES_LOWER;
+        GPG_TRY(gemm_dispatch<T>(h, g, s));
+    }
     GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, grad_partial_kernel<T, KID, D><<<tb.nblocks, 256, 0, s>>>(
                                                        theta, X, (const T *)tb.alpha, Kinv, tb.ld, N, tb.partial)));
     GPG_LAUNCH_CHECK(h);
@@ -599,8 +684,8 @@ static int nll_grad_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta,
                           double jitter, T *nll_out, T *grad_out, int32_t *info, cudaStream_t s) {
     const int64_t ld = gpg_align_up((size_t)N, 64);
     void *ws;
-    GPG_TRY(gpg_ws_reserve(h, train_ws_bytes<T>(N, ld), &ws));
-    TrainBufs tb = train_carve<T>(ws, N, ld);
+    GPG_TRY(gpg_ws_reserve(h, train_ws_bytes<T>(h, N, ld), &ws));
+    TrainBufs tb = train_carve<T>(h, ws, N, ld);
     return nll_grad_core<T>(h, kernel_id, d, theta, X, y, N, jitter, tb, nll_out, grad_out, info, 1, s);
 }
 
@@ -627,8 +712,8 @@ static int fit_entry(gpg_handle_s *h, int kernel_id, int d, int n_ls, const T *X
                      cudaStream_t s) {
     const int64_t ld = gpg_align_up((size_t)N, 64);
     void *ws;
-    GPG_TRY(gpg_ws_reserve(h, train_ws_bytes<T>(N, ld), &ws));
-    TrainBufs tb = train_carve<T>(ws, N, ld);
+    GPG_TRY(gpg_ws_reserve(h, train_ws_bytes<T>(h, N, ld), &ws));
+    TrainBufs tb = train_carve<T>(h, ws, N, ld);
     FitCfg c;
     memset(&c, 0, sizeof(c));
     c.d = d; c.n_ls = n_ls; c.is_rq = (kernel_id == GPG_RATQUAD);

@@ -112,7 +112,7 @@ int gpg_solve_vec(gpg_handle_t h, int dtype, const void *L, const void *Linv, in
 /* K1+K3+trtri+K7a in one call: the factor cache {L, Linv, alpha, vhat} for fixed theta.
  * Replaces the kernel(X)+cholesky that GPRegression.forward redoes on every predict (gpr.py:248).
  * wsplit_out / scales_out (both NULL or both set; f32 only): the tensor-core form of Linv --
- * 2*N*ld fp16 values (hi plane then lo plane, power-of-two scaled) and float[4] operand scales --
+ * 2*N*ld fp16 values (hi plane then lo plane, power-of-two scaled) and float[16] operand scales --
  * which gpg_predict needs to run on the tcgen05 path (without them it runs the SIMT kernels). */
 int gpg_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
                   const void *X, const void *y, int64_t N, double jitter,
