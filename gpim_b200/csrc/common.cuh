@@ -22,6 +22,9 @@ struct gpg_handle_s {
     int opt_gemm_path = 0;
     long long opt_predict_chunk = 0;
     int opt_stage_timing = 0;
+    int opt_factor_algo = 0;
+    int opt_panel_refine = 1;
+    int opt_syrk_chunk = 0;
     void *ws = nullptr;          // grow-only device workspace
     size_t ws_bytes = 0;
     int *tc_counters = nullptr;              // pool of zeroed tile counters for the persistent GEMM

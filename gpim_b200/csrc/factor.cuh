@@ -23,6 +23,14 @@ template <typename T> int gemm_dispatch(gpg_handle_s *h, const GemmArgs<T> &g, c
 // Optional fp16 hi/lo emission (f32 only) of the factor block (Lh/Ll) and of the inverse block,
 // plain (Wh/Wl) and transposed (WTh/WTl), for the tensor-core GEMMs that follow.
 // ---------------------------------------------------------------------------------------------
+// development aid (tools/_scratch/diag_bench.cu): phase timestamps of diag_block_kernel
+#ifdef GPG_DIAG_PROFILE
+__device__ long long g_diag_clk[64];
+#define GPG_PHASE(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_diag_clk[i] = clock64(); } while (0)
+#else
+#define GPG_PHASE(i)
+#endif
+
 struct DiagEmit {
     __half *Lh = nullptr, *Ll = nullptr;        // factor block at [j0+i][j0+k]
     __half *Wh = nullptr, *Wl = nullptr;        // inverse block at [j0+i][j0+k]
@@ -57,9 +65,11 @@ __device__ __forceinline__ void smem_mm(const T *__restrict__ A, const T *__rest
     }
 }
 
-// inverse of the 32 x 32 lower-triangular block at S[b0.., b0..] into W[b0.., b0..]; one warp, lane = column
+// inverse of the 32 x 32 lower-triangular block at S[b0.., b0..] into W[b0.., b0..]; one warp, lane = column.
+// Must be called by all 32 lanes (converged): the reciprocal diagonal travels by warp shuffle.
 template <typename T>
 __device__ __forceinline__ void invert_tri32(const T *__restrict__ S, T *__restrict__ W, int lds, int b0, int lane) {
+    const T rd = T(1) / S[(b0 + lane) * lds + b0 + lane];
     T x[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -70,10 +80,60 @@ __device__ __forceinline__ void invert_tri32(const T *__restrict__ S, T *__restr
             s1 -= S[(b0 + i) * lds + b0 + k + 1] * x[k + 1];
         }
         if (i & 1) s0 -= S[(b0 + i) * lds + b0 + i - 1] * x[i - 1];
-        x[i] = (s0 + s1) / S[(b0 + i) * lds + b0 + i];
+        x[i] = (s0 + s1) * __shfl_sync(0xffffffffu, rd, i);
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) W[(b0 + i) * lds + b0 + lane] = x[i];
+}
+
+__device__ __forceinline__ float gpg_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double gpg_rsqrt(double x) { return 1.0 / sqrt(x); }
+
+// Cholesky of the 32 x 32 block at S[c0.., c0..] in registers (lane = row).  Per pivot: the pivot
+// travels by one warp shuffle, the scaled column goes through a 32-entry shared buffer and comes back
+// as broadcast 128-bit loads (fewer shared-pipe instructions than one shuffle per column, and no
+// divergent code between the collectives).  Returns 0 or 1 + the local index of the first
+// non-positive pivot among the first `valid` columns.
+template <typename T>
+__device__ __forceinline__ int factor_tri32(T *__restrict__ S, int lds, int c0, int lane, int valid,
+                                            T *__restrict__ colbuf) {
+    constexpr unsigned FULL = 0xffffffffu;
+    T row[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) row[k] = S[(c0 + lane) * lds + c0 + k];
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const T djj = __shfl_sync(FULL, row[j], j);
+        bad = (bad == 0 && !(djj > T(0)) && j < valid) ? j + 1 : bad;
+        const T rs = gpg_rsqrt(djj);
+        T lij = row[j] * rs;                          // lane j: djj / sqrt(djj) = l_jj
+        row[j] = lij;
+        if (j < 31) {
+            colbuf[lane] = lij;
+            __syncwarp();
+#pragma unroll
+            for (int k4 = ((j + 1) / 4) * 4; k4 < 32; k4 += 4) {
+                T c[4];
+                if (sizeof(T) == 4) {
+                    const float4 v = *reinterpret_cast<const float4 *>(colbuf + k4);
+                    c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+                } else {
+                    const double2 a = *reinterpret_cast<const double2 *>(colbuf + k4);
+                    const double2 b = *reinterpret_cast<const double2 *>(colbuf + k4 + 2);
+                    c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (k4 + e > j) row[k4 + e] -= lij * c[e];     // meaningful for lane >= k only
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k)
+        if (k <= lane) S[(c0 + lane) * lds + c0 + k] = row[k];
+    return bad;
 }
 
 template <typename T, int NB>
@@ -84,9 +144,9 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int LDS = NB + 1;
     constexpr int NSUB = NB / 32;
-    constexpr unsigned FULL = 0xffffffffu;
     T *S = reinterpret_cast<T *>(smem_raw);
     T *W = S + NB * LDS;
+    __shared__ __align__(16) T colbuf[32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int tx = t & 15, ty = t >> 4;
     const int64_t j0 = j0_first + (int64_t)blockIdx.x * NB;
@@ -99,33 +159,20 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
         S[i * LDS + k] = v;
         W[i * LDS + k] = T(0);
     }
+    GPG_PHASE(0);
     __syncthreads();
+    GPG_PHASE(1);
     if (do_factor) {
         for (int p = 0; p < NSUB; ++p) {
             const int c0 = p * 32;
             if (warp == 0) {                          // 32 x 32 diagonal sub-block in registers, lane = row
-                T row[32];
-#pragma unroll
-                for (int k = 0; k < 32; ++k) row[k] = S[(c0 + lane) * LDS + c0 + k];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const T djj = __shfl_sync(FULL, row[j], j);
-                    if (lane == 0 && !(djj > T(0)) && c0 + j < nb) atomicCAS(info, 0, (int32_t)(j0 + c0 + j + 1));
-                    const T ljj = gpg_sqrt(djj);
-                    T lij = row[j] * (T(1) / ljj);
-                    if (lane == j) lij = ljj;
-                    row[j] = lij;
-#pragma unroll
-                    for (int k = j + 1; k < 32; ++k) {
-                        const T lkj = __shfl_sync(FULL, lij, k);
-                        row[k] -= lij * lkj;          // meaningful for lane >= k only
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 32; ++k)
-                    if (k <= lane) S[(c0 + lane) * LDS + c0 + k] = row[k];
+                GPG_PHASE(2 + 5 * p);
+                const int bad = factor_tri32<T>(S, LDS, c0, lane, nb - c0, colbuf);
                 __syncwarp();
+                GPG_PHASE(3 + 5 * p);
                 invert_tri32<T>(S, W, LDS, c0, lane);  // needed by the panel below and by the block inverse
+                if (lane == 0 && bad) atomicCAS(info, 0, (int32_t)(j0 + c0 + bad));
+                GPG_PHASE(4 + 5 * p);
             }
             __syncthreads();
             const int base = c0 + 32;
@@ -153,6 +200,7 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
                             for (int j = 0; j < 2; ++j)
                                 S[(base + 32 * ch + ty + 16 * i) * LDS + c0 + tx + 16 * j] = pacc[ch][i][j];
                 __syncthreads();
+                GPG_PHASE(5 + 5 * p);
                 // trailing lower triangle: S[i][k] -= sum_m S[i][c0+m] S[k][c0+m], 64 x 64 chunks
                 const int R = NB - base;
                 for (int ib = 0; ib < R; ib += 64) {
@@ -194,12 +242,10 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
                     }
                 }
                 __syncthreads();
+                GPG_PHASE(6 + 5 * p);
             }
         }
-        for (int idx = t; idx < nb * nb; idx += 256) {
-            const int i = idx / nb, k = idx % nb;
-            if (k <= i) Ab[(int64_t)i * ld + k] = S[i * LDS + k];
-        }
+        GPG_PHASE(22);
     } else {
         if (warp < NSUB) invert_tri32<T>(S, W, LDS, warp * 32, lane);
         __syncthreads();
@@ -226,6 +272,7 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
             __syncthreads();
         }
     }
+    GPG_PHASE(23);
     if (NB >= 128) {                                  // hb = 64
         T acc[4][4];
 #pragma unroll
@@ -251,20 +298,82 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
             for (int j = 0; j < 4; ++j) W[(64 + ty + 16 * i) * LDS + tx + 16 * j] = -acc[i][j];
         __syncthreads();
     }
+    GPG_PHASE(24);
     static_assert(NB == 64 || NB == 128, "diag_block_kernel handles NB = 64 or 128");
+    // Outputs, four consecutive columns per thread: factor block (fp32 + fp16 hi/lo), inverse block (fp32 +
+    // hi/lo), then the transposed inverse planes with the roles of row and column swapped.
     T *out = inv_out ? inv_out + (int64_t)blockIdx.x * inv_block_stride : nullptr;
     const float sL = em.scale_L ? *em.scale_L : 1.0f, sW = em.scale_W ? *em.scale_W : 1.0f;
-    for (int idx = t; idx < NB * NB; idx += 256) {
-        const int i = idx / NB, k = idx % NB;
-        const bool inside = (i < nb && k < nb);
-        // dense NB x NB scratch block, or in-place block of Linv (guard the ragged last block)
-        if (out && (dense_out || inside)) out[(int64_t)i * ld_inv + k] = W[i * LDS + k];
-        if (sizeof(T) == 4 && inside) {
-            if (em.Lh) emit_split(em.Lh, em.Ll, (j0 + i) * em.lds + j0 + k, (k <= i) ? (float)S[i * LDS + k] * sL : 0.f);
-            if (em.Wh) emit_split(em.Wh, em.Wl, (j0 + i) * em.lds + j0 + k, (float)W[i * LDS + k] * sW);
-            if (em.WTh) emit_split(em.WTh, em.WTl, (j0 + k) * em.lds + j0 + i, (float)W[i * LDS + k] * sW);
+    const bool f32 = sizeof(T) == 4;
+    const bool vecA = f32 && ((reinterpret_cast<uintptr_t>(Ab) & 15) == 0) && ((ld & 3) == 0);
+    const bool vecO = f32 && out && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((ld_inv & 3) == 0);
+    const bool vecS = ((em.lds & 3) == 0);
+    for (int q = t; q < NB * NB / 4; q += 256) {
+        const int i = q / (NB / 4), k4 = (q % (NB / 4)) * 4;
+        const int nvalid = (i < nb) ? max(0, min(4, nb - k4)) : 0;       // columns of this group inside the block
+        T s4[4], w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { s4[e] = S[i * LDS + k4 + e]; w4[e] = W[i * LDS + k4 + e]; }
+        if (do_factor && nvalid > 0 && k4 <= i) {      // entries right of the diagonal inside the group are zero in S
+            T *dst = Ab + (int64_t)i * ld + k4;
+            if (nvalid == 4 && vecA) *reinterpret_cast<float4 *>(dst) = make_float4((float)s4[0], (float)s4[1], (float)s4[2], (float)s4[3]);
+            else for (int e = 0; e < nvalid; ++e) if (k4 + e <= i) dst[e] = s4[e];
+        }
+        if (out) {
+            const int nw = dense_out ? 4 : nvalid;
+            T *dst = out + (int64_t)i * ld_inv + k4;
+            if (nw == 4 && vecO) *reinterpret_cast<float4 *>(dst) = make_float4((float)w4[0], (float)w4[1], (float)w4[2], (float)w4[3]);
+            else for (int e = 0; e < nw; ++e) dst[e] = w4[e];
+        }
+        if (f32 && nvalid > 0 && (em.Lh || em.Wh)) {
+            const int64_t off = (j0 + i) * em.lds + j0 + k4;
+            __align__(8) __half h4[4], l4[4];
+            if (em.Lh) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float v = (k4 + e <= i) ? (float)s4[e] * sL : 0.f;
+                    h4[e] = __float2half_rn(v);
+                    l4[e] = __float2half_rn(v - __half2float(h4[e]));
+                }
+                if (nvalid == 4 && vecS) {
+                    *reinterpret_cast<uint2 *>(em.Lh + off) = *reinterpret_cast<const uint2 *>(h4);
+                    *reinterpret_cast<uint2 *>(em.Ll + off) = *reinterpret_cast<const uint2 *>(l4);
+                } else for (int e = 0; e < nvalid; ++e) { em.Lh[off + e] = h4[e]; em.Ll[off + e] = l4[e]; }
+            }
+            if (em.Wh) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float v = (float)w4[e] * sW;
+                    h4[e] = __float2half_rn(v);
+                    l4[e] = __float2half_rn(v - __half2float(h4[e]));
+                }
+                if (nvalid == 4 && vecS) {
+                    *reinterpret_cast<uint2 *>(em.Wh + off) = *reinterpret_cast<const uint2 *>(h4);
+                    *reinterpret_cast<uint2 *>(em.Wl + off) = *reinterpret_cast<const uint2 *>(l4);
+                } else for (int e = 0; e < nvalid; ++e) { em.Wh[off + e] = h4[e]; em.Wl[off + e] = l4[e]; }
+            }
         }
     }
+    if (f32 && em.WTh) {
+        for (int q = t; q < NB * NB / 4; q += 256) {
+            const int k = q / (NB / 4), i4 = (q % (NB / 4)) * 4;       // destination row k, columns i4..i4+3
+            if (k >= nb || i4 >= nb) continue;
+            const int nvalid = min(4, nb - i4);
+            __align__(8) __half h4[4], l4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v = (float)W[(i4 + e) * LDS + k] * sW;
+                h4[e] = __float2half_rn(v);
+                l4[e] = __float2half_rn(v - __half2float(h4[e]));
+            }
+            const int64_t off = (j0 + k) * em.lds + j0 + i4;
+            if (nvalid == 4 && vecS) {
+                *reinterpret_cast<uint2 *>(em.WTh + off) = *reinterpret_cast<const uint2 *>(h4);
+                *reinterpret_cast<uint2 *>(em.WTl + off) = *reinterpret_cast<const uint2 *>(l4);
+            } else for (int e = 0; e < nvalid; ++e) { em.WTh[off + e] = h4[e]; em.WTl[off + e] = l4[e]; }
+        }
+    }
+    GPG_PHASE(25);
 }
 
 template <typename T, int NB> static int diag_block_smem() { return 2 * NB * (NB + 1) * (int)sizeof(T); }
@@ -394,14 +503,17 @@ __global__ void __launch_bounds__(256) gemv_tri_kernel(const T *__restrict__ Mx,
     }
 }
 
+// scalars = {0.5 y^T K^-1 y, sum log L_ii}; the quadratic form is |vhat|^2, or y . alpha when both are given
 template <typename T>
 __global__ void __launch_bounds__(256) solve_scalars_kernel(const T *__restrict__ L, int64_t ld, int64_t N,
-                                                            const T *__restrict__ vhat, T *__restrict__ scalars) {
+                                                            const T *__restrict__ vhat, T *__restrict__ scalars,
+                                                            const T *__restrict__ y = nullptr,
+                                                            const T *__restrict__ alpha = nullptr) {
     __shared__ double r0[8], r1[8];
     double q = 0.0, ld_sum = 0.0;
     for (int64_t i = threadIdx.x; i < N; i += 256) {
-        const double v = (double)vhat[i];
-        q += v * v;
+        if (y) q += (double)y[i] * (double)alpha[i];
+        else { const double v = (double)vhat[i]; q += v * v; }
         ld_sum += log((double)L[i * ld + i]);
     }
     q = warp_sum(q);
@@ -416,18 +528,45 @@ __global__ void __launch_bounds__(256) solve_scalars_kernel(const T *__restrict_
     }
 }
 
+// One guarded step of iterative refinement bookkeeping (single CTA): n1 = |r_new|^2; if it beats the best
+// residual so far (*best, < 0 = none yet) the candidate {alpha_new, r_new} replaces {alpha, r}.
+template <typename T>
+__global__ void __launch_bounds__(1024) refine_select_kernel(int64_t N, const T *__restrict__ alpha_new,
+                                                             const T *__restrict__ r_new, T *__restrict__ alpha,
+                                                             T *__restrict__ r, double *__restrict__ best) {
+    __shared__ double red[32];
+    __shared__ int accept;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += 1024) { const double v = (double)r_new[i]; s += v * v; }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 32; ++w) tot += red[w];
+        accept = (*best < 0.0 || tot < *best) ? 1 : 0;        // NaN never wins
+        if (accept) *best = tot;
+    }
+    __syncthreads();
+    if (!accept) return;
+    for (int64_t i = threadIdx.x; i < N; i += 1024) {
+        if (alpha_new != alpha) alpha[i] = alpha_new[i];
+        if (r_new != r) r[i] = r_new[i];
+    }
+}
+
 // vhat = L^-1 y and alpha = L^-T vhat through the explicit inverse plus two residual corrections
 // against L (each correction restores the backward error of a substitution solve).
 // scratch: 2*N elements.
 template <typename T>
 static int solve_vec_refined(gpg_handle_s *h, const T *L, const T *Linv, int64_t N, int64_t ld, const T *y, T *vhat,
-                             T *alpha, T *scalars, T *scratch, cudaStream_t stream) {
+                             T *alpha, T *scalars, T *scratch, cudaStream_t stream, int corrections = 2) {
     T *r = scratch, *dx = scratch + N;
     const int gN = (int)((N + 7) / 8), gT = (int)((N + 31) / 32);
     // forward: L v = y
     gemv_tri_kernel<T, false><<<gN, 256, 0, stream>>>(Linv, ld, N, y, nullptr, T(1), T(0), vhat);
     GPG_LAUNCH_CHECK(h);
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < corrections; ++it) {
         gemv_tri_kernel<T, false><<<gN, 256, 0, stream>>>(L, ld, N, vhat, y, T(-1), T(1), r);        // r = y - L v
         GPG_LAUNCH_CHECK(h);
         gemv_tri_kernel<T, false><<<gN, 256, 0, stream>>>(Linv, ld, N, r, vhat, T(1), T(1), dx);     // dx = v + Linv r
@@ -437,7 +576,7 @@ static int solve_vec_refined(gpg_handle_s *h, const T *L, const T *Linv, int64_t
     // backward: L^T a = v
     gemv_tri_kernel<T, true><<<gT, 256, 0, stream>>>(Linv, ld, N, vhat, nullptr, T(1), T(0), alpha);
     GPG_LAUNCH_CHECK(h);
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < corrections; ++it) {
         gemv_tri_kernel<T, true><<<gT, 256, 0, stream>>>(L, ld, N, alpha, vhat, T(-1), T(1), r);
         GPG_LAUNCH_CHECK(h);
         gemv_tri_kernel<T, true><<<gT, 256, 0, stream>>>(Linv, ld, N, r, alpha, T(1), T(1), dx);

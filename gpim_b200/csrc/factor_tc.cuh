@@ -9,6 +9,7 @@
 //   Ws  = split(s_W L^-1)     diag blocks by diag_block_kernel, off-diagonal blocks by the epilogue
 //   WTs = split(s_W L^-T)     of the level that computes them (plain and transposed emission)
 //   TTs = split(s_T (L21 W11)^T)   intermediate of a doubling level, transposed emission
+//   As  = split(s_A A)        the not-yet-factored part of K: by kmat_kernel, then by every SYRK epilogue
 // The power-of-two scales come from rigorous bounds (scales_from_theta_kernel), so no data pass
 // is needed to find them and nothing can overflow fp16.
 #pragma once
@@ -26,6 +27,8 @@ enum {
     SC_INV_LW = 6,     // 1 / (s_L s_W)
     SC_INV_WT = 7,     // 1 / (s_W s_T)
     SC_INV_WW = 8,     // 1 / s_W^2
+    SC_A = 9,          // s_A   not-yet-factored part of K (Schur complements), |a_ij| <= v + nz
+    SC_INV_AW = 10,    // 1 / (s_A s_W)
     SC_COUNT = 16
 };
 
@@ -47,6 +50,7 @@ __global__ void scales_from_theta_kernel(const T *__restrict__ theta, float jitt
     const int ew = pow2_exp_below(16384.0f * sqrtf(nz));
     const int el = pow2_exp_below(16384.0f / sqrtf(v + nz));
     const int et = pow2_exp_below(16384.0f * sqrtf(nz) / sqrtf(n_rows * v + nz));
+    const int ea = pow2_exp_below(16384.0f / (v + nz));
     for (int i = 0; i < SC_COUNT; ++i) scales[i] = 0.f;
     scales[SC_K] = exp2f((float)ek);
     scales[SC_W] = exp2f((float)ew);
@@ -57,6 +61,8 @@ __global__ void scales_from_theta_kernel(const T *__restrict__ theta, float jitt
     scales[SC_INV_LW] = exp2f((float)(-el - ew));
     scales[SC_INV_WT] = exp2f((float)(-ew - et));
     scales[SC_INV_WW] = exp2f((float)(-2 * ew));
+    scales[SC_A] = exp2f((float)ea);
+    scales[SC_INV_AW] = exp2f((float)(-ea - ew));
 }
 
 // For a caller-supplied SPD matrix (gpg_cholesky): |L_ij| <= sqrt(max_i A_ii).
@@ -77,6 +83,16 @@ __global__ void __launch_bounds__(256) scales_from_diag_kernel(const float *__re
     }
 }
 
+template <typename E>
+__global__ void __launch_bounds__(256) zero_band_kernel(E *__restrict__ p, int64_t ld, int64_t N, int64_t lo_off,
+                                                        int64_t hi_off) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= N) return;
+    const int64_t c0 = max((int64_t)0, i + lo_off), c1 = min(ld, i + hi_off);
+    for (int64_t c = c0 + lane; c < c1; c += 32) p[i * ld + c] = E(0);
+}
+
 struct TcPlanes {             // hi plane followed by lo plane, each N x ld halves
     __half *hi = nullptr, *lo = nullptr;
     TcPlanes() {}
@@ -86,12 +102,17 @@ struct TcPlanes {             // hi plane followed by lo plane, each N x ld halv
 static inline void tc_params_clear(tc::Launch &g) { memset(&g.p, 0, sizeof(g.p)); }
 
 // ---------------------------------------------------------------------------------------------
-// Blocked right-looking Cholesky, NB = 128.  Per block column: diagonal block factor + inverse in
-// one CTA; panel A21 <- A21 inv(L11)^T on the SIMT GEMM (K = 128, also emits the panel's split);
-// trailing A22 -= A21 A21^T (lower tiles) on tcgen05.
+// Two-level blocked right-looking Cholesky.  Inner block NB = 128: the diagonal block is factored and
+// inverted in one CTA (diag_block_kernel), the panel below becomes A21 inv(L11)^T on the SIMT GEMM
+// (K = 128, also emits the panel's fp16 split), and the trailing update A22 -= A21 A21^T runs on
+// tcgen05 -- but only over the columns of the current OUTER panel (width NB2): the rest of the trailing
+// matrix receives one K = NB2 update per outer panel, so the fp32 matrix is read-modified-written
+// N / NB2 times instead of N / 128 times and the big updates are tensor-bound, not HBM-bound.
+// Accumulation chains in TMEM stay <= NB2 long (the tensor core truncates when it accumulates).
 // ---------------------------------------------------------------------------------------------
 static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld, int32_t *info, int reset_info,
-                               float *dinv, TcPlanes Ls, const float *scales, cudaStream_t stream) {
+                               float *dinv, TcPlanes Ls, const float *scales, cudaStream_t stream,
+                               int64_t NB2 = 512) {
     constexpr int NB = 128;
     static bool attr_set = false;
     if (!attr_set) {
@@ -100,40 +121,51 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
         attr_set = true;
     }
     if (reset_info) GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
-    for (int64_t j0 = 0; j0 < N; j0 += NB) {
-        const int64_t nb = std::min<int64_t>(NB, N - j0);
-        DiagEmit em;
-        em.Lh = Ls.hi; em.Ll = Ls.lo; em.lds = ld; em.scale_L = scales + SC_L;
-        diag_block_kernel<float, NB><<<1, 256, diag_block_smem<float, NB>(), stream>>>(A, ld, N, j0, 1, dinv, NB, 0, 1,
-                                                                                       info, em);
-        GPG_LAUNCH_CHECK(h);
-        const int64_t rows = N - j0 - nb;
-        if (rows <= 0) break;
-        float *A21 = A + (j0 + nb) * ld + j0;
-        GemmArgs<float> p;                   // A21 <- A21 * inv(L11)^T (in place: one n-tile), + split
-        p.A = A21; p.lda = ld; p.a_kmajor = 1;
-        p.B = dinv; p.ldb = NB; p.b_kmajor = 1;
-        p.C = A21; p.ldc = ld;
-        p.M = (int)rows; p.N = (int)nb; p.K = (int)nb;
-        p.ke_mode = GEMM_KE_N;
-        p.split_hi = Ls.hi + (j0 + nb) * ld + j0;
-        p.split_lo = Ls.lo + (j0 + nb) * ld + j0;
-        p.ld_split = ld;
-        p.split_scale = scales + SC_L;
-        GPG_TRY(gemm_simt<float>(h, p, stream));
-        tc::Launch g;                        // A22 -= A21 A21^T, lower tiles
+    auto syrk = [&](int64_t row0, int64_t col0, int64_t k0, int64_t rows, int64_t cols, int64_t kk) -> int {
+        // A[row0.., col0..] -= L[row0.., k0..k0+kk) L[col0.., k0..k0+kk)^T on the tiles that touch row >= col
+        if (rows <= 0 || cols <= 0) return GPG_OK;
+        tc::Launch g;
         tc_params_clear(g);
         g.A.hi = Ls.hi; g.A.lo = Ls.lo; g.A.rows = N; g.A.cols = N; g.A.ld = ld;
         g.B = g.A;
-        g.p.M = (int)rows; g.p.N = (int)rows; g.p.K = (int)nb; g.p.batch = 1;
-        g.p.a_row0 = g.p.b_row0 = (int)(j0 + nb);
-        g.p.a_col0 = g.p.b_col0 = (int)j0;
-        g.p.tile_mode = GEMM_TILES_LOWER;
+        g.p.M = (int)rows; g.p.N = (int)cols; g.p.K = (int)kk; g.p.batch = 1;
+        g.p.a_row0 = (int)row0; g.p.b_row0 = (int)col0;
+        g.p.a_col0 = g.p.b_col0 = (int)k0;
+        g.p.tile_mode = GEMM_TILES_LOWER;            // row0 == col0 in every call: C's origin is on the diagonal
         g.p.epi = tc::EPI_STORE;
         g.p.scale_inv = scales + SC_INV_LL;
-        g.p.C = A + (j0 + nb) * ld + (j0 + nb); g.p.ldc = ld;
+        g.p.C = A + row0 * ld + col0; g.p.ldc = ld;
         g.p.alpha = -1.f; g.p.beta = 1.f;
-        GPG_TRY(tc::launch(h, g, stream));
+        return tc::launch(h, g, stream);
+    };
+    for (int64_t J0 = 0; J0 < N; J0 += NB2) {
+        const int64_t Jend = std::min<int64_t>(N, J0 + NB2);
+        for (int64_t j0 = J0; j0 < Jend; j0 += NB) {
+            const int64_t nb = std::min<int64_t>(NB, N - j0);
+            DiagEmit em;
+            em.Lh = Ls.hi; em.Ll = Ls.lo; em.lds = ld; em.scale_L = scales + SC_L;
+            diag_block_kernel<float, NB><<<1, 256, diag_block_smem<float, NB>(), stream>>>(A, ld, N, j0, 1, dinv, NB, 0, 1,
+                                                                                           info, em);
+            GPG_LAUNCH_CHECK(h);
+            const int64_t rows = N - j0 - nb;
+            if (rows <= 0) break;
+            float *A21 = A + (j0 + nb) * ld + j0;
+            GemmArgs<float> p;                   // A21 <- A21 * inv(L11)^T (in place: one n-tile), + split
+            p.A = A21; p.lda = ld; p.a_kmajor = 1;
+            p.B = dinv; p.ldb = NB; p.b_kmajor = 1;
+            p.C = A21; p.ldc = ld;
+            p.M = (int)rows; p.N = (int)nb; p.K = (int)nb;
+            p.ke_mode = GEMM_KE_N;
+            p.split_hi = Ls.hi + (j0 + nb) * ld + j0;
+            p.split_lo = Ls.lo + (j0 + nb) * ld + j0;
+            p.ld_split = ld;
+            p.split_scale = scales + SC_L;
+            GPG_TRY(gemm_simt<float>(h, p, stream));
+            // inner update: the remaining columns of this outer panel, K = nb
+            GPG_TRY(syrk(j0 + nb, j0 + nb, j0, rows, Jend - (j0 + nb), nb));
+        }
+        // outer update: everything right of the panel, K = panel width
+        GPG_TRY(syrk(Jend, Jend, J0, N - Jend, N - Jend, Jend - J0));
     }
     return GPG_OK;
 }
@@ -152,10 +184,22 @@ static int trtri_tc(gpg_handle_s *h, const float *L, int64_t N, int64_t ld, floa
                                             diag_block_smem<float, NB>()));
         attr_set = true;
     }
-    const size_t plane2 = 2 * (size_t)N * ld * sizeof(__half);
-    GPG_CUDA_CHECK(cudaMemsetAsync(Linv, 0, (size_t)N * ld * sizeof(float), stream));
-    GPG_CUDA_CHECK(cudaMemsetAsync(Ws.hi, 0, plane2, stream));
-    GPG_CUDA_CHECK(cudaMemsetAsync(WTs.hi, 0, plane2, stream));
+    // zero what is structurally zero AND read: Linv's strict upper triangle, and the bands of Ws / WTs next to
+    // the diagonal that triangular k-ranges over-read at tile granularity
+    {
+        const unsigned gz = (unsigned)((N + 7) / 8);
+        constexpr int64_t BAND = 384;      // >= tc::BN + tc::BK
+        zero_band_kernel<float><<<gz, 256, 0, stream>>>(Linv, ld, N, 1, ld);
+        GPG_LAUNCH_CHECK(h);
+        for (__half *pl : {Ws.hi, Ws.lo}) {
+            zero_band_kernel<__half><<<gz, 256, 0, stream>>>(pl, ld, N, 1, BAND);
+            GPG_LAUNCH_CHECK(h);
+        }
+        for (__half *pl : {WTs.hi, WTs.lo}) {
+            zero_band_kernel<__half><<<gz, 256, 0, stream>>>(pl, ld, N, -BAND, 0);
+            GPG_LAUNCH_CHECK(h);
+        }
+    }
     const int nblk = (int)((N + NB - 1) / NB);
     DiagEmit em;
     em.Wh = Ws.hi; em.Wl = Ws.lo; em.WTh = WTs.hi; em.WTl = WTs.lo; em.lds = ld; em.scale_W = scales + SC_W;
@@ -226,4 +270,186 @@ static int kinv_tc(gpg_handle_s *h, int64_t N, int64_t ld, TcPlanes WTs, float *
     g.p.alpha = 1.f;
     g.p.C = Kinv; g.p.ldc = ld;
     return tc::launch(h, g, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Recursive Cholesky + inverse, every contraction on tcgen05 with K = half the node size, so the
+// fp32 matrix is read-modified-written O(log N) times instead of N / 128 times:
+//   node [s, s + n), split at h:   (L11, W11) = node(s, h)
+//                                  L21 = A21 W11^T                    (panel through the inverse)
+//                                  A22 -= L21 L21^T                   (SYRK, lower tiles)
+//                                  (L22, W22) = node(s + h, n - h)
+//                                  W21 = -W22 (L21 W11)               (two products)
+//   leaf (n <= 128): diag_block_kernel (Cholesky + inverse of the block in one CTA).
+// In: A fp32 lower triangle and As = split(s_A A) (lower tiles).  Out: L in A (+ Ls), W = L^-1 in Linv
+// (+ Ws, WTs).  Rf is an fp32 N x ld scratch.  Linv's strict upper triangle and the bands of Ws / WTs next to the diagonal that the
+// triangular k-ranges over-read at tile granularity are zeroed first.
+// ---------------------------------------------------------------------------------------------
+struct PotrfCtx {
+    gpg_handle_s *h;
+    float *A, *Linv, *Rf;          // Rf: fp32 N x ld scratch (first panel estimate)
+    int64_t N, ld;
+    TcPlanes As, Ls, Ws, WTs, TTs;
+    const float *scales;
+    int32_t *info;
+    cudaStream_t stream;
+};
+
+static int potrf_inv_node(const PotrfCtx &c, int64_t s, int64_t n) {
+    constexpr int NB = 128;
+    const int64_t ld = c.ld;
+    if (n <= NB) {
+        DiagEmit em;
+        em.Lh = c.Ls.hi; em.Ll = c.Ls.lo; em.Wh = c.Ws.hi; em.Wl = c.Ws.lo; em.WTh = c.WTs.hi; em.WTl = c.WTs.lo;
+        em.lds = ld; em.scale_L = c.scales + SC_L; em.scale_W = c.scales + SC_W;
+        diag_block_kernel<float, NB><<<1, 256, diag_block_smem<float, NB>(), c.stream>>>(
+            c.A, ld, s + n, s, 1, c.Linv + s * (ld + 1), ld, 0, 0, c.info, em);
+        GPG_LAUNCH_CHECK(c.h);
+        return GPG_OK;
+    }
+    const int64_t nblk = (n + NB - 1) / NB;
+    const int64_t h = ((nblk + 1) / 2) * NB, r2 = n - h;
+    GPG_TRY(potrf_inv_node(c, s, h));
+    auto whole = [&](tc::SplitMat &m, const TcPlanes &pl) { m.hi = pl.hi; m.lo = pl.lo; m.rows = c.N; m.cols = c.N; m.ld = ld; };
+    // Panel L21 = A21 L11^-T through the explicit inverse W11, plus one step of iterative refinement
+    // against L11 itself, which restores the backward stability of a triangular solve:
+    //   L0 = A21 W11^T;   R = A21 - L0 L11^T;   L21 = L0 + R W11^T.
+    const bool refine = c.h->opt_panel_refine != 0;
+    {   // L0 = A21 W11^T  -> Rf (fp32; straight into the factor when not refining), Ls
+        tc::Launch g;
+        tc_params_clear(g);
+        whole(g.A, c.As); whole(g.B, c.Ws);
+        g.p.M = (int)r2; g.p.N = (int)h; g.p.K = (int)h; g.p.batch = 1;
+        g.p.a_row0 = (int)(s + h); g.p.a_col0 = (int)s;
+        g.p.b_row0 = (int)s; g.p.b_col0 = (int)s;
+        g.p.ke_mode = GEMM_KE_N;
+        g.p.epi = tc::EPI_STORE;
+        g.p.scale_inv = c.scales + SC_INV_AW;
+        g.p.alpha = 1.f;
+        g.p.C = (refine ? c.Rf : c.A) + (s + h) * ld + s; g.p.ldc = ld;
+        g.p.S_hi = c.Ls.hi + (s + h) * ld + s; g.p.S_lo = c.Ls.lo + (s + h) * ld + s; g.p.lds = ld;
+        g.p.scale_out = c.scales + SC_L;
+        GPG_TRY(tc::launch(c.h, g, c.stream));
+    }
+    if (refine) {   // R = A21 - L0 L11^T  -> fp32 in place of A21, As
+        tc::Launch g;
+        tc_params_clear(g);
+        whole(g.A, c.Ls); whole(g.B, c.Ls);
+        g.p.M = (int)r2; g.p.N = (int)h; g.p.K = (int)h; g.p.batch = 1;
+        g.p.a_row0 = (int)(s + h); g.p.a_col0 = (int)s;
+        g.p.b_row0 = (int)s; g.p.b_col0 = (int)s;
+        g.p.ke_mode = GEMM_KE_N;
+        g.p.epi = tc::EPI_STORE;
+        g.p.scale_inv = c.scales + SC_INV_LL;
+        g.p.alpha = -1.f; g.p.beta = 1.f;
+        g.p.C = c.A + (s + h) * ld + s; g.p.ldc = ld;
+        g.p.S_hi = c.As.hi + (s + h) * ld + s; g.p.S_lo = c.As.lo + (s + h) * ld + s; g.p.lds = ld;
+        g.p.scale_out = c.scales + SC_A;
+        GPG_TRY(tc::launch(c.h, g, c.stream));
+    }
+    if (refine) {   // L21 = L0 + R W11^T  -> Rf, fp32 into the factor, Ls
+        tc::Launch g;
+        tc_params_clear(g);
+        whole(g.A, c.As); whole(g.B, c.Ws);
+        g.p.M = (int)r2; g.p.N = (int)h; g.p.K = (int)h; g.p.batch = 1;
+        g.p.a_row0 = (int)(s + h); g.p.a_col0 = (int)s;
+        g.p.b_row0 = (int)s; g.p.b_col0 = (int)s;
+        g.p.ke_mode = GEMM_KE_N;
+        g.p.epi = tc::EPI_STORE;
+        g.p.scale_inv = c.scales + SC_INV_AW;
+        g.p.alpha = 1.f; g.p.beta = 1.f;
+        g.p.C = c.Rf + (s + h) * ld + s; g.p.ldc = ld;
+        g.p.C2 = c.A + (s + h) * ld + s; g.p.ldc2 = ld;
+        g.p.S_hi = c.Ls.hi + (s + h) * ld + s; g.p.S_lo = c.Ls.lo + (s + h) * ld + s; g.p.lds = ld;
+        g.p.scale_out = c.scales + SC_L;
+        GPG_TRY(tc::launch(c.h, g, c.stream));
+    }
+    // A22 -= L21 L21^T (lower tiles) -> fp32 in place, As.  The sums on and near the diagonal are all-positive
+    // and the tensor core truncates when it adds into the TMEM accumulator, a bias that grows with the length
+    // of the chain (about -6e-9 K relative): K is therefore cut into chunks whose partial results meet in an
+    // fp32 round-to-nearest add (beta = 1).
+    {
+        const int64_t kc = c.h->opt_syrk_chunk > 0 ? c.h->opt_syrk_chunk : h;
+        for (int64_t k0 = 0; k0 < h; k0 += kc) {
+            const int64_t kk = std::min<int64_t>(kc, h - k0);
+            const bool last = k0 + kk >= h;
+            tc::Launch g;
+            tc_params_clear(g);
+            whole(g.A, c.Ls); g.B = g.A;
+            g.p.M = (int)r2; g.p.N = (int)r2; g.p.K = (int)kk; g.p.batch = 1;
+            g.p.a_row0 = g.p.b_row0 = (int)(s + h);
+            g.p.a_col0 = g.p.b_col0 = (int)(s + k0);
+            g.p.tile_mode = GEMM_TILES_LOWER;
+            g.p.epi = tc::EPI_STORE;
+            g.p.scale_inv = c.scales + SC_INV_LL;
+            g.p.alpha = -1.f; g.p.beta = 1.f;
+            g.p.C = c.A + (s + h) * (ld + 1); g.p.ldc = ld;
+            if (last && r2 > NB) {       // a leaf reads the fp32 block; only larger nodes need the split
+                g.p.S_hi = c.As.hi + (s + h) * (ld + 1); g.p.S_lo = c.As.lo + (s + h) * (ld + 1); g.p.lds = ld;
+                g.p.scale_out = c.scales + SC_A;
+            }
+            GPG_TRY(tc::launch(c.h, g, c.stream));
+        }
+    }
+    GPG_TRY(potrf_inv_node(c, s + h, r2));
+    {   // T = L21 W11, emitted transposed into TTs
+        tc::Launch g;
+        tc_params_clear(g);
+        whole(g.A, c.Ls); whole(g.B, c.WTs);
+        g.p.M = (int)r2; g.p.N = (int)h; g.p.K = (int)h; g.p.batch = 1;
+        g.p.a_row0 = (int)(s + h); g.p.a_col0 = (int)s;
+        g.p.b_row0 = (int)s; g.p.b_col0 = (int)s;
+        g.p.kb_mode = GEMM_KB_N0;
+        g.p.epi = tc::EPI_STORE;
+        g.p.scale_inv = c.scales + SC_INV_LW;
+        g.p.alpha = 1.f;
+        g.p.T_hi = c.TTs.hi + s * ld + (s + h); g.p.T_lo = c.TTs.lo + s * ld + (s + h); g.p.ldt = ld;
+        g.p.scale_out = c.scales + SC_T;
+        GPG_TRY(tc::launch(c.h, g, c.stream));
+    }
+    {   // W21 = -W22 T -> Linv, Ws, WTs
+        tc::Launch g;
+        tc_params_clear(g);
+        whole(g.A, c.Ws); whole(g.B, c.TTs);
+        g.p.M = (int)r2; g.p.N = (int)h; g.p.K = (int)r2; g.p.batch = 1;
+        g.p.a_row0 = (int)(s + h); g.p.a_col0 = (int)(s + h);
+        g.p.b_row0 = (int)s; g.p.b_col0 = (int)(s + h);
+        g.p.ke_mode = GEMM_KE_M;
+        g.p.epi = tc::EPI_STORE;
+        g.p.scale_inv = c.scales + SC_INV_WT;
+        g.p.alpha = -1.f;
+        g.p.C = c.Linv + (s + h) * ld + s; g.p.ldc = ld;
+        g.p.S_hi = c.Ws.hi + (s + h) * ld + s; g.p.S_lo = c.Ws.lo + (s + h) * ld + s; g.p.lds = ld;
+        g.p.T_hi = c.WTs.hi + s * ld + (s + h); g.p.T_lo = c.WTs.lo + s * ld + (s + h); g.p.ldt = ld;
+        g.p.scale_out = c.scales + SC_W;
+        GPG_TRY(tc::launch(c.h, g, c.stream));
+    }
+    return GPG_OK;
+}
+
+static int potrf_inv_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld, float *Linv, float *Rf, int32_t *info,
+                        int reset_info, TcPlanes As, TcPlanes Ls, TcPlanes Ws, TcPlanes WTs, TcPlanes TTs,
+                        const float *scales, cudaStream_t stream) {
+    constexpr int NB = 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GPG_CUDA_CHECK(cudaFuncSetAttribute(diag_block_kernel<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            diag_block_smem<float, NB>()));
+        attr_set = true;
+    }
+    if (reset_info) GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
+    const unsigned gz = (unsigned)((N + 7) / 8);
+    constexpr int64_t BAND = 384;      // >= tc::BN + tc::BK: what a triangular k-range can over-read
+    zero_band_kernel<float><<<gz, 256, 0, stream>>>(Linv, ld, N, 1, ld);
+    GPG_LAUNCH_CHECK(h);
+    for (__half *pl : {Ws.hi, Ws.lo, Ls.hi, Ls.lo}) {
+        zero_band_kernel<__half><<<gz, 256, 0, stream>>>(pl, ld, N, 1, BAND);
+        GPG_LAUNCH_CHECK(h);
+    }
+    for (__half *pl : {WTs.hi, WTs.lo}) {
+        zero_band_kernel<__half><<<gz, 256, 0, stream>>>(pl, ld, N, -BAND, 0);
+        GPG_LAUNCH_CHECK(h);
+    }
+    PotrfCtx c{h, A, Linv, Rf, N, ld, As, Ls, Ws, WTs, TTs, scales, info, stream};
+    return potrf_inv_node(c, 0, N);
 }

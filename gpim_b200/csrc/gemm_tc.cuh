@@ -30,6 +30,7 @@
 #include <cudaTypedefs.h>
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include <vector>
 
 namespace tc {
 
@@ -39,7 +40,9 @@ constexpr int SCHED = 4;
 constexpr int A_TILE_BYTES = BM * BK * 2;            // 16 KB per hi or lo
 constexpr int B_TILE_BYTES = BN * BK * 2;            // 32 KB per hi or lo
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // 96 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_LD = 36;                            // floats per staged row: 16-byte aligned, conflict-free float4 access
+constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_LD * 4;  // one 32 x 32 fp32 transpose buffer per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 
@@ -59,6 +62,7 @@ struct Params {
     float *part; long long ldpart;
     // STORE
     float *C; long long ldc; long long c_bs;      // batch b adds c_bs elements
+    float *C2; long long ldc2;                    // optional second copy of the stored value (no batch stride)
     float alpha, beta;
     __half *S_hi, *S_lo; long long lds; long long s_bs;      // split of the result at [m][n]
     __half *T_hi, *T_lo; long long ldt; long long t_bs;      // split of the result at [n][m] (transposed)
@@ -181,6 +185,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
     volatile int *sched_tile = reinterpret_cast<volatile int *>(bars + 16);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16) + SCHED;
+    float *epi_stage = reinterpret_cast<float *>(gen_tiles + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.tiles_m * p.tiles_n * p.batch;
@@ -318,66 +323,116 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 if (lane == 0) mbar_arrive(BAR(6 + buf));
                 if (m < p.M) p.part[(long long)ti.nblk * p.ldpart + m] = (s0 + s1) * sinv * sinv;
             } else {
+                // STORE: the accumulator arrives with one output row per lane; a 32 x 32 transpose through
+                // shared memory turns the global accesses into 128-byte row segments (8 lanes x float4).
                 float *Cb = p.C ? p.C + (long long)ti.batch * p.c_bs : nullptr;
                 __half *Sh = p.S_hi ? p.S_hi + (long long)ti.batch * p.s_bs : nullptr;
                 __half *Sl = p.S_lo ? p.S_lo + (long long)ti.batch * p.s_bs : nullptr;
                 __half *Th = p.T_hi ? p.T_hi + (long long)ti.batch * p.t_bs : nullptr;
                 __half *Tl = p.T_lo ? p.T_lo + (long long)ti.batch * p.t_bs : nullptr;
                 const float a_eff = p.alpha * sinv;
+                const bool c_vec = Cb && ((reinterpret_cast<uintptr_t>(Cb) & 15) == 0) && ((p.ldc & 3) == 0);
+                float *C2b = p.C2;
+                const bool c2_vec = C2b && ((reinterpret_cast<uintptr_t>(C2b) & 15) == 0) && ((p.ldc2 & 3) == 0);
+                const bool s_vec = Sh && ((reinterpret_cast<uintptr_t>(Sh) & 7) == 0) &&
+                                   ((reinterpret_cast<uintptr_t>(Sl) & 7) == 0) && ((p.lds & 3) == 0);
+                float *stg = epi_stage + quarter * (32 * EPI_LD);
+                const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;
+                const int m_base = ti.mblk * BM + quarter * 32;
+                const bool rd = Cb && p.beta != 0.f && c_vec;
+                float4 nxt4[8];
+                auto load_c = [&](int c, float4 (&dst4)[8]) {     // the 8 float4 of C this lane updates in chunk c
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int mm = m_base + it * 4 + sub_r, nn = n0 + c + sub_c;
+                        dst4[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (mm < p.M && nn + 4 <= p.N)
+                            dst4[it] = *reinterpret_cast<const float4 *>(Cb + (long long)mm * p.ldc + nn);
+                    }
+                };
+                if (rd) load_c(0, nxt4);
 #pragma unroll 1
                 for (int c = 0; c < BN; c += 32) {
+                    const int nbase = n0 + c;
+                    if (nbase >= p.N) break;
                     uint32_t r[32];
                     tmem_ld32(taddr + c, r);
                     tmem_ld_wait();
-                    if (m < p.M) {
-                        const int nbase = n0 + c;
-                        float v[32];
+                    float v[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = a_eff * __uint_as_float(r[i]);
-                        if (Cb) {
-                            float *dst = Cb + (long long)m * p.ldc + nbase;
-                            if (nbase + 32 <= p.N && (p.ldc & 3) == 0) {
-                                if (p.beta != 0.f) {
+                    for (int i = 0; i < 32; ++i) v[i] = a_eff * __uint_as_float(r[i]);
+                    if (Th && m < p.M) {         // transposed split (beta == 0 only): lanes = consecutive columns of T
 #pragma unroll
-                                    for (int i = 0; i < 32; i += 4) {
-                                        const float4 o = *reinterpret_cast<const float4 *>(dst + i);
-                                        v[i] += p.beta * o.x; v[i + 1] += p.beta * o.y;
-                                        v[i + 2] += p.beta * o.z; v[i + 3] += p.beta * o.w;
-                                    }
-                                }
-#pragma unroll
-                                for (int i = 0; i < 32; i += 4)
-                                    *reinterpret_cast<float4 *>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                            } else {
-                                for (int i = 0; i < 32; ++i) {
-                                    if (nbase + i < p.N) {
-                                        if (p.beta != 0.f) v[i] += p.beta * dst[i];
-                                        dst[i] = v[i];
-                                    }
-                                }
-                            }
-                        } else if (p.beta != 0.f) {
-                            // no fp32 destination: beta is meaningless; ignored
-                        }
-                        if (Sh || Th) {
-#pragma unroll 4
-                            for (int i = 0; i < 32; ++i) {
-                                if (nbase + i < p.N) {
-                                    __half hi, lo;
-                                    split_fp16(v[i] * sout, hi, lo);
-                                    if (Sh) {
-                                        const long long off = (long long)m * p.lds + nbase + i;
-                                        Sh[off] = hi;
-                                        Sl[off] = lo;
-                                    }
-                                    if (Th) {
-                                        const long long off = (long long)(nbase + i) * p.ldt + m;
-                                        Th[off] = hi;
-                                        Tl[off] = lo;
-                                    }
-                                }
+                        for (int i = 0; i < 32; ++i) {
+                            if (nbase + i < p.N) {
+                                __half hi, lo;
+                                split_fp16(v[i] * sout, hi, lo);
+                                const long long off = (long long)(nbase + i) * p.ldt + m;
+                                Th[off] = hi;
+                                Tl[off] = lo;
                             }
                         }
+                    }
+                    if (Cb || Sh || C2b) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4 *>(stg + lane * EPI_LD + 4 * q) =
+                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        __syncwarp();
+                        // C reads were issued one chunk ahead (old4); queue the next chunk's before this one's stores
+                        float4 old4[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) old4[it] = nxt4[it];
+                        if (rd && c + 32 < BN) load_c(c + 32, nxt4);
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const int rr = it * 4 + sub_r;
+                            const int mm = m_base + rr;
+                            const int nn = nbase + sub_c;
+                            if (mm >= p.M || nn >= p.N) continue;
+                            float4 x = *reinterpret_cast<const float4 *>(stg + rr * EPI_LD + sub_c);
+                            const bool full = nn + 4 <= p.N;
+                            if (Cb) {
+                                float *dst = Cb + (long long)mm * p.ldc + nn;
+                                if (full && c_vec) {
+                                    if (rd) {
+                                        const float4 o = old4[it];
+                                        x.x += p.beta * o.x; x.y += p.beta * o.y; x.z += p.beta * o.z; x.w += p.beta * o.w;
+                                    }
+                                    *reinterpret_cast<float4 *>(dst) = x;
+                                } else {
+                                    float xs[4] = {x.x, x.y, x.z, x.w};
+                                    for (int e = 0; e < 4 && nn + e < p.N; ++e) {
+                                        if (p.beta != 0.f) xs[e] += p.beta * dst[e];
+                                        dst[e] = xs[e];
+                                    }
+                                    x = make_float4(xs[0], xs[1], xs[2], xs[3]);
+                                }
+                            }
+                            if (C2b) {
+                                float *dst2 = C2b + (long long)mm * p.ldc2 + nn;
+                                if (full && c2_vec) *reinterpret_cast<float4 *>(dst2) = x;
+                                else {
+                                    const float xs[4] = {x.x, x.y, x.z, x.w};
+                                    for (int e = 0; e < 4 && nn + e < p.N; ++e) dst2[e] = xs[e];
+                                }
+                            }
+                            if (Sh) {
+                                __align__(8) __half h4[4], l4[4];
+                                split_fp16(x.x * sout, h4[0], l4[0]);
+                                split_fp16(x.y * sout, h4[1], l4[1]);
+                                split_fp16(x.z * sout, h4[2], l4[2]);
+                                split_fp16(x.w * sout, h4[3], l4[3]);
+                                const long long off = (long long)mm * p.lds + nn;
+                                if (full && s_vec) {
+                                    *reinterpret_cast<uint2 *>(Sh + off) = *reinterpret_cast<const uint2 *>(h4);
+                                    *reinterpret_cast<uint2 *>(Sl + off) = *reinterpret_cast<const uint2 *>(l4);
+                                } else {
+                                    for (int e = 0; e < 4 && nn + e < p.N; ++e) { Sh[off + e] = h4[e]; Sl[off + e] = l4[e]; }
+                                }
+                            }
+                        }
+                        __syncwarp();
                     }
                 }
                 tcgen05_fence_before();
@@ -411,8 +466,21 @@ inline PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 // fp16 row-major matrix [rows][cols] with leading dimension ld (elements); box = 64 columns x box_rows rows.
+// Encoded maps are memoised: the factorisation issues hundreds of launches over the same few planes.
+struct TmapKey {
+    const void *base; long long rows, cols, ld; int box_rows;
+    bool operator==(const TmapKey &o) const {
+        return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    }
+};
+struct TmapEntry { TmapKey key; CUtensorMap map; };
+
 inline int make_tensor_map(CUtensorMap *map, const __half *base, long long rows, long long cols, long long ld,
                            int box_rows) {
+    static thread_local std::vector<TmapEntry> cache;
+    const TmapKey key{base, rows, cols, ld, box_rows};
+    for (const TmapEntry &e : cache)
+        if (e.key == key) { *map = e.map; return GPG_OK; }
     auto fn = get_encode_fn();
     if (!fn) { gpg_set_error("cuTensorMapEncodeTiled entry point not available"); return GPG_ECUDA; }
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld * 2) % 16) {
@@ -427,6 +495,8 @@ inline int make_tensor_map(CUtensorMap *map, const __half *base, long long rows,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { gpg_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return GPG_ECUDA; }
+    if (cache.size() >= 64) cache.erase(cache.begin());
+    cache.push_back(TmapEntry{key, *map});
     return GPG_OK;
 }
 
@@ -444,6 +514,7 @@ struct Launch {
 inline int launch(gpg_handle_s *h, Launch &L, cudaStream_t stream) {
     Params &p = L.p;
     if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.batch <= 0) return GPG_OK;
+    if (p.T_hi && p.beta != 0.f) { gpg_set_error("gemm_tc: transposed split emission needs beta == 0"); return GPG_EINVAL; }
     static bool attr_set = false;
     if (!attr_set) {
         GPG_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));

@@ -109,6 +109,9 @@ extern "C" int gpg_set_option(gpg_handle_t h, int key, long long value) {
         case GPG_OPT_GEMM_PATH: GPG_REQUIRE(value >= 0 && value <= 2, "gemm path 0..2"); h->opt_gemm_path = (int)value; break;
         case GPG_OPT_PREDICT_CHUNK: GPG_REQUIRE(value >= 0, "chunk >= 0"); h->opt_predict_chunk = value; break;
         case GPG_OPT_STAGE_TIMING: h->opt_stage_timing = value != 0; break;
+        case GPG_OPT_FACTOR_ALGO: GPG_REQUIRE(value == 0 || value == 1, "factor algorithm 0..1"); h->opt_factor_algo = (int)value; break;
+        case GPG_OPT_PANEL_REFINE: h->opt_panel_refine = value != 0; break;
+        case GPG_OPT_SYRK_CHUNK: GPG_REQUIRE(value >= 0 && value % 64 == 0, "chunk must be a multiple of 64"); h->opt_syrk_chunk = (int)value; break;
         default: gpg_set_error("unknown option %d", key); return GPG_EINVAL;
     }
     return GPG_OK;
@@ -188,14 +191,15 @@ extern "C" int gpg_gemm_nt_f32(gpg_handle_t h, const float *A, int64_t lda, cons
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 static int kmat_launch(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, int64_t N, const T *Z,
-                       int64_t P, double jitter, int lower_only, T *out, int64_t ld, cudaStream_t stream) {
+                       int64_t P, double jitter, int lower_only, T *out, int64_t ld, cudaStream_t stream,
+                       KmatSplit sp = KmatSplit()) {
     const int sym = (Z == nullptr);
     if (sym) { Z = X; P = N; }
     if (N <= 0 || P <= 0) return GPG_OK;
     dim3 block(64, 4);
     dim3 grid((unsigned)((P + 255) / 256), (unsigned)((N + 15) / 16));
     GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, kmat_kernel<T, KID, D><<<grid, block, 0, stream>>>(
-                                                       theta, X, N, Z, P, sym, (T)jitter, sym ? lower_only : 0, out, ld)));
+                                                       theta, X, N, Z, P, sym, (T)jitter, sym ? lower_only : 0, out, ld, sp)));
     GPG_LAUNCH_CHECK(h);
     return GPG_OK;
 }
@@ -301,8 +305,9 @@ extern "C" int gpg_solve_vec(gpg_handle_t h, int dtype, const void *L, const voi
 // fp16 plane pairs Ls / WTs / TTs of factor_tc.cuh (the fourth, Ws, is caller memory: it is part
 // of the factor cache gpg_predict consumes).
 template <typename T> struct FactorWs {
-    T *tmp = nullptr, *dinv = nullptr, *vs = nullptr;
-    void *planes = nullptr;           // 3 x (2 N ld halves) when the tensor-core path is possible
+    T *tmp = nullptr, *dinv = nullptr, *vs = nullptr;       // vs: 4 N vector scratch
+    double *best = nullptr;
+    void *planes = nullptr;           // Ls | WTs | TTs | As (2 N ld halves each) | Rf (N ld floats): tensor-core path
 };
 
 static bool tc_factor_wanted(const gpg_handle_s *h, int64_t N, int64_t ld, const void *wsplit) {
@@ -312,19 +317,61 @@ static bool tc_factor_wanted(const gpg_handle_s *h, int64_t N, int64_t ld, const
 template <typename T> static size_t factor_ws_bytes(const gpg_handle_s *h, int64_t N, int64_t ld, const void *wsplit) {
     constexpr int NB = GemmCfg<T>::BN;
     const bool tcp = std::is_same<T, float>::value && tc_factor_wanted(h, N, ld, wsplit);
-    const size_t big = tcp ? 3 * (size_t)N * ld * 4 : (size_t)N * ld * sizeof(T);
-    return bump_size({big, NB * NB * sizeof(T), 2 * (size_t)N * sizeof(T)});
+    const size_t big = tcp ? 5 * (size_t)N * ld * 4 : (size_t)N * ld * sizeof(T);
+    return bump_size({big, NB * NB * sizeof(T), 4 * (size_t)N * sizeof(T), sizeof(double)});
 }
 
 template <typename T> static FactorWs<T> factor_ws_carve(const gpg_handle_s *h, Bump &b, int64_t N, int64_t ld, const void *wsplit) {
     constexpr int NB = GemmCfg<T>::BN;
     const bool tcp = std::is_same<T, float>::value && tc_factor_wanted(h, N, ld, wsplit);
     FactorWs<T> w;
-    if (tcp) w.planes = b.take<unsigned char>(3 * (size_t)N * ld * 4);
+    if (tcp) w.planes = b.take<unsigned char>(5 * (size_t)N * ld * 4);
     else w.tmp = b.take<T>((size_t)N * ld);
     w.dinv = b.take<T>(NB * NB);
-    w.vs = b.take<T>(2 * N);
+    w.vs = b.take<T>(4 * N);
+    w.best = b.take<double>(1);
     return w;
+}
+
+// Iterative refinement of alpha = K^-1 y against K ITSELF: the residual y - K alpha is formed by
+// re-evaluating the covariance function (no N x N memory traffic), the correction goes through
+// W^T W ~= K^-1.  This removes the factorisation's backward error (split-fp16 contractions, panels
+// through explicit inverses) from the predictive mean.  Each step is guarded on the device: a
+// candidate is kept only if it lowers |y - K alpha|.  scratch: 4 N elements of T + one double.
+__global__ void set_double_kernel(double *p, double v) { if (threadIdx.x == 0 && blockIdx.x == 0) *p = v; }
+
+template <typename T>
+static int refine_alpha_against_K(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y,
+                                  int64_t N, double jitter, const T *Linv, int64_t ld, T *alpha, T *scratch,
+                                  double *best, int rounds, cudaStream_t s) {
+    T *r = scratch, *t = scratch + N, *an = scratch + 2 * N, *rn = scratch + 3 * N;
+    const unsigned gk = (unsigned)((N + 7) / 8), gN = gk, gT = (unsigned)((N + 31) / 32);
+    auto resid = [&](const T *a, T *out) -> int {
+        GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, {
+            TestPoints<T, D> tp;
+            tp.Xs = X; tp.j0 = 0;
+            for (int k = 0; k < GPG_MAX_D; ++k) { tp.dims[k] = 1; tp.step[k] = T(1); }
+            kcross_mean_kernel<T, KID, D, false><<<gk, 256, 0, s>>>(theta, X, N, tp, N, a, nullptr, 0, nullptr, nullptr, 0,
+                                                                     nullptr, out, y, (T)jitter);
+        }));
+        GPG_LAUNCH_CHECK(h);
+        return GPG_OK;
+    };
+    set_double_kernel<<<1, 32, 0, s>>>(best, -1.0);
+    GPG_LAUNCH_CHECK(h);
+    GPG_TRY(resid(alpha, r));
+    refine_select_kernel<T><<<1, 1024, 0, s>>>(N, alpha, r, alpha, r, best);
+    GPG_LAUNCH_CHECK(h);
+    for (int it = 0; it < rounds; ++it) {
+        gemv_tri_kernel<T, false><<<gN, 256, 0, s>>>(Linv, ld, N, r, nullptr, T(1), T(0), t);          // t = W r
+        GPG_LAUNCH_CHECK(h);
+        gemv_tri_kernel<T, true><<<gT, 256, 0, s>>>(Linv, ld, N, t, alpha, T(1), T(1), an);            // an = alpha + W^T t
+        GPG_LAUNCH_CHECK(h);
+        GPG_TRY(resid(an, rn));
+        refine_select_kernel<T><<<1, 1024, 0, s>>>(N, an, rn, alpha, r, best);
+        GPG_LAUNCH_CHECK(h);
+    }
+    return GPG_OK;
 }
 
 // K1 + K3 + trtri + K7a: the factor cache for the theta stored on the device.
@@ -333,7 +380,6 @@ template <typename T>
 static int factorize_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
                           double jitter, T *L, T *Linv, int64_t ld, T *vhat, T *alpha, T *scalars, int32_t *info,
                           int reset_info, const FactorWs<T> &w, void *wsplit, float *scales, cudaStream_t s) {
-    { StageTimer st(h, GPG_ST_KMAT, s); GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, nullptr, N, jitter, 1, L, ld, s)); }
     bool done = false;
     if constexpr (std::is_same<T, float>::value) {
         if (wsplit) {
@@ -342,13 +388,29 @@ static int factorize_core(gpg_handle_s *h, int kernel_id, int d, const T *theta,
         }
         if (w.planes) {
             const size_t pl = (size_t)N * ld * 4;
-            TcPlanes Ls(w.planes, N, ld), WTs((unsigned char *)w.planes + pl, N, ld), TTs((unsigned char *)w.planes + 2 * pl, N, ld);
+            unsigned char *base = (unsigned char *)w.planes;
+            TcPlanes Ls(base, N, ld), WTs(base + pl, N, ld), TTs(base + 2 * pl, N, ld), As(base + 3 * pl, N, ld);
             TcPlanes Ws(wsplit, N, ld);
-            { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked_tc(h, L, N, ld, info, reset_info, w.dinv, Ls, scales, s)); }
-            { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_tc(h, L, N, ld, Linv, Ls, Ws, WTs, TTs, scales, s)); }
+            if (h->opt_factor_algo == 1) {
+                {
+                    StageTimer st(h, GPG_ST_KMAT, s);
+                    KmatSplit sp;
+                    sp.hi = As.hi; sp.lo = As.lo; sp.ld = ld; sp.scale = scales + SC_A;
+                    GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, nullptr, N, jitter, 1, L, ld, s, sp));
+                }
+                // Cholesky and inverse are interleaved by the recursion; the stage clock books both under CHOLESKY
+                float *Rf = reinterpret_cast<float *>(base + 4 * pl);
+                StageTimer st(h, GPG_ST_CHOLESKY, s);
+                GPG_TRY(potrf_inv_tc(h, L, N, ld, Linv, Rf, info, reset_info, As, Ls, Ws, WTs, TTs, scales, s));
+            } else {
+                { StageTimer st(h, GPG_ST_KMAT, s); GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, nullptr, N, jitter, 1, L, ld, s)); }
+                { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked_tc(h, L, N, ld, info, reset_info, w.dinv, Ls, scales, s)); }
+                { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_tc(h, L, N, ld, Linv, Ls, Ws, WTs, TTs, scales, s)); }
+            }
             done = true;
         }
     }
+    if (!done) { StageTimer st(h, GPG_ST_KMAT, s); GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, nullptr, N, jitter, 1, L, ld, s)); }
     if (!done) {
         { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, L, N, ld, info, reset_info, w.dinv, s)); }
         { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, L, N, ld, Linv, ld, w.tmp, s)); }
@@ -360,7 +422,15 @@ static int factorize_core(gpg_handle_s *h, int kernel_id, int d, const T *theta,
             }
         }
     }
-    { StageTimer st(h, GPG_ST_SOLVE, s); GPG_TRY(solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, scalars, w.vs, s)); }
+    {
+        StageTimer st(h, GPG_ST_SOLVE, s);
+        GPG_TRY(solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, nullptr, w.vs, s, 1));
+        GPG_TRY(refine_alpha_against_K<T>(h, kernel_id, d, theta, X, y, N, jitter, Linv, ld, alpha, w.vs, w.best, 2, s));
+        if (scalars) {               // 0.5 y^T K^-1 y from the refined alpha, log-determinant from diag L
+            solve_scalars_kernel<T><<<1, 256, 0, s>>>(L, ld, N, vhat, scalars, y, alpha);
+            GPG_LAUNCH_CHECK(h);
+        }
+    }
     return GPG_OK;
 }
 
@@ -581,7 +651,7 @@ extern "C" int gpg_predict_grid(gpg_handle_t h, int dtype, int kernel_id, int d,
 // ---------------------------------------------------------------------------------------------
 struct TrainBufs {
     void *L, *Linv, *Kinv, *dinv, *vs, *vhat, *alpha, *scalars, *grad, *nll, *theta;
-    void *planes;            // tensor-core path: Ls | WTs | TTs (Kinv aliases TTs, which is dead by then)
+    void *planes;            // tensor-core path: Ls | WTs | TTs | As (Kinv aliases TTs, which is dead by then)
     void *wsplit;            // tensor-core path: Ws
     float *scales;
     double *partial;
@@ -599,8 +669,8 @@ template <typename T> static size_t train_ws_bytes(const gpg_handle_s *h, int64_
     const size_t nn = (size_t)N * ld * sizeof(T);
     const size_t nb = (size_t)((N + 7) / 8);
     const bool tcp = train_uses_tc<T>(h, N, ld);
-    // L, Linv + (SIMT: Kinv | TC: 3 plane pairs + Ws)
-    return bump_size({nn, nn, tcp ? 4 * nn : nn, NB * NB * sizeof(T), 2 * (size_t)N * sizeof(T), (size_t)N * sizeof(T),
+    // L, Linv + (SIMT: Kinv | TC: 4 plane pairs + Rf + Ws)
+    return bump_size({nn, nn, tcp ? 6 * nn : nn, NB * NB * sizeof(T), 4 * (size_t)N * sizeof(T) + 64, (size_t)N * sizeof(T),
                       (size_t)N * sizeof(T), 2 * sizeof(T), GPG_MAX_P * sizeof(T), sizeof(T), GPG_MAX_P * sizeof(T),
                       SC_COUNT * sizeof(float), nb * GPG_MAX_P * sizeof(double), sizeof(FitState)});
 }
@@ -614,17 +684,17 @@ template <typename T> static TrainBufs train_carve(const gpg_handle_s *h, void *
     t.Linv = b.take<T>((size_t)N * ld);
     if (train_uses_tc<T>(h, N, ld)) {
         const size_t pl = (size_t)N * ld * 4;
-        unsigned char *big = b.take<unsigned char>(4 * pl);
-        t.planes = big;
-        t.wsplit = big + 3 * pl;
-        t.Kinv = big + 2 * pl;
+        unsigned char *big = b.take<unsigned char>(6 * pl);
+        t.planes = big;                              // Ls | WTs | TTs | As | Rf
+        t.wsplit = big + 5 * pl;
+        t.Kinv = big + 2 * pl;                       // aliases TTs, dead once the factorisation is done
     } else {
         t.planes = nullptr;
         t.wsplit = nullptr;
         t.Kinv = b.take<T>((size_t)N * ld);
     }
     t.dinv = b.take<T>(NB * NB);
-    t.vs = b.take<T>(2 * N);
+    t.vs = b.take<T>(4 * N + 64 / sizeof(T));        // vector scratch + the refinement's best-residual double
     t.vhat = b.take<T>(N);
     t.alpha = b.take<T>(N);
     t.scalars = b.take<T>(2);
@@ -649,6 +719,7 @@ static int nll_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, 
     w.tmp = tb.planes ? nullptr : Kinv;          // SIMT trtri scratch; Kinv is overwritten afterwards
     w.dinv = (T *)tb.dinv;
     w.vs = (T *)tb.vs;
+    w.best = reinterpret_cast<double *>((T *)tb.vs + 4 * N);       // 16 N or 32 N bytes past a 1 KB boundary: aligned
     GPG_TRY(factorize_core<T>(h, kernel_id, d, theta, X, y, N, jitter, L, Linv, tb.ld, (T *)tb.vhat, (T *)tb.alpha,
                               (T *)tb.scalars, info, reset_info, w, tb.wsplit, tb.scales, s));
     StageTimer st(h, GPG_ST_GRAD, s);

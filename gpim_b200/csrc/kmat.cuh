@@ -40,12 +40,19 @@ template <typename T> __device__ __forceinline__ void store4(T *dst, const T *v,
     }
 }
 
+// Optional fp16 hi/lo planes of the matrix being assembled (operand of the tensor-core factorisation).
+struct KmatSplit {
+    __half *hi = nullptr, *lo = nullptr;
+    int64_t ld = 0;
+    const float *scale = nullptr;
+};
+
 // out[i*ld + j] = k(X_i, Z_j) (+ diag_add on i == j when sym).  Block: 64 x 4 threads, each
 // thread 4 rows x 4 consecutive columns -> tile of 16 rows x 256 columns.
 template <typename T, int KID, int D>
 __global__ void __launch_bounds__(256) kmat_kernel(const T *__restrict__ theta, const T *__restrict__ X, int64_t N,
                                                    const T *__restrict__ Z, int64_t P, int sym, T jitter,
-                                                   int lower_only, T *__restrict__ out, int64_t ld) {
+                                                   int lower_only, T *__restrict__ out, int64_t ld, KmatSplit sp) {
     const int64_t j = ((int64_t)blockIdx.x * 64 + threadIdx.x) * 4;
     const int64_t i0 = ((int64_t)blockIdx.y * 4 + threadIdx.y) * 4;
     if (lower_only && (int64_t)blockIdx.x * 256 > (int64_t)blockIdx.y * 16 + 15) return;
@@ -73,6 +80,22 @@ __global__ void __launch_bounds__(256) kmat_kernel(const T *__restrict__ theta, 
             if (sym && i == j + c) v[c] += diag_add;
         }
         store4(out + i * ld + j, v, vec_ok, nv);
+        if (sizeof(T) == 4 && sp.hi) {
+            const float sc = *sp.scale;
+            __align__(8) __half h4[4], l4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float sv = (float)v[c] * sc;
+                h4[c] = __float2half_rn(sv);
+                l4[c] = __float2half_rn(sv - __half2float(h4[c]));
+            }
+            if (nv == 4 && (sp.ld & 3) == 0) {
+                *reinterpret_cast<uint2 *>(sp.hi + i * sp.ld + j) = *reinterpret_cast<const uint2 *>(h4);
+                *reinterpret_cast<uint2 *>(sp.lo + i * sp.ld + j) = *reinterpret_cast<const uint2 *>(l4);
+            } else {
+                for (int c = 0; c < nv; ++c) { sp.hi[i * sp.ld + j + c] = h4[c]; sp.lo[i * sp.ld + j + c] = l4[c]; }
+            }
+        }
     }
 }
 
@@ -80,13 +103,16 @@ __global__ void __launch_bounds__(256) kmat_kernel(const T *__restrict__ theta, 
 // mean[j] = sum_i Ks[j][i] * alpha[i].  One warp per test point, lanes sweep i four at a time.
 // Test points with a NaN coordinate get a zero row (so the variance GEMM stays finite) and
 // mean = NaN.  SPLIT: additionally/instead emit fp16 hi/lo operands scaled by `scale`
-// (tensor-core path, see gemm_tc.cuh); then Ks is not written.
+// (tensor-core path, see gemm_tc.cuh); then Ks is not written.  Ks == nullptr (non-SPLIT): rows are not
+// stored at all.  y_resid != nullptr: instead of the mean, write the residual of the linear system
+// (K + diag_add I) alpha = y at row j:  y_j - sum_i k(Xs_j, X_i) alpha_i - diag_add alpha_j  (test points = X).
 template <typename T, int KID, int D, bool SPLIT>
 __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ theta, const T *__restrict__ X, int64_t N,
                                                           TestPoints<T, D> tp, int64_t mc, const T *__restrict__ alpha,
                                                           T *__restrict__ Ks, int64_t ldk,
                                                           __half *__restrict__ Khi, __half *__restrict__ Klo, int64_t ldh,
-                                                          const float *__restrict__ scale_ptr, T *__restrict__ mean) {
+                                                          const float *__restrict__ scale_ptr, T *__restrict__ mean,
+                                                          const T *__restrict__ y_resid = nullptr, T jitter = T(0)) {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (j >= mc) return;
@@ -100,7 +126,7 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
     const float scale = SPLIT ? *scale_ptr : 1.0f;
     const bool vec_ok = ((ldk % 4) == 0);
     // row padding [N, ldk) (and [N, ldh)) is zero-filled so K-tiles may over-read it
-    const int64_t width = SPLIT ? ldh : ldk;
+    const int64_t width = SPLIT ? ldh : (Ks ? ldk : N);
     for (int64_t i = (int64_t)lane * 4; i < width; i += 128) {
         T v[4];
 #pragma unroll
@@ -133,12 +159,15 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                     Klo[j * ldh + i + c] = lo[c];
                 }
             }
-        } else {
+        } else if (Ks) {
             store4(Ks + j * ldk + i, v, vec_ok && ((reinterpret_cast<uintptr_t>(Ks) & 15) == 0), nvalid);
         }
     }
     acc = warp_sum(acc);
-    if (lane == 0) mean[j] = bad ? T(NAN) : (T)acc;
+    if (lane == 0) {
+        if (y_resid) acc = (double)y_resid[j] - acc - ((double)th.noise + (double)jitter) * (double)alpha[j];
+        mean[j] = bad ? T(NAN) : (T)acc;
+    }
 }
 
 // K5: sd = sqrt(max(v - sum_tiles part[t][j], 0) + noise); NaN coordinates -> NaN.

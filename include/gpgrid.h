@@ -43,7 +43,12 @@ enum { GPG_ACQ_CB = 0, GPG_ACQ_EI = 1, GPG_ACQ_POI = 2 };
 enum {
     GPG_OPT_GEMM_PATH = 1,      /* 0 auto (tcgen05 for f32 when large enough), 1 SIMT only, 2 force tcgen05 */
     GPG_OPT_PREDICT_CHUNK = 2,  /* test points per internal tile of gpg_predict (0 = auto) */
-    GPG_OPT_STAGE_TIMING = 3    /* != 0: bracket every stage with CUDA events, read by gpg_stage_times */
+    GPG_OPT_STAGE_TIMING = 3,   /* != 0: bracket every stage with CUDA events, read by gpg_stage_times */
+    GPG_OPT_FACTOR_ALGO = 6,    /* f32 tensor-core factorisation: 0 (default) two-level blocked right-looking Cholesky
+                                   followed by the batched triangular inverse; 1 recursive Cholesky + inverse */
+    GPG_OPT_PANEL_REFINE = 4,   /* recursive algorithm: refine every panel solve against L11 (default 1) */
+    GPG_OPT_SYRK_CHUNK = 5      /* recursive algorithm: longest K accumulated in TMEM before an fp32
+                                   round-to-nearest add (multiple of 64; 0 = unlimited, the default) */
 };
 /* stages reported by gpg_stage_times */
 enum {

@@ -181,6 +181,50 @@ def test_predict_3d_matern(eng):
     assert relinf(m.cpu(), ref_mean) < 1e-4 and relinf(s.cpu(), ref_sd) < 1e-3
 
 
+@pytest.mark.parametrize("n", [129, 257, 700, 1111, 2500])
+@pytest.mark.parametrize("algo", [0, 1])
+def test_factorize_tensor_core(eng, n, algo):
+    """gpg_factorize on the forced tcgen05 path (algo 0: two-level blocked Cholesky + batched inverse;
+    algo 1: recursive Cholesky + inverse): L, L^-1, its fp16 hi/lo planes, alpha and logdet against
+    numpy fp64 on ragged sizes."""
+    from gpim_b200._lib import KERNEL_IDS, OPT_GEMM_PATH
+    X = rand_points(n, 2, n, scale=40.0)
+    rng = np.random.RandomState(n + 1)
+    y = np.sin(X[:, 0] / 5.0) + 0.1 * rng.randn(n)
+    v, ls, noise, jitter = 0.5, [3.0, 4.0], 1e-2, 1e-5
+    K = O.kernel_matrix("RBF", torch.tensor(X), torch.tensor(X), torch.tensor(v).double(), torch.tensor(ls).double(),
+                        torch.tensor(1.0).double()).numpy() + (noise + jitter) * np.eye(n)
+    Lref = np.linalg.cholesky(K)
+    th = torch.tensor([v, noise, 1.0, *ls], dtype=torch.float32).cuda()
+    eng.set_option(OPT_GEMM_PATH, 2)
+    eng.set_option(6, algo)                       # GPG_OPT_FACTOR_ALGO
+    try:
+        fac = eng.factorize(KERNEL_IDS["RBF"], th, torch.tensor(X, dtype=torch.float32).cuda(),
+                            torch.tensor(y, dtype=torch.float32).cuda(), jitter)
+    finally:
+        eng.set_option(OPT_GEMM_PATH, 0)
+        eng.set_option(6, 0)
+    assert int(fac["info"].item()) == 0
+    L = torch.tril(fac["L"][:, :n]).cpu().double().numpy()
+    Li = fac["Linv"][:, :n].cpu().double().numpy()
+    assert relinf(L, Lref) < 1e-4          # panels go through explicit inverses of the leading blocks
+    assert np.abs(np.triu(Li, 1)).max() == 0.0
+    assert np.abs(Li @ Lref - np.eye(n)).max() < 2e-4
+    sc = fac["scales"].cpu().numpy()
+    planes = fac["wsplit"][:, :, :n].cpu().double().numpy()
+    Ws = (planes[0] + planes[1]) / sc[1]
+    # the planes are defined on the lower triangle plus a zero band above the diagonal (what the
+    # triangular k-ranges of the variance GEMM can over-read at tile granularity); the rest is never read
+    band = np.triu(np.ones((n, n), dtype=bool), 1) & ~np.triu(np.ones((n, n), dtype=bool), 321)
+    assert np.abs(np.tril(Ws) - Li).max() <= 2e-6 * np.abs(Li).max()
+    assert (Ws[band] == 0).all()
+    alpha_ref = np.linalg.solve(K, y)
+    assert relinf(fac["alpha"].cpu().numpy(), alpha_ref) < 2e-4
+    # the tensor core truncates when it accumulates: same-sign sums (SYRK diagonals) carry a bias of about
+    # -6e-9 per unit of K, visible as a drift of the log-determinant
+    assert abs(float(fac["scalars"][1]) - np.log(np.diag(Lref)).sum()) < 1e-4 * n
+
+
 # ---------------------------------------------------------------------------------------------
 def _torch_nll(kernel, X, y, theta, jitter):
     v, n, a, l = theta[0], theta[1], theta[2], theta[3:]
