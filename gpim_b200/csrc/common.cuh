@@ -27,6 +27,8 @@ struct gpg_handle_s {
     int opt_syrk_chunk = 0;
     void *ws = nullptr;          // grow-only device workspace
     size_t ws_bytes = 0;
+    double *gemv_part = nullptr;             // partial sums of the transposed triangular GEMV (grow-only)
+    size_t gemv_part_elems = 0;
     int *tc_counters = nullptr;              // pool of zeroed tile counters for the persistent GEMM
     int tc_counter_pos = 0;
     std::vector<gpg_stage_span> spans;       // recorded while opt_stage_timing != 0
@@ -58,6 +60,8 @@ void gpg_set_error(const char *fmt, ...);
 int gpg_tc_counter(gpg_handle_s *h, cudaStream_t stream, int **out);
 // returns pointer into the handle workspace, growing it if needed (synchronises on growth)
 int gpg_ws_reserve(gpg_handle_s *h, size_t bytes, void **out);
+// scratch for gemv_tri_T: at least `elems` doubles (synchronises on growth)
+int gpg_gemv_part_reserve(gpg_handle_s *h, size_t elems, double **out);
 
 #define GPG_CUDA_CHECK(expr)                                                              \
     do {                                                                                  \

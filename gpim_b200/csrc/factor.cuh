@@ -504,6 +504,76 @@ __global__ void __launch_bounds__(256) gemv_tri_kernel(const T *__restrict__ Mx,
 }
 
 // scalars = {0.5 y^T K^-1 y, sum log L_ii}; the quadratic form is |vhat|^2, or y . alpha when both are given
+// Transposed triangular GEMV, out = alpha * Mx^T x + beta * yin, in two deterministic passes: a 2-D grid of
+// (128-column strip) x (512-row chunk) blocks streams the lower triangle with 128-bit loads and leaves double
+// partial sums per chunk; a second kernel adds the chunks up.  (One block per strip cannot pull the matrix
+// fast enough: a single SM's load bandwidth caps it.)
+constexpr int GEMVT_ROWS = 512;
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemvT_partial_kernel(const T *__restrict__ Mx, int64_t ld, int64_t N,
+                                                            const T *__restrict__ x, double *__restrict__ part) {
+    __shared__ double red[8][128];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t c0 = (int64_t)blockIdx.x * 128, r0 = (int64_t)blockIdx.y * GEMVT_ROWS;
+    const int64_t r1 = min(N, r0 + GEMVT_ROWS);
+    if (r1 <= c0) return;                              // chunk entirely above the diagonal: never summed
+    const int64_t c = c0 + 4 * lane;
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(Mx) & 15) == 0) && (sizeof(T) == 4);
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = max(r0, c0) + w; i < r1; i += 8) {
+        if (c > i) continue;
+        const double xi = (double)x[i];
+        T m[4];
+        if (vec && c + 3 < ld) {
+            const float4 v = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(Mx) + i * ld + c);
+            m[0] = (T)v.x; m[1] = (T)v.y; m[2] = (T)v.z; m[3] = (T)v.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m[e] = (c + e <= i) ? Mx[i * ld + c + e] : T(0);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (c + e <= i) a[e] += (double)m[e] * xi;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[w][4 * lane + e] = a[e];
+    __syncthreads();
+    if (threadIdx.x < 128 && c0 + threadIdx.x < N) {
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
+        part[(int64_t)blockIdx.y * N + c0 + threadIdx.x] = s;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemvT_finish_kernel(const double *__restrict__ part, int64_t N,
+                                                           const T *__restrict__ yin, T alpha, T beta,
+                                                           T *__restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (k >= N) return;
+    const int64_t first = ((k / 128) * 128) / GEMVT_ROWS;    // first row chunk that reaches this strip's diagonal
+    const int64_t nch = (N + GEMVT_ROWS - 1) / GEMVT_ROWS;
+    double s = 0.0;
+    for (int64_t ch = first; ch < nch; ++ch) s += part[ch * N + k];
+    out[k] = (T)((double)alpha * s + (yin ? (double)beta * (double)yin[k] : 0.0));
+}
+
+template <typename T>
+static int gemv_tri_T(gpg_handle_s *h, const T *Mx, int64_t ld, int64_t N, const T *x, const T *yin, T alpha, T beta,
+                      T *out, cudaStream_t stream) {
+    const int64_t nch = (N + GEMVT_ROWS - 1) / GEMVT_ROWS;
+    double *part;
+    GPG_TRY(gpg_gemv_part_reserve(h, (size_t)nch * N, &part));
+    dim3 grid((unsigned)((N + 127) / 128), (unsigned)nch);
+    gemvT_partial_kernel<T><<<grid, 256, 0, stream>>>(Mx, ld, N, x, part);
+    GPG_LAUNCH_CHECK(h);
+    gemvT_finish_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(part, N, yin, alpha, beta, out);
+    GPG_LAUNCH_CHECK(h);
+    return GPG_OK;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) solve_scalars_kernel(const T *__restrict__ L, int64_t ld, int64_t N,
                                                             const T *__restrict__ vhat, T *__restrict__ scalars,
@@ -562,7 +632,7 @@ template <typename T>
 static int solve_vec_refined(gpg_handle_s *h, const T *L, const T *Linv, int64_t N, int64_t ld, const T *y, T *vhat,
                              T *alpha, T *scalars, T *scratch, cudaStream_t stream, int corrections = 2) {
     T *r = scratch, *dx = scratch + N;
-    const int gN = (int)((N + 7) / 8), gT = (int)((N + 31) / 32);
+    const int gN = (int)((N + 7) / 8);
     // forward: L v = y
     gemv_tri_kernel<T, false><<<gN, 256, 0, stream>>>(Linv, ld, N, y, nullptr, T(1), T(0), vhat);
     GPG_LAUNCH_CHECK(h);
@@ -574,13 +644,10 @@ static int solve_vec_refined(gpg_handle_s *h, const T *L, const T *Linv, int64_t
         GPG_CUDA_CHECK(cudaMemcpyAsync(vhat, dx, N * sizeof(T), cudaMemcpyDeviceToDevice, stream));
     }
     // backward: L^T a = v
-    gemv_tri_kernel<T, true><<<gT, 256, 0, stream>>>(Linv, ld, N, vhat, nullptr, T(1), T(0), alpha);
-    GPG_LAUNCH_CHECK(h);
+    GPG_TRY(gemv_tri_T<T>(h, Linv, ld, N, vhat, nullptr, T(1), T(0), alpha, stream));
     for (int it = 0; it < corrections; ++it) {
-        gemv_tri_kernel<T, true><<<gT, 256, 0, stream>>>(L, ld, N, alpha, vhat, T(-1), T(1), r);
-        GPG_LAUNCH_CHECK(h);
-        gemv_tri_kernel<T, true><<<gT, 256, 0, stream>>>(Linv, ld, N, r, alpha, T(1), T(1), dx);
-        GPG_LAUNCH_CHECK(h);
+        GPG_TRY(gemv_tri_T<T>(h, L, ld, N, alpha, vhat, T(-1), T(1), r, stream));
+        GPG_TRY(gemv_tri_T<T>(h, Linv, ld, N, r, alpha, T(1), T(1), dx, stream));
         GPG_CUDA_CHECK(cudaMemcpyAsync(alpha, dx, N * sizeof(T), cudaMemcpyDeviceToDevice, stream));
     }
     if (scalars) {

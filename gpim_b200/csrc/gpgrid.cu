@@ -40,6 +40,20 @@ int gpg_ws_reserve(gpg_handle_s *h, size_t bytes, void **out) {
     return GPG_OK;
 }
 
+int gpg_gemv_part_reserve(gpg_handle_s *h, size_t elems, double **out) {
+    if (elems > h->gemv_part_elems) {
+        GPG_CUDA_CHECK(cudaDeviceSynchronize());
+        if (h->gemv_part) GPG_CUDA_CHECK(cudaFree(h->gemv_part));
+        h->gemv_part = nullptr;
+        h->gemv_part_elems = 0;
+        const size_t want = elems + elems / 4 + 1024;
+        GPG_CUDA_CHECK(cudaMalloc(&h->gemv_part, want * sizeof(double)));
+        h->gemv_part_elems = want;
+    }
+    *out = h->gemv_part;
+    return GPG_OK;
+}
+
 int gpg_tc_counter(gpg_handle_s *h, cudaStream_t stream, int **out) {
     constexpr int POOL = 8192;
     if (!h->tc_counters) {
@@ -97,6 +111,7 @@ extern "C" int gpg_destroy(gpg_handle_t h) {
     if (!h) return GPG_OK;
     if (h->ws) cudaFree(h->ws);
     if (h->tc_counters) cudaFree(h->tc_counters);
+    if (h->gemv_part) cudaFree(h->gemv_part);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.beg); cudaEventDestroy(sp.end); }
     for (auto &e : h->event_pool) cudaEventDestroy(e);
     delete h;
@@ -345,7 +360,7 @@ static int refine_alpha_against_K(gpg_handle_s *h, int kernel_id, int d, const T
                                   int64_t N, double jitter, const T *Linv, int64_t ld, T *alpha, T *scratch,
                                   double *best, int rounds, cudaStream_t s) {
     T *r = scratch, *t = scratch + N, *an = scratch + 2 * N, *rn = scratch + 3 * N;
-    const unsigned gk = (unsigned)((N + 7) / 8), gN = gk, gT = (unsigned)((N + 31) / 32);
+    const unsigned gk = (unsigned)((N + 7) / 8), gN = gk;
     auto resid = [&](const T *a, T *out) -> int {
         GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, {
             TestPoints<T, D> tp;
@@ -365,8 +380,7 @@ static int refine_alpha_against_K(gpg_handle_s *h, int kernel_id, int d, const T
     for (int it = 0; it < rounds; ++it) {
         gemv_tri_kernel<T, false><<<gN, 256, 0, s>>>(Linv, ld, N, r, nullptr, T(1), T(0), t);          // t = W r
         GPG_LAUNCH_CHECK(h);
-        gemv_tri_kernel<T, true><<<gT, 256, 0, s>>>(Linv, ld, N, t, alpha, T(1), T(1), an);            // an = alpha + W^T t
-        GPG_LAUNCH_CHECK(h);
+        GPG_TRY(gemv_tri_T<T>(h, Linv, ld, N, t, alpha, T(1), T(1), an, s));                            // an = alpha + W^T t
         GPG_TRY(resid(an, rn));
         refine_select_kernel<T><<<1, 1024, 0, s>>>(N, an, rn, alpha, r, best);
         GPG_LAUNCH_CHECK(h);
@@ -424,7 +438,7 @@ static int factorize_core(gpg_handle_s *h, int kernel_id, int d, const T *theta,
     }
     {
         StageTimer st(h, GPG_ST_SOLVE, s);
-        GPG_TRY(solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, nullptr, w.vs, s, 1));
+        GPG_TRY(solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, nullptr, w.vs, s, 0));
         GPG_TRY(refine_alpha_against_K<T>(h, kernel_id, d, theta, X, y, N, jitter, Linv, ld, alpha, w.vs, w.best, 2, s));
         if (scalars) {               // 0.5 y^T K^-1 y from the refined alpha, log-determinant from diag L
             solve_scalars_kernel<T><<<1, 256, 0, s>>>(L, ld, N, vhat, scalars, y, alpha);

@@ -122,47 +122,86 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
     bool bad = false;
 #pragma unroll
     for (int k = 0; k < D; ++k) bad |= (z[k] != z[k]);
-    double acc = 0.0;
+    // mean accumulator: double for T = double; for T = float a Kahan-compensated fp32 pair, which keeps the
+    // long alternating sum accurate without per-element conversions (they run on the slow XU pipe)
+    double accd = 0.0;
+    float acc_s = 0.f, acc_c = 0.f;
     const float scale = SPLIT ? *scale_ptr : 1.0f;
-    const bool vec_ok = ((ldk % 4) == 0);
     // row padding [N, ldk) (and [N, ldh)) is zero-filled so K-tiles may over-read it
     const int64_t width = SPLIT ? ldh : (Ks ? ldk : N);
-    for (int64_t i = (int64_t)lane * 4; i < width; i += 128) {
+    __half *__restrict__ hrow = SPLIT ? Khi + j * ldh : nullptr;
+    __half *__restrict__ lrow = SPLIT ? Klo + j * ldh : nullptr;
+    T *__restrict__ krow = (!SPLIT && Ks) ? Ks + j * ldk : nullptr;
+    const bool fast_ok = (D == 2 && sizeof(T) == 4 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(alpha) & 7) == 0 && !bad);
+    // lane owns the column pairs i0 + 2 lane + {0, 1} and i0 + 64 + 2 lane + {0, 1}: coordinates, alpha and the
+    // fp16 planes are all touched with unit stride across the warp (128-bit / 64-bit / 32-bit per lane)
+    for (int64_t i0 = 0; i0 < width; i0 += 128) {
         T v[4];
+        if (fast_ok && i0 + 128 <= N) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            T val = T(0);
-            if (i + c < N && !bad) {
-                T x[D];
+            for (int hblk = 0; hblk < 2; ++hblk) {
+                const int64_t i = i0 + 64 * hblk + 2 * lane;
+                const float4 xy = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(X) + i * 2);
+                const float2 a2 = *reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(alpha) + i);
+                T xa[D], xb[D];
+                xa[0] = (T)xy.x; xa[D - 1] = (T)xy.y; xb[0] = (T)xy.z; xb[D - 1] = (T)xy.w;
+                v[2 * hblk] = cov_from_r2<T, KID>(scaled_r2<T, D>(z, xa, th), th);
+                v[2 * hblk + 1] = cov_from_r2<T, KID>(scaled_r2<T, D>(z, xb, th), th);
+                const float av[2] = {a2.x, a2.y};
 #pragma unroll
-                for (int k = 0; k < D; ++k) x[k] = X[(i + c) * D + k];
-                val = cov_from_r2<T, KID>(scaled_r2<T, D>(z, x, th), th);
-                acc += (double)val * (double)alpha[i + c];
-            }
-            v[c] = val;
-        }
-        const int nvalid = (int)min((int64_t)4, width - i);
-        if (SPLIT) {
-            __half hi[4], lo[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float s = (float)v[c] * scale;
-                hi[c] = __float2half_rn(s);
-                lo[c] = __float2half_rn(s - __half2float(hi[c]));
-            }
-            if (nvalid == 4 && (ldh % 4) == 0) {
-                *reinterpret_cast<uint2 *>(Khi + j * ldh + i) = *reinterpret_cast<uint2 *>(hi);
-                *reinterpret_cast<uint2 *>(Klo + j * ldh + i) = *reinterpret_cast<uint2 *>(lo);
-            } else {
-                for (int c = 0; c < nvalid; ++c) {
-                    Khi[j * ldh + i + c] = hi[c];
-                    Klo[j * ldh + i + c] = lo[c];
+                for (int e = 0; e < 2; ++e) {            // Kahan: no FMA contraction may touch these
+                    const float yk = __fsub_rn(__fmul_rn((float)v[2 * hblk + e], av[e]), acc_c);
+                    const float t = __fadd_rn(acc_s, yk);
+                    acc_c = __fsub_rn(__fsub_rn(t, acc_s), yk);
+                    acc_s = t;
                 }
             }
-        } else if (Ks) {
-            store4(Ks + j * ldk + i, v, vec_ok && ((reinterpret_cast<uintptr_t>(Ks) & 15) == 0), nvalid);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int64_t i = i0 + 64 * (c >> 1) + 2 * lane + (c & 1);
+                T val = T(0);
+                if (i < N && !bad) {
+                    T x[D];
+#pragma unroll
+                    for (int k = 0; k < D; ++k) x[k] = X[i * D + k];
+                    val = cov_from_r2<T, KID>(scaled_r2<T, D>(z, x, th), th);
+                    if (sizeof(T) == 4) {
+                        const float yk = __fsub_rn(__fmul_rn((float)val, (float)alpha[i]), acc_c);
+                        const float t = __fadd_rn(acc_s, yk);
+                        acc_c = __fsub_rn(__fsub_rn(t, acc_s), yk);
+                        acc_s = t;
+                    } else {
+                        accd += (double)val * (double)alpha[i];
+                    }
+                }
+                v[c] = val;
+            }
+        }
+        if (SPLIT) {
+#pragma unroll
+            for (int hblk = 0; hblk < 2; ++hblk) {
+                const int64_t i = i0 + 64 * hblk + 2 * lane;
+                const float s0 = (float)v[2 * hblk] * scale, s1 = (float)v[2 * hblk + 1] * scale;
+                const __half2 h2 = __floats2half2_rn(s0, s1);
+                const float2 f2 = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(s0 - f2.x, s1 - f2.y);
+                if (i + 1 < width) {                      // width is even: pairs are in or out together
+                    *reinterpret_cast<__half2 *>(hrow + i) = h2;
+                    *reinterpret_cast<__half2 *>(lrow + i) = l2;
+                }
+            }
+        } else if (krow) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int64_t i = i0 + 64 * (c >> 1) + 2 * lane + (c & 1);
+                if (i < width) krow[i] = v[c];
+            }
         }
     }
+    if (sizeof(T) == 4) acc_c = -acc_c;               // Kahan keeps the NEGATIVE of the running error
+    double acc = (sizeof(T) == 4) ? (double)acc_s + (double)acc_c : accd;
     acc = warp_sum(acc);
     if (lane == 0) {
         if (y_resid) acc = (double)y_resid[j] - acc - ((double)th.noise + (double)jitter) * (double)alpha[j];
