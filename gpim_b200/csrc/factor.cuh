@@ -45,23 +45,106 @@ __device__ __forceinline__ void emit_split(__half *hi, __half *lo, int64_t off, 
     lo[off] = __float2half_rn(v - __half2float(h));
 }
 
-// 256 threads as a 16 x 16 grid; thread (ty, tx) accumulates out(ty + 16 a, tx + 16 b), a < TI, b < TJ:
-//   out(i, j) += sum_{k < K} A[i * lds + k] * (B_KMAJOR ? B[j * lds + k] : B[k * lds + j])
-// The strided assignment makes every shared-memory read either a broadcast or conflict-free.
-template <typename T, int TI, int TJ, bool B_KMAJOR>
-__device__ __forceinline__ void smem_mm(const T *__restrict__ A, const T *__restrict__ B, int lds, int K,
-                                        T (&acc)[TI][TJ], int ty, int tx) {
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        T a[TI], b[TJ];
+// 128-bit shared-memory vectors (rows of S / W are 16-byte aligned: lds is a multiple of 4)
+template <typename T> struct V4 { T v[4]; };
+__device__ __forceinline__ V4<float> ld4(const float *p) {
+    const float4 a = *reinterpret_cast<const float4 *>(p);
+    V4<float> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; return r;
+}
+__device__ __forceinline__ V4<double> ld4(const double *p) {
+    const double2 a = *reinterpret_cast<const double2 *>(p), b = *reinterpret_cast<const double2 *>(p + 2);
+    V4<double> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; return r;
+}
+__device__ __forceinline__ void st4(float *p, const V4<float> &r) {
+    *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+}
+__device__ __forceinline__ void st4(double *p, const V4<double> &r) {
+    *reinterpret_cast<double2 *>(p) = make_double2(r.v[0], r.v[1]);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2(r.v[2], r.v[3]);
+}
+
+// 256 threads as a 16 x 16 grid (ty, tx); both products read four k at a time with 128-bit loads.
+//   mm_kk: out(ty + 16 a, tx + 16 b)  += sum_k A[(ty + 16 a) * lds + k] * B[(tx + 16 b) * lds + k]
+//   mm_kn: out(ty + 16 a, TJ tx + b)  += sum_k A[(ty + 16 a) * lds + k] * B[k * lds + TJ tx + b]
+// (rows of A are warp-uniform up to two values -> broadcasts; rows of B in mm_kk are 4 banks apart per lane,
+// conflict-free within each 8-lane phase of a 128-bit access; mm_kn reads B rows contiguously.)
+template <typename T, int TI, int TJ>
+__device__ __forceinline__ void mm_kk(const T *__restrict__ A, const T *__restrict__ B, int lds, int K,
+                                      T (&acc)[TI][TJ], int ty, int tx) {
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+        V4<T> a[TI], b[TJ];
 #pragma unroll
-        for (int i = 0; i < TI; ++i) a[i] = A[(ty + 16 * i) * lds + k];
+        for (int i = 0; i < TI; ++i) a[i] = ld4(A + (ty + 16 * i) * lds + k);
 #pragma unroll
-        for (int j = 0; j < TJ; ++j) b[j] = B_KMAJOR ? B[(tx + 16 * j) * lds + k] : B[k * lds + tx + 16 * j];
+        for (int j = 0; j < TJ; ++j) b[j] = ld4(B + (tx + 16 * j) * lds + k);
 #pragma unroll
-        for (int i = 0; i < TI; ++i)
+        for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int j = 0; j < TJ; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) acc[i][j] = fma(a[i].v[e], b[j].v[e], acc[i][j]);
+    }
+}
+
+template <typename T, int TI, int TJ>
+__device__ __forceinline__ void mm_kn(const T *__restrict__ A, const T *__restrict__ B, int lds, int K,
+                                      T (&acc)[TI][TJ], int ty, int tx) {
+    static_assert(TJ == 2 || TJ == 4, "mm_kn: two or four consecutive columns per thread");
+#pragma unroll 2
+    for (int k = 0; k < K; k += 4) {
+        V4<T> a[TI];
+#pragma unroll
+        for (int i = 0; i < TI; ++i) a[i] = ld4(A + (ty + 16 * i) * lds + k);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            T b[TJ];
+            if (TJ == 4) {
+                const V4<T> bv = ld4(B + (k + e) * lds + 4 * tx);
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) b[j] = bv.v[j];
+            } else {
+                b[0] = B[(k + e) * lds + 2 * tx];
+                b[TJ - 1] = B[(k + e) * lds + 2 * tx + 1];
+            }
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) acc[i][j] = fma(a[i].v[e], b[j], acc[i][j]);
+        }
+    }
+}
+
+// Rows below a freshly factored 32 x 32 diagonal block: X <- X L11^-T by forward substitution, one thread
+// per row (the row lives in registers, the entries of L11 arrive as warp-wide broadcasts, 128 bits at a time).
+template <typename T>
+__device__ __forceinline__ void panel_solve32(T *__restrict__ S, int lds, int c0, int row, const T *__restrict__ rdiag) {
+    T x[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const V4<T> t4 = ld4(S + row * lds + c0 + 4 * q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) x[4 * q + e] = t4.v[e];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        T s[4] = {T(0), T(0), T(0), T(0)};
+#pragma unroll
+        for (int k4 = 0; k4 + 4 <= j; k4 += 4) {
+            const V4<T> l4 = ld4(S + (c0 + j) * lds + c0 + k4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[e] = fma(x[k4 + e], l4.v[e], s[e]);
+        }
+#pragma unroll
+        for (int k = (j / 4) * 4; k < j; ++k) s[k & 3] = fma(x[k], S[(c0 + j) * lds + c0 + k], s[k & 3]);
+        x[j] = (x[j] - ((s[0] + s[1]) + (s[2] + s[3]))) * rdiag[j];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        V4<T> t4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) t4.v[e] = x[4 * q + e];
+        st4(S + row * lds + c0 + 4 * q, t4);
     }
 }
 
@@ -96,7 +179,7 @@ __device__ __forceinline__ double gpg_rsqrt(double x) { return 1.0 / sqrt(x); }
 // non-positive pivot among the first `valid` columns.
 template <typename T>
 __device__ __forceinline__ int factor_tri32(T *__restrict__ S, int lds, int c0, int lane, int valid,
-                                            T *__restrict__ colbuf) {
+                                            T *__restrict__ colbuf, T *__restrict__ rdiag) {
     constexpr unsigned FULL = 0xffffffffu;
     T row[32];
 #pragma unroll
@@ -109,6 +192,7 @@ __device__ __forceinline__ int factor_tri32(T *__restrict__ S, int lds, int c0, 
         const T rs = gpg_rsqrt(djj);
         T lij = row[j] * rs;                          // lane j: djj / sqrt(djj) = l_jj
         row[j] = lij;
+        if (lane == j) rdiag[j] = rs;                 // 1 / l_jj for the panel solve
         if (j < 31) {
             colbuf[lane] = lij;
             __syncwarp();
@@ -142,11 +226,12 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
                                                          int64_t inv_block_stride, int dense_out,
                                                          int32_t *__restrict__ info, DiagEmit em) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int LDS = NB + 1;
+    constexpr int LDS = NB + 4;                       // 16-byte aligned rows, 4 banks of skew per row
     constexpr int NSUB = NB / 32;
     T *S = reinterpret_cast<T *>(smem_raw);
     T *W = S + NB * LDS;
     __shared__ __align__(16) T colbuf[32];
+    __shared__ __align__(16) T rdiag[32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int tx = t & 15, ty = t >> 4;
     const int64_t j0 = j0_first + (int64_t)blockIdx.x * NB;
@@ -163,145 +248,100 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
     __syncthreads();
     GPG_PHASE(1);
     if (do_factor) {
+        // right-looking over 32-column panels: (1) warp 0 factors the 32 x 32 diagonal sub-block in registers,
+        // (2) one thread per row below solves X L11^T = A21 by forward substitution, (3) all threads apply the
+        // rank-32 update to the trailing lower triangle in 32 x 32 chunks
         for (int p = 0; p < NSUB; ++p) {
             const int c0 = p * 32;
-            if (warp == 0) {                          // 32 x 32 diagonal sub-block in registers, lane = row
+            if (warp == 0) {
                 GPG_PHASE(2 + 5 * p);
-                const int bad = factor_tri32<T>(S, LDS, c0, lane, nb - c0, colbuf);
-                __syncwarp();
-                GPG_PHASE(3 + 5 * p);
-                invert_tri32<T>(S, W, LDS, c0, lane);  // needed by the panel below and by the block inverse
+                const int bad = factor_tri32<T>(S, LDS, c0, lane, nb - c0, colbuf, rdiag);
                 if (lane == 0 && bad) atomicCAS(info, 0, (int32_t)(j0 + c0 + bad));
-                GPG_PHASE(4 + 5 * p);
+                GPG_PHASE(3 + 5 * p);
             }
             __syncthreads();
             const int base = c0 + 32;
             if (base < NB) {
-                // panel: A21 <- A21 W11^T, 32 rows per chunk, accumulate everything before overwriting
-                constexpr int MAXCH = NSUB - 1;
-                T pacc[MAXCH > 0 ? MAXCH : 1][2][2];
-                const int nch = (NB - base) / 32;
-#pragma unroll
-                for (int ch = 0; ch < MAXCH; ++ch) {
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) pacc[ch][i][j] = T(0);
-                    if (ch < nch)
-                        smem_mm<T, 2, 2, true>(S + (base + 32 * ch) * LDS + c0, W + c0 * LDS + c0, LDS, 32, pacc[ch], ty, tx);
-                }
+                const int R = NB - base;
+                if (t < R) panel_solve32<T>(S, LDS, c0, base + t, rdiag);
                 __syncthreads();
-#pragma unroll
-                for (int ch = 0; ch < MAXCH; ++ch)
-                    if (ch < nch)
+                GPG_PHASE(5 + 5 * p);
+                // trailing lower triangle: S[i][k] -= sum_m S[i][c0+m] S[k][c0+m]; chunk (ib, kb), kb <= ib,
+                // 32 x 32 outputs = 2 x 2 per thread.  Chunks are independent: walk them without barriers.
+                const int nchunk = R / 32;
+                for (int ib = 0; ib < nchunk; ++ib)
+                    for (int kb = 0; kb <= ib; ++kb) {
+                        T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
+                        mm_kk<T, 2, 2>(S + (base + 32 * ib) * LDS + c0, S + (base + 32 * kb) * LDS + c0, LDS, 32, acc, ty, tx);
 #pragma unroll
                         for (int i = 0; i < 2; ++i)
 #pragma unroll
-                            for (int j = 0; j < 2; ++j)
-                                S[(base + 32 * ch + ty + 16 * i) * LDS + c0 + tx + 16 * j] = pacc[ch][i][j];
-                __syncthreads();
-                GPG_PHASE(5 + 5 * p);
-                // trailing lower triangle: S[i][k] -= sum_m S[i][c0+m] S[k][c0+m], 64 x 64 chunks
-                const int R = NB - base;
-                for (int ib = 0; ib < R; ib += 64) {
-                    for (int kb = 0; kb <= ib; kb += 64) {
-                        T uacc[4][4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) uacc[i][j] = T(0);
-                        // rows beyond NB are never touched: clamp the chunk with the guards below
-                        if (ib + 64 <= R && kb + 64 <= R) {
-                            smem_mm<T, 4, 4, true>(S + (base + ib) * LDS + c0, S + (base + kb) * LDS + c0, LDS, 32, uacc, ty, tx);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const int gi = base + ib + ty + 16 * i, gk = base + kb + tx + 16 * j;
-                                    if (gk <= gi) S[gi * LDS + gk] -= uacc[i][j];
-                                }
-                        } else {                      // ragged 32-wide edge chunk
-                            T eacc[2][2];
-                            for (int si = 0; si < 64 && ib + si < R; si += 32)
-                                for (int sk = 0; sk < 64 && kb + sk < R && kb + sk <= ib + si; sk += 32) {
-#pragma unroll
-                                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                                        for (int j = 0; j < 2; ++j) eacc[i][j] = T(0);
-                                    smem_mm<T, 2, 2, true>(S + (base + ib + si) * LDS + c0, S + (base + kb + sk) * LDS + c0, LDS,
-                                                           32, eacc, ty, tx);
-#pragma unroll
-                                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                                        for (int j = 0; j < 2; ++j) {
-                                            const int gi = base + ib + si + ty + 16 * i, gk = base + kb + sk + tx + 16 * j;
-                                            if (gk <= gi) S[gi * LDS + gk] -= eacc[i][j];
-                                        }
-                                }
-                        }
+                            for (int j = 0; j < 2; ++j) {
+                                const int gi = base + 32 * ib + ty + 16 * i, gk = base + 32 * kb + tx + 16 * j;
+                                if (gk <= gi) S[gi * LDS + gk] -= acc[i][j];
+                            }
                     }
-                }
                 __syncthreads();
                 GPG_PHASE(6 + 5 * p);
             }
         }
         GPG_PHASE(22);
-    } else {
-        if (warp < NSUB) invert_tri32<T>(S, W, LDS, warp * 32, lane);
-        __syncthreads();
     }
+    // inverses of the NSUB diagonal 32 x 32 sub-blocks, one warp each
+    if (warp < NSUB) invert_tri32<T>(S, W, LDS, warp * 32, lane);
+    __syncthreads();
     // recursive doubling inside the block: W21 = -W22 (L21 W11); the upper triangles of S and W are zero,
     // so the products are plain dense ones
     if (NB >= 64) {
-        for (int s0 = 0; s0 < NB; s0 += 64) {        // hb = 32
+        for (int s0 = 0; s0 < NB; s0 += 64) {        // hb = 32: out(ty + 16 i, 2 tx + j)
             T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
-            smem_mm<T, 2, 2, false>(S + (s0 + 32) * LDS + s0, W + s0 * LDS + s0, LDS, 32, acc, ty, tx);
+            mm_kn<T, 2, 2>(S + (s0 + 32) * LDS + s0, W + s0 * LDS + s0, LDS, 32, acc, ty, tx);
             __syncthreads();
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) W[(s0 + 32 + ty + 16 * i) * LDS + s0 + tx + 16 * j] = acc[i][j];
+                for (int j = 0; j < 2; ++j) W[(s0 + 32 + ty + 16 * i) * LDS + s0 + 2 * tx + j] = acc[i][j];
             __syncthreads();
             T acc2[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
-            smem_mm<T, 2, 2, false>(W + (s0 + 32) * LDS + s0 + 32, W + (s0 + 32) * LDS + s0, LDS, 32, acc2, ty, tx);
+            mm_kn<T, 2, 2>(W + (s0 + 32) * LDS + s0 + 32, W + (s0 + 32) * LDS + s0, LDS, 32, acc2, ty, tx);
             __syncthreads();
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) W[(s0 + 32 + ty + 16 * i) * LDS + s0 + tx + 16 * j] = -acc2[i][j];
+                for (int j = 0; j < 2; ++j) W[(s0 + 32 + ty + 16 * i) * LDS + s0 + 2 * tx + j] = -acc2[i][j];
             __syncthreads();
         }
     }
     GPG_PHASE(23);
-    if (NB >= 128) {                                  // hb = 64
+    if (NB >= 128) {                                  // hb = 64: out(ty + 16 i, 4 tx + j)
         T acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-        smem_mm<T, 4, 4, false>(S + 64 * LDS, W, LDS, 64, acc, ty, tx);
+        mm_kn<T, 4, 4>(S + 64 * LDS, W, LDS, 64, acc, ty, tx);
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) W[(64 + ty + 16 * i) * LDS + tx + 16 * j] = acc[i][j];
+            for (int j = 0; j < 4; ++j) W[(64 + ty + 16 * i) * LDS + 4 * tx + j] = acc[i][j];
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
-        smem_mm<T, 4, 4, false>(W + 64 * LDS + 64, W + 64 * LDS, LDS, 64, acc, ty, tx);
+        mm_kn<T, 4, 4>(W + 64 * LDS + 64, W + 64 * LDS, LDS, 64, acc, ty, tx);
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) W[(64 + ty + 16 * i) * LDS + tx + 16 * j] = -acc[i][j];
+            for (int j = 0; j < 4; ++j) W[(64 + ty + 16 * i) * LDS + 4 * tx + j] = -acc[i][j];
         __syncthreads();
     }
     GPG_PHASE(24);
     static_assert(NB == 64 || NB == 128, "diag_block_kernel handles NB = 64 or 128");
     // Outputs, four consecutive columns per thread: factor block (fp32 + fp16 hi/lo), inverse block (fp32 +
-    // hi/lo), then the transposed inverse planes with the roles of row and column swapped.
+    // hi/lo), then the transposed inverse planes.
     T *out = inv_out ? inv_out + (int64_t)blockIdx.x * inv_block_stride : nullptr;
     const float sL = em.scale_L ? *em.scale_L : 1.0f, sW = em.scale_W ? *em.scale_W : 1.0f;
     const bool f32 = sizeof(T) == 4;
@@ -311,72 +351,74 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
     for (int q = t; q < NB * NB / 4; q += 256) {
         const int i = q / (NB / 4), k4 = (q % (NB / 4)) * 4;
         const int nvalid = (i < nb) ? max(0, min(4, nb - k4)) : 0;       // columns of this group inside the block
-        T s4[4], w4[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { s4[e] = S[i * LDS + k4 + e]; w4[e] = W[i * LDS + k4 + e]; }
+        const V4<T> s4 = ld4(S + i * LDS + k4), w4 = ld4(W + i * LDS + k4);
         if (do_factor && nvalid > 0 && k4 <= i) {      // entries right of the diagonal inside the group are zero in S
             T *dst = Ab + (int64_t)i * ld + k4;
-            if (nvalid == 4 && vecA) *reinterpret_cast<float4 *>(dst) = make_float4((float)s4[0], (float)s4[1], (float)s4[2], (float)s4[3]);
-            else for (int e = 0; e < nvalid; ++e) if (k4 + e <= i) dst[e] = s4[e];
+            if (nvalid == 4 && vecA) *reinterpret_cast<float4 *>(dst) = make_float4((float)s4.v[0], (float)s4.v[1], (float)s4.v[2], (float)s4.v[3]);
+            else for (int e = 0; e < nvalid; ++e) if (k4 + e <= i) dst[e] = s4.v[e];
         }
         if (out) {
             const int nw = dense_out ? 4 : nvalid;
             T *dst = out + (int64_t)i * ld_inv + k4;
-            if (nw == 4 && vecO) *reinterpret_cast<float4 *>(dst) = make_float4((float)w4[0], (float)w4[1], (float)w4[2], (float)w4[3]);
-            else for (int e = 0; e < nw; ++e) dst[e] = w4[e];
+            if (nw == 4 && vecO) *reinterpret_cast<float4 *>(dst) = make_float4((float)w4.v[0], (float)w4.v[1], (float)w4.v[2], (float)w4.v[3]);
+            else for (int e = 0; e < nw; ++e) dst[e] = w4.v[e];
         }
         if (f32 && nvalid > 0 && (em.Lh || em.Wh)) {
             const int64_t off = (j0 + i) * em.lds + j0 + k4;
-            __align__(8) __half h4[4], l4[4];
             if (em.Lh) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float v = (k4 + e <= i) ? (float)s4[e] * sL : 0.f;
-                    h4[e] = __float2half_rn(v);
-                    l4[e] = __float2half_rn(v - __half2float(h4[e]));
-                }
+                const float a0 = (k4 <= i) ? (float)s4.v[0] * sL : 0.f, a1 = (k4 + 1 <= i) ? (float)s4.v[1] * sL : 0.f;
+                const float a2 = (k4 + 2 <= i) ? (float)s4.v[2] * sL : 0.f, a3 = (k4 + 3 <= i) ? (float)s4.v[3] * sL : 0.f;
+                const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
                 if (nvalid == 4 && vecS) {
-                    *reinterpret_cast<uint2 *>(em.Lh + off) = *reinterpret_cast<const uint2 *>(h4);
-                    *reinterpret_cast<uint2 *>(em.Ll + off) = *reinterpret_cast<const uint2 *>(l4);
-                } else for (int e = 0; e < nvalid; ++e) { em.Lh[off + e] = h4[e]; em.Ll[off + e] = l4[e]; }
+                    *reinterpret_cast<uint2 *>(em.Lh + off) = make_uint2(*reinterpret_cast<const unsigned *>(&h01), *reinterpret_cast<const unsigned *>(&h23));
+                    *reinterpret_cast<uint2 *>(em.Ll + off) = make_uint2(*reinterpret_cast<const unsigned *>(&l01), *reinterpret_cast<const unsigned *>(&l23));
+                } else {
+                    const __half hh[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
+                    const __half ll[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
+                    for (int e = 0; e < nvalid; ++e) { em.Lh[off + e] = hh[e]; em.Ll[off + e] = ll[e]; }
+                }
             }
             if (em.Wh) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float v = (float)w4[e] * sW;
-                    h4[e] = __float2half_rn(v);
-                    l4[e] = __float2half_rn(v - __half2float(h4[e]));
-                }
+                const float a0 = (float)w4.v[0] * sW, a1 = (float)w4.v[1] * sW, a2 = (float)w4.v[2] * sW, a3 = (float)w4.v[3] * sW;
+                const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
                 if (nvalid == 4 && vecS) {
-                    *reinterpret_cast<uint2 *>(em.Wh + off) = *reinterpret_cast<const uint2 *>(h4);
-                    *reinterpret_cast<uint2 *>(em.Wl + off) = *reinterpret_cast<const uint2 *>(l4);
-                } else for (int e = 0; e < nvalid; ++e) { em.Wh[off + e] = h4[e]; em.Wl[off + e] = l4[e]; }
+                    *reinterpret_cast<uint2 *>(em.Wh + off) = make_uint2(*reinterpret_cast<const unsigned *>(&h01), *reinterpret_cast<const unsigned *>(&h23));
+                    *reinterpret_cast<uint2 *>(em.Wl + off) = make_uint2(*reinterpret_cast<const unsigned *>(&l01), *reinterpret_cast<const unsigned *>(&l23));
+                } else {
+                    const __half hh[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
+                    const __half ll[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
+                    for (int e = 0; e < nvalid; ++e) { em.Wh[off + e] = hh[e]; em.Wl[off + e] = ll[e]; }
+                }
             }
         }
     }
     if (f32 && em.WTh) {
+        // transposed planes: lane = source row i (consecutive destination columns), four source columns k per
+        // thread: 128-bit conflict-free reads of W, 64-byte contiguous stores per warp and plane
         for (int q = t; q < NB * NB / 4; q += 256) {
-            const int k = q / (NB / 4), i4 = (q % (NB / 4)) * 4;       // destination row k, columns i4..i4+3
-            if (k >= nb || i4 >= nb) continue;
-            const int nvalid = min(4, nb - i4);
-            __align__(8) __half h4[4], l4[4];
+            const int i = q % NB, k4 = (q / NB) * 4;
+            if (i >= nb || k4 >= nb) continue;
+            const V4<T> w4 = ld4(W + i * LDS + k4);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float v = (float)W[(i4 + e) * LDS + k] * sW;
-                h4[e] = __float2half_rn(v);
-                l4[e] = __float2half_rn(v - __half2float(h4[e]));
+                if (k4 + e < nb) {
+                    const float a = (float)w4.v[e] * sW;
+                    const __half hh = __float2half_rn(a);
+                    const int64_t off = (j0 + k4 + e) * em.lds + j0 + i;
+                    em.WTh[off] = hh;
+                    em.WTl[off] = __float2half_rn(a - __half2float(hh));
+                }
             }
-            const int64_t off = (j0 + k) * em.lds + j0 + i4;
-            if (nvalid == 4 && vecS) {
-                *reinterpret_cast<uint2 *>(em.WTh + off) = *reinterpret_cast<const uint2 *>(h4);
-                *reinterpret_cast<uint2 *>(em.WTl + off) = *reinterpret_cast<const uint2 *>(l4);
-            } else for (int e = 0; e < nvalid; ++e) { em.WTh[off + e] = h4[e]; em.WTl[off + e] = l4[e]; }
         }
     }
     GPG_PHASE(25);
 }
 
-template <typename T, int NB> static int diag_block_smem() { return 2 * NB * (NB + 1) * (int)sizeof(T); }
+template <typename T, int NB> static int diag_block_smem() { return 2 * NB * (NB + 4) * (int)sizeof(T); }
 
 template <typename T>
 static int cholesky_blocked(gpg_handle_s *h, T *A, int64_t N, int64_t ld, int32_t *info, int reset_info, T *dinv,

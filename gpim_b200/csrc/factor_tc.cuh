@@ -160,7 +160,7 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
             p.split_lo = Ls.lo + (j0 + nb) * ld + j0;
             p.ld_split = ld;
             p.split_scale = scales + SC_L;
-            GPG_TRY(gemm_simt<float>(h, p, stream));
+            GPG_TRY((gemm_simt<float, GemmCfgPanelF32>(h, p, stream)));
             // inner update: the remaining columns of this outer panel, K = nb
             GPG_TRY(syrk(j0 + nb, j0 + nb, j0, rows, Jend - (j0 + nb), nb));
         }

@@ -34,12 +34,14 @@ template <typename T> struct GemmArgs {
 };
 
 template <typename T> struct GemmCfg;
-template <> struct GemmCfg<float> { static constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8; };
-template <> struct GemmCfg<double> { static constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4; };
+template <> struct GemmCfg<float> { static constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8; static constexpr bool COLSUM = true; };
+template <> struct GemmCfg<double> { static constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4; static constexpr bool COLSUM = true; };
+// skinny tiles for the Cholesky panel (M rows x 128 x 128): four times as many CTAs as the square config,
+// which is what the short dependent steps of the factorisation need
+struct GemmCfgPanelF32 { static constexpr int BM = 32, BN = 128, BK = 16, TM = 2, TN = 8; static constexpr bool COLSUM = false; };
 
-template <typename T>
+template <typename T, typename C = GemmCfg<T>>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs<T> g) {
-    using C = GemmCfg<T>;
     constexpr int BM = C::BM, BN = C::BN, BK = C::BK, TM = C::TM, TN = C::TN;
     constexpr int TMH = TM / 2, TNH = TN / 2;
     constexpr int NT = 256;
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs<T> g) {
                 }
             }
         }
-    } else {
+    } else if constexpr (C::COLSUM) {
         // column sums of squares over this tile's rows -> part[tile_m][n]
         __syncthreads();
         T *red = As;   // (BM/TM) x BN values fit: 16 x 128 <= BK * LDS_A
@@ -207,12 +209,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs<T> g) {
     }
 }
 
-template <typename T>
+template <typename T, typename C = GemmCfg<T>>
 static int gemm_simt(gpg_handle_s *h, const GemmArgs<T> &g, cudaStream_t stream) {
-    using C = GemmCfg<T>;
     if (g.M <= 0 || g.N <= 0 || g.batch <= 0) return GPG_OK;
+    if (!C::COLSUM && g.epi != GEMM_EPI_STORE) { gpg_set_error("this GEMM tile config has no reduction epilogue"); return GPG_EINVAL; }
     dim3 grid((g.N + C::BN - 1) / C::BN, (g.M + C::BM - 1) / C::BM, g.batch);
-    gemm_simt_kernel<T><<<grid, 256, 0, stream>>>(g);
+    gemm_simt_kernel<T, C><<<grid, 256, 0, stream>>>(g);
     GPG_LAUNCH_CHECK(h);
     return GPG_OK;
 }

@@ -23,7 +23,14 @@ def tile_bounds(M, world, rank):
 
 def broadcast_factor(fac, src=0, group=None):
     """Broadcast the tensors of a factor cache in place (every rank passes same-shaped buffers)."""
-    for key in ("Linv", "alpha", "wsplit", "scales"):
+    # the tcgen05 predict path (f32, N >= 1024: gpg_predict's routing rule) reads only the fp16 planes of Linv;
+    # the fp32 matrix travels only when the SIMT kernels will consume it
+    planes = fac.get("wsplit")
+    if planes is not None and planes.shape[1] >= 1024:
+        keys = ("alpha", "wsplit", "scales")
+    else:
+        keys = ("Linv", "alpha", "wsplit", "scales")
+    for key in keys:
         if fac.get(key) is not None:
             dist.broadcast(fac[key], src=src, group=group)
     return fac
