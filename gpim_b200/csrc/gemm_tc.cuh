@@ -12,9 +12,9 @@
 // CTA layout (192 threads, 1 CTA / SM, persistent):
 //   warp 0      producer: claims tiles from a global atomic counter, publishes them through a small
 //               shared-memory ring, and issues the TMA loads (4 boxes per k-block: Ahi Alo Bhi Blo,
-//               128-byte swizzle) into a 2-stage ring of 96 KB stages guarded by mbarriers
+//               64-byte swizzle, BK = 32) into a 4-stage ring of 48 KB stages guarded by mbarriers
 //   warp 1      MMA issuer: owns the 512 TMEM columns (two 128 x 256 fp32 accumulators), one
-//               elected lane issues 12 tcgen05.mma per k-block and commits to the mbarriers
+//               elected lane issues 6 tcgen05.mma per k-block and commits to the mbarriers
 //   warps 2..5  epilogue: tcgen05.ld the finished accumulator (one TMEM lane = one output row per
 //               thread) while the MMA warp already works on the next tile in the other buffer
 //
@@ -34,12 +34,21 @@
 
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int STAGES = 2;
+#ifndef GPG_TC_BK
+#define GPG_TC_BK 32
+#endif
+constexpr int BM = 128, BN = 256, BK = GPG_TC_BK;     // BK = 64: 128-byte swizzle; BK = 32: 64-byte swizzle
+constexpr int STAGES = 128 / BK;                       // 192 KB of operand ring either way; more, shorter stages
+                                                       // give the TMA more time to land each one
+static_assert(BK == 32 || BK == 64, "BK must be 32 or 64");
 constexpr int SCHED = 4;
-constexpr int A_TILE_BYTES = BM * BK * 2;            // 16 KB per hi or lo
-constexpr int B_TILE_BYTES = BN * BK * 2;            // 32 KB per hi or lo
-constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;   // 96 KB
+constexpr int SCHED_SLOTS = SCHED;
+constexpr int A_TILE_BYTES = BM * BK * 2;            // per hi or lo plane
+constexpr int B_TILE_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+// mbarrier indices
+constexpr int BAR_FULL = 0, BAR_EMPTY = STAGES, BAR_TFULL = 2 * STAGES, BAR_TEMPTY = 2 * STAGES + 2;
+constexpr int BAR_SFULL = 2 * STAGES + 4, BAR_SEMPTY = 2 * STAGES + 4 + SCHED_SLOTS, BAR_COUNT = 2 * STAGES + 4 + 2 * SCHED_SLOTS;
 constexpr int EPI_LD = 36;                            // floats per staged row: 16-byte aligned, conflict-free float4 access
 constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_LD * 4;  // one 32 x 32 fp32 transpose buffer per epilogue warp
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_STAGE_BYTES;
@@ -127,14 +136,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+// K-major swizzled operand tile: rows of BK halves (128 or 64 bytes = the swizzle span), 8-row groups contiguous.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
     d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)((8 * BK * 2) >> 4) << 32;          // stride byte offset: 8 rows of BK halves
     d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    d |= (uint64_t)(BK == 64 ? 2 : 4) << 61;           // SWIZZLE_128B / SWIZZLE_64B
     return d;
 }
 // kind::f16 instruction descriptor: D fp32, A/B fp16, both K-major, M x N.
@@ -180,20 +189,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     const uint32_t tiles = (raw + 1023u) & ~1023u;                   // 1024-byte aligned operand ring
     unsigned char *gen_tiles = smem_raw + (tiles - raw);
     uint64_t *bars = reinterpret_cast<uint64_t *>(gen_tiles + STAGES * STAGE_BYTES);
-    // barrier map: [0,2) full, [2,4) empty, [4,6) tmem_full, [6,8) tmem_empty, [8,12) sched_full, [12,16) sched_empty
+    // barrier map: BAR_FULL / BAR_EMPTY (operand ring), BAR_TFULL / BAR_TEMPTY (TMEM accumulators),
+    // BAR_SFULL / BAR_SEMPTY (tile scheduler ring)
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-    volatile int *sched_tile = reinterpret_cast<volatile int *>(bars + 16);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16) + SCHED;
+    static_assert(BAR_COUNT * 8 + SCHED * 4 + 4 <= 256, "barrier block too small");
+    volatile int *sched_tile = reinterpret_cast<volatile int *>(bars + BAR_COUNT);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + BAR_COUNT) + SCHED;
     float *epi_stage = reinterpret_cast<float *>(gen_tiles + STAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.tiles_m * p.tiles_n * p.batch;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(2 + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(BAR(4 + i), 1); mbar_init(BAR(6 + i), 4); }
-        for (int i = 0; i < SCHED; ++i) { mbar_init(BAR(8 + i), 1); mbar_init(BAR(12 + i), 5); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(BAR_FULL + i), 1); mbar_init(BAR(BAR_EMPTY + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(BAR(BAR_TFULL + i), 1); mbar_init(BAR(BAR_TEMPTY + i), 4); }
+        for (int i = 0; i < SCHED; ++i) { mbar_init(BAR(BAR_SFULL + i), 1); mbar_init(BAR(BAR_SEMPTY + i), 5); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -216,10 +227,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
             int stage = 0; uint32_t phase = 0;
             int slot = 0; uint32_t sphase = 0;
             while (true) {
-                mbar_wait(BAR(12 + slot), sphase ^ 1);
+                mbar_wait(BAR(BAR_SEMPTY + slot), sphase ^ 1);
                 const int t = atomicAdd(p.tile_counter, 1);
                 sched_tile[slot] = t;
-                mbar_arrive(BAR(8 + slot));
+                mbar_arrive(BAR(BAR_SFULL + slot));
                 if (++slot == SCHED) { slot = 0; sphase ^= 1; }
                 if (t >= total_tiles) break;
                 Tile ti;
@@ -229,13 +240,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 const int brow = p.b_row0 + ti.batch * p.b_bs + ti.nblk * BN;
                 const int bcol = p.b_col0 + ti.batch * p.b_bs;
                 for (int kb = ti.kb_blk; kb < ti.ke_blk; ++kb) {
-                    mbar_wait(BAR(2 + stage), phase ^ 1);
+                    mbar_wait(BAR(BAR_EMPTY + stage), phase ^ 1);
                     const uint32_t sbase = tiles + (uint32_t)stage * STAGE_BYTES;
-                    mbar_arrive_expect_tx(BAR(stage), STAGE_BYTES);
-                    tma_load_2d(sbase, &tmAhi, BAR(stage), acol + kb * BK, arow);
-                    tma_load_2d(sbase + A_TILE_BYTES, &tmAlo, BAR(stage), acol + kb * BK, arow);
-                    tma_load_2d(sbase + 2 * A_TILE_BYTES, &tmBhi, BAR(stage), bcol + kb * BK, brow);
-                    tma_load_2d(sbase + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmBlo, BAR(stage), bcol + kb * BK, brow);
+                    mbar_arrive_expect_tx(BAR(BAR_FULL + stage), STAGE_BYTES);
+                    tma_load_2d(sbase, &tmAhi, BAR(BAR_FULL + stage), acol + kb * BK, arow);
+                    tma_load_2d(sbase + A_TILE_BYTES, &tmAlo, BAR(BAR_FULL + stage), acol + kb * BK, arow);
+                    tma_load_2d(sbase + 2 * A_TILE_BYTES, &tmBhi, BAR(BAR_FULL + stage), bcol + kb * BK, brow);
+                    tma_load_2d(sbase + 2 * A_TILE_BYTES + B_TILE_BYTES, &tmBlo, BAR(BAR_FULL + stage), bcol + kb * BK, brow);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -248,19 +259,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
             int slot = 0; uint32_t sphase = 0;
             int buf = 0; uint32_t bphase = 0;
             while (true) {
-                mbar_wait(BAR(8 + slot), sphase);
+                mbar_wait(BAR(BAR_SFULL + slot), sphase);
                 const int t = sched_tile[slot];
-                mbar_arrive(BAR(12 + slot));
+                mbar_arrive(BAR(BAR_SEMPTY + slot));
                 if (++slot == SCHED) { slot = 0; sphase ^= 1; }
                 if (t >= total_tiles) break;
                 Tile ti;
                 if (!decode_tile(p, t, ti)) continue;
-                mbar_wait(BAR(6 + buf), bphase ^ 1);                  // epilogue has drained this accumulator
+                mbar_wait(BAR(BAR_TEMPTY + buf), bphase ^ 1);         // epilogue has drained this accumulator
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * BN;
                 uint32_t acc = 0;
                 for (int kb = ti.kb_blk; kb < ti.ke_blk; ++kb) {
-                    mbar_wait(BAR(stage), phase);
+                    mbar_wait(BAR(BAR_FULL + stage), phase);
                     tcgen05_fence_after();
                     const uint32_t sbase = tiles + (uint32_t)stage * STAGE_BYTES;
                     const uint64_t dAhi = make_smem_desc(sbase);
@@ -275,10 +286,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                         tcgen05_mma_f16(d_tmem, dAhi + adv, dBlo + adv, idesc, 1);
                         tcgen05_mma_f16(d_tmem, dAlo + adv, dBhi + adv, idesc, 1);
                     }
-                    tcgen05_commit(BAR(2 + stage));                   // smem stage free once these MMAs retire
+                    tcgen05_commit(BAR(BAR_EMPTY + stage));           // smem stage free once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tcgen05_commit(BAR(4 + buf));                         // accumulator complete
+                tcgen05_commit(BAR(BAR_TFULL + buf));                 // accumulator complete
                 if (++buf == 2) { buf = 0; bphase ^= 1; }
             }
         }
@@ -291,15 +302,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         const float sinv = *p.scale_inv;
         const float sout = (p.epi == EPI_STORE && (p.S_hi || p.T_hi) && p.scale_out) ? *p.scale_out : 1.0f;
         while (true) {
-            mbar_wait(BAR(8 + slot), sphase);
+            mbar_wait(BAR(BAR_SFULL + slot), sphase);
             const int t = sched_tile[slot];
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(12 + slot));
+            if (lane == 0) mbar_arrive(BAR(BAR_SEMPTY + slot));
             if (++slot == SCHED) { slot = 0; sphase ^= 1; }
             if (t >= total_tiles) break;
             Tile ti;
             if (!decode_tile(p, t, ti)) continue;
-            mbar_wait(BAR(4 + buf), bphase);
+            mbar_wait(BAR(BAR_TFULL + buf), bphase);
             tcgen05_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * BN;
             const int m = ti.mblk * BM + row;
@@ -320,7 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(6 + buf));
+                if (lane == 0) mbar_arrive(BAR(BAR_TEMPTY + buf));
                 if (m < p.M) p.part[(long long)ti.nblk * p.ldpart + m] = (s0 + s1) * sinv * sinv;
             } else {
                 // STORE: the accumulator arrives with one output row per lane; a 32 x 32 transpose through
@@ -437,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 }
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(BAR(6 + buf));
+                if (lane == 0) mbar_arrive(BAR(BAR_TEMPTY + buf));
             }
             if (++buf == 2) { buf = 0; bphase ^= 1; }
         }
@@ -492,7 +503,8 @@ inline int make_tensor_map(CUtensorMap *map, const __half *base, long long rows,
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half *>(base), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { gpg_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return GPG_ECUDA; }
     if (cache.size() >= 64) cache.erase(cache.begin());
