@@ -38,6 +38,9 @@ if ROOT not in sys.path:
 
 import workloads as W  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the variance GEMM (16 384 test points), from the
+# ncu --set full captures summarised in profiles/r1_03_ncu_pgemm_{c2,h512}.md
+NCU_TRAFFIC_BYTES = {"c2": 2.101251e9 + 5.838592e6, "h512": 10.093680e9 + 7.856384e6}
 METRIC = "predicted grid points/sec (mean+sd)"
 UNIT = "points/s"
 
@@ -82,7 +85,9 @@ def train_rows(R):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi polled every 20 ms from before the warm-up (its start-up takes longer than a short timed
+    region); stop(t0, t1) keeps the samples whose timestamp falls inside the timed window."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -95,10 +100,19 @@ class ClockSampler:
         except OSError:
             pass
 
-    def stop(self):
+    @staticmethod
+    def _ts(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -106,26 +120,29 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, pw, reasons = [], [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+                rows.append((self._ts(c[0]), float(c[2]), float(c[3]), float(c[4]),
+                             [nm for nm, v in zip(names, c[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        if sm:
-            # "under load" = samples at or above half the peak power seen
-            thr = 0.5 * max(pw)
-            load = [s for s, p in zip(sm, pw) if p >= thr] or sm
-            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=float(max(pw)))
+        inside = [r for r in rows if t0 is not None and r[0] is not None and t0 - 0.02 <= r[0] <= t1 + 0.02]
+        window = "timed region"
+        if not inside:                                       # very short region: fall back to the loaded samples
+            thr = 0.5 * max([r[3] for r in rows], default=0.0)
+            inside = [r for r in rows if r[3] >= thr]
+            window = "samples at >= half of peak power (timed region shorter than the polling interval)"
+        if inside:
+            reasons = sorted({nm for r in inside for nm in r[4]})
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=reasons, samples=len(inside), power_w_max=float(max(r[3] for r in inside)),
+                       window=window)
         return out
 
 
@@ -251,6 +268,7 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
                          "(use --impl reference for the host baseline)")
     torch.cuda.set_device(local)
+    clocks = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi takes ~1 s to come up
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = _lib.get_engine(local)
@@ -292,19 +310,20 @@ def run_cuda(args):
     eng.set_option(_lib.OPT_STAGE_TIMING, 1)
     eng.stage_times()
     launches0 = eng.launch_count()
-    clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
         out = step()
     e1.record()
     barrier()
+    wall1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - launches0
     stages = eng.stage_times()
     eng.set_option(_lib.OPT_STAGE_TIMING, 0)
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(wall0, wall1) if clocks else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -351,7 +370,11 @@ def run_cuda(args):
         "config": bench_config(wl, world, N, M),
         "roofline": {"kernel": "predict GEMM Linv x K* + colsumsq epilogue (stage pgemm)", "bound": "tensor",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": None, "launches": pg_n, "avg_launch_ms": pg_ms / max(pg_n, 1),
+                     "traffic": NCU_TRAFFIC_BYTES.get(wl["name"]) if world == 1 else None,
+                     "traffic_note": "bytes per launch (ncu capture, profiles/r1_03_ncu_pgemm_*.md); algorithmic bytes per "
+                                     "launch = 4 B x (16384 x N) K* planes + 2 N^2 B lower-triangle W planes",
+                     "algorithmic_bytes_per_launch": 4.0 * 16384 * N + 2.0 * N * N,
+                     "launches": pg_n, "avg_launch_ms": pg_ms / max(pg_n, 1),
                      "algorithmic_flops_per_launch": flops_per_step * args.steps / max(pg_n, 1),
                      "peak_source": peak_src,
                      "note": "fp32-faithful split-fp16 product: 3 tcgen05 MMAs per algorithmic MAC, so the tensor pipe "

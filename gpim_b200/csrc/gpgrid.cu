@@ -537,8 +537,8 @@ static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, c
                            TestPoints<float, D> tp, int64_t M, float *mean, float *sd, cudaStream_t s) {
     int64_t chunk = h->opt_predict_chunk;
     if (chunk <= 0) {
-        chunk = 8192;
-        while (chunk > 1024 && chunk * ldh * 4 > (int64_t)1 << 30) chunk /= 2;
+        chunk = 16384;               // K* planes of one chunk: at most 2 GiB
+        while (chunk > 1024 && chunk * ldh * 4 > (int64_t)2 << 30) chunk /= 2;
     }
     chunk = gpg_align_up((size_t)std::min<int64_t>(chunk, gpg_align_up((size_t)M, 128)), 128);
     const int tiles_n = (int)((N + tc::BN - 1) / tc::BN);

@@ -225,6 +225,45 @@ def test_factorize_tensor_core(eng, n, algo):
     assert abs(float(fac["scalars"][1]) - np.log(np.diag(Lref)).sum()) < 1e-4 * n
 
 
+def test_full_size_properties_c2(eng):
+    """BASELINE.json configs[1] at FULL size (256 x 256 spiral, N = 7688; the oracle would need minutes
+    here): size-independent properties of the tcgen05 path, and agreement with the engine's own fp64 path."""
+    from gpim_b200._lib import KERNEL_IDS
+    R, X, y = spiral_problem(256)
+    ft = W.FIXED_THETA
+    kid = KERNEL_IDS["RBF"]
+    nz = ft["noise"] + ft["jitter"]
+    th = [ft["variance"], ft["noise"], 1.0, ft["lengthscale"], ft["lengthscale"]]
+    th32 = torch.tensor(th, dtype=torch.float32).cuda()
+    X32, y32 = torch.tensor(X, dtype=torch.float32).cuda(), torch.tensor(y, dtype=torch.float32).cuda()
+    fac = eng.factorize(kid, th32, X32, y32, ft["jitter"])
+    assert int(fac["info"].item()) == 0
+    sel = torch.arange(0, len(y), 3, device="cuda")
+    # (1) at training points the linear system gives  mean = K_f alpha = y - (noise + jitter) alpha
+    m_tr, s_tr = eng.predict(kid, th32, X32, fac, X32[sel])
+    want = (y32[sel].double() - nz * fac["alpha"][sel].double()).cpu().numpy()
+    assert relinf(m_tr.cpu(), want) < 1e-4
+    # (2) noise <= var <= variance + noise everywhere on the dense grid
+    Xf = torch.tensor(O.to_rows(O.full_grid(R)), dtype=torch.float32).cuda()
+    mean, sd = eng.predict(kid, th32, X32, fac, Xf)
+    var = (sd.double() ** 2).cpu().numpy()
+    assert var.min() >= ft["noise"] * (1 - 1e-5) and var.max() <= (ft["variance"] + ft["noise"]) * (1 + 1e-5)
+    assert var[np.isnan(R).ravel()].max() > var[~np.isnan(R).ravel()].max()      # gaps are less certain than scanned pixels
+    # (3) linearity in y: the factor does not depend on y, so sd is bit-identical and mean scales
+    fac2 = eng.factorize(kid, th32, X32, -3.0 * y32, ft["jitter"])
+    mean2, sd2 = eng.predict(kid, th32, X32, fac2, Xf)
+    assert torch.equal(sd, sd2)
+    assert relinf(mean2.cpu(), -3.0 * mean.cpu().double()) < 1e-4
+    # (4) the engine's fp64 SIMT path on a sample of the grid
+    pick = torch.arange(0, Xf.shape[0], 16, device="cuda")
+    th64 = torch.tensor(th, dtype=torch.float64).cuda()
+    X64, y64 = torch.tensor(X).cuda(), torch.tensor(y).cuda()
+    fac64 = eng.factorize(kid, th64, X64, y64, ft["jitter"])
+    m64, s64 = eng.predict(kid, th64, X64, fac64, Xf[pick].double())
+    assert relinf(mean[pick].cpu(), m64.cpu()) < 1e-4
+    assert relinf(sd[pick].cpu(), s64.cpu()) < 1e-3
+
+
 # ---------------------------------------------------------------------------------------------
 def _torch_nll(kernel, X, y, theta, jitter):
     v, n, a, l = theta[0], theta[1], theta[2], theta[3:]

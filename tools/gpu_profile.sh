@@ -5,11 +5,27 @@ TAG=${1:-r1}
 O=gpurun_out
 mkdir -p $O
 NCU="ncu --clock-control none --profile-from-start off"
-$NCU --metrics gpu__time_duration.sum --csv --log-file $O/${TAG}_launches_step_c2.csv python tools/prof_stage.py step c2 > $O/${TAG}_prof.log 2>&1
-$NCU --metrics gpu__time_duration.sum --csv --log-file $O/${TAG}_launches_factor_h512.csv python tools/prof_stage.py factor h512 >> $O/${TAG}_prof.log 2>&1
-$NCU --set full --import-source on -k regex:gemm_tc_kernel -c 1 -o $O/${TAG}_pgemm_h512 -f python tools/prof_stage.py predict h512 >> $O/${TAG}_prof.log 2>&1
-$NCU --set full --import-source on -k regex:kcross_mean -c 1 -o $O/${TAG}_kcross_h512 -f python tools/prof_stage.py predict h512 >> $O/${TAG}_prof.log 2>&1
-$NCU --set full --import-source on -k "regex:gemm_tc_kernel|diag_block_kernel|gemm_simt_kernel" -s 60 -c 3 -o $O/${TAG}_chol_h512 -f python tools/prof_stage.py chol h512 >> $O/${TAG}_prof.log 2>&1
-$NCU --set full --import-source on -k regex:kmat_kernel -c 2 -o $O/${TAG}_kmat_h512 -f python tools/prof_stage.py kmat h512 >> $O/${TAG}_prof.log 2>&1
-tail -3 $O/${TAG}_prof.log
-ls -la $O
+LOG=$O/${TAG}_prof.log
+: > $LOG
+# every launch of one step (c2) and of one factorisation (h512) with its device time
+$NCU --metrics gpu__time_duration.sum --csv --log-file $O/${TAG}_launches_step_c2.csv python tools/prof_stage.py step c2 >> $LOG 2>&1
+$NCU --metrics gpu__time_duration.sum --csv --log-file $O/${TAG}_launches_factor_h512.csv python tools/prof_stage.py factor h512 >> $LOG 2>&1
+# variance GEMM (the dominant kernel) at both sizes
+$NCU --set full --import-source on -k regex:gemm_tc_kernel -c 1 -o $O/${TAG}_pgemm_c2 -f python tools/prof_stage.py predict c2 >> $LOG 2>&1
+$NCU --set full --import-source on -k regex:gemm_tc_kernel -c 1 -o $O/${TAG}_pgemm_h512 -f python tools/prof_stage.py predict h512 >> $LOG 2>&1
+# K* tile assembly
+$NCU --set full --import-source on -k regex:kcross_mean -c 1 -o $O/${TAG}_kcross_h512 -f python tools/prof_stage.py predict h512 >> $LOG 2>&1
+# Cholesky: first outer (K = 512) trailing update = 4th tcgen05 launch; an inner (K = 128) one; diag block + panel
+$NCU --set full --import-source on -k regex:gemm_tc_kernel -s 3 -c 1 -o $O/${TAG}_chol_outer_h512 -f python tools/prof_stage.py chol h512 >> $LOG 2>&1
+$NCU --set full --import-source on -k regex:gemm_tc_kernel -s 4 -c 1 -o $O/${TAG}_chol_inner_h512 -f python tools/prof_stage.py chol h512 >> $LOG 2>&1
+$NCU --set full --import-source on -k "regex:diag_block_kernel|gemm_simt_kernel" -s 8 -c 2 -o $O/${TAG}_chol_diag_panel_h512 -f python tools/prof_stage.py chol h512 >> $LOG 2>&1
+# kernel-matrix assembly (full and lower-only)
+$NCU --set full --import-source on -k regex:kmat_kernel -c 2 -o $O/${TAG}_kmat_h512 -f python tools/prof_stage.py kmat h512 >> $LOG 2>&1
+# summarise on the box: the reports themselves are too big to travel back (64 MiB cap), keep only the GEMM one
+for f in $O/${TAG}_*.ncu-rep; do
+    python tools/ncu_summary.py $f > ${f%.ncu-rep}.md 2>> $LOG
+    ncu -i $f --page raw --csv > ${f%.ncu-rep}.raw.csv 2>> $LOG
+    case $f in *pgemm_h512*) ;; *) rm -f $f ;; esac
+done
+grep -E "^ok|Error|error" $LOG | tail -12
+ls $O | grep ${TAG}_

@@ -26,9 +26,10 @@ def timed(fn, reps=3):
     return best
 
 
-def main(n=256, path=0, dtype=torch.float32):
+def main(n=256, path=0, dtype=torch.float32, chunk=0):
     eng = get_engine()
     eng.set_option(1, path)
+    eng.set_option(2, chunk)
     R = W.spiral_scan(n)
     X, y = O.training_rows(O.sparse_grid(R), R)
     N, M = len(y), n * n
@@ -66,4 +67,4 @@ if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     path = int(sys.argv[2]) if len(sys.argv) > 2 else 0
     dt = torch.float64 if (len(sys.argv) > 3 and sys.argv[3] == "f64") else torch.float32
-    main(n, path, dt)
+    main(n, path, dt, int(sys.argv[4]) if len(sys.argv) > 4 else 0)
