@@ -247,6 +247,8 @@ class Engine:
             mean = self.empty(M, dtype=X.dtype)
         if sd is None:
             sd = self.empty(M, dtype=X.dtype)
+        if M == 0:
+            return mean, sd
         self._check(self.lib.gpg_predict(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), N, _ptr(fac["Linv"]),
                                          fac["ld"], _ptr(fac["alpha"]), _ptr(fac.get("wsplit")), _ptr(fac.get("scales")),
                                          _ptr(Xs), M, _ptr(mean), _ptr(sd), self._stream()))

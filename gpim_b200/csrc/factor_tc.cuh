@@ -110,9 +110,12 @@ static inline void tc_params_clear(tc::Launch &g) { memset(&g.p, 0, sizeof(g.p))
 // N / NB2 times instead of N / 128 times and the big updates are tensor-bound, not HBM-bound.
 // Accumulation chains in TMEM stay <= NB2 long (the tensor core truncates when it accumulates).
 // ---------------------------------------------------------------------------------------------
+// As / Ws given (factor path): the panel runs on tcgen05 too -- As holds split(s_A A) of the NEXT panel's
+// 128 columns (written by kmat_kernel for the first panel, then by the update that last touched them), Ws
+// receives the inverse of each diagonal block.  Without them the panel is a SIMT GEMM.
 static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld, int32_t *info, int reset_info,
                                float *dinv, TcPlanes Ls, const float *scales, cudaStream_t stream,
-                               int64_t NB2 = 512) {
+                               TcPlanes As = TcPlanes(), TcPlanes Ws = TcPlanes(), int64_t NB2 = 512) {
     constexpr int NB = 128;
     static bool attr_set = false;
     if (!attr_set) {
@@ -136,6 +139,11 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
         g.p.scale_inv = scales + SC_INV_LL;
         g.p.C = A + row0 * ld + col0; g.p.ldc = ld;
         g.p.alpha = -1.f; g.p.beta = 1.f;
+        if (As.hi) {                                 // the first 128 columns are the next panel: keep their split current
+            g.p.S_hi = As.hi + row0 * ld + col0; g.p.S_lo = As.lo + row0 * ld + col0; g.p.lds = ld;
+            g.p.s_ncols = NB;
+            g.p.scale_out = scales + SC_A;
+        }
         return tc::launch(h, g, stream);
     };
     for (int64_t J0 = 0; J0 < N; J0 += NB2) {
@@ -144,12 +152,31 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
             const int64_t nb = std::min<int64_t>(NB, N - j0);
             DiagEmit em;
             em.Lh = Ls.hi; em.Ll = Ls.lo; em.lds = ld; em.scale_L = scales + SC_L;
-            diag_block_kernel<float, NB><<<1, 256, diag_block_smem<float, NB>(), stream>>>(A, ld, N, j0, 1, dinv, NB, 0, 1,
-                                                                                           info, em);
+            if (Ws.hi) { em.Wh = Ws.hi; em.Wl = Ws.lo; em.scale_W = scales + SC_W; }
+            diag_block_kernel<float, NB><<<1, 256, diag_block_smem<float, NB>(), stream>>>(
+                A, ld, N, j0, 1, Ws.hi ? nullptr : dinv, NB, 0, 1, info, em);
             GPG_LAUNCH_CHECK(h);
             const int64_t rows = N - j0 - nb;
             if (rows <= 0) break;
             float *A21 = A + (j0 + nb) * ld + j0;
+            if (As.hi && Ws.hi) {                    // A21 <- A21 inv(L11)^T on tcgen05, fp32 in place + Ls planes
+                tc::Launch g;
+                tc_params_clear(g);
+                g.A.hi = As.hi; g.A.lo = As.lo; g.A.rows = N; g.A.cols = N; g.A.ld = ld;
+                g.B.hi = Ws.hi; g.B.lo = Ws.lo; g.B.rows = N; g.B.cols = N; g.B.ld = ld;
+                g.p.M = (int)rows; g.p.N = (int)nb; g.p.K = (int)nb; g.p.batch = 1;
+                g.p.a_row0 = (int)(j0 + nb); g.p.a_col0 = (int)j0;
+                g.p.b_row0 = (int)j0; g.p.b_col0 = (int)j0;
+                g.p.epi = tc::EPI_STORE;
+                g.p.scale_inv = scales + SC_INV_AW;
+                g.p.alpha = 1.f;
+                g.p.C = A21; g.p.ldc = ld;
+                g.p.S_hi = Ls.hi + (j0 + nb) * ld + j0; g.p.S_lo = Ls.lo + (j0 + nb) * ld + j0; g.p.lds = ld;
+                g.p.scale_out = scales + SC_L;
+                GPG_TRY(tc::launch(h, g, stream));
+                GPG_TRY(syrk(j0 + nb, j0 + nb, j0, rows, Jend - (j0 + nb), nb));
+                continue;
+            }
             GemmArgs<float> p;                   // A21 <- A21 * inv(L11)^T (in place: one n-tile), + split
             p.A = A21; p.lda = ld; p.a_kmajor = 1;
             p.B = dinv; p.ldb = NB; p.b_kmajor = 1;

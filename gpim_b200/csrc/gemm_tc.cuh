@@ -74,6 +74,7 @@ struct Params {
     float *C2; long long ldc2;                    // optional second copy of the stored value (no batch stride)
     float alpha, beta;
     __half *S_hi, *S_lo; long long lds; long long s_bs;      // split of the result at [m][n]
+    int s_ncols;                 // > 0: emit the split only for columns n < s_ncols
     __half *T_hi, *T_lo; long long ldt; long long t_bs;      // split of the result at [n][m] (transposed)
     const float *scale_out;      // device scalar multiplied into the emitted splits
     int *tile_counter;           // zero before launch
@@ -428,7 +429,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                                     for (int e = 0; e < 4 && nn + e < p.N; ++e) dst2[e] = xs[e];
                                 }
                             }
-                            if (Sh) {
+                            if (Sh && (p.s_ncols == 0 || nn < p.s_ncols)) {
                                 __align__(8) __half h4[4], l4[4];
                                 split_fp16(x.x * sout, h4[0], l4[0]);
                                 split_fp16(x.y * sout, h4[1], l4[1]);

@@ -417,8 +417,13 @@ static int factorize_core(gpg_handle_s *h, int kernel_id, int d, const T *theta,
                 StageTimer st(h, GPG_ST_CHOLESKY, s);
                 GPG_TRY(potrf_inv_tc(h, L, N, ld, Linv, Rf, info, reset_info, As, Ls, Ws, WTs, TTs, scales, s));
             } else {
-                { StageTimer st(h, GPG_ST_KMAT, s); GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, nullptr, N, jitter, 1, L, ld, s)); }
-                { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked_tc(h, L, N, ld, info, reset_info, w.dinv, Ls, scales, s)); }
+                {
+                    StageTimer st(h, GPG_ST_KMAT, s);
+                    KmatSplit sp;                // fp16 planes of the first panel (the updates keep the next one current)
+                    sp.hi = As.hi; sp.lo = As.lo; sp.ld = ld; sp.scale = scales + SC_A; sp.ncols = 128;
+                    GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, nullptr, N, jitter, 1, L, ld, s, sp));
+                }
+                { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked_tc(h, L, N, ld, info, reset_info, w.dinv, Ls, scales, s, As, Ws)); }
                 { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_tc(h, L, N, ld, Linv, Ls, Ws, WTs, TTs, scales, s)); }
             }
             done = true;

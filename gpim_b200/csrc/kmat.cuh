@@ -45,6 +45,7 @@ struct KmatSplit {
     __half *hi = nullptr, *lo = nullptr;
     int64_t ld = 0;
     const float *scale = nullptr;
+    int64_t ncols = 0;           // > 0: only columns j < ncols are emitted
 };
 
 // out[i*ld + j] = k(X_i, Z_j) (+ diag_add on i == j when sym).  Block: 64 x 4 threads, each
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(256) kmat_kernel(const T *__restrict__ theta, 
             if (sym && i == j + c) v[c] += diag_add;
         }
         store4(out + i * ld + j, v, vec_ok, nv);
-        if (sizeof(T) == 4 && sp.hi) {
+        if (sizeof(T) == 4 && sp.hi && (sp.ncols == 0 || j < sp.ncols)) {
             const float sc = *sp.scale;
             __align__(8) __half h4[4], l4[4];
 #pragma unroll

@@ -225,6 +225,28 @@ def test_factorize_tensor_core(eng, n, algo):
     assert abs(float(fac["scalars"][1]) - np.log(np.diag(Lref)).sum()) < 1e-4 * n
 
 
+@pytest.mark.parametrize("M", [0, 1, 127, 1000, 16385])
+def test_predict_ragged_and_empty_test_sets(eng, M):
+    """Empty, tiny and ragged numbers of test rows (16385 = one full internal chunk + 1) on the tcgen05 path
+    (N = 1111 > 1024) against the oracle."""
+    from gpim_b200._lib import KERNEL_IDS
+    n = 1111
+    X = rand_points(n, 2, 7, scale=40.0)
+    rng = np.random.RandomState(8)
+    y = np.cos(X[:, 1] / 6.0) + 0.05 * rng.randn(n)
+    Xs = rand_points(max(M, 1), 2, 9, scale=40.0)[:M]
+    v, ls, noise = 0.6, [4.0, 5.0], 2e-2
+    th = torch.tensor([v, noise, 1.0, *ls], dtype=torch.float32).cuda()
+    Xd, yd = torch.tensor(X, dtype=torch.float32).cuda(), torch.tensor(y, dtype=torch.float32).cuda()
+    fac = eng.factorize(KERNEL_IDS["RBF"], th, Xd, yd, 1e-5)
+    mean, sd = eng.predict(KERNEL_IDS["RBF"], th, Xd, fac, torch.tensor(Xs, dtype=torch.float32).reshape(M, 2).cuda())
+    assert mean.shape == (M,) and sd.shape == (M,)
+    if M == 0:
+        return
+    ref_mean, ref_sd, _ = O.predict_fixed_theta("RBF", X, y, Xs, v, ls, noise, jitter=1e-5)
+    assert relinf(mean.cpu(), ref_mean) < 1e-4 and relinf(sd.cpu(), ref_sd) < 1e-3
+
+
 def test_full_size_properties_c2(eng):
     """BASELINE.json configs[1] at FULL size (256 x 256 spiral, N = 7688; the oracle would need minutes
     here): size-independent properties of the tcgen05 path, and agreement with the engine's own fp64 path."""
