@@ -98,6 +98,26 @@ int gpg_gemv_part_reserve(gpg_handle_s *h, size_t elems, double **out);
 
 static inline size_t gpg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Programmatic dependent launch (the factorisation is a chain of short dependent kernels): a kernel calls
+// pdl_trigger() on entry, so that the NEXT kernel of the stream -- if it was launched through launch_pdl() --
+// may start its prologue (barrier init, TMEM allocation, descriptor prefetch) right away; that kernel calls
+// pdl_wait() before it touches anything the previous grids produced (returns once they have completed and
+// their writes are visible).  Both are no-ops for plainly launched kernels.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Covariance functions.  r2 is the squared lengthscale-scaled distance computed by DIRECT
 // DIFFERENCE (the reference expands X2 - 2XZ^T + Z2, pyro Isotropy._square_scaled_dist; the

@@ -237,6 +237,8 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
     const int64_t j0 = j0_first + (int64_t)blockIdx.x * NB;
     const int nb = (int)min((int64_t)NB, N - j0);
     T *Ab = A + j0 * ld + j0;
+    pdl_trigger();
+    pdl_wait();
     for (int idx = t; idx < NB * NB; idx += 256) {
         const int i = idx / NB, k = idx % NB;
         T v = (i == k) ? T(1) : T(0);                 // identity padding of a ragged last block

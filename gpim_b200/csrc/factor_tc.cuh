@@ -153,8 +153,9 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
             DiagEmit em;
             em.Lh = Ls.hi; em.Ll = Ls.lo; em.lds = ld; em.scale_L = scales + SC_L;
             if (Ws.hi) { em.Wh = Ws.hi; em.Wl = Ws.lo; em.scale_W = scales + SC_W; }
-            diag_block_kernel<float, NB><<<1, 256, diag_block_smem<float, NB>(), stream>>>(
-                A, ld, N, j0, 1, Ws.hi ? nullptr : dinv, NB, 0, 1, info, em);
+            GPG_CUDA_CHECK(launch_pdl(diag_block_kernel<float, NB>, dim3(1), dim3(256), (size_t)diag_block_smem<float, NB>(),
+                                      stream, A, ld, N, j0, 1, Ws.hi ? (float *)nullptr : dinv, (int64_t)NB, (int64_t)0, 1,
+                                      info, em));
             GPG_LAUNCH_CHECK(h);
             const int64_t rows = N - j0 - nb;
             if (rows <= 0) break;

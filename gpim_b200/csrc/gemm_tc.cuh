@@ -201,6 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.tiles_m * p.tiles_n * p.batch;
+    pdl_trigger();
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(BAR_FULL + i), 1); mbar_init(BAR(BAR_EMPTY + i), 1); }
@@ -217,6 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                  // everything above overlapped the tail of the previous kernel
 
     if (warp == 0) {
         // ===================== producer: scheduler + TMA =====================
@@ -543,7 +545,7 @@ inline int launch(gpg_handle_s *h, Launch &L, cudaStream_t stream) {
     GPG_TRY(gpg_tc_counter(h, stream, &p.tile_counter));
     const long long total = (long long)p.tiles_m * p.tiles_n * p.batch;
     const int grid = (int)std::min<long long>(total, h->sm_count);
-    gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(mAhi, mAlo, mBhi, mBlo, p);
+    GPG_CUDA_CHECK(launch_pdl(gemm_tc_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, mAhi, mAlo, mBhi, mBlo, p));
     GPG_LAUNCH_CHECK(h);
     return GPG_OK;
 }
