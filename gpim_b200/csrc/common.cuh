@@ -23,6 +23,7 @@ struct gpg_handle_s {
     long long opt_predict_chunk = 0;
     int opt_stage_timing = 0;
     int opt_factor_algo = 0;
+    int opt_fit_graph = 1;
     int opt_panel_refine = 1;
     int opt_syrk_chunk = 0;
     void *ws = nullptr;          // grow-only device workspace
@@ -31,6 +32,7 @@ struct gpg_handle_s {
     size_t gemv_part_elems = 0;
     int *tc_counters = nullptr;              // pool of zeroed tile counters for the persistent GEMM
     int tc_counter_pos = 0;
+    cudaStream_t fit_stream = nullptr;       // blocking stream the small-N Adam loop is captured on
     std::vector<gpg_stage_span> spans;       // recorded while opt_stage_timing != 0
     std::vector<cudaEvent_t> event_pool;
 };

@@ -112,6 +112,7 @@ extern "C" int gpg_destroy(gpg_handle_t h) {
     if (h->ws) cudaFree(h->ws);
     if (h->tc_counters) cudaFree(h->tc_counters);
     if (h->gemv_part) cudaFree(h->gemv_part);
+    if (h->fit_stream) cudaStreamDestroy(h->fit_stream);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.beg); cudaEventDestroy(sp.end); }
     for (auto &e : h->event_pool) cudaEventDestroy(e);
     delete h;
@@ -124,6 +125,7 @@ extern "C" int gpg_set_option(gpg_handle_t h, int key, long long value) {
         case GPG_OPT_GEMM_PATH: GPG_REQUIRE(value >= 0 && value <= 2, "gemm path 0..2"); h->opt_gemm_path = (int)value; break;
         case GPG_OPT_PREDICT_CHUNK: GPG_REQUIRE(value >= 0, "chunk >= 0"); h->opt_predict_chunk = value; break;
         case GPG_OPT_STAGE_TIMING: h->opt_stage_timing = value != 0; break;
+        case GPG_OPT_FIT_GRAPH: h->opt_fit_graph = value != 0; break;
         case GPG_OPT_FACTOR_ALGO: GPG_REQUIRE(value == 0 || value == 1, "factor algorithm 0..1"); h->opt_factor_algo = (int)value; break;
         case GPG_OPT_PANEL_REFINE: h->opt_panel_refine = value != 0; break;
         case GPG_OPT_SYRK_CHUNK: GPG_REQUIRE(value >= 0 && value % 64 == 0, "chunk must be a multiple of 64"); h->opt_syrk_chunk = (int)value; break;
@@ -801,6 +803,12 @@ static int fit_entry(gpg_handle_s *h, int kernel_id, int d, int n_ls, const T *X
                      T *u, const double *bounds, int iters, double lr, T *traj, T *theta_out, int32_t *info,
                      cudaStream_t s) {
     const int64_t ld = gpg_align_up((size_t)N, 64);
+    if (s == nullptr && h->opt_fit_graph && iters >= 8 && !train_uses_tc<T>(h, N, ld)) {
+        // The legacy default stream cannot be captured.  A blocking stream is implicitly ordered against it in
+        // both directions, so the loop can run (and be captured) there with unchanged semantics for the caller.
+        if (!h->fit_stream) GPG_CUDA_CHECK(cudaStreamCreate(&h->fit_stream));
+        s = h->fit_stream;
+    }
     void *ws;
     GPG_TRY(gpg_ws_reserve(h, train_ws_bytes<T>(h, N, ld), &ws));
     TrainBufs tb = train_carve<T>(h, ws, N, ld);
@@ -815,12 +823,47 @@ static int fit_entry(gpg_handle_s *h, int kernel_id, int d, int n_ls, const T *X
     GPG_LAUNCH_CHECK(h);
     // info keeps the FIRST failing pivot over all iterations (reset once, atomicCAS afterwards)
     GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
-    for (int it = 0; it < iters; ++it) {
+    auto one_iteration = [&]() -> int {
         GPG_TRY(nll_grad_core<T>(h, kernel_id, d, theta, X, y, N, jitter, tb, (T *)tb.nll, (T *)tb.grad, info, 0, s));
-        adam_step_kernel<T><<<1, 32, 0, s>>>(1, c, u, tb.st, (const T *)tb.grad, (const T *)tb.nll, theta,
-                                             traj ? traj + (size_t)it * (4 + d) : nullptr);
+        adam_step_kernel<T><<<1, 32, 0, s>>>(1, c, u, tb.st, (const T *)tb.grad, (const T *)tb.nll, theta, traj);
         GPG_LAUNCH_CHECK(h);
+        return GPG_OK;
+    };
+    // Small problems are launch-bound (~35 dependent kernels of a few microseconds per iteration: the Bayesian
+    // optimisation regime, N ~ 10..500, 1000 iterations x 50 trainings): after one eager iteration the second is
+    // captured into a CUDA graph and replayed.  Every launch of an iteration is shape-static; the only
+    // per-iteration state (Adam moments, step count, trajectory row) lives on the device.
+    const bool use_graph = iters >= 8 && !h->opt_stage_timing && !train_uses_tc<T>(h, N, ld) && h->opt_fit_graph;
+    int it = 0;
+    if (use_graph) {
+        GPG_TRY(one_iteration());
+        it = 1;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const long long launches_before = h->launches;
+        bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        int rc = GPG_OK;
+        if (ok) {
+            rc = one_iteration();
+            ok = (cudaStreamEndCapture(s, &graph) == cudaSuccess) && rc == GPG_OK && graph != nullptr;
+        }
+        if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+        if (ok) {
+            const long long per_iter = h->launches - launches_before;
+            for (; it < iters; ++it) {
+                if (cudaGraphLaunch(exec, s) != cudaSuccess) { ok = false; break; }
+                if (it > 1) h->launches += per_iter;       // the captured pass counted itself once
+            }
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {
+            cudaGetLastError();
+            if (rc != GPG_OK) return rc;
+            // capture refused (e.g. the caller's stream is already being captured): fall through to eager launches
+        }
     }
+    for (; it < iters; ++it) GPG_TRY(one_iteration());
     if (theta_out) GPG_CUDA_CHECK(cudaMemcpyAsync(theta_out, theta, (3 + d) * sizeof(T), cudaMemcpyDeviceToDevice, s));
     return GPG_OK;
 }

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(const double *__restri
 }
 
 // mode 0: theta = constrain(u) (start of a train() call: fresh Adam state).
-// mode 1: chain rule, one torch.optim.Adam step on u, re-constrain, record {theta, loss}.
+// mode 1: chain rule, one torch.optim.Adam step on u, re-constrain, record {theta, loss} in row step-1 of traj.
 template <typename T>
 __global__ void adam_step_kernel(int mode, FitCfg c, T *__restrict__ u, FitState *__restrict__ st,
                                  const T *__restrict__ grad_theta, const T *__restrict__ nll, T *__restrict__ theta,
@@ -176,6 +176,9 @@ __global__ void adam_step_kernel(int mode, FitCfg c, T *__restrict__ u, FitState
     }
     constrain_params<T>(u, c, theta, st->dtheta_du);
     if (traj_row) {
+        // traj_row is the BASE of the trajectory: the row is picked from the device-side step counter, so that
+        // the same launch (a replayed CUDA graph node) serves every iteration
+        traj_row += (size_t)(st->step - 1) * (4 + c.d);
         for (int p = 0; p < 3 + c.d; ++p) traj_row[p] = theta[p];
         traj_row[3 + c.d] = nll[0];
     }

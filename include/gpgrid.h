@@ -44,6 +44,8 @@ enum {
     GPG_OPT_GEMM_PATH = 1,      /* 0 auto (tcgen05 for f32 when large enough), 1 SIMT only, 2 force tcgen05 */
     GPG_OPT_PREDICT_CHUNK = 2,  /* test points per internal tile of gpg_predict (0 = auto) */
     GPG_OPT_STAGE_TIMING = 3,   /* != 0: bracket every stage with CUDA events, read by gpg_stage_times */
+    GPG_OPT_FIT_GRAPH = 7,      /* gpg_fit_adam on small problems (SIMT path): replay one captured iteration as a CUDA
+                                   graph (default 1) */
     GPG_OPT_FACTOR_ALGO = 6,    /* f32 tensor-core factorisation: 0 (default) two-level blocked right-looking Cholesky
                                    followed by the batched triangular inverse; 1 recursive Cholesky + inverse */
     GPG_OPT_PANEL_REFINE = 4,   /* recursive algorithm: refine every panel solve against L11 (default 1) */
