@@ -270,6 +270,8 @@ def run_cuda(args):
     torch.cuda.set_device(local)
     clocks = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi takes ~1 s to come up
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"                # keep NCCL's banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = _lib.get_engine(local)
     dev = eng.device
