@@ -289,12 +289,15 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
         }
         GPG_PHASE(22);
     }
+    // the inverse is computed only when somebody consumes it (the blocked Cholesky solves its panels against
+    // the factor itself and leaves all inverses to the batched trtri that follows)
+    const bool need_inv = (inv_out != nullptr) || (em.Wh != nullptr) || (em.WTh != nullptr);
     // inverses of the NSUB diagonal 32 x 32 sub-blocks, one warp each
-    if (warp < NSUB) invert_tri32<T>(S, W, LDS, warp * 32, lane);
+    if (need_inv && warp < NSUB) invert_tri32<T>(S, W, LDS, warp * 32, lane);
     __syncthreads();
     // recursive doubling inside the block: W21 = -W22 (L21 W11); the upper triangles of S and W are zero,
     // so the products are plain dense ones
-    if (NB >= 64) {
+    if (need_inv && NB >= 64) {
         for (int s0 = 0; s0 < NB; s0 += 64) {        // hb = 32: out(ty + 16 i, 2 tx + j)
             T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
             mm_kn<T, 2, 2>(S + (s0 + 32) * LDS + s0, W + s0 * LDS + s0, LDS, 32, acc, ty, tx);
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
         }
     }
     GPG_PHASE(23);
-    if (NB >= 128) {                                  // hb = 64: out(ty + 16 i, 4 tx + j)
+    if (need_inv && NB >= 128) {                      // hb = 64: out(ty + 16 i, 4 tx + j)
         T acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -418,6 +421,102 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
         }
     }
     GPG_PHASE(25);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cholesky panel: X <- X L11^-T for the rows below a 128 x 128 diagonal block, by forward substitution
+// against the factor itself (backward stable, and the diagonal block's inverse drops off the critical
+// path).  One thread per row: the row lives in 128 registers, the entries of L11 arrive as warp-wide
+// broadcast 128-bit shared loads.  CTA = 128 rows; global traffic goes through shared memory so that it
+// is coalesced.  Writes the fp32 result in place and its fp16 hi/lo planes.
+// ---------------------------------------------------------------------------------------------
+constexpr int PANEL_NB = 128, PANEL_LDS = PANEL_NB + 4;
+static int panel_trsm_smem() { return (2 * PANEL_NB * PANEL_LDS + PANEL_NB) * (int)sizeof(float); }
+
+__global__ void __launch_bounds__(PANEL_NB) panel_trsm_kernel(float *__restrict__ A, int64_t ld, int64_t j0, int64_t rows,
+                                                               __half *__restrict__ Lh, __half *__restrict__ Ll,
+                                                               int64_t lds_planes, const float *__restrict__ scale_L) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NB = PANEL_NB, LDS = PANEL_LDS;
+    float *Ls = reinterpret_cast<float *>(smem_raw);          // L11, lower triangle
+    float *Xs = Ls + NB * LDS;                                 // this CTA's rows of the panel
+    float *rd = Xs + NB * LDS;                                 // 1 / diag(L11)
+    const int t = threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.x * NB;               // first row of this CTA (relative to the panel)
+    const int nrows = (int)min((int64_t)NB, rows - r0);
+    pdl_trigger();
+    pdl_wait();
+    const float *L11 = A + j0 * ld + j0;
+    float *A21 = A + (j0 + NB + r0) * ld + j0;
+    const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    for (int q = t; q < NB * NB / 4; q += NB) {
+        const int i = q / (NB / 4), k4 = (q % (NB / 4)) * 4;
+        float4 l4 = make_float4(0.f, 0.f, 0.f, 0.f), x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec) {
+            if (k4 <= i) l4 = *reinterpret_cast<const float4 *>(L11 + (int64_t)i * ld + k4);
+            if (i < nrows) x4 = *reinterpret_cast<const float4 *>(A21 + (int64_t)i * ld + k4);
+        } else {
+            float lt[4] = {0.f, 0.f, 0.f, 0.f}, xt[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int e = 0; e < 4; ++e) {
+                if (k4 + e <= i) lt[e] = L11[(int64_t)i * ld + k4 + e];
+                if (i < nrows) xt[e] = A21[(int64_t)i * ld + k4 + e];
+            }
+            l4 = make_float4(lt[0], lt[1], lt[2], lt[3]);
+            x4 = make_float4(xt[0], xt[1], xt[2], xt[3]);
+        }
+        *reinterpret_cast<float4 *>(Ls + i * LDS + k4) = l4;       // entries right of the diagonal are never read
+        *reinterpret_cast<float4 *>(Xs + i * LDS + k4) = x4;
+    }
+    __syncthreads();
+    rd[t] = 1.0f / Ls[t * LDS + t];
+    __syncthreads();
+    float x[NB];
+#pragma unroll
+    for (int q = 0; q < NB / 4; ++q) {
+        const float4 v = *reinterpret_cast<const float4 *>(Xs + t * LDS + 4 * q);
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 + 4 <= j; k4 += 4) {
+            const float4 l4 = *reinterpret_cast<const float4 *>(Ls + j * LDS + k4);
+            s0 = fmaf(x[k4], l4.x, s0); s1 = fmaf(x[k4 + 1], l4.y, s1);
+            s2 = fmaf(x[k4 + 2], l4.z, s2); s3 = fmaf(x[k4 + 3], l4.w, s3);
+        }
+        float tail = 0.f;
+#pragma unroll
+        for (int k = (j / 4) * 4; k < j; ++k) tail = fmaf(x[k], Ls[j * LDS + k], tail);
+        x[j] = (x[j] - (((s0 + s1) + (s2 + s3)) + tail)) * rd[j];
+    }
+#pragma unroll
+    for (int q = 0; q < NB / 4; ++q)
+        *reinterpret_cast<float4 *>(Xs + t * LDS + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+    __syncthreads();
+    const float sL = *scale_L;
+    const bool vecS = ((lds_planes & 3) == 0);
+    for (int q = t; q < NB * NB / 4; q += NB) {
+        const int i = q / (NB / 4), k4 = (q % (NB / 4)) * 4;
+        if (i >= nrows) continue;
+        const float4 v = *reinterpret_cast<const float4 *>(Xs + i * LDS + k4);
+        float *dst = A21 + (int64_t)i * ld + k4;
+        if (vec) *reinterpret_cast<float4 *>(dst) = v;
+        else { dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w; }
+        const float a0 = v.x * sL, a1 = v.y * sL, a2 = v.z * sL, a3 = v.w * sL;
+        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
+        const int64_t off = (j0 + NB + r0 + i) * lds_planes + j0 + k4;
+        if (vecS) {
+            *reinterpret_cast<uint2 *>(Lh + off) = make_uint2(*reinterpret_cast<const unsigned *>(&h01), *reinterpret_cast<const unsigned *>(&h23));
+            *reinterpret_cast<uint2 *>(Ll + off) = make_uint2(*reinterpret_cast<const unsigned *>(&l01), *reinterpret_cast<const unsigned *>(&l23));
+        } else {
+            const __half hh[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
+            const __half ll[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
+            for (int e = 0; e < 4; ++e) { Lh[off + e] = hh[e]; Ll[off + e] = ll[e]; }
+        }
+    }
 }
 
 template <typename T, int NB> static int diag_block_smem() { return 2 * NB * (NB + 4) * (int)sizeof(T); }

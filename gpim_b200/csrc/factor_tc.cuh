@@ -110,9 +110,12 @@ static inline void tc_params_clear(tc::Launch &g) { memset(&g.p, 0, sizeof(g.p))
 // N / NB2 times instead of N / 128 times and the big updates are tensor-bound, not HBM-bound.
 // Accumulation chains in TMEM stay <= NB2 long (the tensor core truncates when it accumulates).
 // ---------------------------------------------------------------------------------------------
-// As / Ws given (factor path): the panel runs on tcgen05 too -- As holds split(s_A A) of the NEXT panel's
-// 128 columns (written by kmat_kernel for the first panel, then by the update that last touched them), Ws
-// receives the inverse of each diagonal block.  Without them the panel is a SIMT GEMM.
+// panel_mode 1 (default; needs As / Ws, else falls back to 2): the panel runs on tcgen05 through the block's
+// inverse -- As holds split(s_A A) of the NEXT panel's 128 columns (written by kmat_kernel for the first panel,
+// then by the update that last touched them), Ws receives the inverse of each diagonal block.
+// panel_mode 0: forward substitution against the diagonal factor (panel_trsm_kernel; diag_block_kernel then
+// computes no inverse) -- backward stable but slower (one thread per row, 8128 dependent FMAs).
+// panel_mode 2: SIMT GEMM through the inverse.
 static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld, int32_t *info, int reset_info,
                                float *dinv, TcPlanes Ls, const float *scales, cudaStream_t stream,
                                TcPlanes As = TcPlanes(), TcPlanes Ws = TcPlanes(), int64_t NB2 = 512) {
@@ -121,8 +124,10 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
     if (!attr_set) {
         GPG_CUDA_CHECK(cudaFuncSetAttribute(diag_block_kernel<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             diag_block_smem<float, NB>()));
+        GPG_CUDA_CHECK(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_trsm_smem()));
         attr_set = true;
     }
+    const int panel_mode = h->opt_panel_mode == 1 && !(As.hi && Ws.hi) ? 2 : h->opt_panel_mode;
     if (reset_info) GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
     auto syrk = [&](int64_t row0, int64_t col0, int64_t k0, int64_t rows, int64_t cols, int64_t kk) -> int {
         // A[row0.., col0..] -= L[row0.., k0..k0+kk) L[col0.., k0..k0+kk)^T on the tiles that touch row >= col
@@ -139,7 +144,7 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
         g.p.scale_inv = scales + SC_INV_LL;
         g.p.C = A + row0 * ld + col0; g.p.ldc = ld;
         g.p.alpha = -1.f; g.p.beta = 1.f;
-        if (As.hi) {                                 // the first 128 columns are the next panel: keep their split current
+        if (panel_mode == 1) {                       // the first 128 columns are the next panel: keep their split current
             g.p.S_hi = As.hi + row0 * ld + col0; g.p.S_lo = As.lo + row0 * ld + col0; g.p.lds = ld;
             g.p.s_ncols = NB;
             g.p.scale_out = scales + SC_A;
@@ -152,15 +157,23 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
             const int64_t nb = std::min<int64_t>(NB, N - j0);
             DiagEmit em;
             em.Lh = Ls.hi; em.Ll = Ls.lo; em.lds = ld; em.scale_L = scales + SC_L;
-            if (Ws.hi) { em.Wh = Ws.hi; em.Wl = Ws.lo; em.scale_W = scales + SC_W; }
+            if (panel_mode == 1) { em.Wh = Ws.hi; em.Wl = Ws.lo; em.scale_W = scales + SC_W; }
             GPG_CUDA_CHECK(launch_pdl(diag_block_kernel<float, NB>, dim3(1), dim3(256), (size_t)diag_block_smem<float, NB>(),
-                                      stream, A, ld, N, j0, 1, Ws.hi ? (float *)nullptr : dinv, (int64_t)NB, (int64_t)0, 1,
-                                      info, em));
+                                      stream, A, ld, N, j0, 1, panel_mode == 2 ? dinv : (float *)nullptr, (int64_t)NB,
+                                      (int64_t)0, 1, info, em));
             GPG_LAUNCH_CHECK(h);
             const int64_t rows = N - j0 - nb;
             if (rows <= 0) break;
             float *A21 = A + (j0 + nb) * ld + j0;
-            if (As.hi && Ws.hi) {                    // A21 <- A21 inv(L11)^T on tcgen05, fp32 in place + Ls planes
+            if (panel_mode == 0) {                   // A21 <- A21 L11^-T by forward substitution, fp32 in place + Ls planes
+                GPG_CUDA_CHECK(launch_pdl(panel_trsm_kernel, dim3((unsigned)((rows + NB - 1) / NB)), dim3(PANEL_NB),
+                                          (size_t)panel_trsm_smem(), stream, A, ld, j0, rows, Ls.hi, Ls.lo, ld,
+                                          scales + SC_L));
+                GPG_LAUNCH_CHECK(h);
+                GPG_TRY(syrk(j0 + nb, j0 + nb, j0, rows, Jend - (j0 + nb), nb));
+                continue;
+            }
+            if (panel_mode == 1) {                   // A21 <- A21 inv(L11)^T on tcgen05, fp32 in place + Ls planes
                 tc::Launch g;
                 tc_params_clear(g);
                 g.A.hi = As.hi; g.A.lo = As.lo; g.A.rows = N; g.A.cols = N; g.A.ld = ld;

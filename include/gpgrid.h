@@ -46,6 +46,8 @@ enum {
     GPG_OPT_STAGE_TIMING = 3,   /* != 0: bracket every stage with CUDA events, read by gpg_stage_times */
     GPG_OPT_FIT_GRAPH = 7,      /* gpg_fit_adam on small problems (SIMT path): replay one captured iteration as a CUDA
                                    graph (default 1) */
+    GPG_OPT_PANEL_MODE = 8,     /* blocked Cholesky panel: 0 forward substitution against the diagonal factor, 1 (default)
+                                   tcgen05 GEMM through the block inverse, 2 SIMT GEMM through the block inverse */
     GPG_OPT_FACTOR_ALGO = 6,    /* f32 tensor-core factorisation: 0 (default) two-level blocked right-looking Cholesky
                                    followed by the batched triangular inverse; 1 recursive Cholesky + inverse */
     GPG_OPT_PANEL_REFINE = 4,   /* recursive algorithm: refine every panel solve against L11 (default 1) */

@@ -182,11 +182,11 @@ def test_predict_3d_matern(eng):
 
 
 @pytest.mark.parametrize("n", [129, 257, 700, 1111, 2500])
-@pytest.mark.parametrize("algo", [0, 1])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3])
 def test_factorize_tensor_core(eng, n, algo):
-    """gpg_factorize on the forced tcgen05 path (algo 0: two-level blocked Cholesky + batched inverse;
-    algo 1: recursive Cholesky + inverse): L, L^-1, its fp16 hi/lo planes, alpha and logdet against
-    numpy fp64 on ragged sizes."""
+    """gpg_factorize on the forced tcgen05 path (algo 0: two-level blocked Cholesky + batched inverse, tcgen05
+    panel; 1: recursive Cholesky + inverse; 2 / 3: blocked with the forward-substitution / SIMT panel):
+    L, L^-1, its fp16 hi/lo planes, alpha and logdet against numpy fp64 on ragged sizes."""
     from gpim_b200._lib import KERNEL_IDS, OPT_GEMM_PATH
     X = rand_points(n, 2, n, scale=40.0)
     rng = np.random.RandomState(n + 1)
@@ -197,13 +197,15 @@ def test_factorize_tensor_core(eng, n, algo):
     Lref = np.linalg.cholesky(K)
     th = torch.tensor([v, noise, 1.0, *ls], dtype=torch.float32).cuda()
     eng.set_option(OPT_GEMM_PATH, 2)
-    eng.set_option(6, algo)                       # GPG_OPT_FACTOR_ALGO
+    eng.set_option(6, 1 if algo == 1 else 0)      # GPG_OPT_FACTOR_ALGO: 0 blocked, 1 recursive
+    eng.set_option(8, {0: 1, 1: 1, 2: 0, 3: 2}[algo])   # GPG_OPT_PANEL_MODE of the blocked algorithm: tcgen05 / trsm / SIMT
     try:
         fac = eng.factorize(KERNEL_IDS["RBF"], th, torch.tensor(X, dtype=torch.float32).cuda(),
                             torch.tensor(y, dtype=torch.float32).cuda(), jitter)
     finally:
         eng.set_option(OPT_GEMM_PATH, 0)
         eng.set_option(6, 0)
+        eng.set_option(8, 1)
     assert int(fac["info"].item()) == 0
     L = torch.tril(fac["L"][:, :n]).cpu().double().numpy()
     Li = fac["Linv"][:, :n].cpu().double().numpy()
