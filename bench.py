@@ -39,8 +39,8 @@ if ROOT not in sys.path:
 import workloads as W  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the variance GEMM (16 384 test points), from the
-# ncu --set full captures summarised in profiles/r1_03_ncu_pgemm_{c2,h512}.md
-NCU_TRAFFIC_BYTES = {"c2": 2.101251e9 + 5.838592e6, "h512": 10.093680e9 + 7.856384e6}
+# ncu --set full captures summarised in profiles/r1_05_ncu_pgemm_{c2,h512}.md
+NCU_TRAFFIC_BYTES = {"c2": 2.099609e9 + 6.744320e6, "h512": 10.066302e9 + 7.414528e6}
 METRIC = "predicted grid points/sec (mean+sd)"
 UNIT = "points/s"
 
@@ -373,7 +373,7 @@ def run_cuda(args):
         "roofline": {"kernel": "predict GEMM Linv x K* + colsumsq epilogue (stage pgemm)", "bound": "tensor",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                      "traffic": NCU_TRAFFIC_BYTES.get(wl["name"]) if world == 1 else None,
-                     "traffic_note": "bytes per launch (ncu capture, profiles/r1_03_ncu_pgemm_*.md); algorithmic bytes per "
+                     "traffic_note": "bytes per launch (ncu capture, profiles/r1_05_ncu_pgemm_*.md); algorithmic bytes per "
                                      "launch = 4 B x (16384 x N) K* planes + 2 N^2 B lower-triangle W planes",
                      "algorithmic_bytes_per_launch": 4.0 * 16384 * N + 2.0 * N * N,
                      "launches": pg_n, "avg_launch_ms": pg_ms / max(pg_n, 1),

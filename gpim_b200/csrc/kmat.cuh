@@ -36,7 +36,9 @@ template <typename T> __device__ __forceinline__ void store4(T *dst, const T *v,
             reinterpret_cast<double2 *>(dst)[1] = reinterpret_cast<const double2 *>(v)[1];
         }
     } else {
-        for (int e = 0; e < n_valid; ++e) dst[e] = v[e];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)                // predicated, fully unrolled: v must stay in registers
+            if (e < n_valid) dst[e] = v[e];
     }
 }
 
@@ -94,7 +96,9 @@ __global__ void __launch_bounds__(256) kmat_kernel(const T *__restrict__ theta, 
                 *reinterpret_cast<uint2 *>(sp.hi + i * sp.ld + j) = *reinterpret_cast<const uint2 *>(h4);
                 *reinterpret_cast<uint2 *>(sp.lo + i * sp.ld + j) = *reinterpret_cast<const uint2 *>(l4);
             } else {
-                for (int c = 0; c < nv; ++c) { sp.hi[i * sp.ld + j + c] = h4[c]; sp.lo[i * sp.ld + j + c] = l4[c]; }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < nv) { sp.hi[i * sp.ld + j + c] = h4[c]; sp.lo[i * sp.ld + j + c] = l4[c]; }
             }
         }
     }

@@ -16,9 +16,15 @@ $NCU --set full --import-source on -k regex:gemm_tc_kernel -c 1 -o $O/${TAG}_pge
 # K* tile assembly
 $NCU --set full --import-source on -k regex:kcross_mean -c 1 -o $O/${TAG}_kcross_h512 -f python tools/prof_stage.py predict h512 >> $LOG 2>&1
 # Cholesky: first outer (K = 512) trailing update = 4th tcgen05 launch; an inner (K = 128) one; diag block + panel
+# (standalone gpg_cholesky: SIMT panel, so per outer panel the tcgen05 launches are 3 inner updates + 1 outer)
 $NCU --set full --import-source on -k regex:gemm_tc_kernel -s 3 -c 1 -o $O/${TAG}_chol_outer_h512 -f python tools/prof_stage.py chol h512 >> $LOG 2>&1
 $NCU --set full --import-source on -k regex:gemm_tc_kernel -s 4 -c 1 -o $O/${TAG}_chol_inner_h512 -f python tools/prof_stage.py chol h512 >> $LOG 2>&1
-$NCU --set full --import-source on -k "regex:diag_block_kernel|gemm_simt_kernel" -s 8 -c 2 -o $O/${TAG}_chol_diag_panel_h512 -f python tools/prof_stage.py chol h512 >> $LOG 2>&1
+# the tensor-core panel of the factor path: 2nd tcgen05 launch of gpg_factorize (after the first panel's inner update)
+$NCU --set full --import-source on -k regex:gemm_tc_kernel -s 2 -c 1 -o $O/${TAG}_chol_panel_h512 -f python tools/prof_stage.py factor h512 >> $LOG 2>&1
+$NCU --set full --import-source on -k "regex:diag_block_kernel" -s 8 -c 1 -o $O/${TAG}_chol_diag_h512 -f python tools/prof_stage.py chol h512 >> $LOG 2>&1
+# marginal-likelihood gradient reduction (one Adam iteration at c2) and the acquisition sweep over 2^20 points
+$NCU --set full --import-source on -k regex:grad_partial -c 1 -o $O/${TAG}_grad_c2 -f python tools/prof_stage.py fit c2 >> $LOG 2>&1
+$NCU --set full --import-source on -k "regex:acq_eval_kernel|topk_round_kernel" -c 2 -o $O/${TAG}_acq_1m -f python tools/prof_stage.py acq c2 >> $LOG 2>&1
 # kernel-matrix assembly (full and lower-only)
 $NCU --set full --import-source on -k regex:kmat_kernel -c 2 -o $O/${TAG}_kmat_h512 -f python tools/prof_stage.py kmat h512 >> $LOG 2>&1
 # summarise on the box: the reports themselves are too big to travel back (64 MiB cap), keep only the GEMM one

@@ -39,6 +39,11 @@ for _ in range(reps):
         eng.factorize(kid, th, Xd, yd, wl["jitter"], out=fac)
     elif stage == "predict":
         eng.predict(kid, th, Xd, fac, Xsd)
+    elif stage == "acq":
+        g = torch.Generator(device="cuda").manual_seed(0)
+        mu = torch.randn(1 << 20, device="cuda", generator=g)
+        sig = torch.rand(1 << 20, device="cuda", generator=g) + 0.1
+        eng.acq_sweep(1, mu, sig, 100, mu_best=1.0, xi=0.01, want_acq=True)
     elif stage == "fit":
         u = torch.zeros(3 + Xd.shape[1], dtype=dt, device="cuda")
         eng.fit_adam(kid, Xd, yd, wl["jitter"], u, [1e-4, 10.0] + [1.0] * Xd.shape[1] + [20.0] * Xd.shape[1],
