@@ -315,6 +315,46 @@ def test_nll_grad_matches_autograd(eng, kernel, d, n):
     np.testing.assert_allclose(grad.cpu().numpy(), g_ref, rtol=1e-7, atol=1e-8)
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_nll_grad_tensor_core_path(eng, kernel):
+    """fp32 marginal likelihood and its gradient on the tcgen05 path (N = 1500 > 1024: blocked Cholesky, batched
+    inverse, K^-1 = W^T W on tensor cores, fused gradient reduction) against fp64 autograd."""
+    from gpim_b200._lib import KERNEL_IDS
+    n, d = 1500, 2
+    X = torch.tensor(rand_points(n, d, 11, scale=30.0))
+    y = torch.sin(X[:, 0] / 4.0) * torch.cos(X[:, 1] / 5.0) + 0.1 * torch.tensor(np.random.RandomState(12).randn(n))
+    theta = make_theta(d, torch.float64, variance=0.8, noise=0.03, ls=(3.0, 4.0)).requires_grad_(True)
+    ref = _torch_nll(kernel, X, y, theta, 1e-5)
+    ref.backward()
+    g_ref = theta.grad.numpy().copy()
+    if kernel != "RationalQuadratic":
+        g_ref[2] = 0.0
+    nll, grad, info = eng.nll_grad(KERNEL_IDS[kernel], theta.detach().float().cuda(), X.float().cuda(), y.float().cuda(), 1e-5)
+    assert int(info.item()) == 0
+    assert abs(nll.item() - ref.item()) < 2e-4 * abs(ref.item()) + 0.2      # log-determinant drift of the TMEM accumulation
+    g = grad.cpu().double().numpy()
+    assert np.abs(g - g_ref).max() < 2e-3 * np.abs(g_ref).max()
+
+
+def test_fit_adam_tensor_core_path_tracks_fp64():
+    """reconstructor.train in fp32 on the tcgen05 path (N = 2887) follows the engine's fp64 trajectory."""
+    import gpim_b200 as gpim
+    R = W.spiral_scan(96)
+    Xs, Xf = O.sparse_grid(R), O.full_grid(R)
+    assert int((~np.isnan(R)).sum()) > 1024
+    traj = {}
+    for precision in ("double", "single"):
+        rec = gpim.reconstructor(Xs, R, Xf, kernel="RBF", lengthscale=[[1., 1.], [4., 4.]], learning_rate=0.1, iterations=12,
+                                 verbose=0, precision=precision, seed=1)
+        # same starting point for both precisions (the prior draw depends on the default dtype)
+        rec.model.kernel.unpack_u(torch.tensor([0.3, 0.0, 0.0, 0.2, -0.1], dtype=rec.model.kernel.dtype))
+        rec.model._u = rec.model.kernel.pack_u().to(rec.model.engine.device)
+        rec.train()
+        traj[precision] = {k: np.array(rec.hyperparams[k]) for k in ("variance", "noise", "lengthscale")}
+    for k in ("variance", "noise", "lengthscale"):
+        np.testing.assert_allclose(traj["single"][k], traj["double"][k], rtol=2e-3)
+
+
 @pytest.mark.parametrize("kernel,iso", [("RBF", False), ("Matern52", False), ("RationalQuadratic", False), ("RBF", True)])
 def test_fit_adam_trajectory_matches_oracle(kernel, iso):
     """reconstructor.train vs OracleGP.train, fp64, 25 iterations: per-iteration hyper-parameters."""
