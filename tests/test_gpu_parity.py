@@ -491,6 +491,39 @@ def test_boptimizer_custom_acquisition_and_mask(tmp_path):
     assert runs[0] == runs[1]
 
 
+def test_boptimizer_batch_update_and_distance_filter(tmp_path):
+    """batch_update (KD-tree ball suppression, boptim.py:326-376) and the dscale / gamma / memory filter
+    (boptim.py:378-429): picks of one batch are farther apart than batch_dscale, no point is measured twice,
+    and the run is deterministic given the numpy seed."""
+    import gpim_b200 as gpim
+    f, Z = _boptim_setup()
+    X_full, X_sparse = gpim.utils.get_full_grid(Z), gpim.utils.get_sparse_grid(Z)
+
+    def run(batch):
+        np.random.seed(3)
+        kw = dict(batch_update=True, batch_dscale=4.0, batch_out_max=4) if batch else dict(dscale=3.0, gamma=0.9, memory=5)
+        bo = gpim.boptimizer(X_sparse, Z.copy(), X_full, f, acquisition_function="cb", exploration_steps=3,
+                             gp_iterations=30, verbose=0, filename=str(tmp_path / "bo"), **kw)
+        bo.run()
+        return bo
+
+    a, b = run(True), run(True)
+    assert a.indices_all == b.indices_all and len(a.indices_all) == 12
+    for s0 in range(0, 12, 4):
+        pts = np.array(a.indices_all[s0:s0 + 4], dtype=float)
+        dist = np.linalg.norm(pts[:, None] - pts[None], axis=-1) + 1e9 * np.eye(len(pts))
+        # the greedy picks are > batch_dscale apart; random padding (when the ball suppression runs dry) is exempt
+        assert (dist > 4.0).sum() >= 2
+    assert np.isfinite(a.target_func_vals[-1]).sum() >= np.isfinite(Z).sum() + 3
+    c = run(False)
+    picks = [tuple(p) for p in c.indices_all]
+    assert len(set(picks)) == len(picks) == 3
+    for k in range(1, 3):
+        assert np.linalg.norm(np.array(picks[k], dtype=float) - np.array(picks[k - 1], dtype=float)) > 3.0
+    saved = np.load(str(tmp_path / "bo.npy"), allow_pickle=True).item()
+    assert set(saved) == {"gp_pred", "func_val", "inds_all", "vals_all"}
+
+
 # ---------------------------------------------------------------------------------------------
 # tensor-core path (tcgen05, split-fp16 operands)
 # ---------------------------------------------------------------------------------------------
