@@ -249,6 +249,27 @@ def test_predict_ragged_and_empty_test_sets(eng, M):
     assert relinf(mean.cpu(), ref_mean) < 1e-4 and relinf(sd.cpu(), ref_sd) < 1e-3
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("n", [400, 1100])
+def test_predict_4d_inputs(eng, kernel, n):
+    """4-D coordinates (the reference supports 2D-4D grids, gprutils.py:108-172), ARD lengthscales, fp32:
+    SIMT path (n = 400) and tcgen05 path (n = 1100) against the fp64 oracle."""
+    from gpim_b200._lib import KERNEL_IDS
+    d = 4
+    X = rand_points(n, d, 21, scale=12.0)
+    rng = np.random.RandomState(22)
+    y = np.sin(X[:, 0] / 3.0) + np.cos(X[:, 3] / 4.0) + 0.05 * rng.randn(n)
+    Xs = rand_points(777, d, 23, scale=12.0)
+    v, ls, noise = 0.9, [3.0, 4.0, 5.0, 6.0], 2e-2
+    ref_mean, ref_sd, _ = O.predict_fixed_theta(kernel, X, y, Xs, v, ls, noise, jitter=1e-5, scale_mixture=1.3)
+    th = torch.tensor([v, noise, 1.3, *ls], dtype=torch.float32).cuda()
+    Xd, yd = torch.tensor(X, dtype=torch.float32).cuda(), torch.tensor(y, dtype=torch.float32).cuda()
+    fac = eng.factorize(KERNEL_IDS[kernel], th, Xd, yd, 1e-5)
+    assert int(fac["info"].item()) == 0
+    mean, sd = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, torch.tensor(Xs, dtype=torch.float32).cuda())
+    assert relinf(mean.cpu(), ref_mean) < 1e-4 and relinf(sd.cpu(), ref_sd) < 1e-3
+
+
 def test_full_size_properties_c2(eng):
     """BASELINE.json configs[1] at FULL size (256 x 256 spiral, N = 7688; the oracle would need minutes
     here): size-independent properties of the tcgen05 path, and agreement with the engine's own fp64 path."""
