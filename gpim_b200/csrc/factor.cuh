@@ -1,10 +1,11 @@
-// factor.cuh -- K3 blocked Cholesky, triangular inverse, and the vector solves (K7a).
+// factor.cuh -- K3 blocked Cholesky, triangular inverse, and the vector solves (K7a): the SIMT
+// (fp64, small fp32) drivers and the kernels both they and the tensor-core drivers of factor_tc.cuh
+// share (diagonal block, panel forward substitution, triangular GEMVs, refinement bookkeeping).
 //
-// Cholesky: right-looking, block NB = GemmCfg<T>::BN.  Per block column: (1) one CTA factors the
-// NB x NB diagonal block in shared memory and inverts it, (2) the panel below becomes
+// Cholesky (this file): right-looking, block NB = GemmCfg<T>::BN.  Per block column: (1) one CTA
+// factors the NB x NB diagonal block in shared memory and inverts it, (2) the panel below becomes
 // A21 * inv(L11)^T (a GEMM against the small inverse), (3) the trailing matrix gets the SYRK
-// update A22 -= A21 A21^T on lower tiles only.  Steps (2)/(3) go through gemm_dispatch(), i.e.
-// tcgen05 when eligible, SIMT otherwise.
+// update A22 -= A21 A21^T on lower tiles only, both on the SIMT GEMM.
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -14,12 +15,13 @@ template <typename T> int gemm_dispatch(gpg_handle_s *h, const GemmArgs<T> &g, c
 // ---------------------------------------------------------------------------------------------
 // diagonal block: Cholesky + inverse of one NB x NB block in shared memory, blocked by 32.
 // grid = 1 CTA (potf2 inside the blocked Cholesky) or one CTA per diagonal block (inverse-only
-// mode, level 0 of trtri).  S: the block / its factor, W: the inverse, both NB x (NB+1).
+// mode, level 0 of trtri).  S: the block / its factor, W: the inverse, both NB x (NB+4).
 //   factor   per 32-column panel: (1) warp 0 factors the 32 x 32 diagonal sub-block in registers
-//            (lane = row, warp shuffles broadcast the pivot column), (2) one thread per row solves
-//            the panel below against it, (3) all threads apply the rank-32 update to the rest;
-//   inverse  32 x 32 diagonal sub-blocks by forward substitution (lane = column), then recursive
-//            doubling W21 = -W22 (L21 W11) with the products held in registers between barriers.
+//            (lane = row; pivot by shuffle, scaled column through a shared buffer), (2) one thread per
+//            row solves the panel below against it by forward substitution, (3) all threads apply the
+//            rank-32 update to the rest (128-bit shared-memory products);
+//   inverse  (only when an output consumes it) the 32 x 32 diagonal sub-blocks by forward substitution,
+//            one warp each, then recursive doubling W21 = -W22 (L21 W11).
 // Optional fp16 hi/lo emission (f32 only) of the factor block (Lh/Ll) and of the inverse block,
 // plain (Wh/Wl) and transposed (WTh/WTl), for the tensor-core GEMMs that follow.
 // ---------------------------------------------------------------------------------------------

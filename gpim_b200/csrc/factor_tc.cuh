@@ -1,15 +1,17 @@
-// factor_tc.cuh -- f32 factorisation on the tensor cores: blocked Cholesky whose trailing SYRK
-// updates run on the split-fp16 tcgen05 GEMM (gemm_tc.cuh), and the triangular inverse by
-// recursive doubling with both GEMMs of every level on the same kernel.
+// factor_tc.cuh -- f32 factorisation on the tensor cores: a two-level blocked Cholesky whose panels and
+// trailing SYRK updates run on the split-fp16 tcgen05 GEMM (gemm_tc.cuh), the triangular inverse by
+// batched recursive doubling with both GEMMs of every level on the same kernel, and (optional
+// alternative) a fully recursive Cholesky + inverse.
 //
 // Operand bookkeeping.  Every tensor-core operand is an fp16 hi/lo pair of K-major planes with the
 // geometry of the N x ld matrix, produced where the fp32 value is born (no separate conversion
 // passes):
-//   Ls  = split(s_L L)        diag blocks by diag_block_kernel, panels by the SIMT panel GEMM
+//   Ls  = split(s_L L)        diag blocks by diag_block_kernel, panels by the panel GEMM's epilogue
 //   Ws  = split(s_W L^-1)     diag blocks by diag_block_kernel, off-diagonal blocks by the epilogue
 //   WTs = split(s_W L^-T)     of the level that computes them (plain and transposed emission)
 //   TTs = split(s_T (L21 W11)^T)   intermediate of a doubling level, transposed emission
-//   As  = split(s_A A)        the not-yet-factored part of K: by kmat_kernel, then by every SYRK epilogue
+//   As  = split(s_A A)        not-yet-factored columns of K: by kmat_kernel, then by the SYRK epilogues
+//                             (blocked algorithm: only the next panel's 128 columns are kept current)
 // The power-of-two scales come from rigorous bounds (scales_from_theta_kernel), so no data pass
 // is needed to find them and nothing can overflow fp16.
 #pragma once
