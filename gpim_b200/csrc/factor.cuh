@@ -25,7 +25,7 @@ template <typename T> int gemm_dispatch(gpg_handle_s *h, const GemmArgs<T> &g, c
 // Optional fp16 hi/lo emission (f32 only) of the factor block (Lh/Ll) and of the inverse block,
 // plain (Wh/Wl) and transposed (WTh/WTl), for the tensor-core GEMMs that follow.
 // ---------------------------------------------------------------------------------------------
-// development aid (tools/_scratch/diag_bench.cu): phase timestamps of diag_block_kernel
+// development aid (tools/diag_bench.cu): phase timestamps of diag_block_kernel
 #ifdef GPG_DIAG_PROFILE
 __device__ long long g_diag_clk[64];
 #define GPG_PHASE(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_diag_clk[i] = clock64(); } while (0)
