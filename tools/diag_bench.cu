@@ -28,11 +28,12 @@ int main() {
     }
 #ifdef GPG_DIAG_PROFILE
     long long clk[64]; cudaMemcpyFromSymbol(clk, g_diag_clk, sizeof(clk));
-    const char *names[26] = {"load", "sync", "p0 wait", "p0 factor32", "p0 invert32", "p0 panel", "p0 trailing", "p1 wait", "p1 factor32", "p1 invert32", "p1 panel", "p1 trailing",
-                             "p2 wait", "p2 factor32", "p2 invert32", "p2 panel", "p2 trailing", "p3 wait", "p3 factor32", "p3 invert32", "-", "-", "writeback L", "doubling 32", "doubling 64", "emit"};
+    const char *names[26] = {"load", "sync", "p0 wait", "p0 factor32", "-", "p0 panel solve", "p0 trailing", "p1 wait", "p1 factor32", "-",
+                             "p1 panel solve", "p1 trailing", "p2 wait", "p2 factor32", "-", "p2 panel solve", "p2 trailing", "p3 wait",
+                             "p3 factor32", "-", "-", "-", "factor done", "invert + doubling 32", "doubling 64", "emit"};
     long long prev = clk[0];
-    int order[] = {1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,22,23,24,25};
-    for (int i : order) { printf("  %-14s %8lld cyc\n", names[i], clk[i] - prev); prev = clk[i]; }
+    int order[] = {1, 2, 3, 5, 6, 7, 8, 10, 11, 12, 13, 15, 16, 17, 18, 22, 23, 24, 25};
+    for (int i : order) { printf("  %-22s %8lld cyc\n", names[i], clk[i] - prev); prev = clk[i]; }
     printf("  total after load %lld cyc\n", clk[25] - clk[0]);
 #endif
     std::vector<float> L(N * ld), W(N * ld);
