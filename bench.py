@@ -268,11 +268,21 @@ def run_cuda(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
                          "(use --impl reference for the host baseline)")
     torch.cuda.set_device(local)
-    clocks = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi takes ~1 s to come up
+    # started early: nvidia-smi takes ~1 s to come up
+    clocks = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"                # keep NCCL's banner off stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator is created: keep stdout for the one
+        # JSON line by pointing fd 1 at stderr while the process group comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     eng = _lib.get_engine(local)
     dev = eng.device
 
@@ -499,6 +509,7 @@ def main():
     ap.add_argument("--cpu-dtype", default="f32", choices=["f32", "f64"], dest="cpu_dtype")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra 512 x 512 measurement")
+    ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "cuda" and world != args.gpus:
