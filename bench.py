@@ -243,6 +243,37 @@ def measure_extra(eng, name, steps, warmup):
     return out
 
 
+def measure_training(eng, name, iters):
+    """Hot loop 1 of the reference (gpr.py:190-197): Adam iterations on the marginal likelihood, all on the
+    device (K assembly, Cholesky, inverse, solves, K^-1, gradient reduction, Adam step), fp32."""
+    import torch
+    from gpim_b200._lib import KERNEL_IDS
+    wl = make_workload(name)
+    X, y = train_rows(wl["R"])
+    d = X.shape[1]
+    dev, dt = eng.device, torch.float32
+    Xd, yd = torch.tensor(X, dtype=dt, device=dev), torch.tensor(y, dtype=dt, device=dev)
+    bounds = [1e-4, 10.0] + [1.0] * d + [4.0] * d            # GP_sparse2Dimages.ipynb cell 11 bounds
+
+    def run(n):
+        u = torch.zeros(3 + d, dtype=dt, device=dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        traj, theta, info = eng.fit_adam(KERNEL_IDS[wl["kernel"]], Xd, yd, wl["jitter"], u, bounds, d, n, 0.1)
+        e1.record()
+        torch.cuda.synchronize()
+        assert int(info.item()) == 0 and bool(torch.isfinite(traj).all())
+        return e0.elapsed_time(e1)
+
+    run(2)
+    ms = run(iters)
+    return {"workload": wl["label"].replace("fixed theta", "Adam on (variance, lengthscales, noise)"), "N_train": int(X.shape[0]),
+            "iterations": iters, "ms_per_adam_iteration": ms / iters,
+            "reference_published": "7.5-9.6 ms per iteration at N ~ 5..400 on a Colab GPU "
+                                   "(examples/contributed/GPIM_BEPS.ipynb:665-672); 3.6-7.0 ms on CPU at N = 5..55"}
+
+
 def bench_config(wl, gpus, N, M):
     return {"workload": wl["label"], "name": wl["name"], "N_train": N, "M_grid": M, "kernel": wl["kernel"],
             "theta": {"variance": wl["theta"][0], "noise": wl["theta"][1], "lengthscale": wl["theta"][3:],
@@ -400,7 +431,8 @@ def run_cuda(args):
     }
     if world == 1 and not args.no_extra and args.workload == "c2":
         # the 512 x 512 reconstruction BASELINE.json's target is quoted on, same step definition
-        line["extra_workloads"] = {"h512": measure_extra(eng, "h512", max(2, args.steps // 2), 2)}
+        line["extra_workloads"] = {"h512": measure_extra(eng, "h512", max(2, args.steps // 2), 2),
+                                   "train_c2": measure_training(eng, "c2", 10)}
     if world == 1 and not args.no_cpu_baseline:
         import torch as _t
         _t.set_num_threads(os.cpu_count() or 1)
