@@ -120,8 +120,9 @@ static inline void tc_params_clear(tc::Launch &g) { memset(&g.p, 0, sizeof(g.p))
 // panel_mode 2: SIMT GEMM through the inverse.
 static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld, int32_t *info, int reset_info,
                                float *dinv, TcPlanes Ls, const float *scales, cudaStream_t stream,
-                               TcPlanes As = TcPlanes(), TcPlanes Ws = TcPlanes(), int64_t NB2 = 512) {
+                               TcPlanes As = TcPlanes(), TcPlanes Ws = TcPlanes()) {
     constexpr int NB = 128;
+    const int64_t NB2 = h->opt_outer_panel;
     static bool attr_set = false;
     if (!attr_set) {
         GPG_CUDA_CHECK(cudaFuncSetAttribute(diag_block_kernel<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -48,6 +48,8 @@ enum {
                                    graph (default 1) */
     GPG_OPT_PANEL_MODE = 8,     /* blocked Cholesky panel: 0 forward substitution against the diagonal factor, 1 (default)
                                    tcgen05 GEMM through the block inverse, 2 SIMT GEMM through the block inverse */
+    GPG_OPT_OUTER_PANEL = 9,    /* blocked Cholesky: width of the outer panel (multiple of 128; default 512: wider is a few per cent faster at N > 15 000
+                                   but doubles the TMEM accumulation bias of the update) */
     GPG_OPT_FACTOR_ALGO = 6,    /* f32 tensor-core factorisation: 0 (default) two-level blocked right-looking Cholesky
                                    followed by the batched triangular inverse; 1 recursive Cholesky + inverse */
     GPG_OPT_PANEL_REFINE = 4,   /* recursive algorithm: refine every panel solve against L11 (default 1) */
