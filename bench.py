@@ -201,11 +201,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def measure_extra(eng, name, steps, warmup):
-    """The same step on another workload of SURVEY 8d (1 GPU, device-resident inputs, CUDA events)."""
+def measure_extra(eng, name, steps, warmup, compact_support=False):
+    """The same step on another workload of SURVEY 8d (1 GPU, device-resident inputs, CUDA events).
+    compact_support: with GPG_OPT_COMPACT_SUPPORT (NOT the headline configuration): the variance GEMM of each
+    128-row tile of test points only visits the training rows whose covariance with the tile exceeds 1e-14 x
+    variance -- same outputs to fp32 rounding, far fewer MMAs when the lengthscale is short against the grid."""
     import torch
+    from gpim_b200 import _lib
     from gpim_b200._lib import KERNEL_IDS
     wl = make_workload(name)
+    if compact_support:
+        eng.set_option(_lib.OPT_COMPACT_SUPPORT, 1)
     X, y = train_rows(wl["R"])
     Xs = rows_of(wl["Xfull"])
     N, M = X.shape[0], Xs.shape[0]
@@ -236,8 +242,14 @@ def measure_extra(eng, name, steps, warmup):
     ms_pred = e1.elapsed_time(e2) / steps
     assert bool(torch.isfinite(mean_t).all()) and bool(torch.isfinite(sd_t).all())
     out = {"workload": wl["label"], "N_train": N, "M_grid": M, "ms_per_step": ms, "value": M / (ms * 1e-3), "unit": UNIT,
-           "factor_cached_ms": ms_pred, "factor_cached_value": M / (ms_pred * 1e-3),
-           "variance_gemm_tflops_algorithmic": float(N) * N * M / (ms_pred * 1e-3) / 1e12, "steps": steps}
+           "factor_cached_ms": ms_pred, "factor_cached_value": M / (ms_pred * 1e-3), "steps": steps}
+    if compact_support:
+        eng.set_option(_lib.OPT_COMPACT_SUPPORT, 0)
+        out["note"] = ("GPG_OPT_COMPACT_SUPPORT = 1 (opt-in, not the headline): variance GEMM restricted per tile to the "
+                       "training rows with covariance > 1e-14 x variance; outputs equal the dense ones to fp32 rounding "
+                       "(tests/test_gpu_parity.py::test_predict_compact_support_option_is_exact)")
+    else:
+        out["variance_gemm_tflops_algorithmic"] = float(N) * N * M / (ms_pred * 1e-3) / 1e12
     del fac, Xsd, mean_t, sd_t
     torch.cuda.empty_cache()
     return out
@@ -432,7 +444,10 @@ def run_cuda(args):
     if world == 1 and not args.no_extra and args.workload == "c2":
         # the 512 x 512 reconstruction BASELINE.json's target is quoted on, same step definition
         line["extra_workloads"] = {"h512": measure_extra(eng, "h512", max(2, args.steps // 2), 2),
-                                   "train_c2": measure_training(eng, "c2", 10)}
+                                   "train_c2": measure_training(eng, "c2", 10),
+                                   "c2_compact_support": measure_extra(eng, "c2", args.steps, 2, compact_support=True),
+                                   "h512_compact_support": measure_extra(eng, "h512", max(2, args.steps // 2), 2,
+                                                                         compact_support=True)}
     if world == 1 and not args.no_cpu_baseline:
         import torch as _t
         _t.set_num_threads(os.cpu_count() or 1)

@@ -17,6 +17,7 @@ GPG_F32, GPG_F64 = 0, 1
 KERNEL_IDS = {"RBF": 0, "Matern52": 1, "RationalQuadratic": 2}
 ACQ_IDS = {"cb": 0, "ei": 1, "poi": 2}
 OPT_GEMM_PATH, OPT_PREDICT_CHUNK, OPT_STAGE_TIMING = 1, 2, 3
+OPT_PANEL_REFINE, OPT_SYRK_CHUNK, OPT_FACTOR_ALGO, OPT_FIT_GRAPH, OPT_PANEL_MODE, OPT_OUTER_PANEL, OPT_COMPACT_SUPPORT = 4, 5, 6, 7, 8, 9, 10
 STAGES = ("kmat", "cholesky", "trtri", "solve", "kcross", "pgemm", "pfinal", "grad", "acq")
 
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double

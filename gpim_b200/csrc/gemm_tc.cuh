@@ -78,6 +78,7 @@ struct Params {
     __half *T_hi, *T_lo; long long ldt; long long t_bs;      // split of the result at [n][m] (transposed)
     const float *scale_out;      // device scalar multiplied into the emitted splits
     int *tile_counter;           // zero before launch
+    const int *krange;           // optional: per m-tile [lo, hi) of the k indices where operand A is non-negligible
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -172,6 +173,11 @@ __device__ __forceinline__ bool decode_tile(const Params &p, int t, Tile &o) {
     else if (p.kb_mode == GEMM_KB_MAXMN) kb = max(m0, n0);
     if (p.ke_mode == GEMM_KE_M) ke = min(p.K, m0 + BM);
     else if (p.ke_mode == GEMM_KE_N) ke = min(p.K, n0 + BN);
+    if (p.krange) {              // compact support of the A rows of this m-tile
+        kb = max(kb, __ldg(p.krange + 2 * o.mblk));
+        ke = min(ke, __ldg(p.krange + 2 * o.mblk + 1));
+        if (ke <= kb) return false;
+    }
     o.kb_blk = kb / BK;
     o.ke_blk = (ke + BK - 1) / BK;
     return o.ke_blk > o.kb_blk;

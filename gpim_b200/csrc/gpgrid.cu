@@ -126,6 +126,7 @@ extern "C" int gpg_set_option(gpg_handle_t h, int key, long long value) {
         case GPG_OPT_PREDICT_CHUNK: GPG_REQUIRE(value >= 0, "chunk >= 0"); h->opt_predict_chunk = value; break;
         case GPG_OPT_STAGE_TIMING: h->opt_stage_timing = value != 0; break;
         case GPG_OPT_FIT_GRAPH: h->opt_fit_graph = value != 0; break;
+        case GPG_OPT_COMPACT_SUPPORT: h->opt_compact_support = value != 0; break;
         case GPG_OPT_OUTER_PANEL: GPG_REQUIRE(value >= 128 && value % 128 == 0, "outer panel: a multiple of 128"); h->opt_outer_panel = (int)value; break;
         case GPG_OPT_PANEL_MODE: GPG_REQUIRE(value >= 0 && value <= 2, "panel mode 0..2"); h->opt_panel_mode = (int)value; break;
         case GPG_OPT_FACTOR_ALGO: GPG_REQUIRE(value == 0 || value == 1, "factor algorithm 0..1"); h->opt_factor_algo = (int)value; break;
@@ -552,22 +553,30 @@ static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, c
     chunk = gpg_align_up((size_t)std::min<int64_t>(chunk, gpg_align_up((size_t)M, 128)), 128);
     const int tiles_n = (int)((N + tc::BN - 1) / tc::BN);
     void *ws;
+    const int mtiles = (int)(chunk / tc::BM);
     GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)chunk * ldh * 2, (size_t)chunk * ldh * 2,
-                                         (size_t)tiles_n * chunk * sizeof(float), 64}), &ws));
+                                         (size_t)tiles_n * chunk * sizeof(float), 2 * (size_t)mtiles * sizeof(int)}), &ws));
     Bump b(ws);
     __half *Khi = b.take<__half>((size_t)chunk * ldh);
     __half *Klo = b.take<__half>((size_t)chunk * ldh);
     float *part = b.take<float>((size_t)tiles_n * chunk);
+    int *krange = h->opt_compact_support ? b.take<int>(2 * (size_t)mtiles) : nullptr;
     // A-operand groups sized to stay L2-resident while the n-blocks sweep over them
     const int m_group = (int)std::max<int64_t>(1, ((int64_t)64 << 20) / (tc::BM * ldh * 4));
     for (int64_t c0 = 0; c0 < M; c0 += chunk) {
         const int64_t mc = std::min<int64_t>(chunk, M - c0);
         TestPoints<float, D> tpc = tp;
         if (tpc.Xs) tpc.Xs += c0 * D; else tpc.j0 += c0;
+        if (krange) {                // tiles outside every support range are skipped: their partial sums must read zero
+            krange_init_kernel<<<(mtiles + 255) / 256, 256, 0, s>>>(krange, mtiles);
+            GPG_LAUNCH_CHECK(h);
+            GPG_CUDA_CHECK(cudaMemsetAsync(part, 0, (size_t)tiles_n * chunk * sizeof(float), s));
+        }
         {
             StageTimer st(h, GPG_ST_KCROSS, s);
             GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<float, KID, D, true><<<(unsigned)((mc + 7) / 8), 256, 0, s>>>(
-                                            theta, X, N, tpc, mc, alpha, nullptr, 0, Khi, Klo, ldh, scales, mean + c0));
+                                            theta, X, N, tpc, mc, alpha, nullptr, 0, Khi, Klo, ldh, scales, mean + c0,
+                                            nullptr, 0.f, krange, 1e-14f));
             GPG_LAUNCH_CHECK(h);
         }
         {
@@ -582,6 +591,7 @@ static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, c
             g.p.epi = tc::EPI_ROWSUMSQ;
             g.p.scale_inv = scales + 2;
             g.p.part = part; g.p.ldpart = chunk;
+            g.p.krange = krange;
             GPG_TRY(tc::launch(h, g, s));
         }
         StageTimer st(h, GPG_ST_PFINAL, s);

@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                                                           T *__restrict__ Ks, int64_t ldk,
                                                           __half *__restrict__ Khi, __half *__restrict__ Klo, int64_t ldh,
                                                           const float *__restrict__ scale_ptr, T *__restrict__ mean,
-                                                          const T *__restrict__ y_resid = nullptr, T jitter = T(0)) {
+                                                          const T *__restrict__ y_resid = nullptr, T jitter = T(0),
+                                                          int *__restrict__ krange = nullptr, float support_rel = 0.f) {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (j >= mc) return;
@@ -132,6 +133,10 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
     double accd = 0.0;
     float acc_s = 0.f, acc_c = 0.f;
     const float scale = SPLIT ? *scale_ptr : 1.0f;
+    // compact support (optional): per 128-row tile of test points, the range [lo, hi) of training indices whose
+    // covariance exceeds support_rel * variance; everything outside contributes below fp32 resolution
+    const float support_thr = support_rel * (float)th.variance;
+    int sup_lo = 0x7fffffff, sup_hi = 0;
     // row padding [N, ldk) (and [N, ldh)) is zero-filled so K-tiles may over-read it
     const int64_t width = SPLIT ? ldh : (Ks ? ldk : N);
     __half *__restrict__ hrow = SPLIT ? Khi + j * ldh : nullptr;
@@ -184,6 +189,16 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                 v[c] = val;
             }
         }
+        if (SPLIT && krange) {
+#pragma unroll
+            for (int hblk = 0; hblk < 2; ++hblk) {
+                const int i = (int)(i0 + 64 * hblk + 2 * lane);
+                if (fabsf((float)v[2 * hblk]) > support_thr || fabsf((float)v[2 * hblk + 1]) > support_thr) {
+                    sup_lo = min(sup_lo, i);
+                    sup_hi = max(sup_hi, i + 2);
+                }
+            }
+        }
         if (SPLIT) {
 #pragma unroll
             for (int hblk = 0; hblk < 2; ++hblk) {
@@ -205,6 +220,17 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
             }
         }
     }
+    if (SPLIT && krange) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sup_lo = min(sup_lo, __shfl_xor_sync(0xffffffffu, sup_lo, o));
+            sup_hi = max(sup_hi, __shfl_xor_sync(0xffffffffu, sup_hi, o));
+        }
+        if (lane == 0 && sup_hi > 0) {
+            atomicMin(krange + 2 * (j / 128), sup_lo);
+            atomicMax(krange + 2 * (j / 128) + 1, sup_hi);
+        }
+    }
     if (sizeof(T) == 4) acc_c = -acc_c;               // Kahan keeps the NEGATIVE of the running error
     double acc = (sizeof(T) == 4) ? (double)acc_s + (double)acc_c : accd;
     acc = warp_sum(acc);
@@ -212,6 +238,12 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
         if (y_resid) acc = (double)y_resid[j] - acc - ((double)th.noise + (double)jitter) * (double)alpha[j];
         mean[j] = bad ? T(NAN) : (T)acc;
     }
+}
+
+// resets the per-tile support ranges to empty
+__global__ void krange_init_kernel(int *__restrict__ krange, int ntiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntiles) { krange[2 * t] = 0x7fffffff; krange[2 * t + 1] = 0; }
 }
 
 // K5: sd = sqrt(max(v - sum_tiles part[t][j], 0) + noise); NaN coordinates -> NaN.

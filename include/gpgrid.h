@@ -50,6 +50,10 @@ enum {
                                    tcgen05 GEMM through the block inverse, 2 SIMT GEMM through the block inverse */
     GPG_OPT_OUTER_PANEL = 9,    /* blocked Cholesky: width of the outer panel (multiple of 128; default 512: wider is a few per cent faster at N > 15 000
                                    but doubles the TMEM accumulation bias of the update) */
+    GPG_OPT_COMPACT_SUPPORT = 10, /* gpg_predict, tcgen05 path (default 0 = dense): per 128-row tile of test points, restrict
+                                   the variance GEMM to the contiguous range of training rows whose covariance with the tile
+                                   exceeds 1e-14 x variance (what lies outside contributes below fp32 resolution).  Pays off
+                                   for lengthscales much shorter than the grid with row-major training rows */
     GPG_OPT_FACTOR_ALGO = 6,    /* f32 tensor-core factorisation: 0 (default) two-level blocked right-looking Cholesky
                                    followed by the batched triangular inverse; 1 recursive Cholesky + inverse */
     GPG_OPT_PANEL_REFINE = 4,   /* recursive algorithm: refine every panel solve against L11 (default 1) */

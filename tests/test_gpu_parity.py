@@ -270,6 +270,34 @@ def test_predict_4d_inputs(eng, kernel, n):
     assert relinf(mean.cpu(), ref_mean) < 1e-4 and relinf(sd.cpu(), ref_sd) < 1e-3
 
 
+@pytest.mark.parametrize("kernel,ls", [("RBF", 3.0), ("RBF", 40.0), ("Matern52", 2.0)])
+def test_predict_compact_support_option_is_exact(eng, kernel, ls):
+    """GPG_OPT_COMPACT_SUPPORT restricts the variance GEMM of each 128-row tile of test points to the training
+    rows whose covariance with the tile exceeds 1e-14 x variance: same mean (bit-identical, the mean does not go
+    through the GEMM) and the same sd to fp32 rounding, for a short lengthscale (most of K* negligible), a long
+    one (nothing negligible) and a slowly decaying kernel."""
+    from gpim_b200._lib import KERNEL_IDS, OPT_COMPACT_SUPPORT
+    n = 128
+    R, X, y = spiral_problem(n)
+    th = torch.tensor([0.05, 5e-3, 1.0, ls, ls], dtype=torch.float32).cuda()
+    Xd, yd = torch.tensor(X, dtype=torch.float32).cuda(), torch.tensor(y, dtype=torch.float32).cuda()
+    fac = eng.factorize(KERNEL_IDS[kernel], th, Xd, yd, 1e-5)
+    assert int(fac["info"].item()) == 0
+    Xf = torch.tensor(O.to_rows(O.full_grid(R)), dtype=torch.float32).cuda()
+    Xf[77, 0] = float("nan")
+    m0, s0 = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, Xf)
+    eng.set_option(OPT_COMPACT_SUPPORT, 1)
+    try:
+        m1, s1 = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, Xf)
+        m2, s2 = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, Xf[:1000])          # ragged last tile
+    finally:
+        eng.set_option(OPT_COMPACT_SUPPORT, 0)
+    ok = ~torch.isnan(m0)
+    assert bool(torch.isnan(s1[~ok]).all()) and torch.equal(m0[ok], m1[ok])
+    assert relinf(s1[ok].cpu(), s0[ok].cpu()) < 2e-6
+    assert relinf(s2[ok[:1000]].cpu(), s0[:1000][ok[:1000]].cpu()) < 2e-6
+
+
 def test_full_size_properties_c2(eng):
     """BASELINE.json configs[1] at FULL size (256 x 256 spiral, N = 7688; the oracle would need minutes
     here): size-independent properties of the tcgen05 path, and agreement with the engine's own fp64 path."""
