@@ -8,4 +8,26 @@ from . import gprutils as utils  # noqa: F401
 from .gpreg.gpr import reconstructor  # noqa: F401
 from .gpbayes.boptim import boptimizer  # noqa: F401
 
+
+
+class _OutOfScope:
+    """The reference also exports the GPyTorch-backed skreconstructor / vreconstructor (gpim/__init__.py:3-4).
+    They are outside the accelerated exact-GP path: importing them works, so that
+    `from gpim import ...` lines keep running, constructing one says so."""
+    _name = ""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError(
+            f"gpim.{self._name} (GPyTorch structured-kernel / multi-output GP) is outside the accelerated exact-GP "
+            f"path of this engine; use gpim.reconstructor / gpim.boptimizer")
+
+
+class skreconstructor(_OutOfScope):
+    _name = "skreconstructor"
+
+
+class vreconstructor(_OutOfScope):
+    _name = "vreconstructor"
+
+
 __version__ = "0.1.0"

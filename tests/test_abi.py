@@ -56,3 +56,14 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith(".py"):
                 assert "oracle" not in open(os.path.join(base, f)).read().replace("the oracle", ""), f
+
+
+def test_alias_package_exports_the_reference_names():
+    """gpim/__init__.py:1-5 of the reference: utils, reconstructor, skreconstructor, vreconstructor, boptimizer."""
+    import gpim
+    import pytest
+    for name in ("utils", "reconstructor", "skreconstructor", "vreconstructor", "boptimizer"):
+        assert hasattr(gpim, name), name
+    for cls in (gpim.skreconstructor, gpim.vreconstructor):
+        with pytest.raises(NotImplementedError):
+            cls(None, None)
