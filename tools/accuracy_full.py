@@ -9,9 +9,11 @@ from gpim_b200._lib import get_engine, KERNEL_IDS, OPT_GEMM_PATH
 def relinf(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max())
 
-def main(name, sub=16384):
+def main(name, sub=16384, noise=None):
     eng = get_engine()
     wl = bench.make_workload(name)
+    if noise is not None:
+        wl["theta"][1] = noise
     X, y = bench.train_rows(wl["R"])
     Xs = bench.rows_of(wl["Xfull"])
     sel = np.linspace(0, len(Xs) - 1, min(sub, len(Xs))).astype(np.int64)
@@ -28,8 +30,8 @@ def main(name, sub=16384):
         del fac
         torch.cuda.empty_cache()
     for tag in ("f32_simt", "f32_tc"):
-        print(f"{name} N={len(y)} M={len(Xs)} {tag}: mean relinf {relinf(out[tag][0], out['f64'][0]):.2e} "
+        print(f"{name} N={len(y)} M={len(Xs)} noise={wl['theta'][1]:g} {tag}: mean relinf {relinf(out[tag][0], out['f64'][0]):.2e} "
               f"sd relinf {relinf(out[tag][1], out['f64'][1]):.2e}")
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else "c2")
+    main(sys.argv[1] if len(sys.argv) > 1 else "c2", noise=float(sys.argv[2]) if len(sys.argv) > 2 else None)
