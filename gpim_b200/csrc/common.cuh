@@ -27,6 +27,7 @@ struct gpg_handle_s {
     int opt_panel_mode = 1;
     int opt_outer_panel = 512;
     int opt_compact_support = 0;
+    int opt_inner_left = 1;
     int opt_panel_refine = 1;
     int opt_syrk_chunk = 0;
     void *ws = nullptr;          // grow-only device workspace

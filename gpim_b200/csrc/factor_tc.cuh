@@ -156,6 +156,15 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
     };
     for (int64_t J0 = 0; J0 < N; J0 += NB2) {
         const int64_t Jend = std::min<int64_t>(N, J0 + NB2);
+        // inner update after the panel of block column j0.  Right-looking (opt_inner_left == 0): all remaining
+        // columns of the outer panel, K = nb.  Left-looking (default): only the NEXT block column, but with the
+        // contributions of every inner panel so far (K = j0 + nb - J0) -- half the epilogue per step and a third
+        // of the fp32 read-modify-write traffic; the columns further right catch up when their turn comes.
+        auto inner_update = [&](int64_t j0, int64_t nb, int64_t rows) -> int {
+            if (h->opt_inner_left)
+                return syrk(j0 + nb, j0 + nb, J0, rows, std::min<int64_t>(NB, Jend - (j0 + nb)), j0 + nb - J0);
+            return syrk(j0 + nb, j0 + nb, j0, rows, Jend - (j0 + nb), nb);
+        };
         for (int64_t j0 = J0; j0 < Jend; j0 += NB) {
             const int64_t nb = std::min<int64_t>(NB, N - j0);
             DiagEmit em;
@@ -173,7 +182,7 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
                                           (size_t)panel_trsm_smem(), stream, A, ld, j0, rows, Ls.hi, Ls.lo, ld,
                                           scales + SC_L));
                 GPG_LAUNCH_CHECK(h);
-                GPG_TRY(syrk(j0 + nb, j0 + nb, j0, rows, Jend - (j0 + nb), nb));
+                GPG_TRY(inner_update(j0, nb, rows));
                 continue;
             }
             if (panel_mode == 1) {                   // A21 <- A21 inv(L11)^T on tcgen05, fp32 in place + Ls planes
@@ -191,7 +200,7 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
                 g.p.S_hi = Ls.hi + (j0 + nb) * ld + j0; g.p.S_lo = Ls.lo + (j0 + nb) * ld + j0; g.p.lds = ld;
                 g.p.scale_out = scales + SC_L;
                 GPG_TRY(tc::launch(h, g, stream));
-                GPG_TRY(syrk(j0 + nb, j0 + nb, j0, rows, Jend - (j0 + nb), nb));
+                GPG_TRY(inner_update(j0, nb, rows));
                 continue;
             }
             GemmArgs<float> p;                   // A21 <- A21 * inv(L11)^T (in place: one n-tile), + split
@@ -205,8 +214,7 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
             p.ld_split = ld;
             p.split_scale = scales + SC_L;
             GPG_TRY((gemm_simt<float, GemmCfgPanelF32>(h, p, stream)));
-            // inner update: the remaining columns of this outer panel, K = nb
-            GPG_TRY(syrk(j0 + nb, j0 + nb, j0, rows, Jend - (j0 + nb), nb));
+            GPG_TRY(inner_update(j0, nb, rows));
         }
         // outer update: everything right of the panel, K = panel width
         GPG_TRY(syrk(Jend, Jend, J0, N - Jend, N - Jend, Jend - J0));

@@ -126,6 +126,7 @@ extern "C" int gpg_set_option(gpg_handle_t h, int key, long long value) {
         case GPG_OPT_PREDICT_CHUNK: GPG_REQUIRE(value >= 0, "chunk >= 0"); h->opt_predict_chunk = value; break;
         case GPG_OPT_STAGE_TIMING: h->opt_stage_timing = value != 0; break;
         case GPG_OPT_FIT_GRAPH: h->opt_fit_graph = value != 0; break;
+        case GPG_OPT_INNER_LEFT: h->opt_inner_left = value != 0; break;
         case GPG_OPT_COMPACT_SUPPORT: h->opt_compact_support = value != 0; break;
         case GPG_OPT_OUTER_PANEL: GPG_REQUIRE(value >= 128 && value % 128 == 0, "outer panel: a multiple of 128"); h->opt_outer_panel = (int)value; break;
         case GPG_OPT_PANEL_MODE: GPG_REQUIRE(value >= 0 && value <= 2, "panel mode 0..2"); h->opt_panel_mode = (int)value; break;

@@ -54,6 +54,8 @@ enum {
                                    the variance GEMM to the contiguous range of training rows whose covariance with the tile
                                    exceeds 1e-14 x variance (what lies outside contributes below fp32 resolution).  Pays off
                                    for lengthscales much shorter than the grid with row-major training rows */
+    GPG_OPT_INNER_LEFT = 11,    /* blocked Cholesky, update inside the outer panel: 1 (default) left-looking (next block column
+                                   only, all inner panels so far), 0 right-looking (all remaining columns, last panel) */
     GPG_OPT_FACTOR_ALGO = 6,    /* f32 tensor-core factorisation: 0 (default) two-level blocked right-looking Cholesky
                                    followed by the batched triangular inverse; 1 recursive Cholesky + inverse */
     GPG_OPT_PANEL_REFINE = 4,   /* recursive algorithm: refine every panel solve against L11 (default 1) */

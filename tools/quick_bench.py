@@ -32,6 +32,8 @@ def main(n=256, path=0, dtype=torch.float32, chunk=0):
     eng.set_option(2, chunk)
     if os.environ.get("GPG_COMPACT_SUPPORT"):
         eng.set_option(10, int(os.environ["GPG_COMPACT_SUPPORT"]))
+    if os.environ.get("GPG_INNER_LEFT"):
+        eng.set_option(11, int(os.environ["GPG_INNER_LEFT"]))
     if os.environ.get("GPG_OUTER_PANEL"):
         eng.set_option(9, int(os.environ["GPG_OUTER_PANEL"]))
     R = W.spiral_scan(n)
