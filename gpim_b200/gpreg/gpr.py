@@ -111,16 +111,23 @@ class ExactGPModel:
         return traj_host
 
     # prediction --------------------------------------------------------------------------
-    def factor(self):
-        if self._factor is None:
-            fac = self.engine.factorize(self.kernel.kernel_id, self._theta, self._X, self._y, self.jitter)
-            self.last_info = int(fac["info"].item())
-            if self.last_info != 0:
-                raise torch.linalg.LinAlgError(
-                    f"linalg.cholesky: The factorization could not be completed because the input is not "
-                    f"positive-definite (the leading minor of order {self.last_info} is not positive-definite).")
-            self._factor = fac
-        return self._factor
+    def _raise_if_not_pd(self, fac):
+        self.last_info = int(fac["info"].item())
+        if self.last_info != 0:
+            self._factor = None
+            raise torch.linalg.LinAlgError(
+                f"linalg.cholesky: The factorization could not be completed because the input is not "
+                f"positive-definite (the leading minor of order {self.last_info} is not positive-definite).")
+
+    def factor(self, check=True):
+        """Factor cache for the current (X, y, theta).  check=False defers the (synchronising) pivot check to the
+        caller, so that the prediction kernels are enqueued right behind the factorisation."""
+        fresh = self._factor is None
+        if fresh:
+            self._factor = self.engine.factorize(self.kernel.kernel_id, self._theta, self._X, self._y, self.jitter)
+        if fresh and check:
+            self._raise_if_not_pd(self._factor)
+        return self._factor, fresh
 
     def __call__(self, Xnew, full_cov=False, noiseless=False):
         """(loc, var) at the rows of Xnew, as GPRegression.forward(full_cov=False)."""
@@ -129,7 +136,7 @@ class ExactGPModel:
         if Xnew.dim() != 2 or Xnew.shape[1] != self._X.shape[1]:
             raise ValueError("Train data and test data should have the same shape of features")
         Xnew = Xnew.to(self.engine.device, self.kernel.dtype).contiguous()
-        mean, sd = self.engine.predict(self.kernel.kernel_id, self._theta, self._X, self.factor(), Xnew)
+        mean, sd = self.predict_sd(Xnew)
         var = sd * sd
         if noiseless:
             var = var - self._theta[1]
@@ -137,7 +144,11 @@ class ExactGPModel:
 
     def predict_sd(self, Xnew):
         Xnew = Xnew.to(self.engine.device, self.kernel.dtype).contiguous()
-        return self.engine.predict(self.kernel.kernel_id, self._theta, self._X, self.factor(), Xnew)
+        fac, fresh = self.factor(check=False)
+        out = self.engine.predict(self.kernel.kernel_id, self._theta, self._X, fac, Xnew)
+        if fresh:
+            self._raise_if_not_pd(fac)               # one sync, after everything has been enqueued
+        return out
 
 
 class reconstructor:
@@ -248,8 +259,8 @@ class reconstructor:
             print("Calculating predictive mean and variance...", end=" ")
         mean_d, sd_d = self.model.predict_sd(self.Xtest)
         self._last_pred_device = (mean_d, sd_d)
-        mean = mean_d.cpu().numpy()
-        sd = sd_d.cpu().numpy()
+        both = torch.stack((mean_d, sd_d)).cpu().numpy()          # one device->host copy, one synchronisation
+        mean, sd = both[0], both[1]
         if mean.size == int(np.prod(self.fulldims)):
             mean, sd = mean.reshape(self.fulldims), sd.reshape(self.fulldims)
         if self.verbose:

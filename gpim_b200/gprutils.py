@@ -17,6 +17,17 @@ def _rows(X):
     return X.reshape(X.shape[0], -1).T
 
 
+def _rows_as(X, np_dtype):
+    """(c, *dims) -> contiguous (prod(dims), c) of np_dtype; one strided assignment per coordinate (several times
+    faster than numpy's generic transposed copy followed by a cast -- this sits on the per-call host path)."""
+    X = np.asarray(X)
+    flat = X.reshape(X.shape[0], -1)
+    out = np.empty((flat.shape[1], flat.shape[0]), dtype=np_dtype)
+    for k in range(flat.shape[0]):
+        out[:, k] = flat[k]
+    return out
+
+
 def prepare_training_data(X, y=None, vector_valued=False, **kwargs):
     """(c, *dims) coordinates and (*dims) observations -> torch (n, c) and (n,), NaN rows dropped
     (gprutils.py:23-59)."""
@@ -37,7 +48,8 @@ def prepare_training_data(X, y=None, vector_valued=False, **kwargs):
 
 def prepare_test_data(X, **kwargs):
     """(c, *dims) -> torch (prod(dims), c); NaN rows are KEPT (gprutils.py:62-85)."""
-    return torch.from_numpy(np.ascontiguousarray(_rows(X))).to(_torch_dtype(kwargs))
+    np_dt = np.float32 if kwargs.get("precision", "double") == "single" else np.float64
+    return torch.from_numpy(_rows_as(X, np_dt))
 
 
 def get_full_grid(R, extent=None, dense_x=1.):
