@@ -242,8 +242,9 @@ class boptimizer:
             self.vals_all.extend(vals)
 
     def run(self):
-        """The exploration loop; boptim.py:459-470."""
-        for i in range(self.exploration_steps):
+        """The exploration loop; boptim.py:459-470.  After resume() the loop continues with the step that
+        follows the checkpoint (the initial training of step 0 is not repeated)."""
+        for i in range(getattr(self, "_first_step", 0), self.exploration_steps):
             self.single_step(i)
             if self.save_checkpoints:
                 self.save_results()
@@ -256,4 +257,31 @@ class boptimizer:
         filename = args[0] if args else self.filename
         results = {'gp_pred': self.gp_predictions, 'func_val': self.target_func_vals,
                    'inds_all': np.array(self.indices_all), 'vals_all': np.array(self.vals_all)}
+        # beyond the reference's four keys: the surrogate's unconstrained hyper-parameters, so that a run can
+        # be resumed exactly where it stopped (the reference writes checkpoints but has no way to load them)
+        results['engine_state'] = {'u': self.surrogate_model.model._u.detach().cpu().numpy().copy(),
+                                   'steps_done': len(self.gp_predictions)}
         np.save(filename + ".npy", results)
+
+    def resume(self, filename=None):
+        """Load a checkpoint written by save_results() and continue from it: measured values, pick history,
+        stored predictions and the trained hyper-parameters are restored, and run() goes on with the next
+        exploration step.  (the reference has no load / resume path.)"""
+        filename = self.filename if filename is None else filename
+        res = np.load(filename + ".npy", allow_pickle=True).item()
+        self.gp_predictions = list(res['gp_pred'])
+        self.target_func_vals = list(res['func_val'])
+        self.indices_all = np.asarray(res['inds_all']).tolist()
+        self.vals_all = np.asarray(res['vals_all']).tolist()
+        self.y_sparse = self.target_func_vals[-1].copy()
+        self.X_sparse = gprutils.get_sparse_grid(self.y_sparse, self.extent)
+        model = self.surrogate_model.model
+        X_new, y_new = gprutils.prepare_training_data(self.X_sparse, self.y_sparse, precision=self.precision)
+        model.X, model.y = X_new, y_new
+        state = res.get('engine_state')
+        if state is None:                                  # a reference-format file: retrain from the prior draw
+            self.surrogate_model.train(verbose=self.verbose)
+        else:
+            model.load_unconstrained(state['u'])
+        self._first_step = max(1, len(self.gp_predictions))
+        return self

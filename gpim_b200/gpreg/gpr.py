@@ -79,6 +79,15 @@ class ExactGPModel:
         self._theta = th.to(self.engine.device)
         self._factor = None
 
+    def load_unconstrained(self, u):
+        """Restore the unconstrained hyper-parameters {variance, noise, scale_mixture, lengthscale[n_ls]} (a
+        checkpoint of boptimizer.save_results) and the constrained values derived from them."""
+        k = self.kernel
+        k.unpack_u(torch.as_tensor(np.asarray(u), dtype=k.dtype))
+        self._u = k.pack_u().to(self.engine.device)
+        self._theta = k.pack_theta().to(self.engine.device)
+        self._factor = None
+
     def parameters(self):
         yield self._u
 

@@ -570,7 +570,29 @@ def test_boptimizer_batch_update_and_distance_filter(tmp_path):
     for k in range(1, 3):
         assert np.linalg.norm(np.array(picks[k], dtype=float) - np.array(picks[k - 1], dtype=float)) > 3.0
     saved = np.load(str(tmp_path / "bo.npy"), allow_pickle=True).item()
-    assert set(saved) == {"gp_pred", "func_val", "inds_all", "vals_all"}
+    assert {"gp_pred", "func_val", "inds_all", "vals_all"} <= set(saved)
+
+
+def test_boptimizer_resume_continues_the_same_run(tmp_path):
+    """save_results() + resume(): 3 steps, checkpoint, a NEW optimizer resumed from the file and run
+    for 3 more steps reproduces the picks and measured values of an uninterrupted 6-step run."""
+    import gpim_b200 as gpim
+    f, Z = _boptim_setup()
+    X_full, X_sparse = gpim.utils.get_full_grid(Z), gpim.utils.get_sparse_grid(Z)
+    kw = dict(acquisition_function="ei", gp_iterations=60, verbose=0)
+    full = gpim.boptimizer(X_sparse, Z.copy(), X_full, f, exploration_steps=6, filename=str(tmp_path / "full"), **kw)
+    full.run()
+    first = gpim.boptimizer(X_sparse, Z.copy(), X_full, f, exploration_steps=3, filename=str(tmp_path / "part"), **kw)
+    first.run()
+    second = gpim.boptimizer(X_sparse, Z.copy(), X_full, f, exploration_steps=6, filename=str(tmp_path / "part"), **kw)
+    second.resume()
+    assert second.indices_all == first.indices_all and len(second.gp_predictions) == 3
+    second.run()
+    assert second.indices_all == full.indices_all
+    np.testing.assert_allclose(second.target_func_vals[-1], full.target_func_vals[-1], equal_nan=True)
+    np.testing.assert_allclose(second.vals_all, full.vals_all, rtol=1e-9)
+    saved = np.load(str(tmp_path / "part.npy"), allow_pickle=True).item()
+    assert {"gp_pred", "func_val", "inds_all", "vals_all"} <= set(saved) and len(saved["inds_all"]) == 6
 
 
 # ---------------------------------------------------------------------------------------------
