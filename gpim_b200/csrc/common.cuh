@@ -104,6 +104,16 @@ int gpg_gemv_part_reserve(gpg_handle_s *h, size_t elems, double **out);
 
 static inline size_t gpg_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Every entry point runs on the handle's device, whatever the caller's current device is (restored on exit).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = (cudaSetDevice(device) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 // Programmatic dependent launch (the factorisation is a chain of short dependent kernels): a kernel calls
 // pdl_trigger() on entry, so that the NEXT kernel of the stream -- if it was launched through launch_pdl() --
 // may start its prologue (barrier init, TMEM allocation, descriptor prefetch) right away; that kernel calls

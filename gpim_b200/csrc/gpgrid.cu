@@ -88,18 +88,35 @@ static size_t bump_size(std::initializer_list<size_t> parts) {
 extern "C" int gpg_version(void) { return GPG_VERSION; }
 extern "C" const char *gpg_last_error(void) { return g_err; }
 
+// Opt-in shared-memory sizes are per device: set them for the handle's device when it is created (the lazy
+// process-wide guards next to the launches only cover the first device a process touches).
+static int set_function_attributes() {
+    GPG_CUDA_CHECK(cudaFuncSetAttribute(diag_block_kernel<float, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        diag_block_smem<float, 128>()));
+    GPG_CUDA_CHECK(cudaFuncSetAttribute(diag_block_kernel<double, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        diag_block_smem<double, 64>()));
+    GPG_CUDA_CHECK(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_trsm_smem()));
+    GPG_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    GPG_CUDA_CHECK(cudaFuncSetAttribute(topk_round_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        2048 * (int)sizeof(Cand<float>)));
+    GPG_CUDA_CHECK(cudaFuncSetAttribute(topk_round_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        2048 * (int)sizeof(Cand<double>)));
+    return GPG_OK;
+}
+
 extern "C" int gpg_create(int device, gpg_handle_t *out) {
     GPG_REQUIRE(out != nullptr, "out is NULL");
     int count = 0;
     GPG_CUDA_CHECK(cudaGetDeviceCount(&count));
     GPG_REQUIRE(device >= 0 && device < count, "device index out of range");
-    GPG_CUDA_CHECK(cudaSetDevice(device));
+    DeviceGuard device_guard(device);              // the caller's current device is restored on return
     cudaDeviceProp prop;
     GPG_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
         gpg_set_error("libgpgrid is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
         return GPG_ECUDA;
     }
+    GPG_TRY(set_function_attributes());
     gpg_handle_s *h = new gpg_handle_s();
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
@@ -140,6 +157,7 @@ extern "C" int gpg_set_option(gpg_handle_t h, int key, long long value) {
 
 extern "C" int gpg_stage_times(gpg_handle_t h, double *ms_host, long long *spans_host) {
     GPG_REQUIRE(h && ms_host && spans_host, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_CUDA_CHECK(cudaDeviceSynchronize());
     for (int i = 0; i < GPG_ST_COUNT; ++i) { ms_host[i] = 0.0; spans_host[i] = 0; }
     for (auto &sp : h->spans) {
@@ -180,6 +198,7 @@ extern "C" int gpg_gemm_nt_f32(gpg_handle_t h, const float *A, int64_t lda, cons
                                int64_t ldc, int64_t M, int64_t N, int64_t K, double alpha, double beta, double scale_a,
                                double scale_b, void *stream) {
     GPG_REQUIRE(h && A && B && C, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(M > 0 && N > 0 && K > 0 && lda >= K && ldb >= K && ldc >= N, "bad size");
     GPG_REQUIRE(scale_a > 0 && scale_b > 0, "scales must be positive");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -228,6 +247,7 @@ static int kmat_launch(gpg_handle_s *h, int kernel_id, int d, const T *theta, co
 extern "C" int gpg_kmat(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X, int64_t N,
                         const void *Z, int64_t P, double jitter, int lower_only, void *out, int64_t ld, void *stream) {
     GPG_REQUIRE(h && theta && X && out, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(N >= 0 && (Z == nullptr || P >= 0), "negative size");
     GPG_REQUIRE(ld >= (Z ? P : N), "ld smaller than row length");
     GPG_REQUIRE((int64_t)((N + 15) / 16) < 65536, "N too large for one launch");
@@ -269,6 +289,7 @@ template <typename T> static int cholesky_entry(gpg_handle_s *h, T *A, int64_t N
 
 extern "C" int gpg_cholesky(gpg_handle_t h, int dtype, void *A, int64_t N, int64_t ld, int32_t *info, void *stream) {
     GPG_REQUIRE(h && A && info, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(N >= 0 && ld >= N, "bad size");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (N == 0) return GPG_OK;
@@ -289,6 +310,7 @@ static int trtri_entry(gpg_handle_s *h, const T *L, int64_t N, int64_t ld, T *Li
 extern "C" int gpg_trtri(gpg_handle_t h, int dtype, const void *L, int64_t N, int64_t ld, void *Linv, int64_t ldinv,
                          void *stream) {
     GPG_REQUIRE(h && L && Linv && L != Linv, "NULL or aliased argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(N >= 0 && ld >= N && ldinv >= N, "bad size");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (N == 0) return GPG_OK;
@@ -310,6 +332,7 @@ static int solve_entry(gpg_handle_s *h, const T *L, const T *Linv, int64_t N, in
 extern "C" int gpg_solve_vec(gpg_handle_t h, int dtype, const void *L, const void *Linv, int64_t N, int64_t ld,
                              const void *y, void *vhat_out, void *alpha_out, void *scalars_out, void *stream) {
     GPG_REQUIRE(h && L && Linv && y && vhat_out && alpha_out, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(N > 0 && ld >= N, "bad size");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == GPG_F32)
@@ -476,6 +499,7 @@ extern "C" int gpg_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, co
                              void *alpha_out, void *scalars_out, int32_t *info, void *wsplit_out, float *scales_out,
                              void *stream) {
     GPG_REQUIRE(h && theta && X && y && L && Linv && vhat_out && alpha_out && info, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(N > 0 && ld >= N, "bad size");
     GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
     GPG_REQUIRE((wsplit_out == nullptr) == (scales_out == nullptr), "wsplit_out and scales_out go together");
@@ -641,6 +665,7 @@ extern "C" int gpg_predict(gpg_handle_t h, int dtype, int kernel_id, int d, cons
                            const void *Linv, int64_t ld, const void *alpha, const void *wsplit, const float *scales,
                            const void *Xs, int64_t M, void *mean_out, void *sd_out, void *stream) {
     GPG_REQUIRE(h && theta && X && Linv && alpha && mean_out && sd_out, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(M == 0 || Xs != nullptr, "Xs is NULL");
     GPG_REQUIRE(N > 0 && M >= 0 && ld >= N, "bad size");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -662,6 +687,7 @@ extern "C" int gpg_predict_grid(gpg_handle_t h, int dtype, int kernel_id, int d,
                                 const double *step_host, int64_t j0, int64_t M, void *mean_out, void *sd_out,
                                 void *stream) {
     GPG_REQUIRE(h && theta && X && Linv && alpha && mean_out && sd_out && dims_host && step_host, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(N > 0 && M >= 0 && ld >= N && j0 >= 0, "bad size");
     GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
     int64_t total = 1;
@@ -798,6 +824,7 @@ extern "C" int gpg_nll_grad(gpg_handle_t h, int dtype, int kernel_id, int d, con
                             const void *y, int64_t N, double jitter, void *nll_out, void *grad_out, int32_t *info,
                             void *stream) {
     GPG_REQUIRE(h && theta && X && y && nll_out && grad_out && info, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(N > 0, "bad size");
     GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -885,6 +912,7 @@ extern "C" int gpg_fit_adam(gpg_handle_t h, int dtype, int kernel_id, int d, int
                             int64_t N, double jitter, void *u, const double *bounds_host, int iters, double lr,
                             void *traj_out, void *theta_out, int32_t *info, void *stream) {
     GPG_REQUIRE(h && X && y && u && bounds_host && info, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(N > 0 && iters >= 0, "bad size");
     GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
     GPG_REQUIRE(n_ls == 1 || n_ls == d, "n_ls must be 1 or d");
@@ -947,6 +975,7 @@ extern "C" int gpg_acq_sweep(gpg_handle_t h, int dtype, int acq_id, const void *
                              int64_t M, double mu_best, double xi, double alpha, double beta, int k, void *topk_val,
                              int64_t *topk_idx, int32_t *count_out, void *acq_out, void *stream) {
     GPG_REQUIRE(h && mean && sd && topk_val && topk_idx && count_out, "NULL argument");
+    DeviceGuard device_guard(h->device);
     GPG_REQUIRE(M > 0, "M must be positive");
     GPG_REQUIRE(k >= 1 && k <= 1024, "k must be in 1..1024");
     GPG_REQUIRE(acq_id >= 0 && acq_id <= 2, "unknown acquisition id");
