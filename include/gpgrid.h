@@ -39,28 +39,28 @@ enum { GPG_F32 = 0, GPG_F64 = 1 };
 enum { GPG_RBF = 0, GPG_MATERN52 = 1, GPG_RATQUAD = 2 };
 /* gpim/gpbayes/acqfunc.py:11-92 */
 enum { GPG_ACQ_CB = 0, GPG_ACQ_EI = 1, GPG_ACQ_POI = 2 };
-/* gpg_set_option keys */
+/* gpg_set_option keys.  Every default is the fastest correct setting; the alternatives exist for A/B measurements. */
 enum {
-    GPG_OPT_GEMM_PATH = 1,      /* 0 auto (tcgen05 for f32 when large enough), 1 SIMT only, 2 force tcgen05 */
-    GPG_OPT_PREDICT_CHUNK = 2,  /* test points per internal tile of gpg_predict (0 = auto) */
-    GPG_OPT_STAGE_TIMING = 3,   /* != 0: bracket every stage with CUDA events, read by gpg_stage_times */
-    GPG_OPT_FIT_GRAPH = 7,      /* gpg_fit_adam on small problems (SIMT path): replay one captured iteration as a CUDA
-                                   graph (default 1) */
-    GPG_OPT_PANEL_MODE = 8,     /* blocked Cholesky panel: 0 forward substitution against the diagonal factor, 1 (default)
-                                   tcgen05 GEMM through the block inverse, 2 SIMT GEMM through the block inverse */
-    GPG_OPT_OUTER_PANEL = 9,    /* blocked Cholesky: width of the outer panel (multiple of 128; default 512: wider is a few per cent faster at N > 15 000
-                                   but doubles the TMEM accumulation bias of the update) */
+    GPG_OPT_GEMM_PATH = 1,        /* 0 auto (tcgen05 for f32 when N >= 1024), 1 SIMT only, 2 force tcgen05 */
+    GPG_OPT_PREDICT_CHUNK = 2,    /* test points per internal tile of gpg_predict (0 = auto: 16384) */
+    GPG_OPT_STAGE_TIMING = 3,     /* != 0: bracket every stage with CUDA events, read by gpg_stage_times */
+    GPG_OPT_PANEL_REFINE = 4,     /* recursive factorisation: refine every panel solve against L11 (default 1) */
+    GPG_OPT_SYRK_CHUNK = 5,       /* recursive factorisation: longest K accumulated in TMEM before an fp32 round-to-nearest
+                                     add (multiple of 64; 0 = unlimited, the default) */
+    GPG_OPT_FACTOR_ALGO = 6,      /* f32 tensor-core factorisation: 0 (default) two-level blocked Cholesky followed by the
+                                     batched triangular inverse; 1 recursive Cholesky + inverse */
+    GPG_OPT_FIT_GRAPH = 7,        /* gpg_fit_adam on small problems (SIMT path): replay one captured iteration as a CUDA
+                                     graph (default 1) */
+    GPG_OPT_PANEL_MODE = 8,       /* blocked Cholesky panel: 0 forward substitution against the diagonal factor, 1 (default)
+                                     tcgen05 GEMM through the block inverse, 2 SIMT GEMM through the block inverse */
+    GPG_OPT_OUTER_PANEL = 9,      /* blocked Cholesky: width of the outer panel (multiple of 128; default 512 -- wider is a
+                                     few per cent faster at N > 15 000 but doubles the TMEM accumulation bias of the update) */
     GPG_OPT_COMPACT_SUPPORT = 10, /* gpg_predict, tcgen05 path (default 0 = dense): per 128-row tile of test points, restrict
-                                   the variance GEMM to the contiguous range of training rows whose covariance with the tile
-                                   exceeds 1e-14 x variance (what lies outside contributes below fp32 resolution).  Pays off
-                                   for lengthscales much shorter than the grid with row-major training rows */
-    GPG_OPT_INNER_LEFT = 11,    /* blocked Cholesky, update inside the outer panel: 1 (default) left-looking (next block column
-                                   only, all inner panels so far), 0 right-looking (all remaining columns, last panel) */
-    GPG_OPT_FACTOR_ALGO = 6,    /* f32 tensor-core factorisation: 0 (default) two-level blocked right-looking Cholesky
-                                   followed by the batched triangular inverse; 1 recursive Cholesky + inverse */
-    GPG_OPT_PANEL_REFINE = 4,   /* recursive algorithm: refine every panel solve against L11 (default 1) */
-    GPG_OPT_SYRK_CHUNK = 5      /* recursive algorithm: longest K accumulated in TMEM before an fp32
-                                   round-to-nearest add (multiple of 64; 0 = unlimited, the default) */
+                                     the variance GEMM to the contiguous range of training rows whose covariance with the
+                                     tile exceeds 1e-14 x variance (what lies outside contributes below fp32 resolution);
+                                     pays off for lengthscales much shorter than the grid with row-major training rows */
+    GPG_OPT_INNER_LEFT = 11       /* blocked Cholesky, update inside the outer panel: 1 (default) left-looking (next block
+                                     column only, all inner panels so far), 0 right-looking (all remaining columns) */
 };
 /* stages reported by gpg_stage_times */
 enum {
