@@ -181,7 +181,7 @@ def test_predict_3d_matern(eng):
     assert relinf(m.cpu(), ref_mean) < 1e-4 and relinf(s.cpu(), ref_sd) < 1e-3
 
 
-@pytest.mark.parametrize("n", [129, 257, 700, 1111, 2500])
+@pytest.mark.parametrize("n", [64, 128, 129, 257, 700, 1024, 1111, 2500])
 @pytest.mark.parametrize("algo", [0, 1, 2, 3])
 def test_factorize_tensor_core(eng, n, algo):
     """gpg_factorize on the forced tcgen05 path (algo 0: two-level blocked Cholesky + batched inverse, tcgen05
