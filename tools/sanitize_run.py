@@ -20,6 +20,9 @@ for dtype, n, d in ((torch.float32, 1111, 2), (torch.float32, 300, 3), (torch.fl
         Xs = torch.tensor(rng.rand(1003, d) * 30.0, dtype=dtype).cuda()
         Xs[5, 0] = float("nan")
         m, s = eng.predict(kid, th, X, fac, Xs)
+        eng.set_option(10, 1)                    # GPG_OPT_COMPACT_SUPPORT
+        eng.predict(kid, th, X, fac, Xs)
+        eng.set_option(10, 0)
         eng.predict_grid(kid, th, X, fac, [31] * d, [1.0] * d, 7, 500)
         eng.nll_grad(kid, th, X, y, 1e-5)
     u = torch.zeros(3 + d, dtype=dtype, device="cuda")
