@@ -8,7 +8,7 @@ only; /root/reference does not exist on the GPU box, which is why the outputs ar
   notebook_kat_ei.json      <- "Final parameter values" lines stored in the output of
                                examples/notebooks/GP_based_exploration_exploitation.ipynb cell 13
                                (boptimizer, EI, np.random.seed(42) seeds, CPU fp64)
-  oracle_*.npz              <- outputs of oracle/gp_oracle.py on seeded inputs (see make_oracle_vectors)
+  oracle_*.npz              <- outputs of oracle/gp_oracle.py on seeded inputs (make_oracle_vectors.py, same directory)
 """
 import hashlib
 import json
@@ -49,6 +49,6 @@ if __name__ == "__main__":
     print(copy_reference_goldens())
     print("notebook KAT trainings:", notebook_kat())
     if "--oracle" in sys.argv:
-        sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-        from tests.golden.make_oracle_vectors import main
+        sys.path.insert(0, HERE)
+        from make_oracle_vectors import main
         main()

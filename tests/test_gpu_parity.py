@@ -298,6 +298,42 @@ def test_predict_compact_support_option_is_exact(eng, kernel, ls):
     assert relinf(s2[ok[:1000]].cpu(), s0[:1000][ok[:1000]].cpu()) < 2e-6
 
 
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("case", ["predict2d", "predict3d"])
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_predict_matches_committed_golden_vectors(eng, kernel, case, precision, golden_dir):
+    """tests/golden/oracle_predict{2d,3d}_*.npz (generated by make_oracle_vectors.py, frozen in the repository):
+    the CUDA path against fixtures, with no oracle in the loop."""
+    import os
+    from gpim_b200._lib import KERNEL_IDS
+    g = np.load(os.path.join(golden_dir, f"oracle_{case}_{kernel}.npz"))
+    v, noise, mix, jitter = (float(t) for t in g["theta"])
+    dtype = torch.float64 if precision == "double" else torch.float32
+    th = torch.tensor([v, noise, mix, *g["lengthscale"]], dtype=dtype).cuda()
+    Xd, yd = torch.tensor(g["X"], dtype=dtype).cuda(), torch.tensor(g["y"], dtype=dtype).cuda()
+    fac = eng.factorize(KERNEL_IDS[kernel], th, Xd, yd, jitter)
+    assert int(fac["info"].item()) == 0
+    mean, sd = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, torch.tensor(g["Xs"], dtype=dtype).cuda())
+    tol_m, tol_s = (1e-9, 1e-9) if precision == "double" else (1e-4, 1e-3)
+    assert relinf(mean.cpu(), g["mean"]) < tol_m and relinf(sd.cpu(), g["sd"]) < tol_s
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_run_matches_committed_training_vectors(kernel, golden_dir):
+    """tests/golden/oracle_train_*.npz: gpim.reconstructor(...).run() in fp64 -- 20 Adam steps from the seeded
+    prior draw, then the dense predict -- against the frozen trajectory and reconstruction."""
+    import os
+    import gpim_b200 as gpim
+    g = np.load(os.path.join(golden_dir, f"oracle_train_{kernel}.npz"))
+    R = g["R"]
+    mean, sd, hp = gpim.reconstructor(gpim.utils.get_sparse_grid(R), R, gpim.utils.get_full_grid(R), kernel=kernel,
+                                      learning_rate=0.1, iterations=20, verbose=0, seed=2).run()
+    np.testing.assert_allclose(np.array(hp["variance"]), g["variance"], rtol=1e-7)
+    np.testing.assert_allclose(np.array(hp["noise"]), g["noise"], rtol=1e-7)
+    np.testing.assert_allclose(np.array(hp["lengthscale"]), g["lengthscale"], rtol=1e-7)
+    assert relinf(mean, g["mean"]) < 1e-7 and relinf(sd, g["sd"]) < 1e-7
+
+
 def test_full_size_properties_c2(eng):
     """BASELINE.json configs[1] at FULL size (256 x 256 spiral, N = 7688; the oracle would need minutes
     here): size-independent properties of the tcgen05 path, and agreement with the engine's own fp64 path."""

@@ -100,3 +100,32 @@ def test_oracle_unknown_kernel_raises():
     _, Zs = _boptim_setup()
     with pytest.raises(KeyError):
         O.OracleGP(O.sparse_grid(Zs), Zs, kernel="Periodic")
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle-generated fixtures (tests/golden/make_oracle_vectors.py): the oracle must keep reproducing them
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kernel", ["RBF", "Matern52", "RationalQuadratic"])
+@pytest.mark.parametrize("case", ["predict2d", "predict3d"])
+def test_oracle_reproduces_its_committed_predict_vectors(kernel, case, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, f"oracle_{case}_{kernel}.npz"))
+    v, noise, mix, jitter = g["theta"]
+    mean, sd, _ = O.predict_fixed_theta(kernel, g["X"], g["y"], g["Xs"], float(v), g["lengthscale"], float(noise),
+                                        jitter=float(jitter), scale_mixture=float(mix))
+    np.testing.assert_allclose(mean, g["mean"], rtol=0, atol=1e-10 * np.abs(g["mean"]).max())
+    np.testing.assert_allclose(sd, g["sd"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "Matern52", "RationalQuadratic"])
+def test_oracle_reproduces_its_committed_training_vectors(kernel, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, f"oracle_train_{kernel}.npz"))
+    R = g["R"]
+    ora = O.OracleGP(O.sparse_grid(R), R, O.full_grid(R), kernel=kernel, learning_rate=0.1, iterations=20, seed=2)
+    mean, sd, hp = ora.run()
+    np.testing.assert_allclose(np.array(hp["variance"]), g["variance"], rtol=1e-8)
+    np.testing.assert_allclose(np.array(hp["noise"]), g["noise"], rtol=1e-8)
+    np.testing.assert_allclose(np.array(hp["lengthscale"]), g["lengthscale"], rtol=1e-8)
+    np.testing.assert_allclose(mean, g["mean"], rtol=0, atol=1e-8 * np.abs(g["mean"]).max())
+    np.testing.assert_allclose(sd, g["sd"], rtol=1e-8)
