@@ -47,6 +47,14 @@ SIGNATURES = {
                       _vp, _vp, _vp, _vp], C.c_int),
     "gpg_acq_sweep": ([_vp, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp],
                       C.c_int),
+    "gpg_sparse_loss_grad": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _f64, _vp, _vp, _vp, _vp, _vp],
+                             C.c_int),
+    "gpg_sparse_fit_adam": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _f64, _vp, C.POINTER(_f64), _i32,
+                             _f64, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "gpg_sparse_factorize": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _f64, _vp, _vp, _i64, _vp, _vp,
+                              _vp], C.c_int),
+    "gpg_sparse_predict": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp],
+                           C.c_int),
 }
 
 _LIB = None
@@ -307,6 +315,63 @@ class Engine:
                                            float(mu_best), float(xi), float(alpha), float(beta), k, _ptr(vals),
                                            _ptr(idx), _ptr(count), _ptr(acq), self._stream()))
         return vals, idx, count, acq
+
+    # -- inducing-point GP (sparse=True) ----------------------------------------------------
+    def sparse_loss_grad(self, kernel_id, theta, X, y, Xu, jitter):
+        """-> (loss [1], grad_theta [3 + d], grad_Xu [m, d], info)."""
+        theta, X, y, Xu = _c(theta), _c(X), _c(y), _c(Xu)
+        N, d = X.shape
+        m = Xu.shape[0]
+        loss = self.empty(1, dtype=X.dtype)
+        grad = self.empty(3 + d, dtype=X.dtype)
+        gxu = self.empty(m, d, dtype=X.dtype)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._check(self.lib.gpg_sparse_loss_grad(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), _ptr(y), N,
+                                                  _ptr(Xu), m, float(jitter), _ptr(loss), _ptr(grad), _ptr(gxu),
+                                                  _ptr(info), self._stream()))
+        return loss, grad, gxu, info
+
+    def sparse_fit_adam(self, kernel_id, X, y, Xu, jitter, u, bounds, n_ls, iters, lr, record_xu=True):
+        """u and Xu (device, in/out).  Returns (traj [iters, 4+d], xu_traj [iters, m, d] | None, theta [3+d], info)."""
+        X, y = _c(X), _c(y)
+        assert u.is_contiguous() and Xu.is_contiguous()
+        N, d = X.shape
+        m = Xu.shape[0]
+        traj = self.empty(max(iters, 1), 4 + d, dtype=X.dtype)
+        xu_traj = self.empty(max(iters, 1), m, d, dtype=X.dtype) if record_xu else None
+        theta = self.empty(3 + d, dtype=X.dtype)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        b = (_f64 * len(bounds))(*[float(v) for v in bounds])
+        self._check(self.lib.gpg_sparse_fit_adam(self.h, self._dt(X), kernel_id, d, n_ls, _ptr(X), _ptr(y), N, _ptr(Xu),
+                                                 m, float(jitter), _ptr(u), b, int(iters), float(lr), _ptr(traj),
+                                                 _ptr(xu_traj), _ptr(theta), _ptr(info), self._stream()))
+        return traj[:iters], (xu_traj[:iters] if record_xu else None), theta, info
+
+    def sparse_factorize(self, kernel_id, theta, X, y, Xu, jitter):
+        """-> dict(Ui, Pm, w, info, ld): the cache gpg_sparse_predict consumes."""
+        theta, X, y, Xu = _c(theta), _c(X), _c(y), _c(Xu)
+        N, d = X.shape
+        m = Xu.shape[0]
+        ld = (m + 63) // 64 * 64
+        fac = {"Ui": self.empty(m, ld, dtype=X.dtype), "Pm": self.empty(m, ld, dtype=X.dtype),
+               "w": self.empty(m, dtype=X.dtype), "info": torch.zeros(1, dtype=torch.int32, device=self.device), "ld": ld}
+        self._check(self.lib.gpg_sparse_factorize(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), _ptr(y), N,
+                                                  _ptr(Xu), m, float(jitter), _ptr(fac["Ui"]), _ptr(fac["Pm"]), ld,
+                                                  _ptr(fac["w"]), _ptr(fac["info"]), self._stream()))
+        return fac
+
+    def sparse_predict(self, kernel_id, theta, Xu, fac, Xs):
+        theta, Xu, Xs = _c(theta), _c(Xu), _c(Xs)
+        m, d = Xu.shape
+        M = Xs.shape[0]
+        mean = self.empty(M, dtype=Xu.dtype)
+        sd = self.empty(M, dtype=Xu.dtype)
+        if M == 0:
+            return mean, sd
+        self._check(self.lib.gpg_sparse_predict(self.h, self._dt(Xu), kernel_id, d, _ptr(theta), _ptr(Xu), m,
+                                                _ptr(fac["Ui"]), _ptr(fac["Pm"]), fac["ld"], _ptr(fac["w"]), _ptr(Xs), M,
+                                                _ptr(mean), _ptr(sd), self._stream()))
+        return mean, sd
 
 
 _ENGINES = {}

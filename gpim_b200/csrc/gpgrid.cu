@@ -13,6 +13,7 @@
 #include "factor_tc.cuh"
 #include "train.cuh"
 #include "acq.cuh"
+#include "sparse.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // errors, handle, workspace
@@ -986,6 +987,367 @@ extern "C" int gpg_acq_sweep(gpg_handle_t h, int dtype, int acq_id, const void *
     if (dtype == GPG_F64)
         return acq_entry<double>(h, acq_id, (const double *)mean, (const double *)sd, (const double *)mask, M, mu_best, xi,
                                  alpha, beta, k, (double *)topk_val, topk_idx, count_out, (double *)acq_out, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inducing-point GP (VFE): reconstructor(sparse=True), gpr.py:145-155 over pyro SparseGPRegression
+// (sparse.cuh has the algebra).  m x m factorisations and m x N products on the SIMT GEMM.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct SgpBufs {
+    int64_t m = 0, N = 0, ldm = 0, ldn = 0;
+    T *Luu, *Ui, *tmp, *Kuf, *B, *S, *Ap, *LA, *LAi, *Ainv, *Phi, *H, *T1, *Guu, *T2;   // Kuf doubles as dF/dKuf
+    T *beta, *c0, *a0, *a, *w, *rho, *dinv, *theta0, *gxu, *grad, *loss, *theta, *m1, *m2;
+    double *sc, *partA, *partB;
+    int nb;
+    FitState *st;
+};
+
+template <typename T> static size_t sgp_ws_bytes(int64_t m, int64_t N, int d) {
+    constexpr int NB = GemmCfg<T>::BN;
+    const int64_t ldm = gpg_align_up((size_t)m, 64), ldn = gpg_align_up((size_t)N, 64);
+    const size_t mm = (size_t)m * ldm * sizeof(T), mn = (size_t)m * ldn * sizeof(T), mv = (size_t)m * sizeof(T);
+    const size_t nb = (size_t)((m + 7) / 8);
+    return bump_size({mm, mm, mm, mn, mn, mm, mm, mm, mm, mm, mm, mm, mm, mm, mm,
+                      mv, mv, mv, mv, mv, (size_t)N * sizeof(T), NB * NB * sizeof(T), GPG_MAX_P * sizeof(T),
+                      mv * d, GPG_MAX_P * sizeof(T), sizeof(T), GPG_MAX_P * sizeof(T), mv * d, mv * d,
+                      SGP_SC_COUNT * sizeof(double), nb * GPG_MAX_P * sizeof(double), nb * GPG_MAX_P * sizeof(double),
+                      sizeof(FitState)});
+}
+
+template <typename T> static SgpBufs<T> sgp_carve(void *ws, int64_t m, int64_t N, int d) {
+    constexpr int NB = GemmCfg<T>::BN;
+    Bump b(ws);
+    SgpBufs<T> s;
+    s.m = m; s.N = N;
+    s.ldm = gpg_align_up((size_t)m, 64); s.ldn = gpg_align_up((size_t)N, 64);
+    const size_t mm = (size_t)m * s.ldm, mn = (size_t)m * s.ldn;
+    s.Luu = b.take<T>(mm); s.Ui = b.take<T>(mm); s.tmp = b.take<T>(mm);
+    s.Kuf = b.take<T>(mn); s.B = b.take<T>(mn);
+    s.S = b.take<T>(mm); s.Ap = b.take<T>(mm); s.LA = b.take<T>(mm); s.LAi = b.take<T>(mm); s.Ainv = b.take<T>(mm);
+    s.Phi = b.take<T>(mm); s.H = b.take<T>(mm); s.T1 = b.take<T>(mm); s.Guu = b.take<T>(mm); s.T2 = b.take<T>(mm);
+    s.beta = b.take<T>(m); s.c0 = b.take<T>(m); s.a0 = b.take<T>(m); s.a = b.take<T>(m); s.w = b.take<T>(m);
+    s.rho = b.take<T>(N);
+    s.dinv = b.take<T>(NB * NB);
+    s.theta0 = b.take<T>(GPG_MAX_P);
+    s.gxu = b.take<T>((size_t)m * d);
+    s.grad = b.take<T>(GPG_MAX_P); s.loss = b.take<T>(1); s.theta = b.take<T>(GPG_MAX_P);
+    s.m1 = b.take<T>((size_t)m * d); s.m2 = b.take<T>((size_t)m * d);
+    s.sc = b.take<double>(SGP_SC_COUNT);
+    s.nb = (int)((m + 7) / 8);
+    s.partA = b.take<double>((size_t)s.nb * GPG_MAX_P);
+    s.partB = b.take<double>((size_t)s.nb * GPG_MAX_P);
+    s.st = b.take<FitState>(1);
+    return s;
+}
+
+// Luu, Ui, B, S, A', LA, LAi, beta, c0, a0, a, w for the theta stored on the device.  info keeps the first failing pivot of
+// either factorisation (the caller resets it).
+template <typename T>
+static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
+                            const T *Xu, int64_t m, double jitter, const SgpBufs<T> &b, int32_t *info, cudaStream_t s) {
+    const int64_t ldm = b.ldm, ldn = b.ldn;
+    sgp_theta0_kernel<T><<<1, 32, 0, s>>>(theta, 3 + d, b.theta0);
+    GPG_LAUNCH_CHECK(h);
+    { StageTimer st(h, GPG_ST_KMAT, s);
+      GPG_TRY(kmat_launch<T>(h, kernel_id, d, b.theta0, Xu, m, nullptr, m, jitter, 0, b.Luu, ldm, s));
+      GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, Xu, m, X, N, 0.0, 0, b.Kuf, ldn, s)); }
+    { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.Luu, m, ldm, info, 0, b.dinv, s)); }
+    { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.Luu, m, ldm, b.Ui, ldm, b.tmp, s)); }
+    {
+        GemmArgs<T> g;               // B = Ui Kuf  (Ui lower triangular: k <= i)
+        g.A = b.Ui; g.lda = ldm; g.a_kmajor = 1;
+        g.B = b.Kuf; g.ldb = ldn; g.b_kmajor = 0;
+        g.C = b.B; g.ldc = ldn;
+        g.M = (int)m; g.N = (int)N; g.K = (int)m;
+        g.ke_mode = GEMM_KE_M;
+        GPG_TRY(gemm_simt<T>(h, g, s));
+    }
+    {
+        GemmArgs<T> g;               // S = B B^T, lower tiles
+        g.A = b.B; g.lda = ldn; g.a_kmajor = 1;
+        g.B = b.B; g.ldb = ldn; g.b_kmajor = 1;
+        g.C = b.S; g.ldc = ldm;
+        g.M = (int)m; g.N = (int)m; g.K = (int)N;
+        g.tile_mode = GEMM_TILES_LOWER;
+        GPG_TRY(gemm_simt<T>(h, g, s));
+    }
+    const dim3 gmm((unsigned)((m + 255) / 256), (unsigned)m);
+    sgp_form_A_kernel<T><<<gmm, 256, 0, s>>>(b.S, ldm, m, theta, b.Ap, b.LA);
+    GPG_LAUNCH_CHECK(h);
+    { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.LA, m, ldm, info, 0, b.dinv, s)); }
+    { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.LA, m, ldm, b.LAi, ldm, b.tmp, s)); }
+    StageTimer st(h, GPG_ST_SOLVE, s);
+    const unsigned gm8 = (unsigned)((m + 7) / 8), gm256 = (unsigned)((m + 255) / 256);
+    gemv_rect_kernel<T><<<gm8, 256, 0, s>>>(b.B, ldn, m, N, y, b.beta);                              // beta = B y
+    GPG_LAUNCH_CHECK(h);
+    gemv_tri_kernel<T, false><<<gm8, 256, 0, s>>>(b.LAi, ldm, m, b.beta, nullptr, T(1), T(0), b.c0);  // c0 = LA^-1 beta
+    GPG_LAUNCH_CHECK(h);
+    GPG_TRY(gemv_tri_T<T>(h, b.LAi, ldm, m, b.c0, nullptr, T(1), T(0), b.a0, s));                     // a0 = A'^-1 beta
+    sgp_div_noise_kernel<T><<<gm256, 256, 0, s>>>(b.a0, m, theta, b.a);                              // a = a0 / s2
+    GPG_LAUNCH_CHECK(h);
+    GPG_TRY(gemv_tri_T<T>(h, b.Ui, ldm, m, b.a, nullptr, T(1), T(0), b.w, s));                        // w = Ui^T a
+    return GPG_OK;
+}
+
+// loss and gradient w.r.t. the constrained theta (b.grad layout of theta) and the inducing inputs (gxu, m x d)
+template <typename T>
+static int sgp_loss_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
+                              const T *Xu, int64_t m, double jitter, const SgpBufs<T> &b, T *loss_out, T *grad_out,
+                              T *gxu_out, int32_t *info, cudaStream_t s) {
+    GPG_TRY(sgp_lowrank_core<T>(h, kernel_id, d, theta, X, y, N, Xu, m, jitter, b, info, s));
+    StageTimer st(h, GPG_ST_GRAD, s);
+    const int64_t ldm = b.ldm, ldn = b.ldn;
+    auto mm_gemm = [&](const T *A, int a_km, const T *Bm, int b_km, T *C, T alpha, int kb_mode, int tile_mode) -> int {
+        GemmArgs<T> g;
+        g.A = A; g.lda = ldm; g.a_kmajor = a_km;
+        g.B = Bm; g.ldb = ldm; g.b_kmajor = b_km;
+        g.C = C; g.ldc = ldm;
+        g.M = (int)m; g.N = (int)m; g.K = (int)m;
+        g.alpha = alpha; g.kb_mode = kb_mode; g.tile_mode = tile_mode;
+        return gemm_simt<T>(h, g, s);
+    };
+    GPG_TRY(mm_gemm(b.LAi, 0, b.LAi, 0, b.Ainv, T(1), GEMM_KB_MAXMN, GEMM_TILES_LOWER));     // A'^-1 = LAi^T LAi (lower)
+    sgp_scalars_kernel<T><<<1, 1024, 0, s>>>(y, N, b.beta, b.a0, b.c0, b.S, b.Ainv, b.LA, ldm, m, b.sc);
+    GPG_LAUNCH_CHECK(h);
+    gemvT_rect_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(b.B, ldn, m, N, b.a, y, T(-1), T(1), b.rho);   // rho = y - B^T a
+    GPG_LAUNCH_CHECK(h);
+    const dim3 gmm((unsigned)((m + 255) / 256), (unsigned)m);
+    sgp_form_phi_kernel<T><<<gmm, 256, 0, s>>>(b.Ainv, b.Ap, b.a, ldm, m, b.Phi, b.H);
+    GPG_LAUNCH_CHECK(h);
+    GPG_TRY(mm_gemm(b.Phi, 1, b.Ui, 0, b.T1, T(1), GEMM_KB_NONE, GEMM_TILES_ALL));           // T1 = Phi Ui
+    GPG_TRY(mm_gemm(b.Ui, 0, b.T1, 0, b.Guu, T(-0.5), GEMM_KB_NONE, GEMM_TILES_ALL));        // dF/dKuu = -1/2 Ui^T T1
+    GPG_TRY(mm_gemm(b.Ui, 0, b.H, 0, b.T2, T(1), GEMM_KB_NONE, GEMM_TILES_ALL));             // T2 = Ui^T H
+    {
+        GemmArgs<T> g;               // s2 dF/dKuf + w rho^T = T2 B   (into the Kuf buffer, which is dead by now)
+        g.A = b.T2; g.lda = ldm; g.a_kmajor = 1;
+        g.B = b.B; g.ldb = ldn; g.b_kmajor = 0;
+        g.C = b.Kuf; g.ldc = ldn;
+        g.M = (int)m; g.N = (int)N; g.K = (int)m;
+        GPG_TRY(gemm_simt<T>(h, g, s));
+    }
+    T *gxu = gxu_out ? gxu_out : b.gxu;
+    GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, {
+        sgp_kgrad_kernel<T, KID, D><<<b.nb, 256, 0, s>>>(theta, Xu, m, Xu, m, b.Guu, ldm, nullptr, nullptr, 1.0, 0, 2.0, 0,
+                                                        b.partA, gxu);
+        sgp_kgrad_kernel<T, KID, D><<<b.nb, 256, 0, s>>>(theta, Xu, m, X, N, b.Kuf, ldn, b.w, b.rho, 1.0, 1, 1.0, 1,
+                                                        b.partB, gxu);
+    }));
+    GPG_LAUNCH_CHECK(h);
+    h->launches++;
+    sgp_finish_kernel<T><<<1, 256, 0, s>>>(b.partA, b.nb, b.partB, b.nb, 3 + d, b.sc, theta, N, m, grad_out, loss_out);
+    GPG_LAUNCH_CHECK(h);
+    return GPG_OK;
+}
+
+#define SGP_COMMON_REQUIRE()                                                                         \
+    GPG_REQUIRE(N > 0 && m > 0 && m <= N, "need 0 < m <= N");                                        \
+    GPG_REQUIRE(m < 65536, "at most 65535 inducing points");                                         \
+    GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");                                          \
+    GPG_REQUIRE(kernel_id >= 0 && kernel_id <= 2, "unknown kernel id")
+
+template <typename T>
+static int sgp_loss_grad_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
+                               const T *Xu, int64_t m, double jitter, T *loss_out, T *grad_out, T *gxu_out, int32_t *info,
+                               cudaStream_t s) {
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, sgp_ws_bytes<T>(m, N, d), &ws));
+    SgpBufs<T> b = sgp_carve<T>(ws, m, N, d);
+    GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
+    return sgp_loss_grad_core<T>(h, kernel_id, d, theta, X, y, N, Xu, m, jitter, b, loss_out, grad_out, gxu_out, info, s);
+}
+
+extern "C" int gpg_sparse_loss_grad(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X,
+                                    const void *y, int64_t N, const void *Xu, int64_t m, double jitter, void *loss_out,
+                                    void *grad_theta_out, void *grad_xu_out, int32_t *info, void *stream) {
+    GPG_REQUIRE(h && theta && X && y && Xu && loss_out && grad_theta_out && grad_xu_out && info, "NULL argument");
+    DeviceGuard device_guard(h->device);
+    SGP_COMMON_REQUIRE();
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return sgp_loss_grad_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, (const float *)y, N,
+                                          (const float *)Xu, m, jitter, (float *)loss_out, (float *)grad_theta_out,
+                                          (float *)grad_xu_out, info, s);
+    if (dtype == GPG_F64)
+        return sgp_loss_grad_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, (const double *)y, N,
+                                           (const double *)Xu, m, jitter, (double *)loss_out, (double *)grad_theta_out,
+                                           (double *)grad_xu_out, info, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+template <typename T>
+static int sgp_fit_entry(gpg_handle_s *h, int kernel_id, int d, int n_ls, const T *X, const T *y, int64_t N, T *Xu,
+                         int64_t m, double jitter, T *u, const double *bounds, int iters, double lr, T *traj, T *xu_traj,
+                         T *theta_out, int32_t *info, cudaStream_t s) {
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, sgp_ws_bytes<T>(m, N, d), &ws));
+    SgpBufs<T> b = sgp_carve<T>(ws, m, N, d);
+    FitCfg c;
+    memset(&c, 0, sizeof(c));
+    c.d = d; c.n_ls = n_ls; c.is_rq = (kernel_id == GPG_RATQUAD);
+    c.var_lo = bounds[0]; c.var_hi = bounds[1];
+    for (int k = 0; k < n_ls; ++k) { c.ls_lo[k] = bounds[2 + k]; c.ls_hi[k] = bounds[2 + n_ls + k]; }
+    c.lr = lr; c.beta1 = 0.9; c.beta2 = 0.999; c.eps = 1e-8;
+    const int64_t nxu = m * d;
+    adam_step_kernel<T><<<1, 32, 0, s>>>(0, c, u, b.st, nullptr, nullptr, b.theta, nullptr);      // fresh Adam state
+    GPG_LAUNCH_CHECK(h);
+    GPG_CUDA_CHECK(cudaMemsetAsync(b.m1, 0, nxu * sizeof(T), s));
+    GPG_CUDA_CHECK(cudaMemsetAsync(b.m2, 0, nxu * sizeof(T), s));
+    GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
+    for (int it = 0; it < iters; ++it) {
+        GPG_TRY(sgp_loss_grad_core<T>(h, kernel_id, d, b.theta, X, y, N, Xu, m, jitter, b, b.loss, b.grad, nullptr, info, s));
+        adam_step_kernel<T><<<1, 32, 0, s>>>(1, c, u, b.st, (const T *)b.grad, (const T *)b.loss, b.theta, traj);
+        GPG_LAUNCH_CHECK(h);
+        sgp_adam_xu_kernel<T><<<(unsigned)((nxu + 255) / 256), 256, 0, s>>>(c, b.st, nxu, Xu, b.gxu, b.m1, b.m2, xu_traj);
+        GPG_LAUNCH_CHECK(h);
+    }
+    if (theta_out) GPG_CUDA_CHECK(cudaMemcpyAsync(theta_out, b.theta, (3 + d) * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    return GPG_OK;
+}
+
+extern "C" int gpg_sparse_fit_adam(gpg_handle_t h, int dtype, int kernel_id, int d, int n_ls, const void *X,
+                                   const void *y, int64_t N, void *Xu, int64_t m, double jitter, void *u,
+                                   const double *bounds_host, int iters, double lr, void *traj_out, void *xu_traj_out,
+                                   void *theta_out, int32_t *info, void *stream) {
+    GPG_REQUIRE(h && X && y && Xu && u && bounds_host && info, "NULL argument");
+    DeviceGuard device_guard(h->device);
+    SGP_COMMON_REQUIRE();
+    GPG_REQUIRE(iters >= 0, "iters must not be negative");
+    GPG_REQUIRE(iters == 0 || traj_out != nullptr, "traj_out is NULL");
+    GPG_REQUIRE(n_ls == 1 || n_ls == d, "n_ls must be 1 or d");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return sgp_fit_entry<float>(h, kernel_id, d, n_ls, (const float *)X, (const float *)y, N, (float *)Xu, m, jitter,
+                                    (float *)u, bounds_host, iters, lr, (float *)traj_out, (float *)xu_traj_out,
+                                    (float *)theta_out, info, s);
+    if (dtype == GPG_F64)
+        return sgp_fit_entry<double>(h, kernel_id, d, n_ls, (const double *)X, (const double *)y, N, (double *)Xu, m,
+                                     jitter, (double *)u, bounds_host, iters, lr, (double *)traj_out,
+                                     (double *)xu_traj_out, (double *)theta_out, info, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+// Factor cache of the inducing-point posterior: Ui = Luu^-1, Pm = LA^-1 Luu^-1 (both m x m lower, leading dimension ld),
+// w = Luu^-T A'^-1 B y / s2, so that mean = k(x*, Xu) w and var = v + noise - |Ui k*|^2 + |Pm k*|^2.
+template <typename T>
+static int sgp_factorize_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
+                               const T *Xu, int64_t m, double jitter, T *Ui_out, T *P_out, int64_t ld, T *w_out,
+                               int32_t *info, cudaStream_t s) {
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, sgp_ws_bytes<T>(m, N, d), &ws));
+    SgpBufs<T> b = sgp_carve<T>(ws, m, N, d);
+    GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
+    GPG_TRY(sgp_lowrank_core<T>(h, kernel_id, d, theta, X, y, N, Xu, m, jitter, b, info, s));
+    GemmArgs<T> g;                   // Pm = LAi Ui (lower x lower)
+    g.A = b.LAi; g.lda = b.ldm; g.a_kmajor = 1;
+    g.B = b.Ui; g.ldb = b.ldm; g.b_kmajor = 0;
+    g.C = P_out; g.ldc = ld;
+    g.M = (int)m; g.N = (int)m; g.K = (int)m;
+    g.ke_mode = GEMM_KE_M;
+    GPG_TRY(gemm_simt<T>(h, g, s));
+    GPG_CUDA_CHECK(cudaMemcpy2DAsync(Ui_out, ld * sizeof(T), b.Ui, b.ldm * sizeof(T), m * sizeof(T), m,
+                                     cudaMemcpyDeviceToDevice, s));
+    GPG_CUDA_CHECK(cudaMemcpyAsync(w_out, b.w, m * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    return GPG_OK;
+}
+
+extern "C" int gpg_sparse_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X,
+                                    const void *y, int64_t N, const void *Xu, int64_t m, double jitter, void *Ui_out,
+                                    void *P_out, int64_t ld, void *w_out, int32_t *info, void *stream) {
+    GPG_REQUIRE(h && theta && X && y && Xu && Ui_out && P_out && w_out && info, "NULL argument");
+    DeviceGuard device_guard(h->device);
+    SGP_COMMON_REQUIRE();
+    GPG_REQUIRE(ld >= m, "ld smaller than m");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return sgp_factorize_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, (const float *)y, N,
+                                          (const float *)Xu, m, jitter, (float *)Ui_out, (float *)P_out, ld,
+                                          (float *)w_out, info, s);
+    if (dtype == GPG_F64)
+        return sgp_factorize_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, (const double *)y, N,
+                                           (const double *)Xu, m, jitter, (double *)Ui_out, (double *)P_out, ld,
+                                           (double *)w_out, info, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+template <typename T, int D>
+static int sgp_predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T *Xu, int64_t m, const T *Ui,
+                            const T *Pm, int64_t ld, const T *w, const T *Xs, int64_t M, T *mean, T *sd, cudaStream_t s) {
+    using C = GemmCfg<T>;
+    const int64_t ldk = gpg_align_up((size_t)m, 64);
+    int64_t chunk = h->opt_predict_chunk > 0 ? h->opt_predict_chunk : 16384;
+    while (chunk > 512 && chunk * ldk * (int64_t)sizeof(T) > (int64_t)768 << 20) chunk /= 2;
+    chunk = std::min<int64_t>(chunk, gpg_align_up((size_t)M, 128));
+    const int tiles_m = (int)((m + C::BM - 1) / C::BM);
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)chunk * ldk * sizeof(T), (size_t)tiles_m * chunk * sizeof(T),
+                                         (size_t)tiles_m * chunk * sizeof(T)}), &ws));
+    Bump b(ws);
+    T *Ks = b.take<T>((size_t)chunk * ldk);
+    T *part1 = b.take<T>((size_t)tiles_m * chunk);
+    T *part2 = b.take<T>((size_t)tiles_m * chunk);
+    TestPoints<T, D> tp;
+    tp.j0 = 0;
+    for (int k = 0; k < GPG_MAX_D; ++k) { tp.dims[k] = 1; tp.step[k] = T(1); }
+    for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+        const int64_t mc = std::min<int64_t>(chunk, M - c0);
+        tp.Xs = Xs + c0 * D;
+        {
+            StageTimer st(h, GPG_ST_KCROSS, s);
+            GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<T, KID, D, false><<<(unsigned)((mc + 7) / 8), 256, 0, s>>>(
+                                            theta, Xu, m, tp, mc, w, Ks, ldk, nullptr, nullptr, 0, nullptr, mean + c0));
+            GPG_LAUNCH_CHECK(h);
+        }
+        {
+            StageTimer st(h, GPG_ST_PGEMM, s);
+            for (int pass = 0; pass < 2; ++pass) {      // colsum((Ui Ks^T)^2), colsum((Pm Ks^T)^2)
+                GemmArgs<T> g;
+                g.A = pass == 0 ? Ui : Pm; g.lda = ld; g.a_kmajor = 1;
+                g.B = Ks; g.ldb = ldk; g.b_kmajor = 1;
+                g.M = (int)m; g.N = (int)mc; g.K = (int)m;
+                g.ke_mode = GEMM_KE_M;
+                g.epi = GEMM_EPI_COLSUMSQ;
+                g.part = pass == 0 ? part1 : part2; g.ldpart = chunk;
+                GPG_TRY(gemm_simt<T>(h, g, s));
+            }
+        }
+        StageTimer st(h, GPG_ST_PFINAL, s);
+        sgp_predict_finalize_kernel<T, D><<<(unsigned)((mc + 255) / 256), 256, 0, s>>>(theta, part1, part2, tiles_m, chunk,
+                                                                                       tp, mc, sd + c0);
+        GPG_LAUNCH_CHECK(h);
+    }
+    return GPG_OK;
+}
+
+template <typename T>
+static int sgp_predict_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *Xu, int64_t m, const T *Ui,
+                             const T *Pm, int64_t ld, const T *w, const T *Xs, int64_t M, T *mean, T *sd, cudaStream_t s) {
+    if (M == 0) return GPG_OK;
+    GPG_DISPATCH_D(d, { return sgp_predict_core<T, D>(h, kernel_id, theta, Xu, m, Ui, Pm, ld, w, Xs, M, mean, sd, s); });
+    return GPG_OK;
+}
+
+extern "C" int gpg_sparse_predict(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *Xu,
+                                  int64_t m, const void *Ui, const void *Pm, int64_t ld, const void *w, const void *Xs,
+                                  int64_t M, void *mean_out, void *sd_out, void *stream) {
+    GPG_REQUIRE(h && theta && Xu && Ui && Pm && w && mean_out && sd_out, "NULL argument");
+    DeviceGuard device_guard(h->device);
+    GPG_REQUIRE(M == 0 || Xs != nullptr, "Xs is NULL");
+    GPG_REQUIRE(m > 0 && M >= 0 && ld >= m, "bad size");
+    GPG_REQUIRE(kernel_id >= 0 && kernel_id <= 2, "unknown kernel id");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return sgp_predict_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)Xu, m, (const float *)Ui,
+                                        (const float *)Pm, ld, (const float *)w, (const float *)Xs, M, (float *)mean_out,
+                                        (float *)sd_out, s);
+    if (dtype == GPG_F64)
+        return sgp_predict_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)Xu, m, (const double *)Ui,
+                                         (const double *)Pm, ld, (const double *)w, (const double *)Xs, M,
+                                         (double *)mean_out, (double *)sd_out, s);
     gpg_set_error("unknown dtype %d", dtype);
     return GPG_EINVAL;
 }

@@ -13,8 +13,9 @@ engine behind libgpgrid.so:
   grid (the reference refactorises on every call and materialises the N x M cross-kernel three
   times, gpr.py:248).
 
-``sparse=True`` (inducing points) is the first item of the "next" list and raises
-NotImplementedError for now.
+``sparse=True`` (gpr.py:145-155: pyro's SparseGPRegression, VFE) runs on :class:`SparseGPModel`:
+``gpg_sparse_fit_adam`` trains the hyper-parameters AND the inducing inputs on the device,
+``gpg_sparse_factorize`` + ``gpg_sparse_predict`` replace SparseGPRegression.forward.
 """
 import time
 import warnings
@@ -160,6 +161,68 @@ class ExactGPModel:
         return out
 
 
+class SparseGPModel(ExactGPModel):
+    """What ``reconstructor.model`` is for ``sparse=True``: the members of pyro's SparseGPRegression (default
+    approximation "VFE") the reference touches -- everything ExactGPModel has plus ``Xu`` (gpr.py:199)."""
+
+    def __init__(self, X, y, kernel, Xu, jitter=1e-6, engine=None):
+        super().__init__(X, y, kernel, jitter=jitter, engine=engine)
+        self._Xu = Xu.to(self.engine.device, kernel.dtype).contiguous().clone()
+        self.approx = "VFE"
+
+    @property
+    def Xu(self):
+        return self._Xu
+
+    @Xu.setter
+    def Xu(self, value):
+        self._Xu = value.to(self.engine.device, self.kernel.dtype).contiguous().clone()
+        self._factor = None
+
+    def parameters(self):
+        yield self._u
+        yield self._Xu
+
+    def fit(self, iterations, learning_rate, record_xu=True):
+        """As ExactGPModel.fit, on the VFE objective, with the inducing inputs trained alongside.  Returns
+        (trajectory [iterations, 4 + d], Xu after every step [iterations, m, d]) as CPU tensors."""
+        k = self.kernel
+        if self._X.shape[0] != self._y.shape[0]:
+            raise ValueError("X and y have different numbers of rows")
+        traj, xu_traj, theta, info = self.engine.sparse_fit_adam(
+            k.kernel_id, self._X, self._y, self._Xu, self.jitter, self._u, k.bounds(), k.n_ls, iterations,
+            learning_rate, record_xu=record_xu)
+        traj_host = traj.cpu()
+        xu_host = xu_traj.cpu() if xu_traj is not None else None
+        self.last_info = int(info.item())
+        if iterations > 0:
+            self._theta = theta
+            k.unpack_u(self._u)
+        self._factor = None
+        if self.last_info != 0:
+            raise torch.linalg.LinAlgError(
+                f"linalg.cholesky: The factorization could not be completed because the input is not "
+                f"positive-definite (the leading minor of order {self.last_info} is not positive-definite).")
+        return traj_host, xu_host
+
+    def factor(self, check=True):
+        fresh = self._factor is None
+        if fresh:
+            self._factor = self.engine.sparse_factorize(self.kernel.kernel_id, self._theta, self._X, self._y, self._Xu,
+                                                        self.jitter)
+        if fresh and check:
+            self._raise_if_not_pd(self._factor)
+        return self._factor, fresh
+
+    def predict_sd(self, Xnew):
+        Xnew = Xnew.to(self.engine.device, self.kernel.dtype).contiguous()
+        fac, fresh = self.factor(check=False)
+        out = self.engine.sparse_predict(self.kernel.kernel_id, self._theta, self._Xu, fac, Xnew)
+        if fresh:
+            self._raise_if_not_pd(fac)
+        return out
+
+
 class reconstructor:
     """
     GP-based reconstruction of sparse 2D images and 3D spectroscopic datasets.
@@ -170,7 +233,8 @@ class reconstructor:
         Xtest (ndarray): "test" grid indices for prediction, shape (c, N', M'[, L'])
         kernel (str): 'RBF', 'Matern52' or 'RationalQuadratic'
         lengthscale (list): [lo, hi] (one shared lengthscale) or [[lo]*c, [hi]*c] (one per dimension)
-        sparse (bool), indpoints (int): inducing-point GP -- not implemented yet
+        sparse (bool): inducing-point GP (pyro SparseGPRegression, VFE) instead of the exact one
+        indpoints (int): number of inducing points (default len(X) // 10)
         learning_rate (float), iterations (int): Adam settings
         use_gpu (bool): the engine ALWAYS computes on the GPU; this flag only selects which
             generator the prior draws come from, so that use_gpu=False reproduces the reference's
@@ -192,9 +256,6 @@ class reconstructor:
         input_dim = np.ndim(y)
         self.X, self.y = gprutils.prepare_training_data(X, y, precision=self.precision)
         self.do_sparse = sparse
-        if sparse:
-            raise NotImplementedError(
-                "sparse=True (inducing points, gpr.py:145-155) is not part of the accelerated exact-GP path yet")
         if lengthscale is None and not kwargs.get("isotropic"):
             lmean = npfloat_(np.mean(np.shape(y)) / 2)
             lengthscale = [[0. for _ in range(input_dim)], [lmean for _ in range(input_dim)]]
@@ -205,7 +266,18 @@ class reconstructor:
         self.fulldims = Xtest.shape[1:] if Xtest is not None else np.shape(X)[1:]
         self.Xtest = gprutils.prepare_test_data(Xtest, precision=self.precision) if Xtest is not None else None
         jitter = kwargs.get("jitter", 1.0e-5)
-        self.model = ExactGPModel(self.X, self.y, kern, jitter=jitter, engine=engine)
+        if not self.do_sparse:
+            self.model = ExactGPModel(self.X, self.y, kern, jitter=jitter, engine=engine)
+        else:                                             # gpr.py:145-155
+            if indpoints is None:
+                indpoints = len(self.X) // 10
+                indpoints = indpoints + 1 if indpoints == 0 else indpoints
+            else:
+                indpoints = len(self.X) if indpoints > len(self.X) else indpoints
+            Xu = self.X[::len(self.X) // indpoints]
+            if self.verbose == 2:
+                print("# of inducing points for sparse GP regression: {}".format(len(Xu)))
+            self.model = SparseGPModel(self.X, self.y, kern, Xu, jitter=jitter, engine=engine)
         self.learning_rate = learning_rate
         self.iterations = iterations
         self.indpoints_all = []
@@ -228,7 +300,12 @@ class reconstructor:
         start_time = time.time()
         if self.verbose:
             print('Model training...')
-        traj = self.model.fit(self.iterations, self.learning_rate).double().numpy()
+        if self.do_sparse:
+            traj, xu_traj = self.model.fit(self.iterations, self.learning_rate)
+            self.indpoints_all.extend(xu_traj.numpy())       # Xu after every step (gpr.py:198-199)
+        else:
+            traj = self.model.fit(self.iterations, self.learning_rate)
+        traj = traj.double().numpy()
         d = self.model.X.shape[1]
         iso = self.model.kernel.isotropic
         for i, row in enumerate(traj):

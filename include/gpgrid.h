@@ -185,6 +185,48 @@ int gpg_acq_sweep(gpg_handle_t h, int dtype, int acq_id, const void *mean, const
                   const void *mask, int64_t M, double mu_best, double xi, double alpha, double beta,
                   int k, void *topk_val, int64_t *topk_idx, int32_t *count_out, void *acq_out, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Inducing-point GP: reconstructor(sparse=True), gpim/gpreg/gpr.py:145-155,198-199 over pyro's
+ * SparseGPRegression with its default VFE approximation.  Xu: m x d inducing inputs
+ * (gpr.py:151: X[::len(X) // indpoints]), 0 < m <= N, m < 65536.  theta as above; jitter goes on the
+ * diagonal of k(Xu, Xu) only.  *info: 0, or 1 + the first non-positive pivot of either m x m
+ * factorisation (k(Xu, Xu) + jitter I, then I + W^T W / noise).
+ * --------------------------------------------------------------------------------------------- */
+
+/* One evaluation of SparseGPRegression.model's objective (Trace_ELBO.differentiable_loss at gpr.py:192
+ * minus the constant Uniform log-priors):
+ *   loss = -log N(y; 0, Qff + noise I) + clamp(tr(Kff - Qff) / noise, 0) / 2,  Qff = Kfu Kuu^-1 Kuf,
+ * and what loss.backward() leaves behind: grad_theta_out dtype[3 + d] (theta layout, constrained
+ * values), grad_xu_out dtype[m * d]. */
+int gpg_sparse_loss_grad(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
+                         const void *X, const void *y, int64_t N, const void *Xu, int64_t m, double jitter,
+                         void *loss_out, void *grad_theta_out, void *grad_xu_out, int32_t *info, void *stream);
+
+/* reconstructor.train with sparse=True (gpr.py:186-199) on the device: `iters` Adam steps on the
+ * unconstrained hyper-parameters (u, bounds_host, n_ls, traj_out, theta_out exactly as gpg_fit_adam)
+ * AND on the inducing inputs Xu (in/out; a plain Parameter in pyro: no constraint), one optimiser.
+ * xu_traj_out (nullable) dtype[iters * m * d]: Xu after every step (hyperparams["inducing_points"],
+ * gpr.py:198-199). */
+int gpg_sparse_fit_adam(gpg_handle_t h, int dtype, int kernel_id, int d, int n_ls,
+                        const void *X, const void *y, int64_t N, void *Xu, int64_t m, double jitter,
+                        void *u, const double *bounds_host, int iters, double lr,
+                        void *traj_out, void *xu_traj_out, void *theta_out, int32_t *info, void *stream);
+
+/* Factor cache of the inducing-point posterior for fixed (theta, Xu) -- what SparseGPRegression.forward
+ * recomputes on every call (gpr.py:248): Ui = Luu^-1 and Pm = LA^-1 Luu^-1 (m x m lower triangular,
+ * row-major, leading dimension ld, strict upper triangle zero) and w (dtype[m]) with
+ * mean(x*) = k(x*, Xu) . w. */
+int gpg_sparse_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
+                         const void *X, const void *y, int64_t N, const void *Xu, int64_t m, double jitter,
+                         void *Ui_out, void *Pm_out, int64_t ld, void *w_out, int32_t *info, void *stream);
+
+/* SparseGPRegression.forward(Xnew, full_cov=False, noiseless=False) + sqrt (gpr.py:248-250), tiled over M:
+ *   mean = K*^T w,  sd = sqrt(v + noise - colsum((Ui K*)^2) + colsum((Pm K*)^2)),  K* = k(Xu, X*).
+ * Rows of Xs that contain NaN give NaN outputs. */
+int gpg_sparse_predict(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
+                       const void *Xu, int64_t m, const void *Ui, const void *Pm, int64_t ld, const void *w,
+                       const void *Xs, int64_t M, void *mean_out, void *sd_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

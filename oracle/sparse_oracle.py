@@ -4,8 +4,8 @@ oracle/sparse_oracle.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 CPU restatement (plain torch + autograd) of the reference's inducing-point path, the first item of the
 "next" list: ``gpim.reconstructor(..., sparse=True)`` (gpim/gpreg/gpr.py:145-155, 198-199)
 over Pyro's ``SparseGPRegression`` with its default approximation (VFE, Titsias 2009).  Nothing under
-``gpim_b200/`` imports this module; the product still raises NotImplementedError for ``sparse=True``.  It is here
-so that the CUDA path of the next round has its checker waiting.
+``gpim_b200/`` imports this module; it is the checker of the CUDA inducing-point path (csrc/sparse.cuh,
+gpg_sparse_* in include/gpgrid.h), used by tests/test_gpu_sparse.py.
 
 PARITY UNPINNED: the reference's tests do not exercise ``sparse=True`` and the stored notebook runs used the
 CUDA generator, so there is no golden vector.  The arithmetic restates the published algorithm of
@@ -29,6 +29,49 @@ import numpy as np
 import torch
 
 from .gp_oracle import OracleGP, kernel_matrix, to_rows
+
+
+def vfe_loss(kernel_name, X, y, Xu, v, ls, noise, a, jitter):
+    """SparseGPRegression.model's objective (minus the constant Uniform log-priors) as a function of the CONSTRAINED
+    hyper-parameters and the inducing inputs -- differentiable, so autograd gives the gradients the CUDA path's
+    closed form must reproduce."""
+    N, M = X.shape[0], Xu.shape[0]
+    dtype = X.dtype
+    Kuu = kernel_matrix(kernel_name, Xu, Xu, v, ls, a) + jitter * torch.eye(M, dtype=dtype)
+    Luu = torch.linalg.cholesky(Kuu)
+    Kuf = kernel_matrix(kernel_name, Xu, X, v, ls, a)
+    W = torch.linalg.solve_triangular(Luu, Kuf, upper=False).t()              # N x M
+    Kffdiag = v.expand(N)                                      # stationary kernels: k(x, x) = variance
+    trace_term = ((Kffdiag - W.pow(2).sum(-1)).sum() / noise).clamp(min=0)
+    # log N(y; 0, W W^T + noise I) by the matrix-determinant / Woodbury lemmas (LowRankMultivariateNormal)
+    A = W.t() @ W / noise + torch.eye(M, dtype=dtype)
+    LA = torch.linalg.cholesky(A)
+    Wty = W.t() @ y / noise
+    c = torch.linalg.solve_triangular(LA, Wty.unsqueeze(-1), upper=False).squeeze(-1)
+    quad = y @ y / noise - c @ c
+    logdet = N * torch.log(noise) + 2.0 * torch.log(torch.diagonal(LA)).sum()
+    log_prob = -0.5 * (quad + logdet + N * math.log(2.0 * math.pi))
+    return -log_prob + 0.5 * trace_term
+
+
+def vfe_predict(kernel_name, X, y, Xu, Xs, v, ls, noise, a, jitter):
+    """SparseGPRegression.forward(Xs, full_cov=False, noiseless=False) -> (loc, var) tensors."""
+    dtype = X.dtype
+    M = Xu.shape[0]
+    Kuu = kernel_matrix(kernel_name, Xu, Xu, v, ls, a) + jitter * torch.eye(M, dtype=dtype)
+    Luu = torch.linalg.cholesky(Kuu)
+    Kuf = kernel_matrix(kernel_name, Xu, X, v, ls, a)
+    W = torch.linalg.solve_triangular(Luu, Kuf, upper=False).t()
+    W_Dinv = W.t() / noise                                     # M x N
+    K = W_Dinv @ W + torch.eye(M, dtype=dtype)
+    L = torch.linalg.cholesky(K)
+    W_Dinv_y = W_Dinv @ y.unsqueeze(-1)
+    Kus = kernel_matrix(kernel_name, Xu, Xs, v, ls, a)
+    Ws = torch.linalg.solve_triangular(Luu, Kus, upper=False)
+    pack = torch.linalg.solve_triangular(L, torch.cat((W_Dinv_y, Ws), dim=1), upper=False)
+    loc = (pack[:, :1].t() @ pack[:, 1:]).squeeze(0)
+    var = v + noise - Ws.pow(2).sum(0) + pack[:, 1:].pow(2).sum(0)
+    return loc, var
 
 
 class SparseOracleGP(OracleGP):
@@ -55,31 +98,10 @@ class SparseOracleGP(OracleGP):
         a = self.tf_n(self.u_a) if self.kernel_name == "RationalQuadratic" else torch.ones((), dtype=self.dtype)
         return v, ls, noise, a
 
-    def _lowrank(self):
-        v, ls, noise, a = self._theta()
-        M = self.Xu.shape[0]
-        Kuu = kernel_matrix(self.kernel_name, self.Xu, self.Xu, v, ls, a)
-        Kuu = Kuu + self.jitter * torch.eye(M, dtype=self.dtype)
-        Luu = torch.linalg.cholesky(Kuu)
-        Kuf = kernel_matrix(self.kernel_name, self.Xu, self.X, v, ls, a)
-        W = torch.linalg.solve_triangular(Luu, Kuf, upper=False).t()          # N x M
-        return v, ls, noise, a, Luu, W
-
     def loss(self):
         """-ELBO of the MAP guide up to the constant Uniform log-priors: VFE bound."""
-        v, ls, noise, a, Luu, W = self._lowrank()
-        N, M = W.shape
-        Kffdiag = v.expand(N)                                  # stationary kernels: k(x, x) = variance
-        trace_term = ((Kffdiag - W.pow(2).sum(-1)).sum() / noise).clamp(min=0)
-        # log N(y; 0, W W^T + noise I) by the matrix-determinant / Woodbury lemmas (LowRankMultivariateNormal)
-        A = W.t() @ W / noise + torch.eye(M, dtype=self.dtype)
-        LA = torch.linalg.cholesky(A)
-        Wty = W.t() @ self.y / noise
-        c = torch.linalg.solve_triangular(LA, Wty.unsqueeze(-1), upper=False).squeeze(-1)
-        quad = self.y @ self.y / noise - c @ c
-        logdet = N * torch.log(noise) + 2.0 * torch.log(torch.diagonal(LA)).sum()
-        log_prob = -0.5 * (quad + logdet + N * math.log(2.0 * math.pi))
-        return -log_prob + 0.5 * trace_term
+        v, ls, noise, a = self._theta()
+        return vfe_loss(self.kernel_name, self.X, self.y, self.Xu, v, ls, noise, a, self.jitter)
 
     def train(self, learning_rate=None, iterations=None):
         lr = self.learning_rate if learning_rate is None else learning_rate
@@ -103,17 +125,8 @@ class SparseOracleGP(OracleGP):
         """(mean, sd) shaped like the test grid; SparseGPRegression.forward(full_cov=False, noiseless=False)."""
         Xs = self.Xtest if Xtest is None else torch.from_numpy(to_rows(np.asarray(Xtest, dtype=np.float64))).to(self.dtype)
         with torch.no_grad():
-            v, ls, noise, a, Luu, W = self._lowrank()
-            M = W.shape[1]
-            W_Dinv = W.t() / noise                             # M x N
-            K = W_Dinv @ W + torch.eye(M, dtype=self.dtype)
-            L = torch.linalg.cholesky(K)
-            W_Dinv_y = W_Dinv @ self.y.unsqueeze(-1)
-            Kus = kernel_matrix(self.kernel_name, self.Xu, Xs, v, ls, a)
-            Ws = torch.linalg.solve_triangular(Luu, Kus, upper=False)
-            pack = torch.linalg.solve_triangular(L, torch.cat((W_Dinv_y, Ws), dim=1), upper=False)
-            loc = (pack[:, :1].t() @ pack[:, 1:]).squeeze(0)
-            var = v + noise - Ws.pow(2).sum(0) + pack[:, 1:].pow(2).sum(0)
+            v, ls, noise, a = self._theta()
+            loc, var = vfe_predict(self.kernel_name, self.X, self.y, self.Xu, Xs, v, ls, noise, a, self.jitter)
         shape = self.fulldims if Xtest is None else np.asarray(Xtest).shape[1:]
         return loc.numpy().reshape(shape), var.sqrt().numpy().reshape(shape)
 
