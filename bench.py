@@ -286,6 +286,62 @@ def measure_training(eng, name, iters):
                                    "(examples/contributed/GPIM_BEPS.ipynb:665-672); 3.6-7.0 ms on CPU at N = 5..55"}
 
 
+def measure_sparse(eng, name, iters, steps):
+    """reconstructor(sparse=True) at the notebook setting (SURVEY 8f-1): len(X) // 10 inducing points picked as
+    gpr.py:151 does, fp64 (the reference default) and fp32.  Reports the Adam iteration of the VFE objective
+    (hyper-parameters + inducing inputs, gpg_sparse_fit_adam) and the prediction over the dense grid
+    (gpg_sparse_factorize + gpg_sparse_predict, refactorising every step like the reference's forward())."""
+    import torch
+    from gpim_b200._lib import KERNEL_IDS
+    wl = make_workload(name)
+    X, y = train_rows(wl["R"])
+    N, d = X.shape
+    m_ind = N // 10
+    Xs_host = rows_of(wl["Xfull"])
+    bounds = [1e-4, 10.0] + [1.0] * d + [4.0] * d
+    kid = KERNEL_IDS[wl["kernel"]]
+    out = {"workload": wl["label"].replace("fixed theta", "VFE inducing points"), "N_train": int(N),
+           "inducing_points": int(len(range(0, N, N // m_ind))), "M_grid": int(Xs_host.shape[0])}
+    for tag, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        dev = eng.device
+        Xd, yd = torch.tensor(X, dtype=dt, device=dev), torch.tensor(y, dtype=dt, device=dev)
+        Xs = torch.tensor(Xs_host, dtype=dt, device=dev)
+        theta = torch.tensor(wl["theta"], dtype=dt, device=dev)
+        jitter = 1e-5 if tag == "f64" else 1e-4
+
+        def fit(n):
+            Xu = Xd[::N // m_ind].clone()
+            u = torch.zeros(3 + d, dtype=dt, device=dev)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            traj, _, _, info = eng.sparse_fit_adam(kid, Xd, yd, Xu, jitter, u, bounds, d, n, 0.05, record_xu=False)
+            e1.record()
+            torch.cuda.synchronize()
+            assert int(info.item()) == 0 and bool(torch.isfinite(traj).all())
+            return e0.elapsed_time(e1) / n
+
+        def predict(n):
+            Xu = Xd[::N // m_ind].clone()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fac = eng.sparse_factorize(kid, theta, Xd, yd, Xu, jitter)
+                mean, sd = eng.sparse_predict(kid, theta, Xu, fac, Xs)
+            e1.record()
+            torch.cuda.synchronize()
+            assert int(fac["info"].item()) == 0 and bool(torch.isfinite(mean).all()) and bool(torch.isfinite(sd).all())
+            return e0.elapsed_time(e1) / n
+
+        fit(2)
+        predict(1)
+        ms_fit, ms_pred = fit(iters), predict(steps)
+        out[tag] = {"ms_per_adam_iteration": ms_fit, "predict_ms_per_step": ms_pred,
+                    "points_per_s": Xs.shape[0] / (ms_pred * 1e-3)}
+    return out
+
+
 def bench_config(wl, gpus, N, M):
     return {"workload": wl["label"], "name": wl["name"], "N_train": N, "M_grid": M, "kernel": wl["kernel"],
             "theta": {"variance": wl["theta"][0], "noise": wl["theta"][1], "lengthscale": wl["theta"][3:],
@@ -447,7 +503,8 @@ def run_cuda(args):
                                    "train_c2": measure_training(eng, "c2", 10),
                                    "c2_compact_support": measure_extra(eng, "c2", args.steps, 2, compact_support=True),
                                    "h512_compact_support": measure_extra(eng, "h512", max(2, args.steps // 2), 2,
-                                                                         compact_support=True)}
+                                                                         compact_support=True),
+                                   "sparse_c2": measure_sparse(eng, "c2", 10, max(2, args.steps // 2))}
     if world == 1 and not args.no_cpu_baseline:
         import torch as _t
         _t.set_num_threads(os.cpu_count() or 1)

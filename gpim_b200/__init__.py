@@ -2,28 +2,26 @@
 gpim_b200 -- B200-native exact-GP-on-grids engine behind the GPim API.
 
 Public surface = the reference's gpim/__init__.py:1-5 restricted to the accelerated path:
-``utils`` (grid / data-layout helpers), ``reconstructor`` and ``boptimizer``.
+``utils`` (grid / data-layout helpers), ``reconstructor`` (exact and inducing-point GP), ``boptimizer`` and
+``skreconstructor`` with ``ski=False`` (GPyTorch's exact-GP semantics).
 """
 from . import gprutils as utils  # noqa: F401
 from .gpreg.gpr import reconstructor  # noqa: F401
+from .gpreg.skgpr import skreconstructor  # noqa: F401
 from .gpbayes.boptim import boptimizer  # noqa: F401
 
 
 
 class _OutOfScope:
-    """The reference also exports the GPyTorch-backed skreconstructor / vreconstructor (gpim/__init__.py:3-4).
-    They are outside the accelerated exact-GP path: importing them works, so that
-    `from gpim import ...` lines keep running, constructing one says so."""
+    """The reference also exports the GPyTorch-backed multi-output vreconstructor (gpim/__init__.py:4).  It is
+    outside the accelerated exact-GP path: importing it works, so that `from gpim import ...`
+    lines keep running, constructing one says so."""
     _name = ""
 
     def __init__(self, *args, **kwargs):
         raise NotImplementedError(
-            f"gpim.{self._name} (GPyTorch structured-kernel / multi-output GP) is outside the accelerated exact-GP "
+            f"gpim.{self._name} (GPyTorch multi-output GP) is outside the accelerated exact-GP "
             f"path of this engine; use gpim.reconstructor / gpim.boptimizer")
-
-
-class skreconstructor(_OutOfScope):
-    _name = "skreconstructor"
 
 
 class vreconstructor(_OutOfScope):

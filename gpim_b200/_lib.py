@@ -45,6 +45,8 @@ SIGNATURES = {
     "gpg_nll_grad": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _vp, _vp, _vp, _vp], C.c_int),
     "gpg_fit_adam": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _f64, _vp, C.POINTER(_f64), _i32, _f64,
                       _vp, _vp, _vp, _vp], C.c_int),
+    "gpg_fit_adam_sk": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _f64, _vp, C.POINTER(_f64), _i32, _f64,
+                         _vp, _vp, _vp, _vp], C.c_int),
     "gpg_acq_sweep": ([_vp, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp],
                       C.c_int),
     "gpg_sparse_loss_grad": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _f64, _vp, _vp, _vp, _vp, _vp],
@@ -288,8 +290,9 @@ class Engine:
                                           float(jitter), _ptr(nll), _ptr(grad), _ptr(info), self._stream()))
         return nll, grad, info
 
-    def fit_adam(self, kernel_id, X, y, jitter, u, bounds, n_ls, iters, lr):
-        """u (device, in/out) layout {variance, noise, scale_mixture, lengthscale[n_ls]}.
+    def fit_adam(self, kernel_id, X, y, jitter, u, bounds, n_ls, iters, lr, gpytorch_params=False):
+        """u (device, in/out) layout {variance, noise, scale_mixture, lengthscale[n_ls]}; with gpytorch_params
+        (skreconstructor) {outputscale, noise, mean constant, lengthscale[n_ls]} in GPyTorch's raw parametrisation.
         Returns (traj [iters, 4+d], theta [3+d], info)."""
         X, y = _c(X), _c(y)
         assert u.is_contiguous()
@@ -298,9 +301,9 @@ class Engine:
         theta = self.empty(3 + d, dtype=X.dtype)
         info = torch.zeros(1, dtype=torch.int32, device=self.device)
         b = (_f64 * len(bounds))(*[float(v) for v in bounds])
-        self._check(self.lib.gpg_fit_adam(self.h, self._dt(X), kernel_id, d, n_ls, _ptr(X), _ptr(y), N, float(jitter),
-                                          _ptr(u), b, int(iters), float(lr), _ptr(traj), _ptr(theta), _ptr(info),
-                                          self._stream()))
+        fn = self.lib.gpg_fit_adam_sk if gpytorch_params else self.lib.gpg_fit_adam
+        self._check(fn(self.h, self._dt(X), kernel_id, d, n_ls, _ptr(X), _ptr(y), N, float(jitter),
+                       _ptr(u), b, int(iters), float(lr), _ptr(traj), _ptr(theta), _ptr(info), self._stream()))
         return traj[:iters], theta, info
 
     def acq_sweep(self, acq_id, mean, sd, k, mu_best=0.0, xi=0.01, alpha=0.0, beta=1.0, mask=None, want_acq=False):

@@ -711,7 +711,7 @@ extern "C" int gpg_predict_grid(gpg_handle_t h, int dtype, int kernel_id, int d,
 // K7: nll + gradient, Adam loop
 // ---------------------------------------------------------------------------------------------
 struct TrainBufs {
-    void *L, *Linv, *Kinv, *dinv, *vs, *vhat, *alpha, *scalars, *grad, *nll, *theta;
+    void *L, *Linv, *Kinv, *dinv, *vs, *vhat, *alpha, *scalars, *grad, *nll, *theta, *yc;
     void *planes;            // tensor-core path: Ls | WTs | TTs | As (Kinv aliases TTs, which is dead by then)
     void *wsplit;            // tensor-core path: Ws
     float *scales;
@@ -733,7 +733,7 @@ template <typename T> static size_t train_ws_bytes(const gpg_handle_s *h, int64_
     // L, Linv + (SIMT: Kinv | TC: 4 plane pairs + Rf + Ws)
     return bump_size({nn, nn, tcp ? 6 * nn : nn, NB * NB * sizeof(T), 4 * (size_t)N * sizeof(T) + 64, (size_t)N * sizeof(T),
                       (size_t)N * sizeof(T), 2 * sizeof(T), GPG_MAX_P * sizeof(T), sizeof(T), GPG_MAX_P * sizeof(T),
-                      SC_COUNT * sizeof(float), nb * GPG_MAX_P * sizeof(double), sizeof(FitState)});
+                      SC_COUNT * sizeof(float), nb * GPG_MAX_P * sizeof(double), sizeof(FitState), (size_t)N * sizeof(T)});
 }
 
 template <typename T> static TrainBufs train_carve(const gpg_handle_s *h, void *ws, int64_t N, int64_t ld) {
@@ -766,6 +766,7 @@ template <typename T> static TrainBufs train_carve(const gpg_handle_s *h, void *
     t.nblocks = (int)((N + 7) / 8);
     t.partial = b.take<double>((size_t)t.nblocks * GPG_MAX_P);
     t.st = b.take<FitState>(1);
+    t.yc = b.take<T>(N);
     return t;
 }
 
@@ -842,7 +843,7 @@ extern "C" int gpg_nll_grad(gpg_handle_t h, int dtype, int kernel_id, int d, con
 template <typename T>
 static int fit_entry(gpg_handle_s *h, int kernel_id, int d, int n_ls, const T *X, const T *y, int64_t N, double jitter,
                      T *u, const double *bounds, int iters, double lr, T *traj, T *theta_out, int32_t *info,
-                     cudaStream_t s) {
+                     cudaStream_t s, int mode = 0) {
     const int64_t ld = gpg_align_up((size_t)N, 64);
     if (s == nullptr && h->opt_fit_graph && iters >= 8 && !train_uses_tc<T>(h, N, ld)) {
         // The legacy default stream cannot be captured.  A blocking stream is implicitly ordered against it in
@@ -855,7 +856,7 @@ static int fit_entry(gpg_handle_s *h, int kernel_id, int d, int n_ls, const T *X
     TrainBufs tb = train_carve<T>(h, ws, N, ld);
     FitCfg c;
     memset(&c, 0, sizeof(c));
-    c.d = d; c.n_ls = n_ls; c.is_rq = (kernel_id == GPG_RATQUAD);
+    c.d = d; c.n_ls = n_ls; c.is_rq = (kernel_id == GPG_RATQUAD); c.mode = mode;
     c.var_lo = bounds[0]; c.var_hi = bounds[1];
     for (int k = 0; k < n_ls; ++k) { c.ls_lo[k] = bounds[2 + k]; c.ls_hi[k] = bounds[2 + n_ls + k]; }
     c.lr = lr; c.beta1 = 0.9; c.beta2 = 0.999; c.eps = 1e-8;
@@ -865,7 +866,17 @@ static int fit_entry(gpg_handle_s *h, int kernel_id, int d, int n_ls, const T *X
     // info keeps the FIRST failing pivot over all iterations (reset once, atomicCAS afterwards)
     GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
     auto one_iteration = [&]() -> int {
-        GPG_TRY(nll_grad_core<T>(h, kernel_id, d, theta, X, y, N, jitter, tb, (T *)tb.nll, (T *)tb.grad, info, 0, s));
+        const T *yt = y;
+        if (mode == 1) {             // GPyTorch semantics: constant mean subtracted, loss and gradient per datum
+            center_y_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(y, N, theta, (T *)tb.yc);
+            GPG_LAUNCH_CHECK(h);
+            yt = (const T *)tb.yc;
+        }
+        GPG_TRY(nll_grad_core<T>(h, kernel_id, d, theta, X, yt, N, jitter, tb, (T *)tb.nll, (T *)tb.grad, info, 0, s));
+        if (mode == 1) {
+            sk_grad_fix_kernel<T><<<1, 256, 0, s>>>((const T *)tb.alpha, N, 3 + d, (T *)tb.grad, (T *)tb.nll);
+            GPG_LAUNCH_CHECK(h);
+        }
         adam_step_kernel<T><<<1, 32, 0, s>>>(1, c, u, tb.st, (const T *)tb.grad, (const T *)tb.nll, theta, traj);
         GPG_LAUNCH_CHECK(h);
         return GPG_OK;
@@ -925,6 +936,26 @@ extern "C" int gpg_fit_adam(gpg_handle_t h, int dtype, int kernel_id, int d, int
     if (dtype == GPG_F64)
         return fit_entry<double>(h, kernel_id, d, n_ls, (const double *)X, (const double *)y, N, jitter, (double *)u,
                                  bounds_host, iters, lr, (double *)traj_out, (double *)theta_out, info, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
+extern "C" int gpg_fit_adam_sk(gpg_handle_t h, int dtype, int kernel_id, int d, int n_ls, const void *X, const void *y,
+                               int64_t N, double jitter, void *u, const double *bounds_host, int iters, double lr,
+                               void *traj_out, void *theta_out, int32_t *info, void *stream) {
+    GPG_REQUIRE(h && X && y && u && bounds_host && info, "NULL argument");
+    DeviceGuard device_guard(h->device);
+    GPG_REQUIRE(N > 0 && iters >= 0, "bad size");
+    GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
+    GPG_REQUIRE(n_ls == 1 || n_ls == d, "n_ls must be 1 or d");
+    GPG_REQUIRE(kernel_id == GPG_RBF || kernel_id == GPG_MATERN52, "gpytorch kernel book: RBF or Matern52");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return fit_entry<float>(h, kernel_id, d, n_ls, (const float *)X, (const float *)y, N, jitter, (float *)u,
+                                bounds_host, iters, lr, (float *)traj_out, (float *)theta_out, info, s, 1);
+    if (dtype == GPG_F64)
+        return fit_entry<double>(h, kernel_id, d, n_ls, (const double *)X, (const double *)y, N, jitter, (double *)u,
+                                 bounds_host, iters, lr, (double *)traj_out, (double *)theta_out, info, s, 1);
     gpg_set_error("unknown dtype %d", dtype);
     return GPG_EINVAL;
 }

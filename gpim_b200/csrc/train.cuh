@@ -12,8 +12,13 @@ struct FitState {               // lives in device workspace, double regardless 
     int step;
 };
 
+// mode 0: pyro parametrisation of reconstructor (Uniform priors -> interval constraints on variance and
+// lengthscale, positive noise / scale mixture through exp; gpr.py + pyro_kernels.py:81-94).
+// mode 1: GPyTorch parametrisation of skreconstructor(ski=False) (skgpr.py:143-150, gpytorch_kernels.py:55-73):
+// slot 0 = ScaleKernel outputscale (Positive: softplus), slot 1 = GaussianLikelihood noise (GreaterThan(1e-4):
+// softplus + 1e-4), slot 2 = ConstantMean constant (unconstrained), lengthscale: Interval (sigmoid).
 struct FitCfg {
-    int d, n_ls, is_rq;
+    int d, n_ls, is_rq, mode;
     double var_lo, var_hi, ls_lo[GPG_MAX_D], ls_hi[GPG_MAX_D];
     double lr, beta1, beta2, eps;
     double half_n_log2pi;
@@ -33,13 +38,28 @@ template <typename T> __device__ __forceinline__ void interval_fwd(T u, double l
 }
 
 // u -> theta (+ d theta / d u).  u layout: {variance, noise, scale_mixture, lengthscale[n_ls]}.
+// torch.nn.functional.softplus (beta = 1, threshold = 20) and its derivative
+template <typename T> __device__ __forceinline__ void softplus_fwd(T u, T &val, double &dval) {
+    if (u > T(20)) { val = u; dval = 1.0; return; }
+    val = gpg_log(T(1) + gpg_exp(u));
+    dval = 1.0 / (1.0 + exp(-(double)u));
+}
+
 template <typename T>
 __device__ void constrain_params(const T *u, const FitCfg &c, T *theta, double *dtheta_du) {
     T val; double dv;
-    interval_fwd<T>(u[0], c.var_lo, c.var_hi, val, dv);
-    theta[0] = val; dtheta_du[0] = dv;
-    theta[1] = gpg_exp(u[1]); dtheta_du[1] = (double)theta[1];
-    theta[2] = c.is_rq ? gpg_exp(u[2]) : T(1); dtheta_du[2] = c.is_rq ? (double)theta[2] : 0.0;
+    if (c.mode == 1) {
+        softplus_fwd<T>(u[0], val, dv);
+        theta[0] = val; dtheta_du[0] = dv;
+        softplus_fwd<T>(u[1], val, dv);
+        theta[1] = val + T(1e-4); dtheta_du[1] = dv;
+        theta[2] = u[2]; dtheta_du[2] = 1.0;
+    } else {
+        interval_fwd<T>(u[0], c.var_lo, c.var_hi, val, dv);
+        theta[0] = val; dtheta_du[0] = dv;
+        theta[1] = gpg_exp(u[1]); dtheta_du[1] = (double)theta[1];
+        theta[2] = c.is_rq ? gpg_exp(u[2]) : T(1); dtheta_du[2] = c.is_rq ? (double)theta[2] : 0.0;
+    }
     for (int k = 0; k < c.n_ls; ++k) {
         interval_fwd<T>(u[3 + k], c.ls_lo[k], c.ls_hi[k], val, dv);
         dtheta_du[3 + k] = dv;
@@ -139,6 +159,32 @@ __global__ void __launch_bounds__(256) grad_finish_kernel(const double *__restri
     if (threadIdx.x == 0 && nll_out) nll_out[0] = (T)((double)scalars[0] + (double)scalars[1] + half_n_log2pi);
 }
 
+// GPyTorch semantics (FitCfg.mode 1).  yc = y - constant (the ConstantMean, theta[2]):
+template <typename T>
+__global__ void center_y_kernel(const T *__restrict__ y, int64_t N, const T *__restrict__ theta, T *__restrict__ yc) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < N) yc[i] = y[i] - theta[2];
+}
+
+// ... and after the exact-GP gradient: d nll / d constant = -sum_i alpha_i, then everything divided by N
+// (ExactMarginalLogLikelihood returns log p(y) / num_data, skgpr.py:189-196).  Single CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) sk_grad_fix_kernel(const T *__restrict__ alpha, int64_t N, int P,
+                                                          T *__restrict__ grad, T *__restrict__ nll) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += 256) s += (double)alpha[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    const double inv_n = 1.0 / (double)N;
+    for (int p = 0; p < P; ++p) grad[p] = (T)((p == 2 ? -tot : (double)grad[p]) * inv_n);
+    nll[0] = (T)((double)nll[0] * inv_n);
+}
+
 // mode 0: theta = constrain(u) (start of a train() call: fresh Adam state).
 // mode 1: chain rule, one torch.optim.Adam step on u, re-constrain, record {theta, loss} in row step-1 of traj.
 template <typename T>
@@ -159,7 +205,7 @@ __global__ void adam_step_kernel(int mode, FitCfg c, T *__restrict__ u, FitState
     const double step_size = c.lr / bc1;
     const double bc2_sqrt = sqrt(bc2);
     for (int p = 0; p < P; ++p) {
-        if (p == 2 && !c.is_rq) continue;
+        if (p == 2 && !c.is_rq && c.mode == 0) continue;
         double gth;
         if (p >= 3 && c.n_ls == 1) {
             gth = 0.0;

@@ -175,6 +175,20 @@ int gpg_fit_adam(gpg_handle_t h, int dtype, int kernel_id, int d, int n_ls,
                  void *u, const double *bounds_host, int iters, double lr,
                  void *traj_out, void *theta_out, int32_t *info, void *stream);
 
+/* gpg_fit_adam with the GPyTorch parametrisation of skreconstructor(ski=False) -- the exact-GP branch of
+ * gpim/gpreg/skgpr.py:143-150,189-203 (ExactGP: ConstantMean + ScaleKernel(RBF | Matern52) + GaussianLikelihood,
+ * loss = -ExactMarginalLogLikelihood = nll / N, torch.optim.Adam on the raw parameters):
+ *   u  dtype[3 + n_ls] in/out: raw {outputscale, noise, mean constant, lengthscale[n_ls]}
+ *      outputscale = softplus(u0) (Positive), noise = softplus(u1) + 1e-4 (GreaterThan(1e-4)), constant = u2,
+ *      lengthscale = lo + (hi - lo) sigmoid(u) (gpytorch.constraints.Interval, gpytorch_kernels.py:55-57)
+ *   bounds_host  as gpg_fit_adam; only the lengthscale bounds are used
+ *   traj_out / theta_out  as gpg_fit_adam, with theta[0] = outputscale and theta[2] = mean constant; the recorded
+ *      loss is nll / N.  kernel_id: GPG_RBF or GPG_MATERN52 (gpytorch_kernels.py:60-69); jitter is normally 0. */
+int gpg_fit_adam_sk(gpg_handle_t h, int dtype, int kernel_id, int d, int n_ls,
+                    const void *X, const void *y, int64_t N, double jitter,
+                    void *u, const double *bounds_host, int iters, double lr,
+                    void *traj_out, void *theta_out, int32_t *info, void *stream);
+
 /* K6 -- acquisition sweep + top-k (acqfunc.py:11-92, boptim.py:303-315).
  *   acq_id CB: alpha*mean + beta*sd;  EI: imp*Phi(z) + sd*phi(z), imp = mean - mu_best - xi,
  *   z = imp/sd;  POI: Phi(z).   mask (nullable, dtype[M]): multiplied in, NaN entries excluded.
