@@ -1087,6 +1087,7 @@ static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *thet
     { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.Luu, m, ldm, info, 0, b.dinv, s)); }
     { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.Luu, m, ldm, b.Ui, ldm, b.tmp, s)); }
     {
+        StageTimer stg(h, GPG_ST_PGEMM, s);      // the two m x m x N products (booked under the predict GEMM's stage)
         GemmArgs<T> g;               // B = Ui Kuf  (Ui lower triangular: k <= i)
         g.A = b.Ui; g.lda = ldm; g.a_kmajor = 1;
         g.B = b.Kuf; g.ldb = ldn; g.b_kmajor = 0;
@@ -1096,6 +1097,7 @@ static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *thet
         GPG_TRY(gemm_simt<T>(h, g, s));
     }
     {
+        StageTimer stg(h, GPG_ST_PFINAL, s);
         GemmArgs<T> g;               // S = B B^T, lower tiles
         g.A = b.B; g.lda = ldn; g.a_kmajor = 1;
         g.B = b.B; g.ldb = ldn; g.b_kmajor = 1;
