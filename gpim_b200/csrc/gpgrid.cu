@@ -1028,6 +1028,9 @@ extern "C" int gpg_acq_sweep(gpg_handle_t h, int dtype, int acq_id, const void *
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct SgpBufs {
     int64_t m = 0, N = 0, ldm = 0, ldn = 0;
+    int nz = 1;                  // split-K factor of S = B B^T; ldn = nz * kchunk (columns [N, ldn) of B are kept zero)
+    int64_t kchunk = 0;
+    T *Spart;
     T *Luu, *Ui, *tmp, *Kuf, *B, *S, *Ap, *LA, *LAi, *Ainv, *Phi, *H, *T1, *Guu, *T2;   // Kuf doubles as dF/dKuf
     T *beta, *c0, *a0, *a, *w, *rho, *dinv, *theta0, *gxu, *grad, *loss, *theta, *m1, *m2;
     double *sc, *partA, *partB;
@@ -1035,12 +1038,22 @@ template <typename T> struct SgpBufs {
     FitState *st;
 };
 
+// S = B B^T has only (m / tile)^2 / 2 output tiles against a contraction length of N: it is split along K into nz
+// batches of kchunk columns (nz * kchunk >= N; the tail columns of B are zero) whose partial products
+// sgp_form_A_kernel adds up.
+static void sgp_split(int64_t N, int &nz, int64_t &kchunk) {
+    nz = (int)std::min<int64_t>(16, std::max<int64_t>(1, N / 1024));
+    kchunk = (int64_t)gpg_align_up((size_t)((N + nz - 1) / nz), 64);
+}
+
 template <typename T> static size_t sgp_ws_bytes(int64_t m, int64_t N, int d) {
     constexpr int NB = GemmCfg<T>::BN;
-    const int64_t ldm = gpg_align_up((size_t)m, 64), ldn = gpg_align_up((size_t)N, 64);
+    int nz; int64_t kchunk;
+    sgp_split(N, nz, kchunk);
+    const int64_t ldm = gpg_align_up((size_t)m, 64), ldn = nz * kchunk;
     const size_t mm = (size_t)m * ldm * sizeof(T), mn = (size_t)m * ldn * sizeof(T), mv = (size_t)m * sizeof(T);
     const size_t nb = (size_t)((m + 7) / 8);
-    return bump_size({mm, mm, mm, mn, mn, mm, mm, mm, mm, mm, mm, mm, mm, mm, mm,
+    return bump_size({(size_t)nz * mm, mm, mm, mm, mn, mn, mm, mm, mm, mm, mm, mm, mm, mm, mm, mm,
                       mv, mv, mv, mv, mv, (size_t)N * sizeof(T), NB * NB * sizeof(T), GPG_MAX_P * sizeof(T),
                       mv * d, GPG_MAX_P * sizeof(T), sizeof(T), GPG_MAX_P * sizeof(T), mv * d, mv * d,
                       SGP_SC_COUNT * sizeof(double), nb * GPG_MAX_P * sizeof(double), nb * GPG_MAX_P * sizeof(double),
@@ -1052,8 +1065,10 @@ template <typename T> static SgpBufs<T> sgp_carve(void *ws, int64_t m, int64_t N
     Bump b(ws);
     SgpBufs<T> s;
     s.m = m; s.N = N;
-    s.ldm = gpg_align_up((size_t)m, 64); s.ldn = gpg_align_up((size_t)N, 64);
+    sgp_split(N, s.nz, s.kchunk);
+    s.ldm = gpg_align_up((size_t)m, 64); s.ldn = s.nz * s.kchunk;
     const size_t mm = (size_t)m * s.ldm, mn = (size_t)m * s.ldn;
+    s.Spart = b.take<T>((size_t)s.nz * mm);
     s.Luu = b.take<T>(mm); s.Ui = b.take<T>(mm); s.tmp = b.take<T>(mm);
     s.Kuf = b.take<T>(mn); s.B = b.take<T>(mn);
     s.S = b.take<T>(mm); s.Ap = b.take<T>(mm); s.LA = b.take<T>(mm); s.LAi = b.take<T>(mm); s.Ainv = b.take<T>(mm);
@@ -1087,7 +1102,9 @@ static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *thet
     { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.Luu, m, ldm, info, 0, b.dinv, s)); }
     { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.Luu, m, ldm, b.Ui, ldm, b.tmp, s)); }
     {
-        StageTimer stg(h, GPG_ST_PGEMM, s);      // the two m x m x N products (booked under the predict GEMM's stage)
+        StageTimer stg(h, GPG_ST_PGEMM, s);      // B = Ui Kuf (booked under the predict GEMM's stage; S = B B^T under PFINAL)
+        if (ldn > N)                 // the split-K batches of S = B B^T read B up to column ldn
+            GPG_CUDA_CHECK(cudaMemset2DAsync(b.B + N, ldn * sizeof(T), 0, (ldn - N) * sizeof(T), m, s));
         GemmArgs<T> g;               // B = Ui Kuf  (Ui lower triangular: k <= i)
         g.A = b.Ui; g.lda = ldm; g.a_kmajor = 1;
         g.B = b.Kuf; g.ldb = ldn; g.b_kmajor = 0;
@@ -1098,17 +1115,18 @@ static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *thet
     }
     {
         StageTimer stg(h, GPG_ST_PFINAL, s);
-        GemmArgs<T> g;               // S = B B^T, lower tiles
+        GemmArgs<T> g;               // S = B B^T, lower tiles, split along K into nz batches (see sgp_split)
         g.A = b.B; g.lda = ldn; g.a_kmajor = 1;
         g.B = b.B; g.ldb = ldn; g.b_kmajor = 1;
-        g.C = b.S; g.ldc = ldm;
-        g.M = (int)m; g.N = (int)m; g.K = (int)N;
+        g.C = b.Spart; g.ldc = ldm;
+        g.M = (int)m; g.N = (int)m; g.K = (int)b.kchunk;
+        g.batch = b.nz; g.strideA = b.kchunk; g.strideB = b.kchunk; g.strideC = m * ldm;
         g.tile_mode = GEMM_TILES_LOWER;
         GPG_TRY(gemm_simt<T>(h, g, s));
+        const dim3 gmm((unsigned)((m + 255) / 256), (unsigned)m);
+        sgp_form_A_kernel<T><<<gmm, 256, 0, s>>>(b.Spart, b.nz, m * ldm, ldm, m, theta, b.S, b.Ap, b.LA);
+        GPG_LAUNCH_CHECK(h);
     }
-    const dim3 gmm((unsigned)((m + 255) / 256), (unsigned)m);
-    sgp_form_A_kernel<T><<<gmm, 256, 0, s>>>(b.S, ldm, m, theta, b.Ap, b.LA);
-    GPG_LAUNCH_CHECK(h);
     { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.LA, m, ldm, info, 0, b.dinv, s)); }
     { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.LA, m, ldm, b.LAi, ldm, b.tmp, s)); }
     StageTimer st(h, GPG_ST_SOLVE, s);
@@ -1139,12 +1157,15 @@ static int sgp_loss_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *th
         g.C = C; g.ldc = ldm;
         g.M = (int)m; g.N = (int)m; g.K = (int)m;
         g.alpha = alpha; g.kb_mode = kb_mode; g.tile_mode = tile_mode;
-        return gemm_simt<T>(h, g, s);
+        // m ~ 10^3: with 128 x 128 tiles an fp32 product has (m / 128)^2 ~ 50 CTAs for 148 SMs; the 32-row panel
+        // tiles give four times as many (fp64 already runs 64 x 64 tiles)
+        if constexpr (std::is_same<T, float>::value) return gemm_simt<T, GemmCfgPanelF32>(h, g, s);
+        else return gemm_simt<T>(h, g, s);
     };
     GPG_TRY(mm_gemm(b.LAi, 0, b.LAi, 0, b.Ainv, T(1), GEMM_KB_MAXMN, GEMM_TILES_LOWER));     // A'^-1 = LAi^T LAi (lower)
     sgp_scalars_kernel<T><<<1, 1024, 0, s>>>(y, N, b.beta, b.a0, b.c0, b.S, b.Ainv, b.LA, ldm, m, b.sc);
     GPG_LAUNCH_CHECK(h);
-    gemvT_rect_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(b.B, ldn, m, N, b.a, y, T(-1), T(1), b.rho);   // rho = y - B^T a
+    gemvT_rect_kernel<T><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(b.B, ldn, m, N, b.a, y, T(-1), T(1), b.rho);   // rho = y - B^T a
     GPG_LAUNCH_CHECK(h);
     const dim3 gmm((unsigned)((m + 255) / 256), (unsigned)m);
     sgp_form_phi_kernel<T><<<gmm, 256, 0, s>>>(b.Ainv, b.Ap, b.a, ldm, m, b.Phi, b.H);

@@ -27,29 +27,42 @@ template <typename T> __global__ void sgp_theta0_kernel(const T *__restrict__ th
     if (blockIdx.x == 0 && p < P) theta0[p] = (p == 1) ? T(0) : theta[p];
 }
 
-// out[i] = sum_j A[i][j] x[j]   (rows x cols, one warp per row, double accumulation)
+// out[i] = sum_j A[i][j] x[j]   (rows x cols, one warp per row, double accumulation, four loads in flight per lane)
 template <typename T>
 __global__ void __launch_bounds__(256) gemv_rect_kernel(const T *__restrict__ A, int64_t lda, int64_t rows, int64_t cols,
                                                         const T *__restrict__ x, T *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= rows) return;
-    double acc = 0.0;
-    for (int64_t j = lane; j < cols; j += 32) acc += (double)A[i * lda + j] * (double)x[j];
-    acc = warp_sum(acc);
-    if (lane == 0) out[i] = (T)acc;
+    const T *__restrict__ row = A + i * lda;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int64_t j = lane;
+    for (; j + 96 < cols; j += 128) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] += (double)row[j + 32 * e] * (double)x[j + 32 * e];
+    }
+    for (; j < cols; j += 32) acc[0] += (double)row[j] * (double)x[j];
+    const double tot = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
+    if (lane == 0) out[i] = (T)tot;
 }
 
-// out[j] = beta * yin[j] + alpha * sum_i A[i][j] x[i]   (thread per column, coalesced across the warp)
+// out[j] = beta * yin[j] + alpha * sum_i A[i][j] x[i]   (thread per column, coalesced across the warp, four
+// independent accumulators so that the row loop keeps several loads in flight)
 template <typename T>
-__global__ void __launch_bounds__(256) gemvT_rect_kernel(const T *__restrict__ A, int64_t lda, int64_t rows, int64_t cols,
+__global__ void __launch_bounds__(128) gemvT_rect_kernel(const T *__restrict__ A, int64_t lda, int64_t rows, int64_t cols,
                                                          const T *__restrict__ x, const T *__restrict__ yin, T alpha,
                                                          T beta, T *__restrict__ out) {
-    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cols) return;
-    double acc = 0.0;
-    for (int64_t i = 0; i < rows; ++i) acc += (double)A[i * lda + j] * (double)x[i];
-    out[j] = (T)((double)alpha * acc + (yin ? (double)beta * (double)yin[j] : 0.0));
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int64_t i = 0;
+    for (; i + 3 < rows; i += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] += (double)A[(i + e) * lda + j] * (double)x[i + e];
+    }
+    for (; i < rows; ++i) acc[0] += (double)A[i * lda + j] * (double)x[i];
+    const double tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    out[j] = (T)((double)alpha * tot + (yin ? (double)beta * (double)yin[j] : 0.0));
 }
 
 // out[i] = v[i] / theta[1]
@@ -59,15 +72,19 @@ __global__ void sgp_div_noise_kernel(const T *__restrict__ v, int64_t n, const T
     if (i < n) out[i] = (T)((double)v[i] / (double)theta[1]);
 }
 
-// A' = I + S / s2 from the lower triangle of S = B B^T: written in full to Ap and (lower is what matters) to LA
+// S = sum_z Spart[z] (the split-K partial products of B B^T, lower tiles valid) and A' = I + S / s2: S, Ap and LA
+// are written in full (symmetric)
 template <typename T>
-__global__ void __launch_bounds__(256) sgp_form_A_kernel(const T *__restrict__ S, int64_t ld, int64_t m,
-                                                         const T *__restrict__ theta, T *__restrict__ Ap,
-                                                         T *__restrict__ LA) {
+__global__ void __launch_bounds__(256) sgp_form_A_kernel(const T *__restrict__ Spart, int nz, int64_t zstride, int64_t ld,
+                                                         int64_t m, const T *__restrict__ theta, T *__restrict__ S,
+                                                         T *__restrict__ Ap, T *__restrict__ LA) {
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
     if (j >= m || i >= m) return;
-    const T s = (j <= i) ? S[i * ld + j] : S[j * ld + i];
-    const T v = (T)((double)s / (double)theta[1]) + (i == j ? T(1) : T(0));
+    const int64_t src = (j <= i) ? i * ld + j : j * ld + i;
+    double s = 0.0;
+    for (int z = 0; z < nz; ++z) s += (double)Spart[(int64_t)z * zstride + src];
+    const T v = (T)(s / (double)theta[1]) + (i == j ? T(1) : T(0));
+    S[i * ld + j] = (T)s;
     Ap[i * ld + j] = v;
     LA[i * ld + j] = v;
 }

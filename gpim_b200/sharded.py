@@ -26,7 +26,9 @@ def broadcast_factor(fac, src=0, group=None):
     # the tcgen05 predict path (f32, N >= 1024: gpg_predict's routing rule) reads only the fp16 planes of Linv;
     # the fp32 matrix travels only when the SIMT kernels will consume it
     planes = fac.get("wsplit")
-    if planes is not None and planes.shape[1] >= 1024:
+    if "Ui" in fac:                  # inducing-point cache (gpg_sparse_factorize): two m x m factors and a vector
+        keys = ("Ui", "Pm", "w")
+    elif planes is not None and planes.shape[1] >= 1024:
         keys = ("alpha", "wsplit", "scales")
     else:
         keys = ("Linv", "alpha", "wsplit", "scales")

@@ -99,3 +99,20 @@ def test_sk_out_of_path_branches_raise():
         gpim.skreconstructor(Xs, R, Xf, kernel="Spectral")
     with pytest.raises(KeyError):
         gpim.skreconstructor(Xs, R, Xf, kernel="nope", ski=False)
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "Matern52"])
+def test_sk_run_matches_committed_training_vectors(kernel, golden_dir):
+    """tests/golden/oracle_sk_train_*.npz: gpim.skreconstructor(ski=False).run() in fp64 against the frozen
+    trajectory and reconstruction -- no oracle in the loop."""
+    import os
+    import gpim
+    g = np.load(os.path.join(golden_dir, f"oracle_sk_train_{kernel}.npz"))
+    R = g["R"]
+    rec = gpim.skreconstructor(gpim.utils.get_sparse_grid(R), R, gpim.utils.get_full_grid(R), kernel=kernel, ski=False,
+                               lengthscale=[[1.0, 1.0], [10.0, 10.0]], learning_rate=0.1, iterations=15, verbose=0)
+    mean, sd, hp = rec.run()
+    np.testing.assert_allclose(np.array(hp["noise"]), g["noise"], rtol=1e-6)
+    np.testing.assert_allclose(np.array(hp["lengthscale"]), g["lengthscale"], rtol=1e-6)
+    np.testing.assert_allclose(np.array(rec.loss_all), g["loss"], rtol=1e-7, atol=1e-9)
+    assert relinf(mean, g["mean"]) < 1e-6 and relinf(sd, g["sd"]) < 1e-6

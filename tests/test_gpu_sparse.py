@@ -203,3 +203,21 @@ def test_boptimizer_with_sparse_surrogate(tmp_path):
     assert len(bo.indices_all) == 3 and bo.surrogate_model.model.Xu.shape[0] == m0
     assert int((~np.isnan(bo.target_func_vals[-1])).sum()) == int((~np.isnan(y_seed)).sum()) + 3
     assert np.isfinite(bo.gp_predictions[-1][0]).all()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_sparse_run_matches_committed_training_vectors(kernel, golden_dir):
+    """tests/golden/oracle_sparse_train_*.npz: gpim.reconstructor(sparse=True).run() in fp64 against the frozen
+    trajectory (hyper-parameters, inducing inputs, loss) and reconstruction -- no oracle in the loop."""
+    import os
+    import gpim
+    g = np.load(os.path.join(golden_dir, f"oracle_sparse_train_{kernel}.npz"))
+    R = g["R"]
+    rec = gpim.reconstructor(gpim.utils.get_sparse_grid(R), R, gpim.utils.get_full_grid(R), kernel=kernel, sparse=True,
+                             indpoints=14, learning_rate=0.1, iterations=15, verbose=0, seed=2)
+    mean, sd, hp = rec.run()
+    for key in ("variance", "noise", "lengthscale"):
+        np.testing.assert_allclose(np.array(hp[key]), g[key], rtol=1e-6)
+    np.testing.assert_allclose(np.array(hp["inducing_points"]), g["inducing_points"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(np.array(rec.loss_all), g["loss"], rtol=1e-8)
+    assert relinf(mean, g["mean"]) < 1e-6 and relinf(sd, g["sd"]) < 1e-6

@@ -38,6 +38,21 @@ def _worker(rank, world, port, M, out_dir):
 
     mean, sd = sharded.predict_sharded(factorize, alloc, tile, Xs)
     np.save(os.path.join(out_dir, f"r{rank}.npy"), np.stack([mean.numpy(), sd.numpy()]))
+
+    # the inducing-point cache {Ui, Pm, w} (reconstructor(sparse=True)) shards the same way
+    def sfactorize():
+        return {"Ui": torch.full((N, N), 2.0, dtype=torch.float64), "Pm": torch.eye(N, dtype=torch.float64),
+                "w": torch.arange(N, dtype=torch.float64), "ld": N}
+
+    def salloc():
+        return {"Ui": torch.zeros(N, N, dtype=torch.float64), "Pm": torch.zeros(N, N, dtype=torch.float64),
+                "w": torch.zeros(N, dtype=torch.float64), "ld": N}
+
+    def stile(fac, X):
+        return X[:, 0] * fac["Ui"][1, 1] + fac["w"].sum(), X[:, 1] + fac["Pm"].sum()
+
+    mean, sd = sharded.predict_sharded(sfactorize, salloc, stile, Xs)
+    np.save(os.path.join(out_dir, f"s{rank}.npy"), np.stack([mean.numpy(), sd.numpy()]))
     dist.destroy_process_group()
 
 
@@ -47,5 +62,7 @@ def test_sharded_predict_world2_gloo(tmp_path, M):
     mp.spawn(_worker, args=(2, port, M, str(tmp_path)), nprocs=2, join=True)
     Xs = np.arange(M * 2, dtype=np.float64).reshape(M, 2)
     want = np.stack([Xs[:, 0] * 3.0 + 10.0, Xs[:, 1] + 75.0])
+    swant = np.stack([Xs[:, 0] * 2.0 + 10.0, Xs[:, 1] + 5.0])
     for r in range(2):
         np.testing.assert_array_equal(np.load(tmp_path / f"r{r}.npy"), want)
+        np.testing.assert_array_equal(np.load(tmp_path / f"s{r}.npy"), swant)

@@ -85,3 +85,19 @@ def test_sk_reconstructor_glue_follows_the_oracle(monkeypatch, kernel, iso):
     np.testing.assert_allclose(np.array(hp1["noise"]), np.array(hp0["noise"]), rtol=1e-10)
     np.testing.assert_allclose(np.array(hp1["lengthscale"]), np.array(hp0["lengthscale"]), rtol=1e-10)
     assert abs(float(rec.model.mean_module.constant)) > 1e-3                                        # it was trained
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "Matern52"])
+def test_sk_oracle_reproduces_its_committed_training_vectors(kernel, golden_dir):
+    """tests/golden/oracle_sk_train_*.npz (make_oracle_vectors.py): the restatement must keep reproducing them."""
+    import os
+    g = np.load(os.path.join(golden_dir, f"oracle_sk_train_{kernel}.npz"))
+    R = g["R"]
+    ora = SKOracleGP(O.sparse_grid(R), R, O.full_grid(R), kernel=kernel, lengthscale=[[1.0, 1.0], [10.0, 10.0]],
+                     learning_rate=0.1, iterations=15)
+    mean, sd, hp = ora.run()
+    np.testing.assert_allclose(np.array(hp["noise"]), g["noise"], rtol=1e-9)
+    np.testing.assert_allclose(np.array(hp["lengthscale"]), g["lengthscale"], rtol=1e-9)
+    np.testing.assert_allclose(np.array(ora.losses), g["loss"], rtol=1e-9)
+    np.testing.assert_allclose(mean, g["mean"], rtol=0, atol=1e-9 * np.abs(g["mean"]).max())
+    np.testing.assert_allclose(sd, g["sd"], rtol=1e-9)

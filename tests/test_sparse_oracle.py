@@ -59,3 +59,24 @@ def test_vfe_objective_upper_bounds_the_exact_nll_and_training_lowers_it():
     assert np.abs(hp["inducing_points"][-1] - xu0).max() > 1e-3            # the inducing inputs are trained too
     # recorded AFTER the step: entry 0 is one Adam step away from noise = 1 (exp(-/+ lr))
     assert abs(abs(np.log(hp["noise"][0])) - 0.1) < 1e-6
+
+
+# oracle-generated fixtures (tests/golden/make_oracle_vectors.py): the restatement must keep reproducing them
+import os  # noqa: E402
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "Matern52", "RationalQuadratic"])
+def test_sparse_oracle_reproduces_its_committed_training_vectors(kernel, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"oracle_sparse_train_{kernel}.npz"))
+    R = g["R"]
+    ora = SparseOracleGP(O.sparse_grid(R), R, O.full_grid(R), indpoints=14, kernel=kernel, learning_rate=0.1,
+                         iterations=15, seed=2)
+    mean, sd, hp = ora.run()
+    for key in ("variance", "noise", "lengthscale"):
+        np.testing.assert_allclose(np.array(hp[key]), g[key], rtol=1e-8)
+    np.testing.assert_allclose(np.array(hp["inducing_points"]), g["inducing_points"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(np.array(ora.losses), g["loss"], rtol=1e-9)
+    np.testing.assert_allclose(mean, g["mean"], rtol=0, atol=1e-8 * np.abs(g["mean"]).max())
+    np.testing.assert_allclose(sd, g["sd"], rtol=1e-8)
