@@ -85,7 +85,7 @@ def load_library(build_if_missing=True):
         fn = getattr(lib, name)                       # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = restype
-    if lib.gpg_version() < 100:
+    if lib.gpg_version() < 110:
         raise RuntimeError("libgpgrid.so is older than this package")
     _LIB = lib
     return lib

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GPG_VERSION 100
+#define GPG_VERSION 110
 
 enum { GPG_OK = 0, GPG_EINVAL = 1, GPG_ENOTPD = 2, GPG_ECUDA = 3 };
 enum { GPG_F32 = 0, GPG_F64 = 1 };

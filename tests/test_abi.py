@@ -29,7 +29,7 @@ def test_library_exports_every_header_symbol():
     for name in header_symbols():
         assert hasattr(raw, name), f"{name} declared in include/gpgrid.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in gpim_b200/_lib.py"
-    assert lib.gpg_version() >= 100
+    assert lib.gpg_version() >= 110
 
 
 def test_binding_has_no_stale_signatures():

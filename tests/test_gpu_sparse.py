@@ -221,3 +221,53 @@ def test_sparse_run_matches_committed_training_vectors(kernel, golden_dir):
     np.testing.assert_allclose(np.array(hp["inducing_points"]), g["inducing_points"], rtol=0, atol=1e-6)
     np.testing.assert_allclose(np.array(rec.loss_all), g["loss"], rtol=1e-8)
     assert relinf(mean, g["mean"]) < 1e-6 and relinf(sd, g["sd"]) < 1e-6
+
+
+def test_sparse_full_size_properties_c2(eng):
+    """BASELINE.json configs[1] at FULL size with the notebook setting (256 x 256 spiral, N = 7688, 769 inducing
+    points; the oracle's autograd would need minutes here): size-independent properties of the VFE path."""
+    from gpim_b200._lib import KERNEL_IDS
+    R = W.spiral_scan(256)
+    X, y = O.training_rows(O.sparse_grid(R), R)
+    N = len(y)
+    ft = W.FIXED_THETA
+    kid = KERNEL_IDS["RBF"]
+    th = [ft["variance"], ft["noise"], 1.0, ft["lengthscale"], ft["lengthscale"]]
+    th64 = torch.tensor(th, dtype=torch.float64).cuda()
+    X64, y64 = torch.tensor(X).cuda(), torch.tensor(y).cuda()
+    Xu64 = X64[::N // (N // 10)].clone()
+    assert Xu64.shape[0] == 769
+    # (1) the collapsed bound is an upper bound of the exact negative log marginal likelihood (engine's own fp64 path)
+    loss, grad, gxu, info = eng.sparse_loss_grad(kid, th64, X64, y64, Xu64, 1e-5)
+    nll, _, info2 = eng.nll_grad(kid, th64, X64, y64, 1e-5)
+    assert int(info.item()) == 0 and int(info2.item()) == 0
+    assert float(loss.item()) >= float(nll.item())
+    # (2) the closed-form gradient is the derivative of the loss: central differences along one lengthscale,
+    #     the noise and one inducing coordinate
+    def loss_at(theta, Xu):
+        return float(eng.sparse_loss_grad(kid, theta, X64, y64, Xu, 1e-5)[0].item())
+    for p, h in ((3, 1e-4), (1, 1e-6)):
+        tp, tm = th64.clone(), th64.clone()
+        tp[p] += h
+        tm[p] -= h
+        fd = (loss_at(tp, Xu64) - loss_at(tm, Xu64)) / (2 * h)
+        assert abs(fd - float(grad[p].item())) <= 1e-4 * abs(fd) + 1e-6 * abs(float(loss.item()))
+    up, um = Xu64.clone(), Xu64.clone()
+    up[100, 1] += 1e-4
+    um[100, 1] -= 1e-4
+    fd = (loss_at(th64, up) - loss_at(th64, um)) / 2e-4
+    assert abs(fd - float(gxu[100, 1].item())) <= 1e-4 * abs(fd) + 1e-6 * abs(float(loss.item()))
+    # (3) fp32 prediction against the engine's fp64 one on a sample of the dense grid, north-star tolerances;
+    #     variance bounds: noise <= var <= variance + noise
+    Xf = torch.tensor(O.to_rows(O.full_grid(R))).cuda()[::4].contiguous()
+    m64, s64 = eng.sparse_predict(kid, th64, Xu64, eng.sparse_factorize(kid, th64, X64, y64, Xu64, 1e-5), Xf)
+    th32, X32, y32, Xu32 = th64.float(), X64.float(), y64.float(), Xu64.float()
+    fac32 = eng.sparse_factorize(kid, th32, X32, y32, Xu32, 1e-5)
+    assert int(fac32["info"].item()) == 0
+    m32, s32 = eng.sparse_predict(kid, th32, Xu32, fac32, Xf.float())
+    assert relinf(m32.cpu(), m64.cpu()) < 1e-4 and relinf(s32.cpu(), s64.cpu()) < 1e-3
+    var = (s64 ** 2).cpu().numpy()
+    assert var.min() >= ft["noise"] * (1 - 1e-6) and var.max() <= (ft["variance"] + ft["noise"]) * (1 + 1e-6)
+    # (4) linearity in y: the factors do not depend on y, so sd is bit-identical and the mean scales
+    m2, s2 = eng.sparse_predict(kid, th64, Xu64, eng.sparse_factorize(kid, th64, X64, -3.0 * y64, Xu64, 1e-5), Xf)
+    assert torch.equal(s2, s64) and relinf(m2.cpu(), -3.0 * m64.cpu()) < 1e-9
