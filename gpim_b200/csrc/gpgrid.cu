@@ -1031,6 +1031,11 @@ template <typename T> struct SgpBufs {
     int nz = 1;                  // split-K factor of S = B B^T; ldn = nz * kchunk (columns [N, ldn) of B are kept zero)
     int64_t kchunk = 0;
     T *Spart;
+    // tcgen05 route of the two m x m x N products with contraction length m (fp32, large problems): fp16 hi/lo planes
+    bool tc = false;
+    int64_t ldk = 0;             // leading dimension of the N x m operands
+    float *Kfu = nullptr, *scales = nullptr;
+    __half *Kfus = nullptr, *Bts = nullptr, *Uis = nullptr, *T2s = nullptr;      // hi plane, then lo plane
     T *Luu, *Ui, *tmp, *Kuf, *B, *S, *Ap, *LA, *LAi, *Ainv, *Phi, *H, *T1, *Guu, *T2;   // Kuf doubles as dF/dKuf
     T *beta, *c0, *a0, *a, *w, *rho, *dinv, *theta0, *gxu, *grad, *loss, *theta, *m1, *m2;
     double *sc, *partA, *partB;
@@ -1046,10 +1051,21 @@ static void sgp_split(int64_t N, int &nz, int64_t &kchunk) {
     kchunk = (int64_t)gpg_align_up((size_t)((N + nz - 1) / nz), 64);
 }
 
-template <typename T> static size_t sgp_ws_bytes(int64_t m, int64_t N, int d) {
+// B = Ui k(Xu, X) and dF/dKuf = T2 B go to the split-fp16 tcgen05 GEMM when they are large enough to matter (fp32 only).
+// S = B B^T stays on the SIMT kernel: its diagonal is a same-sign sum of length N, which the truncating TMEM
+// accumulation would bias.
+template <typename T> static bool sgp_uses_tc(const gpg_handle_s *h, int64_t m, int64_t N) {
+    return std::is_same<T, float>::value && h->opt_gemm_path != 1 && (h->opt_gemm_path == 2 || (m >= 512 && N >= 2048));
+}
+
+template <typename T> static size_t sgp_ws_bytes(const gpg_handle_s *h, int64_t m, int64_t N, int d) {
     constexpr int NB = GemmCfg<T>::BN;
     int nz; int64_t kchunk;
     sgp_split(N, nz, kchunk);
+    const bool tcp = sgp_uses_tc<T>(h, m, N);
+    const size_t ldk_ = gpg_align_up((size_t)m, 64), ldm_ = ldk_;
+    const size_t tc_bytes = tcp ? bump_size({(size_t)N * ldk_ * 4, (size_t)N * ldk_ * 4, (size_t)N * ldk_ * 4,
+                                             (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4, SGP_S_COUNT * sizeof(float)}) : 0;
     const int64_t ldm = gpg_align_up((size_t)m, 64), ldn = nz * kchunk;
     const size_t mm = (size_t)m * ldm * sizeof(T), mn = (size_t)m * ldn * sizeof(T), mv = (size_t)m * sizeof(T);
     const size_t nb = (size_t)((m + 7) / 8);
@@ -1057,10 +1073,10 @@ template <typename T> static size_t sgp_ws_bytes(int64_t m, int64_t N, int d) {
                       mv, mv, mv, mv, mv, (size_t)N * sizeof(T), NB * NB * sizeof(T), GPG_MAX_P * sizeof(T),
                       mv * d, GPG_MAX_P * sizeof(T), sizeof(T), GPG_MAX_P * sizeof(T), mv * d, mv * d,
                       SGP_SC_COUNT * sizeof(double), nb * GPG_MAX_P * sizeof(double), nb * GPG_MAX_P * sizeof(double),
-                      sizeof(FitState)});
+                      sizeof(FitState)}) + tc_bytes;
 }
 
-template <typename T> static SgpBufs<T> sgp_carve(void *ws, int64_t m, int64_t N, int d) {
+template <typename T> static SgpBufs<T> sgp_carve(const gpg_handle_s *h, void *ws, int64_t m, int64_t N, int d) {
     constexpr int NB = GemmCfg<T>::BN;
     Bump b(ws);
     SgpBufs<T> s;
@@ -1085,7 +1101,36 @@ template <typename T> static SgpBufs<T> sgp_carve(void *ws, int64_t m, int64_t N
     s.partA = b.take<double>((size_t)s.nb * GPG_MAX_P);
     s.partB = b.take<double>((size_t)s.nb * GPG_MAX_P);
     s.st = b.take<FitState>(1);
+    s.tc = sgp_uses_tc<T>(h, m, N);
+    s.ldk = gpg_align_up((size_t)m, 64);
+    if (s.tc) {
+        s.Kfu = b.take<float>((size_t)N * s.ldk);
+        s.Kfus = b.take<__half>(2 * (size_t)N * s.ldk);
+        s.Bts = b.take<__half>(2 * (size_t)N * s.ldk);
+        s.Uis = b.take<__half>(2 * (size_t)m * s.ldm);
+        s.T2s = b.take<__half>(2 * (size_t)m * s.ldm);
+        s.scales = b.take<float>(SGP_S_COUNT);
+    }
     return s;
+}
+
+// C (m x N, fp32, leading dimension ldc) = A (m x m, fp16 planes As) * Bt^T with Bt (N x m, fp16 planes) on tcgen05;
+// optionally emits the transposed split of the result (N x m planes Ts, scaled by *scale_out).
+static int sgp_tc_product(gpg_handle_s *h, int64_t m, int64_t N, const __half *As, int64_t lda, const __half *Bts,
+                          int64_t ldb, float *C, int64_t ldc, const float *scale_inv, int ke_mode, __half *Ts,
+                          const float *scale_out, cudaStream_t s) {
+    tc::Launch g;
+    memset(&g.p, 0, sizeof(g.p));
+    g.A.hi = As; g.A.lo = As + (size_t)m * lda; g.A.rows = m; g.A.cols = m; g.A.ld = lda;
+    g.B.hi = Bts; g.B.lo = Bts + (size_t)N * ldb; g.B.rows = N; g.B.cols = m; g.B.ld = ldb;
+    g.p.M = (int)m; g.p.N = (int)N; g.p.K = (int)m; g.p.batch = 1;
+    g.p.ke_mode = ke_mode;
+    g.p.epi = tc::EPI_STORE;
+    g.p.scale_inv = scale_inv;
+    g.p.C = C; g.p.ldc = ldc;
+    g.p.alpha = 1.0f; g.p.beta = 0.0f;
+    if (Ts) { g.p.T_hi = Ts; g.p.T_lo = Ts + (size_t)N * ldb; g.p.ldt = ldb; g.p.scale_out = scale_out; }
+    return tc::launch(h, g, s);
 }
 
 // Luu, Ui, B, S, A', LA, LAi, beta, c0, a0, a, w for the theta stored on the device.  info keeps the first failing pivot of
@@ -1098,20 +1143,42 @@ static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *thet
     GPG_LAUNCH_CHECK(h);
     { StageTimer st(h, GPG_ST_KMAT, s);
       GPG_TRY(kmat_launch<T>(h, kernel_id, d, b.theta0, Xu, m, nullptr, m, jitter, 0, b.Luu, ldm, s));
-      GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, Xu, m, X, N, 0.0, 0, b.Kuf, ldn, s)); }
+      if constexpr (std::is_same<T, float>::value) {
+          if (b.tc) {                // k(X, Xu) (N x m) straight into the fp16 planes the tcgen05 product reads
+              sgp_scales_theta_kernel<T><<<1, 32, 0, s>>>(theta, b.scales);
+              GPG_LAUNCH_CHECK(h);
+              KmatSplit sp;
+              sp.hi = b.Kfus; sp.lo = b.Kfus + (size_t)N * b.ldk; sp.ld = b.ldk; sp.scale = b.scales + SGP_S_K;
+              GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, X, N, Xu, m, 0.0, 0, b.Kfu, b.ldk, s, sp));
+          }
+      }
+      if (!b.tc) GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, Xu, m, X, N, 0.0, 0, b.Kuf, ldn, s)); }
     { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.Luu, m, ldm, info, 0, b.dinv, s)); }
     { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.Luu, m, ldm, b.Ui, ldm, b.tmp, s)); }
     {
         StageTimer stg(h, GPG_ST_PGEMM, s);      // B = Ui Kuf (booked under the predict GEMM's stage; S = B B^T under PFINAL)
         if (ldn > N)                 // the split-K batches of S = B B^T read B up to column ldn
             GPG_CUDA_CHECK(cudaMemset2DAsync(b.B + N, ldn * sizeof(T), 0, (ldn - N) * sizeof(T), m, s));
-        GemmArgs<T> g;               // B = Ui Kuf  (Ui lower triangular: k <= i)
-        g.A = b.Ui; g.lda = ldm; g.a_kmajor = 1;
-        g.B = b.Kuf; g.ldb = ldn; g.b_kmajor = 0;
-        g.C = b.B; g.ldc = ldn;
-        g.M = (int)m; g.N = (int)N; g.K = (int)m;
-        g.ke_mode = GEMM_KE_M;
-        GPG_TRY(gemm_simt<T>(h, g, s));
+        bool done = false;
+        if constexpr (std::is_same<T, float>::value) {
+            if (b.tc) {              // B = Ui k(X, Xu)^T on tcgen05; the epilogue also leaves B^T as fp16 planes for dF/dKuf
+                sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(b.Ui, ldm, m, m, b.scales, SGP_S_U, SGP_S_K, SGP_S_UK_INV);
+                GPG_LAUNCH_CHECK(h);
+                GPG_TRY(tc::split_matrix(h, b.Ui, ldm, m, m, b.scales + SGP_S_U, b.Uis, b.Uis + (size_t)m * ldm, ldm, 1, s));
+                GPG_TRY(sgp_tc_product(h, m, N, b.Uis, ldm, b.Kfus, b.ldk, b.B, ldn, b.scales + SGP_S_UK_INV, GEMM_KE_M,
+                                       b.Bts, b.scales + SGP_S_B, s));
+                done = true;
+            }
+        }
+        if (!done) {
+            GemmArgs<T> g;           // B = Ui Kuf  (Ui lower triangular: k <= i)
+            g.A = b.Ui; g.lda = ldm; g.a_kmajor = 1;
+            g.B = b.Kuf; g.ldb = ldn; g.b_kmajor = 0;
+            g.C = b.B; g.ldc = ldn;
+            g.M = (int)m; g.N = (int)N; g.K = (int)m;
+            g.ke_mode = GEMM_KE_M;
+            GPG_TRY(gemm_simt<T>(h, g, s));
+        }
     }
     {
         StageTimer stg(h, GPG_ST_PFINAL, s);
@@ -1173,8 +1240,19 @@ static int sgp_loss_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *th
     GPG_TRY(mm_gemm(b.Phi, 1, b.Ui, 0, b.T1, T(1), GEMM_KB_NONE, GEMM_TILES_ALL));           // T1 = Phi Ui
     GPG_TRY(mm_gemm(b.Ui, 0, b.T1, 0, b.Guu, T(-0.5), GEMM_KB_NONE, GEMM_TILES_ALL));        // dF/dKuu = -1/2 Ui^T T1
     GPG_TRY(mm_gemm(b.Ui, 0, b.H, 0, b.T2, T(1), GEMM_KB_NONE, GEMM_TILES_ALL));             // T2 = Ui^T H
-    {
-        GemmArgs<T> g;               // s2 dF/dKuf + w rho^T = T2 B   (into the Kuf buffer, which is dead by now)
+    bool guf_done = false;           // s2 dF/dKuf + w rho^T = T2 B   (into the Kuf buffer, which is dead by now)
+    if constexpr (std::is_same<T, float>::value) {
+        if (b.tc) {
+            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(b.T2, ldm, m, m, b.scales, SGP_S_T, SGP_S_B, SGP_S_TB_INV);
+            GPG_LAUNCH_CHECK(h);
+            GPG_TRY(tc::split_matrix(h, b.T2, ldm, m, m, b.scales + SGP_S_T, b.T2s, b.T2s + (size_t)m * ldm, ldm, 0, s));
+            GPG_TRY(sgp_tc_product(h, m, N, b.T2s, ldm, b.Bts, b.ldk, b.Kuf, ldn, b.scales + SGP_S_TB_INV, GEMM_KE_NONE,
+                                   nullptr, nullptr, s));
+            guf_done = true;
+        }
+    }
+    if (!guf_done) {
+        GemmArgs<T> g;
         g.A = b.T2; g.lda = ldm; g.a_kmajor = 1;
         g.B = b.B; g.ldb = ldn; g.b_kmajor = 0;
         g.C = b.Kuf; g.ldc = ldn;
@@ -1206,8 +1284,8 @@ static int sgp_loss_grad_entry(gpg_handle_s *h, int kernel_id, int d, const T *t
                                const T *Xu, int64_t m, double jitter, T *loss_out, T *grad_out, T *gxu_out, int32_t *info,
                                cudaStream_t s) {
     void *ws;
-    GPG_TRY(gpg_ws_reserve(h, sgp_ws_bytes<T>(m, N, d), &ws));
-    SgpBufs<T> b = sgp_carve<T>(ws, m, N, d);
+    GPG_TRY(gpg_ws_reserve(h, sgp_ws_bytes<T>(h, m, N, d), &ws));
+    SgpBufs<T> b = sgp_carve<T>(h, ws, m, N, d);
     GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
     return sgp_loss_grad_core<T>(h, kernel_id, d, theta, X, y, N, Xu, m, jitter, b, loss_out, grad_out, gxu_out, info, s);
 }
@@ -1236,8 +1314,8 @@ static int sgp_fit_entry(gpg_handle_s *h, int kernel_id, int d, int n_ls, const 
                          int64_t m, double jitter, T *u, const double *bounds, int iters, double lr, T *traj, T *xu_traj,
                          T *theta_out, int32_t *info, cudaStream_t s) {
     void *ws;
-    GPG_TRY(gpg_ws_reserve(h, sgp_ws_bytes<T>(m, N, d), &ws));
-    SgpBufs<T> b = sgp_carve<T>(ws, m, N, d);
+    GPG_TRY(gpg_ws_reserve(h, sgp_ws_bytes<T>(h, m, N, d), &ws));
+    SgpBufs<T> b = sgp_carve<T>(h, ws, m, N, d);
     FitCfg c;
     memset(&c, 0, sizeof(c));
     c.d = d; c.n_ls = n_ls; c.is_rq = (kernel_id == GPG_RATQUAD);
@@ -1291,8 +1369,8 @@ static int sgp_factorize_entry(gpg_handle_s *h, int kernel_id, int d, const T *t
                                const T *Xu, int64_t m, double jitter, T *Ui_out, T *P_out, int64_t ld, T *w_out,
                                int32_t *info, cudaStream_t s) {
     void *ws;
-    GPG_TRY(gpg_ws_reserve(h, sgp_ws_bytes<T>(m, N, d), &ws));
-    SgpBufs<T> b = sgp_carve<T>(ws, m, N, d);
+    GPG_TRY(gpg_ws_reserve(h, sgp_ws_bytes<T>(h, m, N, d), &ws));
+    SgpBufs<T> b = sgp_carve<T>(h, ws, m, N, d);
     GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
     GPG_TRY(sgp_lowrank_core<T>(h, kernel_id, d, theta, X, y, N, Xu, m, jitter, b, info, s));
     GemmArgs<T> g;                   // Pm = LAi Ui (lower x lower)

@@ -21,6 +21,48 @@
 enum { SGP_SC_YY = 0, SGP_SC_A0BETA = 1, SGP_SC_A0A0 = 2, SGP_SC_TRAINV = 3, SGP_SC_BFRO = 4, SGP_SC_LOGDET = 5,
        SGP_SC_C0C0 = 6, SGP_SC_COUNT = 8 };
 
+// Operand scales of the tcgen05 products (fp32 path, large m and N).  The split-fp16 GEMM wants every operand
+// multiplied by a power of two that brings its largest entry just under 2^14.
+//   SGP_S_K  k(X, Xu) entries are <= variance                         (rigorous, from theta)
+//   SGP_S_B  B = Luu^-1 k(Xu, X): column norms^2 = Qff_nn <= k(x, x) = variance, so |B_ij| <= sqrt(variance)
+//   SGP_S_U, SGP_S_T  Luu^-1 and T2 = Ui^T (A'^-1 - I): measured (one pass over an m x m matrix)
+enum { SGP_S_K = 0, SGP_S_U = 1, SGP_S_UK_INV = 2, SGP_S_B = 3, SGP_S_T = 4, SGP_S_TB_INV = 5, SGP_S_COUNT = 8 };
+
+__device__ __forceinline__ float sgp_pow2_scale(float bound) {
+    return (bound > 0.f && bound < 3.0e38f) ? exp2f(floorf(log2f(16384.f / bound))) : 1.f;
+}
+
+template <typename T> __global__ void sgp_scales_theta_kernel(const T *__restrict__ theta, float *__restrict__ scales) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float v = (float)theta[0];
+    scales[SGP_S_K] = sgp_pow2_scale(v);
+    scales[SGP_S_B] = sgp_pow2_scale(sqrtf(v));
+}
+
+// scales[slot] = power-of-two scale for max |M_ij| over rows x cols; scales[slot_inv] = 1 / (scales[slot] * scales[other])
+__global__ void __launch_bounds__(1024) sgp_absmax_scale_kernel(const float *__restrict__ M, int64_t ld, int64_t rows,
+                                                                int64_t cols, float *__restrict__ scales, int slot,
+                                                                int other, int slot_inv) {
+    __shared__ float red[32];
+    float mx = 0.f;
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = threadIdx.x >> 5; i < rows; i += 32)
+        for (int64_t j = lane; j < cols; j += 32) {
+            const float a = fabsf(M[i * ld + j]);
+            if (a < 3.0e38f) mx = fmaxf(mx, a);      // ignores inf / NaN (a failed factorisation is reported through info)
+        }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 32; ++w) t = fmaxf(t, red[w]);
+        const float sc = sgp_pow2_scale(t);
+        scales[slot] = sc;
+        scales[slot_inv] = 1.0f / (sc * scales[other]);
+    }
+}
+
 // theta0 = theta with the noise entry cleared (Kuu carries jitter only on its diagonal)
 template <typename T> __global__ void sgp_theta0_kernel(const T *__restrict__ theta, int P, T *__restrict__ theta0) {
     const int p = threadIdx.x;

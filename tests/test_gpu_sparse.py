@@ -271,3 +271,40 @@ def test_sparse_full_size_properties_c2(eng):
     # (4) linearity in y: the factors do not depend on y, so sd is bit-identical and the mean scales
     m2, s2 = eng.sparse_predict(kid, th64, Xu64, eng.sparse_factorize(kid, th64, X64, -3.0 * y64, Xu64, 1e-5), Xf)
     assert torch.equal(s2, s64) and relinf(m2.cpu(), -3.0 * m64.cpu()) < 1e-9
+
+
+def test_sparse_tensor_core_products_match_the_simt_route(eng):
+    """fp32 at C2 size (m = 769, N = 7688): B = Luu^-1 k(Xu, X) and dF/dKuf = T2 B run on the tcgen05 split-fp16 GEMM.
+    Loss and gradients (theta and inducing inputs) against the engine's fp64 path; the tensor-core route must be as
+    close to it as the all-SIMT fp32 route (GPG_OPT_GEMM_PATH = 1) is."""
+    from gpim_b200._lib import KERNEL_IDS, OPT_GEMM_PATH
+    R = W.spiral_scan(256)
+    X, y = O.training_rows(O.sparse_grid(R), R)
+    N = len(y)
+    ft = W.FIXED_THETA
+    th = [ft["variance"], ft["noise"], 1.0, ft["lengthscale"], ft["lengthscale"]]
+    for kernel in ("RBF", "Matern52"):
+        kid = KERNEL_IDS[kernel]
+        th64 = torch.tensor(th, dtype=torch.float64).cuda()
+        X64, y64 = torch.tensor(X).cuda(), torch.tensor(y).cuda()
+        Xu64 = X64[::N // (N // 10)].clone()
+        l64, g64, x64, _ = eng.sparse_loss_grad(kid, th64, X64, y64, Xu64, 1e-4)
+        g64, x64 = g64.cpu().numpy(), x64.cpu().numpy()
+        err = {}
+        try:
+            for path in (1, 0):
+                eng.set_option(OPT_GEMM_PATH, path)
+                l32, g32, x32, info = eng.sparse_loss_grad(kid, th64.float(), X64.float(), y64.float(), Xu64.float(), 1e-4)
+                assert int(info.item()) == 0
+                g = g32.double().cpu().numpy()
+                sel = [0, 1, 3, 4]                    # variance, noise, lengthscales (no scale mixture here)
+                err[path] = (abs(float(l32.item()) - float(l64.item())),
+                             float(np.abs(g[sel] - g64[sel]).max() / np.abs(g64[sel]).max()),
+                             float(np.abs(x32.double().cpu().numpy() - x64).max() / np.abs(x64).max()))
+        finally:
+            eng.set_option(OPT_GEMM_PATH, 0)
+        print(kernel, "fp32 vs fp64 (loss abs, grad theta rel, grad Xu rel): SIMT", err[1], "tcgen05", err[0])
+        scale = 1e-5 * N * abs(np.log(ft["noise"]))
+        assert err[0][0] <= max(2 * err[1][0], scale)
+        assert err[0][1] <= max(2 * err[1][1], 2e-3)
+        assert err[0][2] <= max(2 * err[1][2], 2e-3)

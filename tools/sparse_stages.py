@@ -15,6 +15,8 @@ from gpim_b200._lib import get_engine, KERNEL_IDS, OPT_STAGE_TIMING  # noqa: E40
 
 def main(name="c2", iters=10, only=None):
     eng = get_engine()
+    if os.environ.get("GPG_GEMM_PATH"):               # 1: all-SIMT, 0 (default): tcgen05 for the large fp32 products
+        eng.set_option(1, int(os.environ["GPG_GEMM_PATH"]))
     wl = bench.make_workload(name)
     X, y = bench.train_rows(wl["R"])
     N, d = X.shape
