@@ -65,6 +65,7 @@ struct Params {
     // operand placement inside the matrices described by the tensor maps (elements)
     int a_row0, a_col0, a_bs;    // batch b adds a_bs to both row and column
     int b_row0, b_col0, b_bs;
+    int a_kbs, b_kbs;            // batch b additionally adds b * a_kbs / b * b_kbs to the COLUMN (k) only: split-K batches
     int epi;
     const float *scale_inv;      // device scalar: 1 / (scale_A * scale_B)
     // ROWSUMSQ
@@ -245,9 +246,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 Tile ti;
                 if (!decode_tile(p, t, ti)) continue;
                 const int arow = p.a_row0 + ti.batch * p.a_bs + ti.mblk * BM;
-                const int acol = p.a_col0 + ti.batch * p.a_bs;
+                const int acol = p.a_col0 + ti.batch * (p.a_bs + p.a_kbs);
                 const int brow = p.b_row0 + ti.batch * p.b_bs + ti.nblk * BN;
-                const int bcol = p.b_col0 + ti.batch * p.b_bs;
+                const int bcol = p.b_col0 + ti.batch * (p.b_bs + p.b_kbs);
                 for (int kb = ti.kb_blk; kb < ti.ke_blk; ++kb) {
                     mbar_wait(BAR(BAR_EMPTY + stage), phase ^ 1);
                     const uint32_t sbase = tiles + (uint32_t)stage * STAGE_BYTES;

@@ -1035,7 +1035,9 @@ template <typename T> struct SgpBufs {
     bool tc = false;
     int64_t ldk = 0;             // leading dimension of the N x m operands
     float *Kfu = nullptr, *scales = nullptr;
-    __half *Kfus = nullptr, *Bts = nullptr, *Uis = nullptr, *T2s = nullptr;      // hi plane, then lo plane
+    __half *Kfus = nullptr, *Bts = nullptr, *Uis = nullptr, *T2s = nullptr, *Bs = nullptr;      // hi plane, then lo plane
+    int nzt = 0;                 // S = B B^T on tcgen05: split-K batches of SGP_TC_KCHUNK columns, partial products in SpartTc
+    float *SpartTc = nullptr;
     T *Luu, *Ui, *tmp, *Kuf, *B, *S, *Ap, *LA, *LAi, *Ainv, *Phi, *H, *T1, *Guu, *T2;   // Kuf doubles as dF/dKuf
     T *beta, *c0, *a0, *a, *w, *rho, *dinv, *theta0, *gxu, *grad, *loss, *theta, *m1, *m2;
     double *sc, *partA, *partB;
@@ -1051,9 +1053,14 @@ static void sgp_split(int64_t N, int &nz, int64_t &kchunk) {
     kchunk = (int64_t)gpg_align_up((size_t)((N + nz - 1) / nz), 64);
 }
 
-// B = Ui k(Xu, X) and dF/dKuf = T2 B go to the split-fp16 tcgen05 GEMM when they are large enough to matter (fp32 only).
-// S = B B^T stays on the SIMT kernel: its diagonal is a same-sign sum of length N, which the truncating TMEM
-// accumulation would bias.
+// The three m x m x N products -- B = Ui k(Xu, X), S = B B^T and dF/dKuf = T2 B -- go to the split-fp16 tcgen05 GEMM when
+// they are large enough to matter (fp32 only).
+// S = B B^T is a sum of N same-sign-dominated products per diagonal entry; the TMEM accumulation truncates (a bias of
+// about -6e-9 per accumulated term), so the contraction is cut into batches of 512 columns whose
+// partial products are added in double by sgp_form_A_kernel: the bias stays at 3e-6 relative, the level of the
+// rounding error of an fp32 SIMT accumulation of this length.
+constexpr int SGP_TC_KCHUNK = 512;
+
 template <typename T> static bool sgp_uses_tc(const gpg_handle_s *h, int64_t m, int64_t N) {
     return std::is_same<T, float>::value && h->opt_gemm_path != 1 && (h->opt_gemm_path == 2 || (m >= 512 && N >= 2048));
 }
@@ -1064,8 +1071,10 @@ template <typename T> static size_t sgp_ws_bytes(const gpg_handle_s *h, int64_t 
     sgp_split(N, nz, kchunk);
     const bool tcp = sgp_uses_tc<T>(h, m, N);
     const size_t ldk_ = gpg_align_up((size_t)m, 64), ldm_ = ldk_;
+    const size_t nzt_ = (size_t)((N + SGP_TC_KCHUNK - 1) / SGP_TC_KCHUNK);
     const size_t tc_bytes = tcp ? bump_size({(size_t)N * ldk_ * 4, (size_t)N * ldk_ * 4, (size_t)N * ldk_ * 4,
-                                             (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4, SGP_S_COUNT * sizeof(float)}) : 0;
+                                             (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4, SGP_S_COUNT * sizeof(float),
+                                             (size_t)m * (size_t)(nz * kchunk) * 4, nzt_ * m * ldm_ * 4}) : 0;
     const int64_t ldm = gpg_align_up((size_t)m, 64), ldn = nz * kchunk;
     const size_t mm = (size_t)m * ldm * sizeof(T), mn = (size_t)m * ldn * sizeof(T), mv = (size_t)m * sizeof(T);
     const size_t nb = (size_t)((m + 7) / 8);
@@ -1110,6 +1119,9 @@ template <typename T> static SgpBufs<T> sgp_carve(const gpg_handle_s *h, void *w
         s.Uis = b.take<__half>(2 * (size_t)m * s.ldm);
         s.T2s = b.take<__half>(2 * (size_t)m * s.ldm);
         s.scales = b.take<float>(SGP_S_COUNT);
+        s.Bs = b.take<__half>(2 * (size_t)m * s.ldn);
+        s.nzt = (int)((N + SGP_TC_KCHUNK - 1) / SGP_TC_KCHUNK);
+        s.SpartTc = b.take<float>((size_t)s.nzt * m * s.ldm);
     }
     return s;
 }
@@ -1118,7 +1130,7 @@ template <typename T> static SgpBufs<T> sgp_carve(const gpg_handle_s *h, void *w
 // optionally emits the transposed split of the result (N x m planes Ts, scaled by *scale_out).
 static int sgp_tc_product(gpg_handle_s *h, int64_t m, int64_t N, const __half *As, int64_t lda, const __half *Bts,
                           int64_t ldb, float *C, int64_t ldc, const float *scale_inv, int ke_mode, __half *Ts,
-                          const float *scale_out, cudaStream_t s) {
+                          const float *scale_out, cudaStream_t s, __half *Ss = nullptr) {
     tc::Launch g;
     memset(&g.p, 0, sizeof(g.p));
     g.A.hi = As; g.A.lo = As + (size_t)m * lda; g.A.rows = m; g.A.cols = m; g.A.ld = lda;
@@ -1130,6 +1142,7 @@ static int sgp_tc_product(gpg_handle_s *h, int64_t m, int64_t N, const __half *A
     g.p.C = C; g.p.ldc = ldc;
     g.p.alpha = 1.0f; g.p.beta = 0.0f;
     if (Ts) { g.p.T_hi = Ts; g.p.T_lo = Ts + (size_t)N * ldb; g.p.ldt = ldb; g.p.scale_out = scale_out; }
+    if (Ss) { g.p.S_hi = Ss; g.p.S_lo = Ss + (size_t)m * ldc; g.p.lds = ldc; g.p.scale_out = scale_out; }   // same geometry as C
     return tc::launch(h, g, s);
 }
 
@@ -1166,7 +1179,7 @@ static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *thet
                 GPG_LAUNCH_CHECK(h);
                 GPG_TRY(tc::split_matrix(h, b.Ui, ldm, m, m, b.scales + SGP_S_U, b.Uis, b.Uis + (size_t)m * ldm, ldm, 1, s));
                 GPG_TRY(sgp_tc_product(h, m, N, b.Uis, ldm, b.Kfus, b.ldk, b.B, ldn, b.scales + SGP_S_UK_INV, GEMM_KE_M,
-                                       b.Bts, b.scales + SGP_S_B, s));
+                                       b.Bts, b.scales + SGP_S_B, s, b.Bs));
                 done = true;
             }
         }
@@ -1182,17 +1195,39 @@ static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *thet
     }
     {
         StageTimer stg(h, GPG_ST_PFINAL, s);
-        GemmArgs<T> g;               // S = B B^T, lower tiles, split along K into nz batches (see sgp_split)
-        g.A = b.B; g.lda = ldn; g.a_kmajor = 1;
-        g.B = b.B; g.ldb = ldn; g.b_kmajor = 1;
-        g.C = b.Spart; g.ldc = ldm;
-        g.M = (int)m; g.N = (int)m; g.K = (int)b.kchunk;
-        g.batch = b.nz; g.strideA = b.kchunk; g.strideB = b.kchunk; g.strideC = m * ldm;
-        g.tile_mode = GEMM_TILES_LOWER;
-        GPG_TRY(gemm_simt<T>(h, g, s));
         const dim3 gmm((unsigned)((m + 255) / 256), (unsigned)m);
-        sgp_form_A_kernel<T><<<gmm, 256, 0, s>>>(b.Spart, b.nz, m * ldm, ldm, m, theta, b.S, b.Ap, b.LA);
-        GPG_LAUNCH_CHECK(h);
+        bool done = false;
+        if constexpr (std::is_same<T, float>::value) {
+            if (b.tc) {              // S = B B^T on tcgen05 from the fp16 planes of B, lower tiles, split-K batches
+                tc::Launch g;
+                memset(&g.p, 0, sizeof(g.p));
+                g.A.hi = b.Bs; g.A.lo = b.Bs + (size_t)m * ldn; g.A.rows = m; g.A.cols = N; g.A.ld = ldn;
+                g.B = g.A;
+                g.p.M = (int)m; g.p.N = (int)m; g.p.K = SGP_TC_KCHUNK; g.p.batch = b.nzt;
+                g.p.a_kbs = SGP_TC_KCHUNK; g.p.b_kbs = SGP_TC_KCHUNK;
+                g.p.tile_mode = GEMM_TILES_LOWER;
+                g.p.epi = tc::EPI_STORE;
+                g.p.scale_inv = b.scales + SGP_S_BB_INV;
+                g.p.C = b.SpartTc; g.p.ldc = ldm; g.p.c_bs = m * ldm;
+                g.p.alpha = 1.0f; g.p.beta = 0.0f;
+                GPG_TRY(tc::launch(h, g, s));
+                sgp_form_A_kernel<T><<<gmm, 256, 0, s>>>(b.SpartTc, b.nzt, m * ldm, ldm, m, theta, b.S, b.Ap, b.LA);
+                GPG_LAUNCH_CHECK(h);
+                done = true;
+            }
+        }
+        if (!done) {
+            GemmArgs<T> g;           // S = B B^T, lower tiles, split along K into nz batches (see sgp_split)
+            g.A = b.B; g.lda = ldn; g.a_kmajor = 1;
+            g.B = b.B; g.ldb = ldn; g.b_kmajor = 1;
+            g.C = b.Spart; g.ldc = ldm;
+            g.M = (int)m; g.N = (int)m; g.K = (int)b.kchunk;
+            g.batch = b.nz; g.strideA = b.kchunk; g.strideB = b.kchunk; g.strideC = m * ldm;
+            g.tile_mode = GEMM_TILES_LOWER;
+            GPG_TRY(gemm_simt<T>(h, g, s));
+            sgp_form_A_kernel<T><<<gmm, 256, 0, s>>>(b.Spart, b.nz, m * ldm, ldm, m, theta, b.S, b.Ap, b.LA);
+            GPG_LAUNCH_CHECK(h);
+        }
     }
     { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.LA, m, ldm, info, 0, b.dinv, s)); }
     { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.LA, m, ldm, b.LAi, ldm, b.tmp, s)); }
