@@ -1036,6 +1036,7 @@ template <typename T> struct SgpBufs {
     int64_t ldk = 0;             // leading dimension of the N x m operands
     float *Kfu = nullptr, *scales = nullptr;
     __half *Kfus = nullptr, *Bts = nullptr, *Uis = nullptr, *T2s = nullptr, *Bs = nullptr;      // hi plane, then lo plane
+    __half *P1 = nullptr, *P2 = nullptr, *P3 = nullptr;      // m x m operand planes of the gradient chain
     int nzt = 0;                 // S = B B^T on tcgen05: split-K batches of SGP_TC_KCHUNK columns, partial products in SpartTc
     float *SpartTc = nullptr;
     T *Luu, *Ui, *tmp, *Kuf, *B, *S, *Ap, *LA, *LAi, *Ainv, *Phi, *H, *T1, *Guu, *T2;   // Kuf doubles as dF/dKuf
@@ -1074,7 +1075,8 @@ template <typename T> static size_t sgp_ws_bytes(const gpg_handle_s *h, int64_t 
     const size_t nzt_ = (size_t)((N + SGP_TC_KCHUNK - 1) / SGP_TC_KCHUNK);
     const size_t tc_bytes = tcp ? bump_size({(size_t)N * ldk_ * 4, (size_t)N * ldk_ * 4, (size_t)N * ldk_ * 4,
                                              (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4, SGP_S_COUNT * sizeof(float),
-                                             (size_t)m * (size_t)(nz * kchunk) * 4, nzt_ * m * ldm_ * 4}) : 0;
+                                             (size_t)m * (size_t)(nz * kchunk) * 4, nzt_ * m * ldm_ * 4,
+                                             (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4}) : 0;
     const int64_t ldm = gpg_align_up((size_t)m, 64), ldn = nz * kchunk;
     const size_t mm = (size_t)m * ldm * sizeof(T), mn = (size_t)m * ldn * sizeof(T), mv = (size_t)m * sizeof(T);
     const size_t nb = (size_t)((m + 7) / 8);
@@ -1122,6 +1124,9 @@ template <typename T> static SgpBufs<T> sgp_carve(const gpg_handle_s *h, void *w
         s.Bs = b.take<__half>(2 * (size_t)m * s.ldn);
         s.nzt = (int)((N + SGP_TC_KCHUNK - 1) / SGP_TC_KCHUNK);
         s.SpartTc = b.take<float>((size_t)s.nzt * m * s.ldm);
+        s.P1 = b.take<__half>(2 * (size_t)m * s.ldm);
+        s.P2 = b.take<__half>(2 * (size_t)m * s.ldm);
+        s.P3 = b.take<__half>(2 * (size_t)m * s.ldm);
     }
     return s;
 }
@@ -1144,6 +1149,31 @@ static int sgp_tc_product(gpg_handle_s *h, int64_t m, int64_t N, const __half *A
     if (Ts) { g.p.T_hi = Ts; g.p.T_lo = Ts + (size_t)N * ldb; g.p.ldt = ldb; g.p.scale_out = scale_out; }
     if (Ss) { g.p.S_hi = Ss; g.p.S_lo = Ss + (size_t)m * ldc; g.p.lds = ldc; g.p.scale_out = scale_out; }   // same geometry as C
     return tc::launch(h, g, s);
+}
+
+// C (m x m, fp32) = alpha * A Bm^T on tcgen05, both operands m x m fp16 plane pairs with leading dimension ld
+static int sgp_tc_mm(gpg_handle_s *h, int64_t m, int64_t ld, const __half *As, const __half *Bms, float *C,
+                     const float *scale_inv, float alpha, int kb_mode, int tile_mode, cudaStream_t s) {
+    tc::Launch g;
+    memset(&g.p, 0, sizeof(g.p));
+    g.A.hi = As; g.A.lo = As + (size_t)m * ld; g.A.rows = m; g.A.cols = m; g.A.ld = ld;
+    g.B.hi = Bms; g.B.lo = Bms + (size_t)m * ld; g.B.rows = m; g.B.cols = m; g.B.ld = ld;
+    g.p.M = (int)m; g.p.N = (int)m; g.p.K = (int)m; g.p.batch = 1;
+    g.p.kb_mode = kb_mode; g.p.tile_mode = tile_mode;
+    g.p.epi = tc::EPI_STORE;
+    g.p.scale_inv = scale_inv;
+    g.p.C = C; g.p.ldc = ld;
+    g.p.alpha = alpha; g.p.beta = 0.0f;
+    return tc::launch(h, g, s);
+}
+
+// fp16 planes of M^T (m x m, leading dimension ld) scaled by *scale
+static int sgp_split_T(gpg_handle_s *h, const float *M, int64_t m, int64_t ld, const float *scale, __half *planes,
+                       cudaStream_t s) {
+    const dim3 grid((unsigned)((m + 31) / 32), (unsigned)((m + 31) / 32));
+    tc::split_transpose_kernel<<<grid, 256, 0, s>>>(M, ld, m, m, scale, planes, planes + (size_t)m * ld, ld);
+    GPG_LAUNCH_CHECK(h);
+    return GPG_OK;
 }
 
 // Luu, Ui, B, S, A', LA, LAi, beta, c0, a0, a, w for the theta stored on the device.  info keeps the first failing pivot of
@@ -1264,7 +1294,16 @@ static int sgp_loss_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *th
         if constexpr (std::is_same<T, float>::value) return gemm_simt<T, GemmCfgPanelF32>(h, g, s);
         else return gemm_simt<T>(h, g, s);
     };
-    GPG_TRY(mm_gemm(b.LAi, 0, b.LAi, 0, b.Ainv, T(1), GEMM_KB_MAXMN, GEMM_TILES_LOWER));     // A'^-1 = LAi^T LAi (lower)
+    bool tcmm = false;               // fp32, large m: the m x m x m products on tcgen05 as well
+    if constexpr (std::is_same<T, float>::value) tcmm = b.tc;
+    if constexpr (std::is_same<T, float>::value) {
+        if (tcmm) {                  // A'^-1 = LAi^T LAi (lower) = (LAi^T) (LAi^T)^T: operand = transposed planes of LAi
+            GPG_TRY(sgp_split_T(h, b.LAi, m, ldm, b.scales + SGP_S_LA, b.P1, s));
+            GPG_TRY(sgp_tc_mm(h, m, ldm, b.P1, b.P1, b.Ainv, b.scales + SGP_S_LALA_INV, 1.0f, GEMM_KB_MAXMN,
+                              GEMM_TILES_LOWER, s));
+        }
+    }
+    if (!tcmm) GPG_TRY(mm_gemm(b.LAi, 0, b.LAi, 0, b.Ainv, T(1), GEMM_KB_MAXMN, GEMM_TILES_LOWER));     // A'^-1 = LAi^T LAi (lower)
     sgp_scalars_kernel<T><<<1, 1024, 0, s>>>(y, N, b.beta, b.a0, b.c0, b.S, b.Ainv, b.LA, ldm, m, b.sc);
     GPG_LAUNCH_CHECK(h);
     gemvT_rect_kernel<T><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(b.B, ldn, m, N, b.a, y, T(-1), T(1), b.rho);   // rho = y - B^T a
@@ -1272,9 +1311,30 @@ static int sgp_loss_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *th
     const dim3 gmm((unsigned)((m + 255) / 256), (unsigned)m);
     sgp_form_phi_kernel<T><<<gmm, 256, 0, s>>>(b.Ainv, b.Ap, b.a, ldm, m, b.Phi, b.H);
     GPG_LAUNCH_CHECK(h);
-    GPG_TRY(mm_gemm(b.Phi, 1, b.Ui, 0, b.T1, T(1), GEMM_KB_NONE, GEMM_TILES_ALL));           // T1 = Phi Ui
-    GPG_TRY(mm_gemm(b.Ui, 0, b.T1, 0, b.Guu, T(-0.5), GEMM_KB_NONE, GEMM_TILES_ALL));        // dF/dKuu = -1/2 Ui^T T1
-    GPG_TRY(mm_gemm(b.Ui, 0, b.H, 0, b.T2, T(1), GEMM_KB_NONE, GEMM_TILES_ALL));             // T2 = Ui^T H
+    if constexpr (std::is_same<T, float>::value) {
+        if (tcmm) {
+            // with UiT = planes of Ui^T (P2):  T1^T = Ui^T Phi = UiT Phi^T (Phi symmetric),  T2 = Ui^T H = UiT H^T,
+            // dF/dKuu = -1/2 (Ui^T Phi) Ui = -1/2 T1^T UiT^T;  P3 carries Phi, H and T1^T in turn
+            GPG_TRY(sgp_split_T(h, b.Ui, m, ldm, b.scales + SGP_S_U, b.P2, s));
+            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(b.Phi, ldm, m, m, b.scales, SGP_S_PHI, SGP_S_U, SGP_S_UPHI_INV);
+            GPG_LAUNCH_CHECK(h);
+            GPG_TRY(tc::split_matrix(h, b.Phi, ldm, m, m, b.scales + SGP_S_PHI, b.P3, b.P3 + (size_t)m * ldm, ldm, 0, s));
+            GPG_TRY(sgp_tc_mm(h, m, ldm, b.P2, b.P3, b.T1, b.scales + SGP_S_UPHI_INV, 1.0f, GEMM_KB_NONE, GEMM_TILES_ALL, s));
+            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(b.H, ldm, m, m, b.scales, SGP_S_H, SGP_S_U, SGP_S_UH_INV);
+            GPG_LAUNCH_CHECK(h);
+            GPG_TRY(tc::split_matrix(h, b.H, ldm, m, m, b.scales + SGP_S_H, b.P3, b.P3 + (size_t)m * ldm, ldm, 0, s));
+            GPG_TRY(sgp_tc_mm(h, m, ldm, b.P2, b.P3, b.T2, b.scales + SGP_S_UH_INV, 1.0f, GEMM_KB_NONE, GEMM_TILES_ALL, s));
+            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(b.T1, ldm, m, m, b.scales, SGP_S_XT, SGP_S_U, SGP_S_XTU_INV);
+            GPG_LAUNCH_CHECK(h);
+            GPG_TRY(tc::split_matrix(h, b.T1, ldm, m, m, b.scales + SGP_S_XT, b.P3, b.P3 + (size_t)m * ldm, ldm, 0, s));
+            GPG_TRY(sgp_tc_mm(h, m, ldm, b.P3, b.P2, b.Guu, b.scales + SGP_S_XTU_INV, -0.5f, GEMM_KB_N0, GEMM_TILES_ALL, s));
+        }
+    }
+    if (!tcmm) {
+        GPG_TRY(mm_gemm(b.Phi, 1, b.Ui, 0, b.T1, T(1), GEMM_KB_NONE, GEMM_TILES_ALL));           // T1 = Phi Ui
+        GPG_TRY(mm_gemm(b.Ui, 0, b.T1, 0, b.Guu, T(-0.5), GEMM_KB_NONE, GEMM_TILES_ALL));        // dF/dKuu = -1/2 Ui^T T1
+        GPG_TRY(mm_gemm(b.Ui, 0, b.H, 0, b.T2, T(1), GEMM_KB_NONE, GEMM_TILES_ALL));             // T2 = Ui^T H
+    }
     bool guf_done = false;           // s2 dF/dKuf + w rho^T = T2 B   (into the Kuf buffer, which is dead by now)
     if constexpr (std::is_same<T, float>::value) {
         if (b.tc) {

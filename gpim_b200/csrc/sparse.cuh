@@ -26,8 +26,11 @@ enum { SGP_SC_YY = 0, SGP_SC_A0BETA = 1, SGP_SC_A0A0 = 2, SGP_SC_TRAINV = 3, SGP
 //   SGP_S_K  k(X, Xu) entries are <= variance                         (rigorous, from theta)
 //   SGP_S_B  B = Luu^-1 k(Xu, X): column norms^2 = Qff_nn <= k(x, x) = variance, so |B_ij| <= sqrt(variance)
 //   SGP_S_U, SGP_S_T  Luu^-1 and T2 = Ui^T (A'^-1 - I): measured (one pass over an m x m matrix)
+//   SGP_S_LA LA^-1: A' = I + B B^T / s2 >= I, so |LA^-1_ij| <= 1    (rigorous)
+//   SGP_S_PHI, SGP_S_H, SGP_S_XT  the m x m operands of the gradient chain: measured
 enum { SGP_S_K = 0, SGP_S_U = 1, SGP_S_UK_INV = 2, SGP_S_B = 3, SGP_S_T = 4, SGP_S_TB_INV = 5, SGP_S_BB_INV = 6,
-       SGP_S_COUNT = 8 };
+       SGP_S_LA = 7, SGP_S_LALA_INV = 8, SGP_S_PHI = 9, SGP_S_UPHI_INV = 10, SGP_S_H = 11, SGP_S_UH_INV = 12,
+       SGP_S_XT = 13, SGP_S_XTU_INV = 14, SGP_S_COUNT = 16 };
 
 __device__ __forceinline__ float sgp_pow2_scale(float bound) {
     return (bound > 0.f && bound < 3.0e38f) ? exp2f(floorf(log2f(16384.f / bound))) : 1.f;
@@ -39,6 +42,8 @@ template <typename T> __global__ void sgp_scales_theta_kernel(const T *__restric
     scales[SGP_S_K] = sgp_pow2_scale(v);
     scales[SGP_S_B] = sgp_pow2_scale(sqrtf(v));
     scales[SGP_S_BB_INV] = 1.0f / (scales[SGP_S_B] * scales[SGP_S_B]);
+    scales[SGP_S_LA] = 16384.f;
+    scales[SGP_S_LALA_INV] = 1.0f / (16384.f * 16384.f);
 }
 
 // scales[slot] = power-of-two scale for max |M_ij| over rows x cols; scales[slot_inv] = 1 / (scales[slot] * scales[other])
