@@ -54,9 +54,9 @@ SIGNATURES = {
     "gpg_sparse_fit_adam": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _f64, _vp, C.POINTER(_f64), _i32,
                              _f64, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "gpg_sparse_factorize": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _f64, _vp, _vp, _i64, _vp, _vp,
-                              _vp], C.c_int),
-    "gpg_sparse_predict": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp],
-                           C.c_int),
+                              _vp, _vp, _vp], C.c_int),
+    "gpg_sparse_predict": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp,
+                            _vp], C.c_int),
 }
 
 _LIB = None
@@ -356,11 +356,16 @@ class Engine:
         N, d = X.shape
         m = Xu.shape[0]
         ld = (m + 63) // 64 * 64
+        f32 = X.dtype == torch.float32
         fac = {"Ui": self.empty(m, ld, dtype=X.dtype), "Pm": self.empty(m, ld, dtype=X.dtype),
-               "w": self.empty(m, dtype=X.dtype), "info": torch.zeros(1, dtype=torch.int32, device=self.device), "ld": ld}
+               "w": self.empty(m, dtype=X.dtype), "info": torch.zeros(1, dtype=torch.int32, device=self.device), "ld": ld,
+               # tensor-core form of the two factors (fp16 hi / lo planes of Ui and Pm) + operand scales; f32 only
+               "split": torch.empty(4, m, ld, dtype=torch.float16, device=self.device) if f32 else None,
+               "scales": torch.zeros(24, dtype=torch.float32, device=self.device) if f32 else None}
         self._check(self.lib.gpg_sparse_factorize(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), _ptr(y), N,
                                                   _ptr(Xu), m, float(jitter), _ptr(fac["Ui"]), _ptr(fac["Pm"]), ld,
-                                                  _ptr(fac["w"]), _ptr(fac["info"]), self._stream()))
+                                                  _ptr(fac["w"]), _ptr(fac["info"]), _ptr(fac["split"]),
+                                                  _ptr(fac["scales"]), self._stream()))
         return fac
 
     def sparse_predict(self, kernel_id, theta, Xu, fac, Xs):
@@ -372,7 +377,8 @@ class Engine:
         if M == 0:
             return mean, sd
         self._check(self.lib.gpg_sparse_predict(self.h, self._dt(Xu), kernel_id, d, _ptr(theta), _ptr(Xu), m,
-                                                _ptr(fac["Ui"]), _ptr(fac["Pm"]), fac["ld"], _ptr(fac["w"]), _ptr(Xs), M,
+                                                _ptr(fac["Ui"]), _ptr(fac["Pm"]), fac["ld"], _ptr(fac["w"]),
+                                                _ptr(fac.get("split")), _ptr(fac.get("scales")), _ptr(Xs), M,
                                                 _ptr(mean), _ptr(sd), self._stream()))
         return mean, sd
 

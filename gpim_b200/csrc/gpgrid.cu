@@ -1462,7 +1462,7 @@ extern "C" int gpg_sparse_fit_adam(gpg_handle_t h, int dtype, int kernel_id, int
 template <typename T>
 static int sgp_factorize_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y, int64_t N,
                                const T *Xu, int64_t m, double jitter, T *Ui_out, T *P_out, int64_t ld, T *w_out,
-                               int32_t *info, cudaStream_t s) {
+                               int32_t *info, void *split_out, float *scales_out, cudaStream_t s) {
     void *ws;
     GPG_TRY(gpg_ws_reserve(h, sgp_ws_bytes<T>(h, m, N, d), &ws));
     SgpBufs<T> b = sgp_carve<T>(h, ws, m, N, d);
@@ -1478,25 +1478,42 @@ static int sgp_factorize_entry(gpg_handle_s *h, int kernel_id, int d, const T *t
     GPG_CUDA_CHECK(cudaMemcpy2DAsync(Ui_out, ld * sizeof(T), b.Ui, b.ldm * sizeof(T), m * sizeof(T), m,
                                      cudaMemcpyDeviceToDevice, s));
     GPG_CUDA_CHECK(cudaMemcpyAsync(w_out, b.w, m * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    if constexpr (std::is_same<T, float>::value) {
+        if (split_out) {             // tensor-core form of the two factors: fp16 planes {Ui hi, Ui lo, Pm hi, Pm lo} + scales
+            __half *pl = (__half *)split_out;
+            const size_t plane = (size_t)m * ld;
+            sgp_scales_theta_kernel<T><<<1, 32, 0, s>>>(theta, scales_out);
+            GPG_LAUNCH_CHECK(h);
+            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(Ui_out, ld, m, m, scales_out, SGP_S_U, SGP_S_K, SGP_S_UK_INV);
+            GPG_LAUNCH_CHECK(h);
+            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(P_out, ld, m, m, scales_out, SGP_S_P, SGP_S_K, SGP_S_KP_INV);
+            GPG_LAUNCH_CHECK(h);
+            GPG_TRY(tc::split_matrix(h, Ui_out, ld, m, m, scales_out + SGP_S_U, pl, pl + plane, ld, 1, s));
+            GPG_TRY(tc::split_matrix(h, P_out, ld, m, m, scales_out + SGP_S_P, pl + 2 * plane, pl + 3 * plane, ld, 1, s));
+        }
+    }
     return GPG_OK;
 }
 
 extern "C" int gpg_sparse_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *X,
                                     const void *y, int64_t N, const void *Xu, int64_t m, double jitter, void *Ui_out,
-                                    void *P_out, int64_t ld, void *w_out, int32_t *info, void *stream) {
+                                    void *P_out, int64_t ld, void *w_out, int32_t *info, void *split_out,
+                                    float *scales_out, void *stream) {
     GPG_REQUIRE(h && theta && X && y && Xu && Ui_out && P_out && w_out && info, "NULL argument");
     DeviceGuard device_guard(h->device);
     SGP_COMMON_REQUIRE();
     GPG_REQUIRE(ld >= m, "ld smaller than m");
+    GPG_REQUIRE((split_out == nullptr) == (scales_out == nullptr), "split_out and scales_out go together");
+    GPG_REQUIRE(split_out == nullptr || (dtype == GPG_F32 && ld % 8 == 0), "the split factors need f32 and ld % 8 == 0");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == GPG_F32)
         return sgp_factorize_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)X, (const float *)y, N,
                                           (const float *)Xu, m, jitter, (float *)Ui_out, (float *)P_out, ld,
-                                          (float *)w_out, info, s);
+                                          (float *)w_out, info, split_out, scales_out, s);
     if (dtype == GPG_F64)
         return sgp_factorize_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)X, (const double *)y, N,
                                            (const double *)Xu, m, jitter, (double *)Ui_out, (double *)P_out, ld,
-                                           (double *)w_out, info, s);
+                                           (double *)w_out, info, nullptr, nullptr, s);
     gpg_set_error("unknown dtype %d", dtype);
     return GPG_EINVAL;
 }
@@ -1550,18 +1567,85 @@ static int sgp_predict_core(gpg_handle_s *h, int kernel_id, const T *theta, cons
     return GPG_OK;
 }
 
+// fp32 tensor-core route: K* rows are generated directly as fp16 planes, both column-sum-of-squares reductions run in
+// the epilogue of the tcgen05 GEMM (the machinery of predict_core_tc on the two m x m factors).
+template <int D>
+static int sgp_predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, const float *Xu, int64_t m,
+                               const __half *planes, int64_t ld, const float *scales, const float *w, const float *Xs,
+                               int64_t M, float *mean, float *sd, cudaStream_t s) {
+    const int64_t ldh = gpg_align_up((size_t)m, 64);
+    int64_t chunk = h->opt_predict_chunk > 0 ? h->opt_predict_chunk : 16384;
+    chunk = gpg_align_up((size_t)std::min<int64_t>(chunk, gpg_align_up((size_t)M, 128)), 128);
+    const int tiles_n = (int)((m + tc::BN - 1) / tc::BN);
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)chunk * ldh * 2, (size_t)chunk * ldh * 2,
+                                         (size_t)tiles_n * chunk * sizeof(float), (size_t)tiles_n * chunk * sizeof(float)}), &ws));
+    Bump b(ws);
+    __half *Khi = b.take<__half>((size_t)chunk * ldh);
+    __half *Klo = b.take<__half>((size_t)chunk * ldh);
+    float *part1 = b.take<float>((size_t)tiles_n * chunk);
+    float *part2 = b.take<float>((size_t)tiles_n * chunk);
+    const size_t plane = (size_t)m * ld;
+    const int m_group = (int)std::max<int64_t>(1, ((int64_t)64 << 20) / (tc::BM * ldh * 4));
+    TestPoints<float, D> tp;
+    tp.j0 = 0;
+    for (int k = 0; k < GPG_MAX_D; ++k) { tp.dims[k] = 1; tp.step[k] = 1.0f; }
+    for (int64_t c0 = 0; c0 < M; c0 += chunk) {
+        const int64_t mc = std::min<int64_t>(chunk, M - c0);
+        tp.Xs = Xs + c0 * D;
+        {
+            StageTimer st(h, GPG_ST_KCROSS, s);
+            GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<float, KID, D, true><<<(unsigned)((mc + 7) / 8), 256, 0, s>>>(
+                                            theta, Xu, m, tp, mc, w, nullptr, 0, Khi, Klo, ldh, scales + SGP_S_K, mean + c0));
+            GPG_LAUNCH_CHECK(h);
+        }
+        {
+            StageTimer st(h, GPG_ST_PGEMM, s);
+            for (int pass = 0; pass < 2; ++pass) {      // rowsum((K* Ui^T)^2), rowsum((K* Pm^T)^2)
+                tc::Launch g;
+                memset(&g.p, 0, sizeof(g.p));
+                g.A.hi = Khi; g.A.lo = Klo; g.A.rows = mc; g.A.cols = m; g.A.ld = ldh;
+                g.B.hi = planes + 2 * pass * plane; g.B.lo = planes + (2 * pass + 1) * plane;
+                g.B.rows = m; g.B.cols = m; g.B.ld = ld;
+                g.p.M = (int)mc; g.p.N = (int)m; g.p.K = (int)m; g.p.batch = 1;
+                g.p.m_group = m_group;
+                g.p.ke_mode = GEMM_KE_N;
+                g.p.epi = tc::EPI_ROWSUMSQ;
+                g.p.scale_inv = scales + (pass == 0 ? SGP_S_UK_INV : SGP_S_KP_INV);
+                g.p.part = pass == 0 ? part1 : part2; g.p.ldpart = chunk;
+                GPG_TRY(tc::launch(h, g, s));
+            }
+        }
+        StageTimer st(h, GPG_ST_PFINAL, s);
+        sgp_predict_finalize_kernel<float, D><<<(unsigned)((mc + 255) / 256), 256, 0, s>>>(theta, part1, part2, tiles_n, chunk,
+                                                                                           tp, mc, sd + c0);
+        GPG_LAUNCH_CHECK(h);
+    }
+    return GPG_OK;
+}
+
 template <typename T>
 static int sgp_predict_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *Xu, int64_t m, const T *Ui,
-                             const T *Pm, int64_t ld, const T *w, const T *Xs, int64_t M, T *mean, T *sd, cudaStream_t s) {
+                             const T *Pm, int64_t ld, const T *w, const void *split, const float *scales, const T *Xs,
+                             int64_t M, T *mean, T *sd, cudaStream_t s) {
     if (M == 0) return GPG_OK;
+    if constexpr (std::is_same<T, float>::value) {
+        if (split != nullptr && h->opt_gemm_path != 1 && (h->opt_gemm_path == 2 || m >= 512)) {
+            GPG_DISPATCH_D(d, { return sgp_predict_core_tc<D>(h, kernel_id, theta, Xu, m, (const __half *)split, ld, scales, w,
+                                                              Xs, M, mean, sd, s); });
+        }
+    }
     GPG_DISPATCH_D(d, { return sgp_predict_core<T, D>(h, kernel_id, theta, Xu, m, Ui, Pm, ld, w, Xs, M, mean, sd, s); });
     return GPG_OK;
 }
 
 extern "C" int gpg_sparse_predict(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta, const void *Xu,
-                                  int64_t m, const void *Ui, const void *Pm, int64_t ld, const void *w, const void *Xs,
-                                  int64_t M, void *mean_out, void *sd_out, void *stream) {
+                                  int64_t m, const void *Ui, const void *Pm, int64_t ld, const void *w, const void *split,
+                                  const float *scales, const void *Xs, int64_t M, void *mean_out, void *sd_out,
+                                  void *stream) {
     GPG_REQUIRE(h && theta && Xu && Ui && Pm && w && mean_out && sd_out, "NULL argument");
+    GPG_REQUIRE((split == nullptr) == (scales == nullptr), "split and scales go together");
+    GPG_REQUIRE(split == nullptr || (dtype == GPG_F32 && ld % 8 == 0), "the split factors need f32 and ld % 8 == 0");
     DeviceGuard device_guard(h->device);
     GPG_REQUIRE(M == 0 || Xs != nullptr, "Xs is NULL");
     GPG_REQUIRE(m > 0 && M >= 0 && ld >= m, "bad size");
@@ -1569,11 +1653,11 @@ extern "C" int gpg_sparse_predict(gpg_handle_t h, int dtype, int kernel_id, int 
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (dtype == GPG_F32)
         return sgp_predict_entry<float>(h, kernel_id, d, (const float *)theta, (const float *)Xu, m, (const float *)Ui,
-                                        (const float *)Pm, ld, (const float *)w, (const float *)Xs, M, (float *)mean_out,
-                                        (float *)sd_out, s);
+                                        (const float *)Pm, ld, (const float *)w, split, scales, (const float *)Xs, M,
+                                        (float *)mean_out, (float *)sd_out, s);
     if (dtype == GPG_F64)
         return sgp_predict_entry<double>(h, kernel_id, d, (const double *)theta, (const double *)Xu, m, (const double *)Ui,
-                                         (const double *)Pm, ld, (const double *)w, (const double *)Xs, M,
+                                         (const double *)Pm, ld, (const double *)w, nullptr, nullptr, (const double *)Xs, M,
                                          (double *)mean_out, (double *)sd_out, s);
     gpg_set_error("unknown dtype %d", dtype);
     return GPG_EINVAL;

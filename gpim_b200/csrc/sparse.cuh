@@ -30,7 +30,9 @@ enum { SGP_SC_YY = 0, SGP_SC_A0BETA = 1, SGP_SC_A0A0 = 2, SGP_SC_TRAINV = 3, SGP
 //   SGP_S_PHI, SGP_S_H, SGP_S_XT  the m x m operands of the gradient chain: measured
 enum { SGP_S_K = 0, SGP_S_U = 1, SGP_S_UK_INV = 2, SGP_S_B = 3, SGP_S_T = 4, SGP_S_TB_INV = 5, SGP_S_BB_INV = 6,
        SGP_S_LA = 7, SGP_S_LALA_INV = 8, SGP_S_PHI = 9, SGP_S_UPHI_INV = 10, SGP_S_H = 11, SGP_S_UH_INV = 12,
-       SGP_S_XT = 13, SGP_S_XTU_INV = 14, SGP_S_COUNT = 16 };
+       SGP_S_XT = 13, SGP_S_XTU_INV = 14,
+       SGP_S_P = 16, SGP_S_KP_INV = 17,      // predict: Pm = LA^-1 Luu^-1 operand (measured) and 1 / (s_K s_P)
+       SGP_S_COUNT = 24 };
 
 __device__ __forceinline__ float sgp_pow2_scale(float bound) {
     return (bound > 0.f && bound < 3.0e38f) ? exp2f(floorf(log2f(16384.f / bound))) : 1.f;

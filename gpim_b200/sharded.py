@@ -27,7 +27,7 @@ def broadcast_factor(fac, src=0, group=None):
     # the fp32 matrix travels only when the SIMT kernels will consume it
     planes = fac.get("wsplit")
     if "Ui" in fac:                  # inducing-point cache (gpg_sparse_factorize): two m x m factors and a vector
-        keys = ("Ui", "Pm", "w")
+        keys = ("Ui", "Pm", "w", "split", "scales")
     elif planes is not None and planes.shape[1] >= 1024:
         keys = ("alpha", "wsplit", "scales")
     else:

@@ -229,16 +229,21 @@ int gpg_sparse_fit_adam(gpg_handle_t h, int dtype, int kernel_id, int d, int n_l
 /* Factor cache of the inducing-point posterior for fixed (theta, Xu) -- what SparseGPRegression.forward
  * recomputes on every call (gpr.py:248): Ui = Luu^-1 and Pm = LA^-1 Luu^-1 (m x m lower triangular,
  * row-major, leading dimension ld, strict upper triangle zero) and w (dtype[m]) with
- * mean(x*) = k(x*, Xu) . w. */
+ * mean(x*) = k(x*, Xu) . w.
+ * split_out / scales_out (both NULL or both set; f32 with ld % 8 == 0 only): the tensor-core form of the two factors
+ * -- 4 * m * ld fp16 values (Ui hi plane, Ui lo plane, Pm hi, Pm lo, power-of-two scaled) and float[24] operand scales
+ * -- which gpg_sparse_predict needs to run on the tcgen05 path (without them it runs the SIMT kernels). */
 int gpg_sparse_factorize(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
                          const void *X, const void *y, int64_t N, const void *Xu, int64_t m, double jitter,
-                         void *Ui_out, void *Pm_out, int64_t ld, void *w_out, int32_t *info, void *stream);
+                         void *Ui_out, void *Pm_out, int64_t ld, void *w_out, int32_t *info,
+                         void *split_out, float *scales_out, void *stream);
 
 /* SparseGPRegression.forward(Xnew, full_cov=False, noiseless=False) + sqrt (gpr.py:248-250), tiled over M:
  *   mean = K*^T w,  sd = sqrt(v + noise - colsum((Ui K*)^2) + colsum((Pm K*)^2)),  K* = k(Xu, X*).
  * Rows of Xs that contain NaN give NaN outputs. */
 int gpg_sparse_predict(gpg_handle_t h, int dtype, int kernel_id, int d, const void *theta,
                        const void *Xu, int64_t m, const void *Ui, const void *Pm, int64_t ld, const void *w,
+                       const void *split, const float *scales,
                        const void *Xs, int64_t M, void *mean_out, void *sd_out, void *stream);
 
 #ifdef __cplusplus
