@@ -1037,6 +1037,7 @@ template <typename T> struct SgpBufs {
     float *Kfu = nullptr, *scales = nullptr;
     __half *Kfus = nullptr, *Bts = nullptr, *Uis = nullptr, *T2s = nullptr, *Bs = nullptr;      // hi plane, then lo plane
     __half *P1 = nullptr, *P2 = nullptr, *P3 = nullptr;      // m x m operand planes of the gradient chain
+    float *amax = nullptr;       // per-block maxima of the operand-scale measurement
     int nzt = 0;                 // S = B B^T on tcgen05: split-K batches of SGP_TC_KCHUNK columns, partial products in SpartTc
     float *SpartTc = nullptr;
     T *Luu, *Ui, *tmp, *Kuf, *B, *S, *Ap, *LA, *LAi, *Ainv, *Phi, *H, *T1, *Guu, *T2;   // Kuf doubles as dF/dKuf
@@ -1076,7 +1077,8 @@ template <typename T> static size_t sgp_ws_bytes(const gpg_handle_s *h, int64_t 
     const size_t tc_bytes = tcp ? bump_size({(size_t)N * ldk_ * 4, (size_t)N * ldk_ * 4, (size_t)N * ldk_ * 4,
                                              (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4, SGP_S_COUNT * sizeof(float),
                                              (size_t)m * (size_t)(nz * kchunk) * 4, nzt_ * m * ldm_ * 4,
-                                             (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4}) : 0;
+                                             (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4,
+                                             SGP_AMAX_BLOCKS * sizeof(float)}) : 0;
     const int64_t ldm = gpg_align_up((size_t)m, 64), ldn = nz * kchunk;
     const size_t mm = (size_t)m * ldm * sizeof(T), mn = (size_t)m * ldn * sizeof(T), mv = (size_t)m * sizeof(T);
     const size_t nb = (size_t)((m + 7) / 8);
@@ -1127,6 +1129,7 @@ template <typename T> static SgpBufs<T> sgp_carve(const gpg_handle_s *h, void *w
         s.P1 = b.take<__half>(2 * (size_t)m * s.ldm);
         s.P2 = b.take<__half>(2 * (size_t)m * s.ldm);
         s.P3 = b.take<__half>(2 * (size_t)m * s.ldm);
+        s.amax = b.take<float>(SGP_AMAX_BLOCKS);
     }
     return s;
 }
@@ -1149,6 +1152,30 @@ static int sgp_tc_product(gpg_handle_s *h, int64_t m, int64_t N, const __half *A
     if (Ts) { g.p.T_hi = Ts; g.p.T_lo = Ts + (size_t)N * ldb; g.p.ldt = ldb; g.p.scale_out = scale_out; }
     if (Ss) { g.p.S_hi = Ss; g.p.S_lo = Ss + (size_t)m * ldc; g.p.lds = ldc; g.p.scale_out = scale_out; }   // same geometry as C
     return tc::launch(h, g, s);
+}
+
+// measured power-of-two operand scale of an fp32 matrix (see sgp_absmax_partial_kernel)
+static int sgp_absmax_scale(gpg_handle_s *h, const float *M, int64_t ld, int64_t rows, int64_t cols, float *amax,
+                            float *scales, int slot, int other, int slot_inv, cudaStream_t s) {
+    sgp_absmax_partial_kernel<<<SGP_AMAX_BLOCKS, 256, 0, s>>>(M, ld, rows, cols, amax);
+    GPG_LAUNCH_CHECK(h);
+    sgp_absmax_finish_kernel<<<1, 32, 0, s>>>(amax, SGP_AMAX_BLOCKS, scales, slot, other, slot_inv);
+    GPG_LAUNCH_CHECK(h);
+    return GPG_OK;
+}
+
+// rho = beta * yin + alpha * A^T x for a rows x cols matrix, deterministic two-pass reduction (scratch from the handle)
+template <typename T>
+static int sgp_gemvT_rect(gpg_handle_s *h, const T *A, int64_t lda, int64_t rows, int64_t cols, const T *x, const T *yin,
+                          T alpha, T beta, T *out, cudaStream_t s) {
+    double *part;
+    GPG_TRY(gpg_gemv_part_reserve(h, (size_t)SGP_GEMVT_CHUNKS * cols, &part));
+    const dim3 grid((unsigned)((cols + 127) / 128), SGP_GEMVT_CHUNKS);
+    gemvT_rect_partial_kernel<T><<<grid, 128, 0, s>>>(A, lda, rows, cols, x, part);
+    GPG_LAUNCH_CHECK(h);
+    gemvT_rect_finish_kernel<T><<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(part, SGP_GEMVT_CHUNKS, cols, yin, alpha, beta, out);
+    GPG_LAUNCH_CHECK(h);
+    return GPG_OK;
 }
 
 // C (m x m, fp32) = alpha * A Bm^T on tcgen05, both operands m x m fp16 plane pairs with leading dimension ld
@@ -1205,8 +1232,7 @@ static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *thet
         bool done = false;
         if constexpr (std::is_same<T, float>::value) {
             if (b.tc) {              // B = Ui k(X, Xu)^T on tcgen05; the epilogue also leaves B^T as fp16 planes for dF/dKuf
-                sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(b.Ui, ldm, m, m, b.scales, SGP_S_U, SGP_S_K, SGP_S_UK_INV);
-                GPG_LAUNCH_CHECK(h);
+                GPG_TRY(sgp_absmax_scale(h, b.Ui, ldm, m, m, b.amax, b.scales, SGP_S_U, SGP_S_K, SGP_S_UK_INV, s));
                 GPG_TRY(tc::split_matrix(h, b.Ui, ldm, m, m, b.scales + SGP_S_U, b.Uis, b.Uis + (size_t)m * ldm, ldm, 1, s));
                 GPG_TRY(sgp_tc_product(h, m, N, b.Uis, ldm, b.Kfus, b.ldk, b.B, ldn, b.scales + SGP_S_UK_INV, GEMM_KE_M,
                                        b.Bts, b.scales + SGP_S_B, s, b.Bs));
@@ -1306,8 +1332,7 @@ static int sgp_loss_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *th
     if (!tcmm) GPG_TRY(mm_gemm(b.LAi, 0, b.LAi, 0, b.Ainv, T(1), GEMM_KB_MAXMN, GEMM_TILES_LOWER));     // A'^-1 = LAi^T LAi (lower)
     sgp_scalars_kernel<T><<<1, 1024, 0, s>>>(y, N, b.beta, b.a0, b.c0, b.S, b.Ainv, b.LA, ldm, m, b.sc);
     GPG_LAUNCH_CHECK(h);
-    gemvT_rect_kernel<T><<<(unsigned)((N + 127) / 128), 128, 0, s>>>(b.B, ldn, m, N, b.a, y, T(-1), T(1), b.rho);   // rho = y - B^T a
-    GPG_LAUNCH_CHECK(h);
+    GPG_TRY(sgp_gemvT_rect<T>(h, b.B, ldn, m, N, b.a, y, T(-1), T(1), b.rho, s));                  // rho = y - B^T a
     const dim3 gmm((unsigned)((m + 255) / 256), (unsigned)m);
     sgp_form_phi_kernel<T><<<gmm, 256, 0, s>>>(b.Ainv, b.Ap, b.a, ldm, m, b.Phi, b.H);
     GPG_LAUNCH_CHECK(h);
@@ -1316,16 +1341,13 @@ static int sgp_loss_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *th
             // with UiT = planes of Ui^T (P2):  T1^T = Ui^T Phi = UiT Phi^T (Phi symmetric),  T2 = Ui^T H = UiT H^T,
             // dF/dKuu = -1/2 (Ui^T Phi) Ui = -1/2 T1^T UiT^T;  P3 carries Phi, H and T1^T in turn
             GPG_TRY(sgp_split_T(h, b.Ui, m, ldm, b.scales + SGP_S_U, b.P2, s));
-            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(b.Phi, ldm, m, m, b.scales, SGP_S_PHI, SGP_S_U, SGP_S_UPHI_INV);
-            GPG_LAUNCH_CHECK(h);
+            GPG_TRY(sgp_absmax_scale(h, b.Phi, ldm, m, m, b.amax, b.scales, SGP_S_PHI, SGP_S_U, SGP_S_UPHI_INV, s));
             GPG_TRY(tc::split_matrix(h, b.Phi, ldm, m, m, b.scales + SGP_S_PHI, b.P3, b.P3 + (size_t)m * ldm, ldm, 0, s));
             GPG_TRY(sgp_tc_mm(h, m, ldm, b.P2, b.P3, b.T1, b.scales + SGP_S_UPHI_INV, 1.0f, GEMM_KB_NONE, GEMM_TILES_ALL, s));
-            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(b.H, ldm, m, m, b.scales, SGP_S_H, SGP_S_U, SGP_S_UH_INV);
-            GPG_LAUNCH_CHECK(h);
+            GPG_TRY(sgp_absmax_scale(h, b.H, ldm, m, m, b.amax, b.scales, SGP_S_H, SGP_S_U, SGP_S_UH_INV, s));
             GPG_TRY(tc::split_matrix(h, b.H, ldm, m, m, b.scales + SGP_S_H, b.P3, b.P3 + (size_t)m * ldm, ldm, 0, s));
             GPG_TRY(sgp_tc_mm(h, m, ldm, b.P2, b.P3, b.T2, b.scales + SGP_S_UH_INV, 1.0f, GEMM_KB_NONE, GEMM_TILES_ALL, s));
-            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(b.T1, ldm, m, m, b.scales, SGP_S_XT, SGP_S_U, SGP_S_XTU_INV);
-            GPG_LAUNCH_CHECK(h);
+            GPG_TRY(sgp_absmax_scale(h, b.T1, ldm, m, m, b.amax, b.scales, SGP_S_XT, SGP_S_U, SGP_S_XTU_INV, s));
             GPG_TRY(tc::split_matrix(h, b.T1, ldm, m, m, b.scales + SGP_S_XT, b.P3, b.P3 + (size_t)m * ldm, ldm, 0, s));
             GPG_TRY(sgp_tc_mm(h, m, ldm, b.P3, b.P2, b.Guu, b.scales + SGP_S_XTU_INV, -0.5f, GEMM_KB_N0, GEMM_TILES_ALL, s));
         }
@@ -1338,8 +1360,7 @@ static int sgp_loss_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *th
     bool guf_done = false;           // s2 dF/dKuf + w rho^T = T2 B   (into the Kuf buffer, which is dead by now)
     if constexpr (std::is_same<T, float>::value) {
         if (b.tc) {
-            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(b.T2, ldm, m, m, b.scales, SGP_S_T, SGP_S_B, SGP_S_TB_INV);
-            GPG_LAUNCH_CHECK(h);
+            GPG_TRY(sgp_absmax_scale(h, b.T2, ldm, m, m, b.amax, b.scales, SGP_S_T, SGP_S_B, SGP_S_TB_INV, s));
             GPG_TRY(tc::split_matrix(h, b.T2, ldm, m, m, b.scales + SGP_S_T, b.T2s, b.T2s + (size_t)m * ldm, ldm, 0, s));
             GPG_TRY(sgp_tc_product(h, m, N, b.T2s, ldm, b.Bts, b.ldk, b.Kuf, ldn, b.scales + SGP_S_TB_INV, GEMM_KE_NONE,
                                    nullptr, nullptr, s));
@@ -1484,10 +1505,9 @@ static int sgp_factorize_entry(gpg_handle_s *h, int kernel_id, int d, const T *t
             const size_t plane = (size_t)m * ld;
             sgp_scales_theta_kernel<T><<<1, 32, 0, s>>>(theta, scales_out);
             GPG_LAUNCH_CHECK(h);
-            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(Ui_out, ld, m, m, scales_out, SGP_S_U, SGP_S_K, SGP_S_UK_INV);
-            GPG_LAUNCH_CHECK(h);
-            sgp_absmax_scale_kernel<<<1, 1024, 0, s>>>(P_out, ld, m, m, scales_out, SGP_S_P, SGP_S_K, SGP_S_KP_INV);
-            GPG_LAUNCH_CHECK(h);
+            float *amax = b.Spart;   // dead by now (>= 64 x m floats): scratch for the per-block maxima
+            GPG_TRY(sgp_absmax_scale(h, Ui_out, ld, m, m, amax, scales_out, SGP_S_U, SGP_S_K, SGP_S_UK_INV, s));
+            GPG_TRY(sgp_absmax_scale(h, P_out, ld, m, m, amax, scales_out, SGP_S_P, SGP_S_K, SGP_S_KP_INV, s));
             GPG_TRY(tc::split_matrix(h, Ui_out, ld, m, m, scales_out + SGP_S_U, pl, pl + plane, ld, 1, s));
             GPG_TRY(tc::split_matrix(h, P_out, ld, m, m, scales_out + SGP_S_P, pl + 2 * plane, pl + 3 * plane, ld, 1, s));
         }

@@ -48,28 +48,74 @@ template <typename T> __global__ void sgp_scales_theta_kernel(const T *__restric
     scales[SGP_S_LALA_INV] = 1.0f / (16384.f * 16384.f);
 }
 
-// scales[slot] = power-of-two scale for max |M_ij| over rows x cols; scales[slot_inv] = 1 / (scales[slot] * scales[other])
-__global__ void __launch_bounds__(1024) sgp_absmax_scale_kernel(const float *__restrict__ M, int64_t ld, int64_t rows,
-                                                                int64_t cols, float *__restrict__ scales, int slot,
-                                                                int other, int slot_inv) {
-    __shared__ float red[32];
+// max |M_ij| over rows x cols in two launches: per-block maxima (SGP_AMAX_BLOCKS blocks), then
+// scales[slot] = power-of-two scale for the maximum and scales[slot_inv] = 1 / (scales[slot] * scales[other])
+constexpr int SGP_AMAX_BLOCKS = 64;
+
+__global__ void __launch_bounds__(256) sgp_absmax_partial_kernel(const float *__restrict__ M, int64_t ld, int64_t rows,
+                                                                 int64_t cols, float *__restrict__ blockmax) {
+    __shared__ float red[8];
     float mx = 0.f;
     const int lane = threadIdx.x & 31;
-    for (int64_t i = threadIdx.x >> 5; i < rows; i += 32)
+    for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < rows; i += (int64_t)gridDim.x * 8)
         for (int64_t j = lane; j < cols; j += 32) {
             const float a = fabsf(M[i * ld + j]);
             if (a < 3.0e38f) mx = fmaxf(mx, a);      // ignores inf / NaN (a failed factorisation is reported through info)
         }
     mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    if (lane == 0) red[threadIdx.x >> 5] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
-        for (int w = 0; w < 32; ++w) t = fmaxf(t, red[w]);
+        for (int w = 0; w < 8; ++w) t = fmaxf(t, red[w]);
+        blockmax[blockIdx.x] = t;
+    }
+}
+
+__global__ void sgp_absmax_finish_kernel(const float *__restrict__ blockmax, int nblocks, float *__restrict__ scales,
+                                         int slot, int other, int slot_inv) {
+    float t = 0.f;
+    for (int b = threadIdx.x; b < nblocks; b += 32) t = fmaxf(t, blockmax[b]);
+    t = warp_max(t);
+    if (threadIdx.x == 0) {
         const float sc = sgp_pow2_scale(t);
         scales[slot] = sc;
         scales[slot_inv] = 1.0f / (sc * scales[other]);
     }
+}
+
+// out[j] = beta * yin[j] + alpha * sum_i A[i][j] x[i] in two deterministic passes: a 2-D grid of (128-column strip) x
+// (row chunk) blocks leaves double partial sums per chunk, a second kernel adds the chunks up.  (One thread per
+// column over all rows keeps too few loads in flight: 7688 x 769 took 110 us.)
+constexpr int SGP_GEMVT_CHUNKS = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(128) gemvT_rect_partial_kernel(const T *__restrict__ A, int64_t lda, int64_t rows,
+                                                                 int64_t cols, const T *__restrict__ x,
+                                                                 double *__restrict__ part) {
+    const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (j >= cols) return;
+    const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = (int64_t)blockIdx.y * per, r1 = min(rows, r0 + per);
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    int64_t i = r0;
+    for (; i + 3 < r1; i += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] += (double)A[(i + e) * lda + j] * (double)x[i + e];
+    }
+    for (; i < r1; ++i) acc[0] += (double)A[i * lda + j] * (double)x[i];
+    part[(int64_t)blockIdx.y * cols + j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gemvT_rect_finish_kernel(const double *__restrict__ part, int nchunks, int64_t cols,
+                                                                const T *__restrict__ yin, T alpha, T beta,
+                                                                T *__restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= cols) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += part[(int64_t)c * cols + j];
+    out[j] = (T)((double)alpha * s + (yin ? (double)beta * (double)yin[j] : 0.0));
 }
 
 // theta0 = theta with the noise entry cleared (Kuu carries jitter only on its diagonal)
@@ -95,25 +141,6 @@ __global__ void __launch_bounds__(256) gemv_rect_kernel(const T *__restrict__ A,
     for (; j < cols; j += 32) acc[0] += (double)row[j] * (double)x[j];
     const double tot = warp_sum((acc[0] + acc[1]) + (acc[2] + acc[3]));
     if (lane == 0) out[i] = (T)tot;
-}
-
-// out[j] = beta * yin[j] + alpha * sum_i A[i][j] x[i]   (thread per column, coalesced across the warp, four
-// independent accumulators so that the row loop keeps several loads in flight)
-template <typename T>
-__global__ void __launch_bounds__(128) gemvT_rect_kernel(const T *__restrict__ A, int64_t lda, int64_t rows, int64_t cols,
-                                                         const T *__restrict__ x, const T *__restrict__ yin, T alpha,
-                                                         T beta, T *__restrict__ out) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cols) return;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    int64_t i = 0;
-    for (; i + 3 < rows; i += 4) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] += (double)A[(i + e) * lda + j] * (double)x[i + e];
-    }
-    for (; i < rows; ++i) acc[0] += (double)A[i * lda + j] * (double)x[i];
-    const double tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-    out[j] = (T)((double)alpha * tot + (yin ? (double)beta * (double)yin[j] : 0.0));
 }
 
 // out[i] = v[i] / theta[1]
