@@ -350,20 +350,24 @@ class Engine:
                                                  _ptr(xu_traj), _ptr(theta), _ptr(info), self._stream()))
         return traj[:iters], (xu_traj[:iters] if record_xu else None), theta, info
 
-    def sparse_factorize(self, kernel_id, theta, X, y, Xu, jitter):
-        """-> dict(Ui, Pm, w, info, ld): the cache gpg_sparse_predict consumes."""
+    def alloc_sparse_factor(self, m, dtype):
+        """Empty inducing-point factor cache (what a non-factorising rank receives by broadcast, sharded.py)."""
+        ld = (m + 63) // 64 * 64
+        f32 = dtype == torch.float32
+        return {"Ui": self.empty(m, ld, dtype=dtype), "Pm": self.empty(m, ld, dtype=dtype),
+                "w": self.empty(m, dtype=dtype), "info": torch.zeros(1, dtype=torch.int32, device=self.device), "ld": ld,
+                # tensor-core form of the two factors (fp16 hi / lo planes of Ui and Pm) + operand scales; f32 only
+                "split": torch.empty(4, m, ld, dtype=torch.float16, device=self.device) if f32 else None,
+                "scales": torch.zeros(24, dtype=torch.float32, device=self.device) if f32 else None}
+
+    def sparse_factorize(self, kernel_id, theta, X, y, Xu, jitter, out=None):
+        """-> dict(Ui, Pm, w, info, ld[, split, scales]): the cache gpg_sparse_predict consumes."""
         theta, X, y, Xu = _c(theta), _c(X), _c(y), _c(Xu)
         N, d = X.shape
         m = Xu.shape[0]
-        ld = (m + 63) // 64 * 64
-        f32 = X.dtype == torch.float32
-        fac = {"Ui": self.empty(m, ld, dtype=X.dtype), "Pm": self.empty(m, ld, dtype=X.dtype),
-               "w": self.empty(m, dtype=X.dtype), "info": torch.zeros(1, dtype=torch.int32, device=self.device), "ld": ld,
-               # tensor-core form of the two factors (fp16 hi / lo planes of Ui and Pm) + operand scales; f32 only
-               "split": torch.empty(4, m, ld, dtype=torch.float16, device=self.device) if f32 else None,
-               "scales": torch.zeros(24, dtype=torch.float32, device=self.device) if f32 else None}
+        fac = out if out is not None else self.alloc_sparse_factor(m, X.dtype)
         self._check(self.lib.gpg_sparse_factorize(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), _ptr(y), N,
-                                                  _ptr(Xu), m, float(jitter), _ptr(fac["Ui"]), _ptr(fac["Pm"]), ld,
+                                                  _ptr(Xu), m, float(jitter), _ptr(fac["Ui"]), _ptr(fac["Pm"]), fac["ld"],
                                                   _ptr(fac["w"]), _ptr(fac["info"]), _ptr(fac["split"]),
                                                   _ptr(fac["scales"]), self._stream()))
         return fac

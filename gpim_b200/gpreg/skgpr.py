@@ -146,9 +146,13 @@ class SKExactGPModel(ExactGPModel):
             self._raise_if_not_pd(self._factor)
         return self._factor, fresh
 
+    def mean_shift(self):
+        """The constant mean (device scalar) that goes back onto a prediction made on y - constant."""
+        return self._theta[2]
+
     def predict_sd(self, Xnew):
         mean, sd = super().predict_sd(Xnew)
-        return mean + self._theta[2], sd
+        return mean + self.mean_shift(), sd
 
 
 class skreconstructor:

@@ -79,3 +79,35 @@ def predict_sharded(factorize_fn, alloc_fn, predict_tile_fn, Xs, group=None):
     if world == 1:
         return mean_t, sd_t
     return gather_tiles(mean_t, M, group), gather_tiles(sd_t, M, group)
+
+
+def predict_model_sharded(model, Xs, src=0, group=None):
+    """Tile-sharded ``model.predict_sd`` for the model object of a reconstructor / skreconstructor (ExactGPModel,
+    SparseGPModel, SKExactGPModel): rank ``src``'s hyper-parameters (and inducing inputs) are broadcast first --
+    training is replicas-only, so the ranks may hold different values -- then rank ``src`` factorises, the cache
+    is broadcast, every rank predicts its tile of ``Xs`` and the tiles are all-gathered.  Every rank passes a model
+    built on the same (X, y); returns (mean, sd) for all of ``Xs`` on every rank."""
+    eng = model.engine
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    Xs = Xs.to(eng.device, model.kernel.dtype).contiguous()
+    sparse = hasattr(model, "Xu")
+    if world > 1:
+        dist.broadcast(model._theta, src=src, group=group)
+        if sparse:
+            dist.broadcast(model._Xu, src=src, group=group)
+        model._factor = None
+    kid = model.kernel.kernel_id
+
+    def factorize():
+        fac, _ = model.factor(check=True)
+        return fac
+
+    if sparse:
+        alloc = lambda: eng.alloc_sparse_factor(model._Xu.shape[0], model.kernel.dtype)
+        tile = lambda fac, X: eng.sparse_predict(kid, model._theta, model._Xu, fac, X)
+    else:
+        alloc = lambda: eng.alloc_factor(model._X.shape[0], model.kernel.dtype, with_L=False)
+        tile = lambda fac, X: eng.predict(kid, model._theta, model._X, fac, X)
+    mean, sd = predict_sharded(factorize, alloc, tile, Xs, group)
+    shift = getattr(model, "mean_shift", None)          # constant mean of the GPyTorch-semantics model
+    return (mean + shift() if shift is not None else mean), sd

@@ -308,3 +308,20 @@ def test_sparse_tensor_core_products_match_the_simt_route(eng):
         assert err[0][0] <= max(2 * err[1][0], scale)
         assert err[0][1] <= max(2 * err[1][1], 2e-3)
         assert err[0][2] <= max(2 * err[1][2], 2e-3)
+
+
+def test_predict_model_sharded_single_rank_equals_predict_sd():
+    """gpim_b200.sharded.predict_model_sharded on one rank (no process group) is model.predict_sd for the exact, the
+    inducing-point and the GPyTorch-semantics model (the world-size-2 plumbing is tests/test_sharded.py on gloo)."""
+    import gpim
+    from gpim_b200 import sharded
+    R = W.dummy_blob(16, 100)
+    Xs, Xf = gpim.utils.get_sparse_grid(R), gpim.utils.get_full_grid(R)
+    rows = torch.tensor(O.to_rows(Xf))
+    kw = dict(kernel="RBF", learning_rate=0.1, iterations=3, verbose=0)
+    for rec in (gpim.reconstructor(Xs, R, Xf, **kw), gpim.reconstructor(Xs, R, Xf, sparse=True, indpoints=12, **kw),
+                gpim.skreconstructor(Xs, R, Xf, ski=False, **kw)):
+        rec.train()
+        m0, s0 = rec.model.predict_sd(rows)
+        m1, s1 = sharded.predict_model_sharded(rec.model, rows)
+        assert torch.equal(m0, m1) and torch.equal(s0, s1)

@@ -56,6 +56,65 @@ def _worker(rank, world, port, M, out_dir):
     dist.destroy_process_group()
 
 
+class _StandInEngine:
+    """CPU stand-in with the Engine methods predict_model_sharded touches."""
+    device = torch.device("cpu")
+
+    def alloc_factor(self, N, dtype, with_L=True):
+        return {"Linv": torch.zeros(N, N, dtype=dtype), "alpha": torch.zeros(N, dtype=dtype)}
+
+    def alloc_sparse_factor(self, m, dtype):
+        return {"Ui": torch.zeros(m, m, dtype=dtype), "Pm": torch.zeros(m, m, dtype=dtype), "w": torch.zeros(m, dtype=dtype)}
+
+    def predict(self, kid, theta, X, fac, Xs):
+        return Xs[:, 0] * theta[0] + fac["alpha"].sum(), Xs[:, 1] + fac["Linv"].sum()
+
+    def sparse_predict(self, kid, theta, Xu, fac, Xs):
+        return Xs[:, 0] * theta[0] + fac["w"].sum() + Xu.sum(), Xs[:, 1] + fac["Ui"].sum()
+
+
+class _StandInModel:
+    def __init__(self, rank, sparse):
+        import types
+        self.engine = _StandInEngine()
+        self.kernel = types.SimpleNamespace(dtype=torch.float64, kernel_id=0)
+        self._X = torch.zeros(4, 2, dtype=torch.float64)
+        self._theta = torch.full((5,), 2.0 if rank == 0 else -7.0, dtype=torch.float64)     # ranks disagree before the call
+        self._factor = None
+        if sparse:
+            self._Xu = torch.full((3, 2), 1.0 if rank == 0 else 9.0, dtype=torch.float64)
+            self.Xu = self._Xu
+
+    def factor(self, check=True):
+        if hasattr(self, "_Xu"):
+            return {"Ui": torch.full((3, 3), 2.0, dtype=torch.float64), "Pm": torch.eye(3, dtype=torch.float64),
+                    "w": torch.arange(3, dtype=torch.float64)}, True
+        return {"Linv": torch.full((4, 4), 3.0, dtype=torch.float64), "alpha": torch.arange(4, dtype=torch.float64)}, True
+
+
+def _model_worker(rank, world, port, M, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    Xs = torch.arange(M * 2, dtype=torch.float64).reshape(M, 2)
+    for tag, sparse in (("e", False), ("s", True)):
+        mean, sd = sharded.predict_model_sharded(_StandInModel(rank, sparse), Xs)
+        np.save(os.path.join(out_dir, f"{tag}{rank}.npy"), np.stack([mean.numpy(), sd.numpy()]))
+    dist.destroy_process_group()
+
+
+def test_predict_model_sharded_world2_gloo(tmp_path):
+    """Model-level helper: rank 0's hyper-parameters and inducing inputs win, cache broadcast, tiles gathered."""
+    M = 21
+    port = 29900 + os.getpid() % 90
+    mp.spawn(_model_worker, args=(2, port, M, str(tmp_path)), nprocs=2, join=True)
+    Xs = np.arange(M * 2, dtype=np.float64).reshape(M, 2)
+    want_e = np.stack([Xs[:, 0] * 2.0 + 6.0, Xs[:, 1] + 48.0])
+    want_s = np.stack([Xs[:, 0] * 2.0 + 3.0 + 6.0, Xs[:, 1] + 18.0])
+    for r in range(2):
+        np.testing.assert_array_equal(np.load(tmp_path / f"e{r}.npy"), want_e)
+        np.testing.assert_array_equal(np.load(tmp_path / f"s{r}.npy"), want_s)
+
+
 @pytest.mark.parametrize("M", [64, 37])
 def test_sharded_predict_world2_gloo(tmp_path, M):
     port = 29600 + (os.getpid() + M) % 300
