@@ -25,6 +25,11 @@ $NCU --set full --import-source on -k "regex:diag_block_kernel" -s 8 -c 1 -o $O/
 # marginal-likelihood gradient reduction (one Adam iteration at c2) and the acquisition sweep over 2^20 points
 $NCU --set full --import-source on -k regex:grad_partial -c 1 -o $O/${TAG}_grad_c2 -f python tools/prof_stage.py fit c2 >> $LOG 2>&1
 $NCU --set full --import-source on -k "regex:acq_eval_kernel|topk_round_kernel" -c 2 -o $O/${TAG}_acq_1m -f python tools/prof_stage.py acq c2 >> $LOG 2>&1
+# inducing-point path (fp32, C2 size): launch list of two Adam iterations, the fused kernel-derivative reduction over the
+# m x N sensitivity matrix (2nd launch of an iteration) and the split-K S = B B^T product (2nd tcgen05 launch)
+$NCU --profile-from-start on --metrics gpu__time_duration.sum -c 300 --csv --log-file $O/${TAG}_launches_sparse_c2_f32.csv python tools/sparse_stages.py c2 2 f32 >> $LOG 2>&1
+$NCU --profile-from-start on --set full --import-source on -k regex:sgp_kgrad_kernel -s 1 -c 1 -o $O/${TAG}_sparse_kgrad_c2 -f python tools/sparse_stages.py c2 2 f32 >> $LOG 2>&1
+$NCU --profile-from-start on --set full --import-source on -k regex:gemm_tc_kernel -s 1 -c 1 -o $O/${TAG}_sparse_syrk_c2 -f python tools/sparse_stages.py c2 2 f32 >> $LOG 2>&1
 # kernel-matrix assembly (full and lower-only)
 $NCU --set full --import-source on -k regex:kmat_kernel -c 2 -o $O/${TAG}_kmat_h512 -f python tools/prof_stage.py kmat h512 >> $LOG 2>&1
 # summarise on the box: the reports themselves are too big to travel back (64 MiB cap), keep only the GEMM one
