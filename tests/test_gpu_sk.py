@@ -39,8 +39,8 @@ def test_sk_run_matches_oracle(kernel, iso):
     np.testing.assert_allclose(np.array(hp1["lengthscale"]), np.array(hp0["lengthscale"]), rtol=1e-6)
     np.testing.assert_allclose(np.array(rec.loss_all), np.array(ref.losses), rtol=1e-7, atol=1e-9)
     v, noise, c, l = ref.theta()
-    assert abs(float(rec.model.mean_module.constant) - float(c)) < 1e-6
-    assert abs(float(rec.model.covar_module.outputscale) - float(v)) < 1e-6 * float(v)
+    assert abs(float(rec.model.mean_module.constant) - float(c.detach())) < 1e-6
+    assert abs(float(rec.model.covar_module.outputscale) - float(v.detach())) < 1e-6 * float(v.detach())
     assert relinf(m1, m0) < 1e-6 and relinf(s1, s0) < 1e-6
     # first recorded noise is one Adam step away from softplus(0) + 1e-4
     assert abs(hp1["noise"][0] - (np.log1p(np.exp(-0.1)) + 1e-4)) < 1e-6 or abs(hp1["noise"][0] - (np.log1p(np.exp(0.1)) + 1e-4)) < 1e-6

@@ -80,3 +80,74 @@ def test_sparse_oracle_reproduces_its_committed_training_vectors(kernel, golden_
     np.testing.assert_allclose(np.array(ora.losses), g["loss"], rtol=1e-9)
     np.testing.assert_allclose(mean, g["mean"], rtol=0, atol=1e-8 * np.abs(g["mean"]).max())
     np.testing.assert_allclose(sd, g["sd"], rtol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The closed form the CUDA path evaluates (csrc/sparse.cuh header), written out with the same
+# intermediates and in the same order as csrc/sparse_driver.cuh, against autograd of the restated objective.
+# ---------------------------------------------------------------------------------------------------------------
+def _closed_form(kname, X, y, Xu, v, ls, s2, al, jitter):
+    from oracle.gp_oracle import kernel_matrix
+    import math
+    N, m = X.shape[0], Xu.shape[0]
+    I = torch.eye(m, dtype=X.dtype)
+    Luu = torch.linalg.cholesky(kernel_matrix(kname, Xu, Xu, v, ls, al) + jitter * I)
+    Ui = torch.linalg.inv(Luu)
+    B = Ui @ kernel_matrix(kname, Xu, X, v, ls, al)               # m x N
+    S = B @ B.T
+    Ap = S / s2 + I
+    LA = torch.linalg.cholesky(Ap)
+    LAi = torch.linalg.inv(LA)
+    beta = B @ y
+    c0 = LAi @ beta
+    a0 = LAi.T @ c0
+    a = a0 / s2
+    rho = y - B.T @ a
+    w = Ui.T @ a
+    Ainv = LAi.T @ LAi
+    Phi = 2 * I - Ainv - Ap - torch.outer(a, a)
+    H = Ainv - I
+    Guu = -0.5 * Ui.T @ (Phi @ Ui)                                # dF/dKuu
+    Guf = ((Ui.T @ H) @ B - torch.outer(w, rho)) / s2             # dF/dKuf
+    yy, T_ = y @ y, N * v - torch.diagonal(S).sum()
+    loss = 0.5 * (yy / s2 - (c0 @ c0) / s2 ** 2 + N * torch.log(s2) + 2 * torch.log(torch.diagonal(LA)).sum()
+                  + N * math.log(2 * math.pi)) + 0.5 * torch.clamp(T_ / s2, min=0)
+    ab, aa = (a0 @ beta) / s2, (a0 @ a0) / s2 ** 2
+    ds2 = (-yy / (2 * s2 ** 2) + ab / s2 ** 2 - (ab / s2 - aa) / (2 * s2) + N / (2 * s2)
+           - (m - torch.diagonal(Ainv).sum()) / (2 * s2) - T_ / (2 * s2 ** 2))
+    return loss, ds2, Guu, Guf
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "Matern52", "RationalQuadratic"])
+def test_closed_form_gradient_of_the_vfe_bound_matches_autograd(kernel):
+    from oracle.gp_oracle import kernel_matrix
+    from oracle.sparse_oracle import vfe_loss
+    rng = np.random.RandomState(1)
+    n1 = 14
+    R = rng.rand(n1, n1)
+    R[rng.rand(n1, n1) < 0.3] = np.nan
+    Xg = np.mgrid[:n1, :n1].astype(float)
+    Xg[:, np.isnan(R)] = np.nan
+    o = SparseOracleGP(Xg, R, kernel=kernel, lengthscale=[[1., 1.], [5., 5.]], indpoints=12, jitter=1e-5)
+    N = o.X.shape[0]
+    leaf = lambda t: t.detach().clone().requires_grad_(True)
+    # autograd of the restated objective w.r.t. the constrained hyper-parameters and the inducing inputs
+    v, ls, s2, al = (leaf(t) for t in o._theta())
+    Xu = leaf(o.Xu)
+    ref = vfe_loss(kernel, o.X, o.y, Xu, v, ls, s2, al, o.jitter)
+    ref.backward()
+    # closed form: sensitivities of the two kernel matrices + explicit noise / variance terms; the chain onto the
+    # kernel parameters and Xu (sgp_kgrad_kernel on the device) is taken by autograd of sum(G * K) here
+    loss, ds2, Guu, Guf = _closed_form(kernel, o.X, o.y, Xu.detach(), v.detach(), ls.detach(), s2.detach(), al.detach(), o.jitter)
+    v2, ls2, al2, Xu2 = leaf(v), leaf(ls), leaf(al), leaf(Xu)
+    chain = ((Guu * kernel_matrix(kernel, Xu2, Xu2, v2, ls2, al2)).sum()
+             + (Guf * kernel_matrix(kernel, Xu2, o.X, v2, ls2, al2)).sum() + N * v2 / (2 * s2.detach()))
+    chain.backward()
+    assert abs(float(loss) - float(ref.detach())) < 1e-10 * abs(float(ref.detach()))
+    assert abs(float(ds2) - float(s2.grad)) < 1e-9 * abs(float(s2.grad))
+    assert abs(float(v2.grad) - float(v.grad)) < 1e-9 * abs(float(v.grad))
+    np.testing.assert_allclose(ls2.grad.numpy(), ls.grad.numpy(), rtol=1e-9)
+    np.testing.assert_allclose(Xu2.grad.numpy(), Xu.grad.numpy(), rtol=0, atol=1e-9 * float(Xu.grad.abs().max()))
+    if kernel == "RationalQuadratic":
+        assert abs(float(al2.grad) - float(al.grad)) < 1e-8 * abs(float(al.grad))
+    assert float((Guu - Guu.T).abs().max()) < 1e-9 * float(Guu.abs().max())       # the kernel's factor 2 on dF/dXu relies on it
