@@ -6,10 +6,10 @@
 #pragma once
 template <typename T> struct SgpBufs {
     int64_t m = 0, N = 0, ldm = 0, ldn = 0;
-    int nz = 1;                  // split-K factor of S = B B^T; ldn = nz * kchunk (columns [N, ldn) of B are kept zero)
+    int nz = 1;                  // SIMT route: split-K factor of S = B B^T; ldn = nz * kchunk (columns [N, ldn) of B are kept zero)
     int64_t kchunk = 0;
     T *Spart;
-    // tcgen05 route of the two m x m x N products with contraction length m (fp32, large problems): fp16 hi/lo planes
+    // tcgen05 route (fp32, m >= 512 and N >= 2048, see sgp_uses_tc): fp16 hi/lo planes of the operands and their scales
     bool tc = false;
     int64_t ldk = 0;             // leading dimension of the N x m operands
     float *Kfu = nullptr, *scales = nullptr;
