@@ -339,7 +339,35 @@ def measure_sparse(eng, name, iters, steps):
         ms_fit, ms_pred = fit(iters), predict(steps)
         out[tag] = {"ms_per_adam_iteration": ms_fit, "predict_ms_per_step": ms_pred,
                     "points_per_s": Xs.shape[0] / (ms_pred * 1e-3)}
+    try:                                              # context only: must never take the bench line down
+        out["cpu_oracle"] = cpu_sparse_sample(X, y, m_ind, wl["kernel"], wl["theta"])
+    except Exception as e:                            # noqa: BLE001
+        out["cpu_oracle"] = {"error": repr(e)[:200]}
     return out
+
+
+def cpu_sparse_sample(X, y, m_ind, kernel, theta, iters=2):
+    """The reference's CPU arithmetic for the same Adam iteration (oracle/sparse_oracle.py: the VFE objective through
+    torch autograd, fp64, all host threads), timed on a bounded sample of `iters` iterations after one warm-up."""
+    import torch
+    from oracle.sparse_oracle import vfe_loss
+    torch.set_num_threads(os.cpu_count() or 1)
+    N, d = X.shape
+    Xt, yt = torch.tensor(X, dtype=torch.float64), torch.tensor(y, dtype=torch.float64)
+    leaf = lambda v: torch.tensor(v, dtype=torch.float64, requires_grad=True)
+    v, s2, al, ls = leaf(theta[0]), leaf(theta[1]), leaf(theta[2]), leaf(theta[3:3 + d])
+    Xu = Xt[::N // m_ind].clone().requires_grad_(True)
+    opt = torch.optim.Adam([v, s2, ls, Xu], lr=1e-3)
+    times = []
+    for it in range(iters + 1):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = vfe_loss(kernel, Xt, yt, Xu, v, ls, s2, al, 1e-5)
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    return {"ms_per_adam_iteration": 1e3 * sum(times[1:]) / iters, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{iters} iterations after 1 warm-up, fp64, N={N}, m={int(Xu.shape[0])}"}
 
 
 def bench_config(wl, gpus, N, M):
