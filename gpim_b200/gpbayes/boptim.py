@@ -261,6 +261,8 @@ class boptimizer:
         # be resumed exactly where it stopped (the reference writes checkpoints but has no way to load them)
         results['engine_state'] = {'u': self.surrogate_model.model._u.detach().cpu().numpy().copy(),
                                    'steps_done': len(self.gp_predictions)}
+        if hasattr(self.surrogate_model.model, "Xu"):      # sparse surrogate: the trained inducing inputs belong to the state
+            results['engine_state']['Xu'] = self.surrogate_model.model.Xu.detach().cpu().numpy().copy()
         np.save(filename + ".npy", results)
 
     def resume(self, filename=None):
@@ -283,5 +285,7 @@ class boptimizer:
             self.surrogate_model.train(verbose=self.verbose)
         else:
             model.load_unconstrained(state['u'])
+            if state.get('Xu') is not None and hasattr(model, "Xu"):
+                model.Xu = torch.as_tensor(state['Xu'])
         self._first_step = max(1, len(self.gp_predictions))
         return self

@@ -197,3 +197,35 @@ def test_update_points_ball_suppression():
     bo = _bare_boptimizer(batch_out_max=5)                    # fewer survivors than requested: random padding
     v, idx = bo.update_points(vals, cand, dscale=2.5)
     assert len(idx) == 5 and idx[:3] == [[10, 10], [20, 20], [0, 0]] and all(i in cand for i in idx[3:])
+
+
+def test_checkpoint_carries_the_inducing_inputs_of_a_sparse_surrogate(tmp_path):
+    """save_results() / resume() with a sparse surrogate: the trained inducing inputs are part of the engine state
+    (host logic only: the surrogate is a stand-in object with the members the two methods touch)."""
+    import types
+    import torch
+
+    def surrogate(xu_value):
+        model = types.SimpleNamespace(_u=torch.tensor([0.1, -0.2, 0.0, 0.3, 0.4], dtype=torch.float64),
+                                      Xu=torch.full((3, 2), xu_value, dtype=torch.float64), X=None, y=None)
+        model.load_unconstrained = lambda u: setattr(model, "_u", torch.as_tensor(np.asarray(u)))
+        return types.SimpleNamespace(model=model, train=lambda **kw: None)
+
+    y = np.full((4, 4), np.nan)
+    y[1, 2] = 0.5
+    y[3, 0] = -1.0
+    common = dict(filename=str(tmp_path / "bo"), extent=None, precision="double", exploration_steps=4,
+                  gp_predictions=[(np.zeros((4, 4)), np.ones((4, 4)))], target_func_vals=[y.copy()],
+                  indices_all=[[1, 2]], vals_all=[0.7])
+    first = _bare_boptimizer(surrogate_model=surrogate(2.5), **common)
+    first.save_results()
+    saved = np.load(str(tmp_path / "bo.npy"), allow_pickle=True).item()
+    assert {"gp_pred", "func_val", "inds_all", "vals_all"} <= set(saved)             # the reference's four keys
+    np.testing.assert_array_equal(saved["engine_state"]["Xu"], np.full((3, 2), 2.5))
+    second = _bare_boptimizer(surrogate_model=surrogate(-9.0), **{**common, "gp_predictions": [], "target_func_vals": [],
+                                                                  "indices_all": [], "vals_all": []})
+    second.resume()
+    np.testing.assert_array_equal(second.surrogate_model.model.Xu.numpy(), np.full((3, 2), 2.5))
+    np.testing.assert_allclose(second.surrogate_model.model._u.numpy(), [0.1, -0.2, 0.0, 0.3, 0.4])
+    assert second.indices_all == [[1, 2]] and second._first_step == 1
+    assert tuple(second.surrogate_model.model.X.shape) == (2, 2)                     # the two measured pixels
