@@ -9,18 +9,29 @@ reconstructor.predict does per call (gpr.py:248): K(X,X) assembly, Cholesky of K
 the triangular solves, K(X*,X), the diagonal predictive variance and the mean, for all M points
 of X_full.  Metric: predicted grid points per second (mean + sd), whole job.
 
-* `value`  : inputs (X, y, theta, X_full rows) already resident in HBM, outputs left in HBM.
-* `e2e`    : the same pass through the reference-facing API gpim.reconstructor (host numpy
-             arrays in, numpy arrays out; host<->device copies inside the timed region).
-* `roofline`: the dominant kernel (the Linv x K* product with the fused column-sum-of-squares
-             epilogue), CUDA-event bracketed inside libgpgrid.so on the launching stream.
-* `cpu_baseline` / `--impl reference`: oracle/gp_oracle.py (the CPU restatement of the
-             reference's Pyro path -- pyro-ppl is not installable here) timed on the
-             host cores on a bounded sample of the same workload.
+Headline workload (N = 1): BASELINE.json configs[1] = C2, the 256 x 256 spiral scan (RBF, fp32).  The other
+single-GPU configurations -- the 512 x 512 reconstruction the north-star target is quoted on, C3 (64 x 64 x 16
+Matern52) and C4 (Bayesian optimisation, EI, 128 x 128, 50 steps) -- ride in the same JSON line under `workloads`,
+each with its own `value`, `e2e`, `roofline` and `cpu_baseline`.
 
-N > 1 (torchrun, one rank per GPU): weak scaling -- the dense grid gets N times more rows (step
-1/N), rank 0 factorises, one NCCL broadcast of {Linv, alpha}, every rank predicts its row tile,
-one all-gather of (mean, sd).
+* `value`  : inputs (X, y, theta, X_full rows) already resident in HBM, outputs left in HBM; CUDA events.
+* `e2e`    : the same pass through the reference-facing API gpim.reconstructor (host numpy arrays in, numpy arrays
+             out; host<->device copies inside the timed region).
+* `roofline`: the dominant kernel (the Linv x K* product with the fused column-sum-of-squares epilogue), CUDA-event
+             bracketed inside libgpgrid.so on the launching stream; `cholesky` and `kmat_assembly` carry the
+             rooflines BASELINE.json's metric names next to it.
+* `cpu_baseline`: oracle/gp_oracle.py (the CPU restatement of the reference's Pyro path -- pyro-ppl is not
+             installable here) on the host cores on a bounded sample of the same workload: the FULL
+             factorisation at N plus the per-point stages on a sample of grid rows.  Its outputs are kept and
+             compared with the CUDA path's at the same rows (`parity_vs_oracle`).
+* `--impl reference`: the same oracle on the WHOLE workload, unextrapolated, capped at 2 timed steps.
+* `torch_cuda_baseline`: the oracle's torch ops on device="cuda" -- what the reference's use_gpu=True dispatches to
+             on the same box (cuSOLVER potrf, cuBLAS trsm; gpr.py:136-140,248).  A baseline leg, not the product.
+
+N > 1 (torchrun, one rank per GPU): weak scaling on the headline workload -- the dense grid gets N times more rows
+-- through gpg_predict_sharded (rank 0 factorises, pipelined NCCL broadcast of the cache, every rank predicts its
+row tile, one all-gather); `shard_parity_max_rel` compares the gathered result with an unsharded predict on rank 0;
+`strong_c5` is BASELINE.json configs[4] as configured (1024 x 1024, M fixed at 1 048 576, tiles of M / N rows).
 """
 import argparse
 import json
@@ -37,41 +48,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 import workloads as W  # noqa: E402
+from workloads import make_workload, rows_of  # noqa: E402,F401
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the variance GEMM (16 384 test points), from the
-# ncu --set full captures summarised in profiles/r1_05_ncu_pgemm_{c2,h512}.md
-NCU_TRAFFIC_BYTES = {"c2": 2.099609e9 + 6.744320e6, "h512": 10.066302e9 + 7.414528e6}
 METRIC = "predicted grid points/sec (mean+sd)"
 UNIT = "points/s"
-
-
-# ---------------------------------------------------------------------------------------------
-# workloads
-# ---------------------------------------------------------------------------------------------
-def make_workload(name, dense=1):
-    """-> dict(R, kernel, theta(list), d, label).  `dense` multiplies the number of X_full rows."""
-    ft = W.FIXED_THETA
-    if name in ("c2", "h512", "c5", "c1k"):
-        n = {"c2": 256, "h512": 512, "c5": 1024, "c1k": 128}[name]
-        R = W.spiral_scan(n)
-        theta = [ft["variance"], ft["noise"], 1.0, ft["lengthscale"], ft["lengthscale"]]
-        kern = "RBF"
-        label = f"2D {n}x{n} sparse spiral scan, RBF, fixed theta"
-    elif name == "c3":
-        R = W.hyperspectral((64, 64, 16))
-        theta = [ft["variance"], ft["noise"], 1.0, ft["lengthscale"], ft["lengthscale"], ft["lengthscale_z"]]
-        kern = "Matern52"
-        label = "3D 64x64x16 hyperspectral, Matern52, fixed theta"
-    else:
-        raise SystemExit(f"unknown workload {name}")
-    sl = [slice(0, R.shape[0], 1.0 / dense)] + [slice(0, e, 1.0) for e in R.shape[1:]]
-    Xfull = np.array(np.mgrid[tuple(sl)])                     # gprutils.get_full_grid layout (c, *dims)
-    return {"name": name, "R": R, "kernel": kern, "theta": theta, "d": R.ndim, "label": label,
-            "Xfull": Xfull, "jitter": ft["jitter"]}
-
-
-def rows_of(Xgrid):
-    return Xgrid.reshape(Xgrid.shape[0], -1).T
+PREDICT_CHUNK = 16384            # test points per variance-GEMM launch (gpg_predict's internal tile)
 
 
 def train_rows(R):
@@ -79,6 +60,29 @@ def train_rows(R):
     from gpim_b200 import gprutils
     X, y = gprutils.prepare_training_data(gprutils.get_sparse_grid(R), R)
     return X.numpy(), y.numpy()
+
+
+def relinf(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:                                        # noqa: BLE001
+        return {}
+
+
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the variance GEMM from the newest committed ncu
+    --set full capture of this workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        e = t.get(name)
+        return (float(e["bytes_per_launch"]), e.get("source")) if e else (None, None)
+    except Exception:                                        # noqa: BLE001
+        return None, None
 
 
 # ---------------------------------------------------------------------------------------------
@@ -147,31 +151,55 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle on the host cores, bounded sample
+# CPU legs: the oracle on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_predict_sample(wl, m_sample, dtype_name="f32"):
-    """One reference-style predict on the host: full factorisation (K, Cholesky) + K*, TRSM and
-    reductions on `m_sample` grid points; whole-grid time extrapolated linearly in M for the
-    per-point stages.  Returns (points_per_s, seconds_measured, stage dict)."""
+def cpu_predict(wl, rows, dtype_name):
+    """One reference-style predict on the host (oracle): full K assembly + Cholesky at N, then K*, TRSM and the
+    reductions on the grid rows `rows` (None = all of them).  -> (mean, sd, stage seconds, wall seconds)."""
     import torch
     from oracle import gp_oracle as O
     X, y = train_rows(wl["R"])
     Xs = rows_of(wl["Xfull"])
-    M = Xs.shape[0]
-    sel = np.linspace(0, M - 1, m_sample).astype(np.int64)
+    if rows is not None:
+        Xs = Xs[rows]
     th = wl["theta"]
     dt = torch.float32 if dtype_name == "f32" else torch.float64
     t0 = time.perf_counter()
-    _, _, st = O.predict_fixed_theta(wl["kernel"], X, y, Xs[sel], th[0], th[3:], th[1], jitter=wl["jitter"], dtype=dt,
-                                     scale_mixture=th[2])
-    wall = time.perf_counter() - t0
+    mean, sd, st = O.predict_fixed_theta(wl["kernel"], X, y, Xs, th[0], th[3:], th[1], jitter=wl["jitter"], dtype=dt,
+                                         scale_mixture=th[2])
+    return mean, sd, st, time.perf_counter() - t0
+
+
+def cpu_baseline_block(wl, m_sample, dtype_name, cuda_out=None):
+    """Bounded CPU sample of one workload: full factorisation + `m_sample` grid rows; the whole-grid time scales the
+    per-point stages by M / m_sample.  cuda_out = (mean, sd) numpy arrays of the CUDA path over the whole grid:
+    compared with the oracle at the sampled rows (fp64 oracle = the parity reference of north_star)."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    M = rows_of(wl["Xfull"]).shape[0]
+    N = int((~np.isnan(wl["R"])).sum())
+    rows = W.sample_rows(M, min(m_sample, M))
+    mean, sd, st, wall = cpu_predict(wl, rows, dtype_name)
     t_fact = st["kmat"] + st["cholesky"]
     t_pts = st["kcross"] + st["trsm"] + st["reduce"]
-    t_full = t_fact + t_pts * (M / m_sample)
-    return M / t_full, wall, st
+    t_full = t_fact + t_pts * (M / len(rows))
+    out = {"value": M / t_full, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "dtype": dtype_name,
+           "sample": f"oracle predict: K + Cholesky at the full N = {N}, K* / TRSM / reduce on {len(rows)} of {M} grid rows "
+                     f"(per-point stages scaled by M / {len(rows)}); {wall:.1f} s measured, torch {torch.__version__} CPU",
+           "stages_s": {k: round(v, 4) for k, v in st.items()}, "measured_s": wall}
+    if cuda_out is not None:
+        out["parity_vs_oracle"] = {"rows": int(len(rows)), "oracle_dtype": dtype_name,
+                                   "mean_relinf": relinf(cuda_out[0][rows], mean), "sd_relinf": relinf(cuda_out[1][rows], sd),
+                                   "tolerance": {"mean": 1e-4, "sd": 1e-3},
+                                   "note": "max |cuda - oracle| / max |oracle| over the sampled rows (north_star)"}
+    return out
 
 
 def run_reference(args):
+    """--impl reference: the oracle (kind "port": pyro-ppl is not installable) on the WHOLE
+    workload, all host threads, nothing extrapolated.  One full C2 predict is minutes of CPU time (fp32 TRSM with
+    65 536 right-hand sides runs at ~30 GFLOP/s in torch's LAPACK path), so the timed steps are capped at 2 and the
+    warm-up is a small matmul that only spins the thread pool up; `steps` reports what was timed."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -180,79 +208,403 @@ def run_reference(args):
     torch.set_num_threads(cores)
     wl = make_workload(args.workload, dense=args.gpus)
     M = rows_of(wl["Xfull"]).shape[0]
-    m_sample = args.cpu_sample
-    for _ in range(min(args.warmup, 1)):
-        cpu_predict_sample(wl, m_sample, args.cpu_dtype)
-    vals, walls = [], []
-    for _ in range(args.steps):
-        v, wall, st = cpu_predict_sample(wl, m_sample, args.cpu_dtype)
-        vals.append(v); walls.append(wall)
-    value = float(np.mean(vals))
     N = int((~np.isnan(wl["R"])).sum())
-    sample = (f"full K assembly + Cholesky (N={N}) and K*/TRSM/reduce on {m_sample} of {M} grid points per step, "
-              f"per-point stages scaled by M/{m_sample}; torch {torch.__version__} CPU {args.cpu_dtype}")
+    steps = max(1, min(args.steps, args.cpu_full_steps))
+    a = torch.randn(2048, 2048)
+    (a @ a).sum().item()
+    walls, stages = [], None
+    for _ in range(steps):
+        _, _, st, wall = cpu_predict(wl, None, args.cpu_dtype)
+        walls.append(wall); stages = st
+    sec = float(np.mean(walls))
+    value = M / sec
+    sample = (f"whole workload, nothing extrapolated: K + Cholesky at N = {N} and K* / TRSM / reduce on all {M} grid rows, "
+              f"{steps} timed step(s) (requested {args.steps}; capped: one step is {sec:.0f} s), thread-pool warm-up only; "
+              f"torch {torch.__version__} CPU {args.cpu_dtype}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * M / value, "higher_is_better": True,
+            "steps": steps, "steps_requested": args.steps, "warmup": 0, "warmup_requested": args.warmup,
+            "ms_per_step": 1e3 * sec, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.cpu_dtype, "data": "synthetic",
             "config": bench_config(wl, args.gpus, N, M),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample, "measured_s_per_step": float(np.mean(walls))},
+                             "sample": sample, "stages_s": {k: round(v, 3) for k, v in stages.items()}},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def measure_extra(eng, name, steps, warmup, compact_support=False):
-    """The same step on another workload of SURVEY 8d (1 GPU, device-resident inputs, CUDA events).
-    compact_support: with GPG_OPT_COMPACT_SUPPORT (NOT the headline configuration): the variance GEMM of each
-    128-row tile of test points only visits the training rows whose covariance with the tile exceeds 1e-14 x
-    variance -- same outputs to fp32 rounding, far fewer MMAs when the lengthscale is short against the grid."""
+def torch_cuda_baseline(wl, steps=3):
+    """The reference's use_gpu=True dispatch on the same box: the oracle's torch ops (kernel by matmul expansion,
+    torch.linalg.cholesky -> cuSOLVER potrf, solve_triangular -> cuBLAS trsm on the N x (M + 1) pack) on
+    device="cuda", device-resident inputs, CUDA-synchronised wall clock.  A baseline leg: the product never runs
+    through it."""
     import torch
-    from gpim_b200 import _lib
-    from gpim_b200._lib import KERNEL_IDS
-    wl = make_workload(name)
-    if compact_support:
-        eng.set_option(_lib.OPT_COMPACT_SUPPORT, 1)
+    from oracle import gp_oracle as O
     X, y = train_rows(wl["R"])
     Xs = rows_of(wl["Xfull"])
+    th = wl["theta"]
     N, M = X.shape[0], Xs.shape[0]
-    dev, dt = eng.device, torch.float32
+    dev = torch.device("cuda")
+    Xd, yd, Xsd = (torch.tensor(a, dtype=torch.float32, device=dev) for a in (X, y, Xs))
+    try:
+        def run():
+            return O.predict_fixed_theta(wl["kernel"], Xd, yd, Xsd, th[0], th[3:], th[1], jitter=wl["jitter"],
+                                         dtype=torch.float32, scale_mixture=th[2], device=dev, to_numpy=False)
+        run()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            mean, sd, st = run()
+        torch.cuda.synchronize()
+        sec = (time.perf_counter() - t0) / steps
+        out = {"value": M / sec, "unit": UNIT, "ms_per_step": 1e3 * sec, "steps": steps, "dtype": "f32",
+               "what": "oracle.predict_fixed_theta on device='cuda' (torch " + torch.__version__ + ": cuSOLVER potrf + cuBLAS "
+                       "trsm with the whole N x M cross-kernel materialised) -- the reference's use_gpu=True path "
+                       "(gpr.py:136-140,248)",
+               "stages_s": {k: round(v, 5) for k, v in st.items()},
+               "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+        out["_mean"], out["_sd"] = mean.cpu().numpy(), sd.cpu().numpy()
+        return out
+    except Exception as e:                                   # noqa: BLE001  (e.g. out of memory at C5 sizes)
+        return {"error": repr(e)[:300]}
+    finally:
+        del Xd, yd, Xsd
+        torch.cuda.empty_cache()
+
+
+# ---------------------------------------------------------------------------------------------
+# the CUDA arm: one workload, device-resident
+# ---------------------------------------------------------------------------------------------
+def bench_config(wl, gpus, N, M):
+    return {"workload": wl["label"], "name": wl["name"], "N_train": N, "M_grid": M, "kernel": wl["kernel"],
+            "theta": {"variance": wl["theta"][0], "noise": wl["theta"][1], "lengthscale": wl["theta"][3:],
+                      "jitter": wl["jitter"]},
+            "sharding": "1 GPU" if gpus == 1 else f"X_full row tiles over {gpus} GPUs: pipelined NCCL broadcast of the "
+                                                  f"factor cache from rank 0 + 1 all-gather of (mean, sd)",
+            "l2_policy": "inputs larger than L2: every step rewrites and rereads K/L/Linv (N x N fp32 each) and the "
+                         "K* tiles; no explicit flush"}
+
+
+def measure_predict(eng, wl, steps, warmup, world=1, rank=0, keep_outputs=True):
+    """`steps` timed passes (factorise + predict) with device-resident inputs, CUDA events, stage clocks.
+    world > 1: gpg_predict_sharded (rank 0 factorises).  Returns a dict; on rank 0 it carries the gathered outputs."""
+    import torch
+    import torch.distributed as dist
+    from gpim_b200 import _lib, sharded
+    from gpim_b200._lib import KERNEL_IDS
+    X, y = train_rows(wl["R"])
+    Xs = rows_of(wl["Xfull"])
+    N, M, d = X.shape[0], Xs.shape[0], X.shape[1]
     kid = KERNEL_IDS[wl["kernel"]]
+    dev, dt = eng.device, torch.float32
     th = torch.tensor(wl["theta"], dtype=dt, device=dev)
-    Xd, yd, Xsd = (torch.tensor(a, dtype=dt, device=dev) for a in (X, y, Xs))
-    fac = eng.alloc_factor(N, dt)
-    mean_t, sd_t = torch.empty(M, dtype=dt, device=dev), torch.empty(M, dtype=dt, device=dev)
+    Xd = torch.tensor(X, dtype=dt, device=dev)
+    yd = torch.tensor(y, dtype=dt, device=dev)
+    lo, hi = sharded.tile_bounds(M, world, rank)
+    Xsd = torch.tensor(Xs[lo:hi], dtype=dt, device=dev)
+    fac = eng.alloc_factor(N, dt, with_L=(rank == 0))
+    width = sharded.tile_width(M, world)
+    pred_local = torch.zeros(2, width, dtype=dt, device=dev)
+    pred_all = torch.empty(world, 2, width, dtype=dt, device=dev) if world > 1 else None
 
     def step():
-        eng.factorize(kid, th, Xd, yd, wl["jitter"], out=fac)
-        eng.predict(kid, th, Xd, fac, Xsd, mean=mean_t, sd=sd_t)
+        if rank == 0:
+            eng.factorize(kid, th, Xd, yd, wl["jitter"], out=fac)
+        if world > 1:
+            eng.predict_sharded(kid, th, Xd, fac, Xsd, width, root=0, pred_local=pred_local, pred_all=pred_all)
+        else:
+            eng.predict(kid, th, Xd, fac, Xsd, mean=pred_local[0], sd=pred_local[1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     for _ in range(warmup):
         step()
-    torch.cuda.synchronize()
-    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    barrier()
+    eng.set_option(_lib.OPT_STAGE_TIMING, 1)
+    eng.stage_times()
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
-    for _ in range(steps):
-        eng.predict(kid, th, Xd, fac, Xsd, mean=mean_t, sd=sd_t)
-    e2.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
-    ms_pred = e1.elapsed_time(e2) / steps
-    assert bool(torch.isfinite(mean_t).all()) and bool(torch.isfinite(sd_t).all())
-    out = {"workload": wl["label"], "N_train": N, "M_grid": M, "ms_per_step": ms, "value": M / (ms * 1e-3), "unit": UNIT,
-           "factor_cached_ms": ms_pred, "factor_cached_value": M / (ms_pred * 1e-3), "steps": steps}
-    if compact_support:
-        eng.set_option(_lib.OPT_COMPACT_SUPPORT, 0)
-        out["note"] = ("GPG_OPT_COMPACT_SUPPORT = 1 (opt-in, not the headline): variance GEMM restricted per tile to the "
-                       "training rows with covariance > 1e-14 x variance; outputs equal the dense ones to fp32 rounding "
-                       "(tests/test_gpu_parity.py::test_predict_compact_support_option_is_exact)")
+    barrier()
+    wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    stages = eng.stage_times()
+    eng.set_option(_lib.OPT_STAGE_TIMING, 0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    info = int(fac["info"].item())
+    assert info == 0, f"factorisation failed at pivot {info}"
+    if world > 1:
+        counts = [sharded.tile_bounds(M, world, r)[1] - sharded.tile_bounds(M, world, r)[0] for r in range(world)]
+        mean = torch.cat([pred_all[r, 0, :c] for r, c in enumerate(counts)])
+        sd = torch.cat([pred_all[r, 1, :c] for r, c in enumerate(counts)])
     else:
-        out["variance_gemm_tflops_algorithmic"] = float(N) * N * M / (ms_pred * 1e-3) / 1e12
-    del fac, Xsd, mean_t, sd_t
+        mean, sd = pred_local[0, :M], pred_local[1, :M]
+    assert bool(torch.isfinite(mean).all()) and bool(torch.isfinite(sd).all()), "non-finite prediction"
+    # factor-cached passes (L reused): the per-point part alone, 1 GPU only
+    ms_cached = None
+    if world == 1:
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(max(1, steps // 2)):
+            eng.predict(kid, th, Xd, fac, Xsd, mean=pred_local[0], sd=pred_local[1])
+        e3.record()
+        torch.cuda.synchronize()
+        ms_cached = e2.elapsed_time(e3) / max(1, steps // 2)
+    out = {"N": N, "M": M, "d": d, "m_local": hi - lo, "ms_per_step": ms / steps, "value": M / (ms / steps * 1e-3),
+           "launches": launches, "stages": stages, "steps": steps, "wall": (wall0, wall1), "ms_cached": ms_cached}
+    if world > 1 and rank == 0:
+        # sharded == unsharded: the same kernels on the same inputs, tile by tile -> must be bit-identical
+        m1, s1 = eng.predict(kid, th, Xd, fac, torch.tensor(Xs, dtype=dt, device=dev))
+        out["shard_parity_max_rel"] = max(relinf(mean.cpu().numpy(), m1.cpu().numpy()), relinf(sd.cpu().numpy(), s1.cpu().numpy()))
+        del m1, s1
+    if keep_outputs and rank == 0:
+        out["mean"], out["sd"] = mean.cpu().numpy(), sd.cpu().numpy()
+    del fac, Xsd, pred_local, pred_all
     torch.cuda.empty_cache()
     return out
+
+
+def roofline_blocks(res, wl, steps, peaks, timed_region_s):
+    """roofline of the dominant kernel + the two rooflines BASELINE.json's metric names (Cholesky, assembly)."""
+    N, d, m_local = res["N"], res["d"], res["m_local"]
+    stages = res["stages"]
+    # burst peak for a sub-2-second timed region at full clocks, the sustained (power-capped) one for a long step
+    burst = timed_region_s < 2.0
+    key = "bf16_tflops" if burst else "bf16_tflops_sustained"
+    peak_tf = peaks.get(key) or (1590.0 if burst else 1400.0)
+    peak_src = (f"MEASURED_PEAKS.json {key} (measured cuBLAS bf16 rate; "
+                + ("burst figure: the timed region is %.2f s at full clocks" % timed_region_s if burst else
+                   "sustained figure: the timed region is %.1f s under the power cap" % timed_region_s) + ")") if peaks else \
+        "fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)"
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    pg_ms, pg_n = stages["pgemm"]
+    flops_per_step = float(N) * float(N) * float(m_local)    # SURVEY 8d: N^2 FLOP per predicted point
+    achieved = flops_per_step * steps / (pg_ms * 1e-3) / 1e12 if pg_ms > 0 else 0.0
+    traffic, traffic_src = ncu_traffic(wl["name"])
+    pts_per_launch = min(PREDICT_CHUNK, m_local)
+    roof = {"kernel": "gemm_tc_kernel as the predict GEMM: Linv x K* + column-sum-of-squares epilogue (stage pgemm)",
+            "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": 4.0 * pts_per_launch * N + 2.0 * N * N,
+            "algorithmic_bytes_note": "4 B x (points per launch x N) K* planes + 2 N^2 B lower-triangle planes of Linv",
+            "launches": pg_n, "avg_launch_ms": pg_ms / max(pg_n, 1),
+            "algorithmic_flops_per_launch": flops_per_step * steps / max(pg_n, 1),
+            "peak_source": peak_src,
+            "note": "fp32-faithful split-fp16 product: 3 tcgen05 MMAs per algorithmic MAC, so the tensor pipe "
+                    "executes 3 x achieved",
+            "tensor_pipe_tflops": 3.0 * achieved, "tensor_pipe_frac": 3.0 * achieved / peak_tf}
+    ch_ms, ch_n = stages["cholesky"]
+    ch_tf = (N ** 3 / 3.0) * ch_n / (ch_ms * 1e-3) / 1e12 if ch_ms > 0 else 0.0
+    chol = {"kernel": "blocked Cholesky (stage cholesky: diagonal blocks + tcgen05 panels and SYRK updates)",
+            "bound": "tensor", "achieved": ch_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ch_tf / peak_tf,
+            "algorithmic_flops": N ** 3 / 3.0, "ms": ch_ms / max(ch_n, 1), "peak_source": peak_src}
+    km_ms, km_n = stages["kmat"]
+    kmat_gbps = (4.0 * N * N / 2 + 8.0 * d * N) * km_n / (km_ms * 1e-3) / 1e9 if km_ms > 0 else 0.0
+    kmat = {"kernel": "kmat_kernel (stage kmat)", "bound": "hbm", "achieved": kmat_gbps, "peak": hbm, "unit": "GB/s",
+            "frac": kmat_gbps / hbm, "note": "lower-triangle tiles only: 2 N^2 + 8 d N bytes per launch",
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"}
+    return roof, chol, kmat
+
+
+def run_e2e(wl, steps):
+    """gpim.reconstructor: swap the training set in (host -> device), predict over X_full given as
+    a host numpy grid, results back as numpy arrays.  Factor cache invalidated every step, as the
+    reference refactorises on every predict (gpr.py:248)."""
+    import torch
+    import gpim_b200 as gpim
+    R = wl["R"]
+    Xsp = gpim.utils.get_sparse_grid(R)
+    rec = gpim.reconstructor(Xsp, R, wl["Xfull"], kernel=wl["kernel"], iterations=0, verbose=0, precision="single",
+                             jitter=wl["jitter"], lengthscale=[[1.0] * R.ndim, [20.0] * R.ndim], shard=False)
+    th = wl["theta"]
+    rec.model.set_theta(th[0], th[3:], th[1], th[2])
+    Xh = rec.X.cpu().pin_memory()
+    yh = rec.y.cpu().pin_memory()
+    Xfull = wl["Xfull"]
+
+    def step():
+        rec.model.X = Xh
+        rec.model.y = yh
+        return rec.predict(Xfull, verbose=0)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        mean, sd = step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    M = mean.size
+    h2d = Xh.numel() * 4 + yh.numel() * 4 + M * R.ndim * 4
+    del rec
+    torch.cuda.empty_cache()
+    return {"value": M / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * M * 4),
+            "ms_per_step": dt * 1e3, "steps": steps,
+            "api": "gpim.reconstructor.predict(X_full) after model.X/.y swap (host numpy in/out)"}
+
+
+def run_e2e_sharded(wl, steps, world, rank):
+    """N > 1 through the kept API: every rank builds the reconstructor from host arrays and calls predict(X_full)
+    (a collective: rank 0 factorises, rows tiled over the ranks, numpy (mean, sd) on every rank)."""
+    import torch
+    import torch.distributed as dist
+    import gpim_b200 as gpim
+    R = wl["R"]
+    Xsp = gpim.utils.get_sparse_grid(R)
+    rec = gpim.reconstructor(Xsp, R, wl["Xfull"], kernel=wl["kernel"], iterations=0, verbose=0, precision="single",
+                             jitter=wl["jitter"], lengthscale=[[1.0] * R.ndim, [20.0] * R.ndim])
+    th = wl["theta"]
+    rec.model.set_theta(th[0], th[3:], th[1], th[2])
+    Xh = rec.X.cpu().pin_memory()
+    yh = rec.y.cpu().pin_memory()
+    Xfull = wl["Xfull"]
+
+    def step():
+        rec.model.X = Xh
+        rec.model.y = yh
+        return rec.predict(Xfull, verbose=0)
+
+    for _ in range(2):
+        step()
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        mean, sd = step()
+    dist.barrier(); torch.cuda.synchronize()
+    sec = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=rec.model.engine.device)
+    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+    sec = float(sec.item())
+    M = mean.size
+    h2d = (Xh.numel() + yh.numel()) * 4 * world + M * R.ndim * 4 * world
+    del rec
+    torch.cuda.empty_cache()
+    return {"value": M / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * M * 4 * world),
+            "ms_per_step": sec * 1e3, "steps": steps,
+            "api": "gpim.reconstructor.predict(X_full) on every rank (host numpy in/out; shard='auto' under NCCL)"}
+
+
+def workload_block(eng, name, steps, warmup, peaks, cpu_sample, with_torch_cuda=True, with_cpu=True, e2e_steps=None):
+    """One single-GPU configuration with all its blocks: value, e2e, roofline, cholesky, kmat, cpu_baseline (+ parity),
+    torch_cuda_baseline."""
+    wl = make_workload(name)
+    res = measure_predict(eng, wl, steps, warmup)
+    roof, chol, kmat = roofline_blocks(res, wl, steps, peaks, res["ms_per_step"] * steps * 1e-3)
+    blk = {"config": bench_config(wl, 1, res["N"], res["M"]), "value": res["value"], "unit": UNIT,
+           "ms_per_step": res["ms_per_step"], "steps": steps, "warmup": warmup, "dtype": "f32",
+           "factor_cached_ms": res["ms_cached"], "factor_cached_value": res["M"] / (res["ms_cached"] * 1e-3),
+           "gpu_launches": res["launches"],
+           "stages_ms_per_step": {k: v[0] / steps for k, v in res["stages"].items() if v[1]},
+           "roofline": roof, "cholesky": chol, "kmat_assembly": kmat,
+           "e2e": run_e2e(wl, e2e_steps or steps)}
+    if with_cpu:
+        blk["cpu_baseline"] = cpu_baseline_block(wl, cpu_sample, "f64", cuda_out=(res["mean"], res["sd"]))
+    if with_torch_cuda:
+        tcb = torch_cuda_baseline(wl)
+        if "_mean" in tcb:
+            tcb["agrees_with_engine"] = {"mean_relinf": relinf(tcb.pop("_mean"), res["mean"]),
+                                         "sd_relinf": relinf(tcb.pop("_sd"), res["sd"])}
+            tcb["engine_speedup"] = res["value"] / tcb["value"]
+        blk["torch_cuda_baseline"] = tcb
+    return blk, res, wl
+
+
+def measure_c4(eng, peaks, steps=50, gp_iterations=1000, cpu_steps=1):
+    """BASELINE.json configs[3]: GP-BO with EI on a 128 x 128 grid, 100 seed pixels, `steps` exploration steps x
+    `gp_iterations` Adam iterations, all defaults (fp64), through gpim.boptimizer -- host numpy in/out by construction,
+    so the run IS the end-to-end number.  CPU baseline: the oracle's bo_run on `cpu_steps` exploration step(s)."""
+    import torch
+    import gpim_b200 as gpim
+    from gpim_b200 import _lib
+    n = 128
+    f = W.bo_trial_func(n)
+    np.random.seed(0)
+    idx = np.random.randint(0, n, size=(100, 2))
+    Zs = np.full((n, n), np.nan)
+    for i, j in idx:
+        Zs[i, j] = f((i, j))
+    X_full, X_sparse = gpim.utils.get_full_grid(Zs), gpim.utils.get_sparse_grid(Zs)
+    M = n * n
+    out_dir = tempfile.mkdtemp()
+
+    def run(nsteps):
+        bo = gpim.boptimizer(X_sparse, Zs.copy(), X_full, f, acquisition_function="ei", exploration_steps=nsteps,
+                             gp_iterations=gp_iterations, verbose=0, filename=os.path.join(out_dir, "bo"))
+        torch.cuda.synchronize()
+        l0 = eng.launch_count()
+        t0 = time.perf_counter()
+        bo.run()
+        torch.cuda.synchronize()
+        return bo, time.perf_counter() - t0, eng.launch_count() - l0
+
+    run(1)                                               # warm-up: workspace, graph capture path, caches
+    eng.set_option(_lib.OPT_STAGE_TIMING, 0)
+    bo, sec, launches = run(steps)
+    iters = (steps + 1) * gp_iterations
+    predicts = 2 * steps                                 # dense grid + measured rows (the EI incumbent) per step
+    # acquisition sweep alone, against its HBM roofline (K6: 8 B read + 4 B... per point)
+    mean_d, sd_d = bo.surrogate_model._last_pred_device
+    eng.acq_sweep(_lib.ACQ_IDS["ei"], mean_d, sd_d, 100)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        eng.acq_sweep(_lib.ACQ_IDS["ei"], mean_d, sd_d, 100)
+    e1.record()
+    torch.cuda.synchronize()
+    acq_ms = e0.elapsed_time(e1) / 20
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    eb = mean_d.element_size()
+    acq_gbps = (2 * eb * M) / (acq_ms * 1e-3) / 1e9
+    blk = {"config": {"workload": "GP-BO, EI, 128x128 grid, 100 seed pixels, RBF, fp64 (reference defaults)", "name": "c4",
+                      "exploration_steps": steps, "gp_iterations": gp_iterations, "M_grid": M, "N_train": f"100..{100 + steps}"},
+           "value": M * steps / sec, "unit": UNIT, "dtype": "f64",
+           "value_note": "dense-grid points predicted (mean + sd) per second over the WHOLE run: trainings, predicts, "
+                         "acquisition sweeps and the host loop included",
+           "seconds_whole_run": sec, "adam_iterations": iters, "ms_per_adam_iteration_incl_everything": 1e3 * sec / iters,
+           "gpu_launches": launches, "dense_predicts": predicts,
+           "e2e": {"value": M * steps / sec, "unit": UNIT, "h2d_bytes_per_step": int((100 + steps) * 3 * 8 + M * 2 * 8),
+                   "d2h_bytes_per_step": int(2 * M * 8 + gp_iterations * 6 * 8),
+                   "api": "gpim.boptimizer(...).run(): numpy in, numpy out; per exploration step the grown training set and "
+                          "X_full go host -> device, (mean, sd) and the Adam trajectory come back"},
+           "roofline": {"kernel": "acquisition sweep + top-k (gpg_acq_sweep) on the 128 x 128 grid", "bound": "hbm",
+                        "achieved": acq_gbps, "peak": hbm, "unit": "GB/s", "frac": acq_gbps / hbm, "traffic": None,
+                        "avg_launch_ms": acq_ms,
+                        "note": "the run as a whole is latency-bound (N <= 150: ~35 dependent few-microsecond kernels per "
+                                "Adam iteration, replayed as a CUDA graph); this entry is the one HBM-bound kernel of the "
+                                "config -- 16 384 points are 256 KB, far too small to reach the HBM roofline"},
+           "picks": [list(map(int, p)) for p in bo.indices_all[:5]]}
+    try:
+        import torch as _t
+        from oracle import gp_oracle as O
+        _t.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        O.bo_run(X_sparse, Zs.copy(), X_full, f, acquisition="ei", exploration_steps=cpu_steps, gp_iterations=gp_iterations)
+        csec = time.perf_counter() - t0
+        per_step = csec / (cpu_steps + 1)                # cpu_steps + 1 trainings dominate
+        blk["cpu_baseline"] = {"value": M * steps / (per_step * (steps + 1)), "unit": UNIT, "cores": _t.get_num_threads(),
+                               "kind": "port", "dtype": "f64",
+                               "sample": f"oracle bo_run, {cpu_steps} exploration step(s) = {cpu_steps + 1} trainings x "
+                                         f"{gp_iterations} Adam iterations + {2 * cpu_steps} dense predicts in {csec:.1f} s; "
+                                         f"whole run scaled to {steps + 1} trainings",
+                               "ms_per_adam_iteration": 1e3 * csec / ((cpu_steps + 1) * gp_iterations)}
+    except Exception as e:                                   # noqa: BLE001
+        blk["cpu_baseline"] = {"error": repr(e)[:200]}
+    return blk
 
 
 def measure_training(eng, name, iters):
@@ -339,54 +691,28 @@ def measure_sparse(eng, name, iters, steps):
         ms_fit, ms_pred = fit(iters), predict(steps)
         out[tag] = {"ms_per_adam_iteration": ms_fit, "predict_ms_per_step": ms_pred,
                     "points_per_s": Xs.shape[0] / (ms_pred * 1e-3)}
-    try:                                              # context only: must never take the bench line down
-        out["cpu_oracle"] = cpu_sparse_sample(X, y, m_ind, wl["kernel"], wl["theta"])
-    except Exception as e:                            # noqa: BLE001
-        out["cpu_oracle"] = {"error": repr(e)[:200]}
     return out
 
 
-def cpu_sparse_sample(X, y, m_ind, kernel, theta, iters=2):
-    """The reference's CPU arithmetic for the same Adam iteration (oracle/sparse_oracle.py: the VFE objective through
-    torch autograd, fp64, all host threads), timed on a bounded sample of `iters` iterations after one warm-up."""
-    import torch
-    from oracle.sparse_oracle import vfe_loss
-    torch.set_num_threads(os.cpu_count() or 1)
-    N, d = X.shape
-    Xt, yt = torch.tensor(X, dtype=torch.float64), torch.tensor(y, dtype=torch.float64)
-    leaf = lambda v: torch.tensor(v, dtype=torch.float64, requires_grad=True)
-    v, s2, al, ls = leaf(theta[0]), leaf(theta[1]), leaf(theta[2]), leaf(theta[3:3 + d])
-    Xu = Xt[::N // m_ind].clone().requires_grad_(True)
-    opt = torch.optim.Adam([v, s2, ls, Xu], lr=1e-3)
-    times = []
-    for it in range(iters + 1):
-        t0 = time.perf_counter()
-        opt.zero_grad()
-        loss = vfe_loss(kernel, Xt, yt, Xu, v, ls, s2, al, 1e-5)
-        loss.backward()
-        opt.step()
-        times.append(time.perf_counter() - t0)
-    return {"ms_per_adam_iteration": 1e3 * sum(times[1:]) / iters, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{iters} iterations after 1 warm-up, fp64, N={N}, m={int(Xu.shape[0])}"}
+def measure_compact(eng, name, steps, warmup):
+    """GPG_OPT_COMPACT_SUPPORT = 1 (opt-in, NOT the headline): the variance GEMM of each 128-row tile of test points
+    only visits the training rows whose covariance with the tile exceeds 1e-14 x variance."""
+    from gpim_b200 import _lib
+    eng.set_option(_lib.OPT_COMPACT_SUPPORT, 1)
+    try:
+        res = measure_predict(eng, make_workload(name), steps, warmup, keep_outputs=False)
+    finally:
+        eng.set_option(_lib.OPT_COMPACT_SUPPORT, 0)
+    return {"ms_per_step": res["ms_per_step"], "value": res["value"], "unit": UNIT, "factor_cached_ms": res["ms_cached"],
+            "note": "variance GEMM restricted per tile to the training rows with covariance > 1e-14 x variance; outputs "
+                    "equal the dense ones to fp32 rounding (tests/test_gpu_parity.py::"
+                    "test_predict_compact_support_option_is_exact); speed depends on the hyper-parameters"}
 
 
-def bench_config(wl, gpus, N, M):
-    return {"workload": wl["label"], "name": wl["name"], "N_train": N, "M_grid": M, "kernel": wl["kernel"],
-            "theta": {"variance": wl["theta"][0], "noise": wl["theta"][1], "lengthscale": wl["theta"][3:],
-                      "jitter": wl["jitter"]},
-            "sharding": "1 GPU" if gpus == 1 else f"X_full row tiles over {gpus} GPUs, 1 broadcast {{Linv,alpha}} + 1 all-gather",
-            "l2_policy": "inputs larger than L2: every step rewrites and rereads K/L/Linv (N x N fp32 each) and the "
-                         "K* tiles; no explicit flush"}
-
-
-# ---------------------------------------------------------------------------------------------
-# the CUDA arm
-# ---------------------------------------------------------------------------------------------
 def run_cuda(args):
     import torch
     import torch.distributed as dist
     from gpim_b200 import _lib, sharded
-    from gpim_b200._lib import KERNEL_IDS
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -399,235 +725,97 @@ def run_cuda(args):
     clocks = ClockSampler(local) if (rank == 0 and not args.no_clocks) else None
     if world > 1:
         # NCCL prints its version banner on stdout when the communicator is created: keep stdout for the one
-        # JSON line by pointing fd 1 at stderr while the process group comes up
+        # JSON line by pointing fd 1 at stderr while the process groups come up
         sys.stdout.flush()
         saved = os.dup(1)
         os.dup2(2, 1)
         try:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
             dist.barrier()
+            eng = _lib.get_engine(local)
+            sharded.ensure_comm(eng)
         finally:
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
     eng = _lib.get_engine(local)
-    dev = eng.device
+    peaks = load_peaks()
+    warmup = max(args.warmup, 3)
 
     wl = make_workload(args.workload, dense=world)
-    X, y = train_rows(wl["R"])
-    Xs = rows_of(wl["Xfull"])
-    N, M, d = X.shape[0], Xs.shape[0], X.shape[1]
-    kid = KERNEL_IDS[wl["kernel"]]
-    dt = torch.float32
-    th = torch.tensor(wl["theta"], dtype=dt, device=dev)
-    Xd = torch.tensor(X, dtype=dt, device=dev)
-    yd = torch.tensor(y, dtype=dt, device=dev)
-    Xsd = torch.tensor(Xs, dtype=dt, device=dev)
-    fac = eng.alloc_factor(N, dt)
-    lo, hi = sharded.tile_bounds(M, world, rank)
-    mean_t = torch.empty(hi - lo, dtype=dt, device=dev)
-    sd_t = torch.empty(hi - lo, dtype=dt, device=dev)
+    res = measure_predict(eng, wl, args.steps, warmup, world, rank)
+    clk = clocks.stop(*res["wall"]) if clocks else None
+    e2e = run_e2e(wl, args.steps) if world == 1 else run_e2e_sharded(wl, max(2, args.steps // 2), world, rank)
 
-    def step():
+    strong = None
+    if world > 1 and not args.no_extra:
+        # BASELINE.json configs[4] as configured: M fixed at 1024 x 1024, N = 30 757, tiles of M / world rows
+        c5 = make_workload("c5")
+        r5 = measure_predict(eng, c5, max(2, args.steps // 4), 2, world, rank, keep_outputs=False)
         if rank == 0:
-            eng.factorize(kid, th, Xd, yd, wl["jitter"], out=fac)
-        if world > 1:
-            sharded.broadcast_factor(fac, 0)
-        eng.predict(kid, th, Xd, fac, Xsd[lo:hi], mean=mean_t, sd=sd_t)
-        if world > 1:
-            return sharded.gather_tiles(mean_t, M), sharded.gather_tiles(sd_t, M)
-        return mean_t, sd_t
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    eng.set_option(_lib.OPT_STAGE_TIMING, 1)
-    eng.stage_times()
-    launches0 = eng.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    wall0 = time.time()
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    e1.record()
-    barrier()
-    wall1 = time.time()
-    ms = e0.elapsed_time(e1)
-    launches = eng.launch_count() - launches0
-    stages = eng.stage_times()
-    eng.set_option(_lib.OPT_STAGE_TIMING, 0)
-    clk = clocks.stop(wall0, wall1) if clocks else None
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt)
-        launches = int(lt.item())
-    assert bool(torch.isfinite(out[0]).all()) and bool(torch.isfinite(out[1]).all()), "non-finite prediction"
-    ms_per_step = ms / args.steps
-    value = M / (ms_per_step * 1e-3)
-
-    # ---- end to end through the reference-facing API (host arrays in / out), all ranks idle but 0 at N>1
-    e2e = None
-    if world == 1:
-        e2e = run_e2e(args, wl, eng)
-    else:
-        e2e = run_e2e_sharded(args, wl, eng, world, rank)
+            st5 = {k: v[0] / r5["steps"] for k, v in r5["stages"].items() if v[1]}
+            serial = sum(st5.get(k, 0.0) for k in ("kmat", "cholesky", "trtri", "solve"))
+            strong = {"config": bench_config(c5, world, r5["N"], r5["M"]), "scaling": "strong", "value": r5["value"],
+                      "unit": UNIT, "ms_per_step": r5["ms_per_step"], "steps": r5["steps"], "rows_per_gpu": r5["m_local"],
+                      "stages_ms_per_step_rank0": st5,
+                      "serial_ms_rank0": serial, "serial_fraction_of_step": serial / r5["ms_per_step"],
+                      "serial_note": "K assembly + Cholesky + inverse + solves run on rank 0 only (training / factorisation "
+                                     "are replicas-only); the other ranks wait for the first row block of the broadcast",
+                      "shard_parity_max_rel": r5.get("shard_parity_max_rel"), "gpu_launches": r5["launches"]}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:                                        # noqa: BLE001
-        pass
-    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (dense 16-bit tensor rate, kernel timed inside a long step)" \
-        if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-    pg_ms, pg_n = stages["pgemm"]
-    m_local = hi - lo
-    flops_per_step = float(N) * float(N) * float(m_local)    # N^2 FLOP per predicted point
-    achieved = flops_per_step * args.steps / (pg_ms * 1e-3) / 1e12 if pg_ms > 0 else 0.0
-    km_ms, km_n = stages["kmat"]
-    hbm = peaks.get("hbm_gbs") or 6650.0
-    kmat_gbps = (4.0 * N * N / 2 + 8.0 * d * N) * km_n / (km_ms * 1e-3) / 1e9 if km_ms > 0 else 0.0
-    ch_ms, ch_n = stages["cholesky"]
+    roof, chol, kmat = roofline_blocks(res, wl, args.steps, peaks, res["ms_per_step"] * args.steps * 1e-3)
+    if world > 1:
+        roof["traffic"] = None
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": bench_config(wl, world, N, M),
-        "roofline": {"kernel": "predict GEMM Linv x K* + colsumsq epilogue (stage pgemm)", "bound": "tensor",
-                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                     "traffic": NCU_TRAFFIC_BYTES.get(wl["name"]) if world == 1 else None,
-                     "traffic_note": "bytes per launch (ncu capture, profiles/r1_05_ncu_pgemm_*.md); algorithmic bytes per "
-                                     "launch = 4 B x (16384 x N) K* planes + 2 N^2 B lower-triangle W planes",
-                     "algorithmic_bytes_per_launch": 4.0 * 16384 * N + 2.0 * N * N,
-                     "launches": pg_n, "avg_launch_ms": pg_ms / max(pg_n, 1),
-                     "algorithmic_flops_per_launch": flops_per_step * args.steps / max(pg_n, 1),
-                     "peak_source": peak_src,
-                     "note": "fp32-faithful split-fp16 product: 3 tcgen05 MMAs per algorithmic MAC, so the tensor pipe "
-                             "executes 3 x achieved",
-                     "tensor_pipe_tflops": 3.0 * achieved, "tensor_pipe_frac": 3.0 * achieved / peak_tf},
-        "stages_ms_per_step": {k: v[0] / args.steps for k, v in stages.items() if v[1]},
-        "kmat_assembly": {"bound": "hbm", "achieved": kmat_gbps, "peak": hbm, "unit": "GB/s", "frac": kmat_gbps / hbm,
-                          "note": "lower-triangle tiles only: 2 N^2 + 8 d N bytes per launch"},
-        "cholesky_tflops": (N ** 3 / 3.0) * ch_n / (ch_ms * 1e-3) / 1e12 if ch_ms > 0 else None,
-        "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+        "config": bench_config(wl, world, res["N"], res["M"]),
+        "roofline": roof, "cholesky": chol, "kmat_assembly": kmat,
+        "stages_ms_per_step": {k: v[0] / args.steps for k, v in res["stages"].items() if v[1]},
+        "e2e": e2e, "gpu_launches": res["launches"], "clocks": clk,
     }
-    if world == 1 and not args.no_extra and args.workload == "c2":
-        # the 512 x 512 reconstruction BASELINE.json's target is quoted on, same step definition
-        line["extra_workloads"] = {"h512": measure_extra(eng, "h512", max(2, args.steps // 2), 2),
-                                   "train_c2": measure_training(eng, "c2", 10),
-                                   "c2_compact_support": measure_extra(eng, "c2", args.steps, 2, compact_support=True),
-                                   "h512_compact_support": measure_extra(eng, "h512", max(2, args.steps // 2), 2,
-                                                                         compact_support=True),
-                                   "sparse_c2": measure_sparse(eng, "c2", 10, max(2, args.steps // 2))}
+    if res["ms_cached"]:
+        line["factor_cached"] = {"ms_per_step": res["ms_cached"], "value": res["M"] / (res["ms_cached"] * 1e-3), "unit": UNIT}
+    if "shard_parity_max_rel" in res:
+        line["shard_parity_max_rel"] = res["shard_parity_max_rel"]
+    if strong is not None:
+        line["strong_c5"] = strong
     if world == 1 and not args.no_cpu_baseline:
-        import torch as _t
-        _t.set_num_threads(os.cpu_count() or 1)
-        v, wall, st = cpu_predict_sample(wl, args.cpu_sample, args.cpu_dtype)
-        line["cpu_baseline"] = {
-            "value": v, "unit": UNIT, "cores": _t.get_num_threads(), "kind": "port",
-            "sample": f"oracle predict (K + Cholesky at N={N}, K*/TRSM/reduce on {args.cpu_sample} of {M} points, "
-                      f"per-point stages scaled to M), {args.cpu_dtype}, {wall:.1f} s measured",
-            "stages_s": st}
+        # the parity reference of north_star is the fp64 oracle; the f32 sample is the timing baseline of the fp32 config
+        cb = cpu_baseline_block(wl, args.cpu_sample, args.cpu_dtype, cuda_out=None)
+        par = cpu_baseline_block(wl, 1024, "f64", cuda_out=(res["mean"], res["sd"]))
+        cb["parity_vs_oracle"] = par["parity_vs_oracle"]
+        cb["f64"] = {"value": par["value"], "stages_s": par["stages_s"], "sample": par["sample"]}
+        line["cpu_baseline"] = cb
+        line["parity_vs_oracle"] = par["parity_vs_oracle"]
+    if world == 1 and not args.no_extra:
+        tcb = torch_cuda_baseline(wl)
+        if "_mean" in tcb:
+            tcb["agrees_with_engine"] = {"mean_relinf": relinf(tcb.pop("_mean"), res["mean"]),
+                                         "sd_relinf": relinf(tcb.pop("_sd"), res["sd"])}
+            tcb["engine_speedup"] = res["value"] / tcb["value"]
+        line["torch_cuda_baseline"] = tcb
+        wls = {}
+        if args.workload == "c2":
+            for name, st_, cs in (("h512", max(3, args.steps // 4), 1024), ("c3", max(3, args.steps // 4), 1024)):
+                blk, _, _ = workload_block(eng, name, st_, 2, peaks, cs, with_cpu=not args.no_cpu_baseline,
+                                           e2e_steps=max(2, st_ // 2))
+                wls[name] = blk
+            wls["c4"] = measure_c4(eng, peaks, steps=args.c4_steps)
+        line["workloads"] = wls
+        line["extra_workloads"] = {"train_c2": measure_training(eng, "c2", 10),
+                                   "c2_compact_support": measure_compact(eng, "c2", max(3, args.steps // 2), 2),
+                                   "h512_compact_support": measure_compact(eng, "h512", max(3, args.steps // 4), 2),
+                                   "sparse_c2": measure_sparse(eng, "c2", 10, max(2, args.steps // 2))}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-
-
-def run_e2e(args, wl, eng):
-    """gpim.reconstructor: swap the training set in (host -> device), predict over X_full given as
-    a host numpy grid, results back as numpy arrays.  Factor cache invalidated every step, as the
-    reference refactorises on every predict (gpr.py:248)."""
-    import torch
-    import gpim_b200 as gpim
-    R = wl["R"]
-    Xsp = gpim.utils.get_sparse_grid(R)
-    rec = gpim.reconstructor(Xsp, R, wl["Xfull"], kernel=wl["kernel"], iterations=0, verbose=0, precision="single",
-                             jitter=wl["jitter"], lengthscale=[[1.0] * R.ndim, [20.0] * R.ndim])
-    th = wl["theta"]
-    rec.model.set_theta(th[0], th[3:], th[1], th[2])
-    Xh = rec.X.cpu().pin_memory()
-    yh = rec.y.cpu().pin_memory()
-    Xfull = wl["Xfull"]
-
-    def step():
-        rec.model.X = Xh
-        rec.model.y = yh
-        return rec.predict(Xfull, verbose=0)
-
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        mean, sd = step()
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / args.steps
-    M = mean.size
-    h2d = Xh.numel() * 4 + yh.numel() * 4 + M * R.ndim * 4
-    return {"value": M / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * M * 4),
-            "ms_per_step": dt * 1e3, "api": "gpim.reconstructor.predict(X_full) after model.X/.y swap (host numpy in/out)"}
-
-
-def run_e2e_sharded(args, wl, eng, world, rank):
-    """N > 1: host rows in, every rank copies its tile to the device, sharded predict, rank 0 reads
-    the gathered result back to the host."""
-    import torch
-    import torch.distributed as dist
-    from gpim_b200 import sharded
-    from gpim_b200._lib import KERNEL_IDS
-    dev = eng.device
-    dt = torch.float32
-    X, y = train_rows(wl["R"])
-    Xs = rows_of(wl["Xfull"])
-    N, M = X.shape[0], Xs.shape[0]
-    kid = KERNEL_IDS[wl["kernel"]]
-    Xh = torch.tensor(X, dtype=dt).pin_memory()
-    yh = torch.tensor(y, dtype=dt).pin_memory()
-    lo, hi = sharded.tile_bounds(M, world, rank)
-    Xsh = torch.tensor(Xs[lo:hi], dtype=dt).pin_memory()
-    th = torch.tensor(wl["theta"], dtype=dt, device=dev)
-    fac = eng.alloc_factor(N, dt)
-
-    def step():
-        Xd = Xh.to(dev, non_blocking=True)
-        yd = yh.to(dev, non_blocking=True)
-        Xsd = Xsh.to(dev, non_blocking=True)
-        if rank == 0:
-            eng.factorize(kid, th, Xd, yd, wl["jitter"], out=fac)
-        sharded.broadcast_factor(fac, 0)
-        m, s = eng.predict(kid, th, Xd, fac, Xsd)
-        m, s = sharded.gather_tiles(m, M), sharded.gather_tiles(s, M)
-        if rank == 0:
-            return m.cpu().numpy(), s.cpu().numpy()
-        return None
-
-    for _ in range(2):
-        step()
-    dist.barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dist.barrier(); torch.cuda.synchronize()
-    sec = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
-    dist.all_reduce(sec, op=dist.ReduceOp.MAX)
-    sec = float(sec.item())
-    h2d = (Xh.numel() + yh.numel()) * 4 * world + M * Xs.shape[1] * 4
-    return {"value": M / sec, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(2 * M * 4),
-            "ms_per_step": sec * 1e3, "api": "sharded.predict: pinned host rows -> per-rank tiles -> gathered numpy on rank 0"}
 
 
 def main():
@@ -637,12 +825,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="c2")
-    ap.add_argument("--cpu-sample", type=int, default=1024, dest="cpu_sample")
+    ap.add_argument("--cpu-sample", type=int, default=4096, dest="cpu_sample",
+                    help="grid rows of the bounded CPU sample in the CUDA arm's cpu_baseline")
+    ap.add_argument("--cpu-full-steps", type=int, default=1, dest="cpu_full_steps",
+                    help="--impl reference: cap on the number of full-workload steps timed (max 2)")
     ap.add_argument("--cpu-dtype", default="f32", choices=["f32", "f64"], dest="cpu_dtype")
+    ap.add_argument("--c4-steps", type=int, default=50, dest="c4_steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the extra 512 x 512 measurement")
+    ap.add_argument("--no-extra", action="store_true", help="headline workload only")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed region")
     args = ap.parse_args()
+    args.cpu_full_steps = max(1, min(args.cpu_full_steps, 2))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "cuda" and world != args.gpus:
         if args.gpus > 1 and world == 1:

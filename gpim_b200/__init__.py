@@ -2,30 +2,14 @@
 gpim_b200 -- B200-native exact-GP-on-grids engine behind the GPim API.
 
 Public surface = the reference's gpim/__init__.py:1-5 restricted to the accelerated path:
-``utils`` (grid / data-layout helpers), ``reconstructor`` (exact and inducing-point GP), ``boptimizer`` and
-``skreconstructor`` with ``ski=False`` (GPyTorch's exact-GP semantics).
+``utils`` (grid / data-layout helpers), ``reconstructor`` (exact and inducing-point GP), ``boptimizer``,
+``skreconstructor`` with ``ski=False`` (GPyTorch's exact-GP semantics) and ``vreconstructor`` with
+``independent=True`` (independent multi-output GP).
 """
 from . import gprutils as utils  # noqa: F401
 from .gpreg.gpr import reconstructor  # noqa: F401
 from .gpreg.skgpr import skreconstructor  # noqa: F401
+from .gpreg.vgpr import vreconstructor  # noqa: F401
 from .gpbayes.boptim import boptimizer  # noqa: F401
 
-
-
-class _OutOfScope:
-    """The reference also exports the GPyTorch-backed multi-output vreconstructor (gpim/__init__.py:4).  It is
-    outside the accelerated exact-GP path: importing it works, so that `from gpim import ...`
-    lines keep running, constructing one says so."""
-    _name = ""
-
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError(
-            f"gpim.{self._name} (GPyTorch multi-output GP) is outside the accelerated exact-GP "
-            f"path of this engine; use gpim.reconstructor / gpim.boptimizer")
-
-
-class vreconstructor(_OutOfScope):
-    _name = "vreconstructor"
-
-
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found; cannot build libgpgrid.so")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB + ".tmp", os.path.join(CSRC, "gpgrid.cu")]
+        ["-o", LIB + ".tmp", os.path.join(CSRC, "gpgrid.cu"), "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

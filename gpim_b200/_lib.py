@@ -47,6 +47,8 @@ SIGNATURES = {
                       _vp, _vp, _vp, _vp], C.c_int),
     "gpg_fit_adam_sk": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _f64, _vp, C.POINTER(_f64), _i32, _f64,
                          _vp, _vp, _vp, _vp], C.c_int),
+    "gpg_fit_adam_mt": ([_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _f64, _vp, C.POINTER(_f64), _i32, _f64,
+                         _vp, _vp, _vp, _vp], C.c_int),
     "gpg_acq_sweep": ([_vp, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp],
                       C.c_int),
     "gpg_sparse_loss_grad": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _f64, _vp, _vp, _vp, _vp, _vp],
@@ -57,6 +59,18 @@ SIGNATURES = {
                               _vp, _vp, _vp], C.c_int),
     "gpg_sparse_predict": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp,
                             _vp], C.c_int),
+    # multi-GPU (NCCL bound at run time inside the library)
+    "gpg_comm_unique_id": ([_vp], C.c_int),
+    "gpg_comm_init": ([_vp, _i32, _i32, _vp], C.c_int),
+    "gpg_comm_destroy": ([_vp], C.c_int),
+    "gpg_comm_info": ([_vp, C.POINTER(_i32), C.POINTER(_i32)], C.c_int),
+    "gpg_predict_uses_planes": ([_vp, _i32, _i64, _i32], C.c_int),
+    "gpg_bcast_factor": ([_vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp], C.c_int),
+    "gpg_allgather_pred": ([_vp, _i32, _vp, _i64, _vp, _vp], C.c_int),
+    "gpg_predict_sharded": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp,
+                             _i64, _vp, _vp], C.c_int),
+    "gpg_acq_sweep_sharded": ([_vp, _i32, _i32, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _f64, _f64, _i32, _vp, _vp, _vp,
+                               _vp, _vp], C.c_int),
 }
 
 _LIB = None
@@ -85,7 +99,7 @@ def load_library(build_if_missing=True):
         fn = getattr(lib, name)                       # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = restype
-    if lib.gpg_version() < 110:
+    if lib.gpg_version() < 120:
         raise RuntimeError("libgpgrid.so is older than this package")
     _LIB = lib
     return lib
@@ -306,6 +320,24 @@ class Engine:
                        _ptr(u), b, int(iters), float(lr), _ptr(traj), _ptr(theta), _ptr(info), self._stream()))
         return traj[:iters], theta, info
 
+    def fit_adam_mt(self, kernel_id, X, Y, jitter, u, ls_bounds, n_ls, iters, lr):
+        """vreconstructor(independent=True): Y [T, N] task-major, u raw {outputscale[T] | task noise[T] | noise |
+        constant[T] | lengthscale[n_ls]} (device, in/out), ls_bounds [lo..., hi...] or None (softplus lengthscale).
+        Returns (traj [iters, d + 1] = {lengthscale[d], loss}, theta [T, 3 + d], info)."""
+        X, Y = _c(X), _c(Y)
+        assert u.is_contiguous()
+        N, d = X.shape
+        T = Y.shape[0]
+        assert Y.shape[1] == N and u.numel() == 3 * T + 1 + n_ls
+        traj = self.empty(max(iters, 1), d + 1, dtype=X.dtype)
+        theta = self.empty(T, 3 + d, dtype=X.dtype)
+        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+        b = (_f64 * len(ls_bounds))(*[float(v) for v in ls_bounds]) if ls_bounds is not None else None
+        self._check(self.lib.gpg_fit_adam_mt(self.h, self._dt(X), kernel_id, d, n_ls, T, _ptr(X), _ptr(Y), N, float(jitter),
+                                             _ptr(u), b, int(iters), float(lr), _ptr(traj), _ptr(theta), _ptr(info),
+                                             self._stream()))
+        return traj[:iters], theta, info
+
     def acq_sweep(self, acq_id, mean, sd, k, mu_best=0.0, xi=0.01, alpha=0.0, beta=1.0, mask=None, want_acq=False):
         mean, sd, mask = _c(mean), _c(sd), _c(mask)
         M = mean.numel()
@@ -385,6 +417,85 @@ class Engine:
                                                 _ptr(fac.get("split")), _ptr(fac.get("scales")), _ptr(Xs), M,
                                                 _ptr(mean), _ptr(sd), self._stream()))
         return mean, sd
+
+
+    # -- multi-GPU: one process per GPU, the library's own NCCL communicator -------------
+    def comm_unique_id(self):
+        """128-byte NCCL unique id (bytes); rank 0 draws it, every rank passes it to comm_init."""
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.gpg_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, nranks, rank, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.gpg_comm_init(self.h, int(nranks), int(rank), buf))
+
+    def comm_destroy(self):
+        self._check(self.lib.gpg_comm_destroy(self.h))
+
+    def comm_info(self):
+        """(nranks, rank) of the handle's communicator; (0, -1) without one."""
+        n, r = _i32(0), _i32(-1)
+        self._check(self.lib.gpg_comm_info(self.h, C.byref(n), C.byref(r)))
+        return n.value, r.value
+
+    def predict_uses_planes(self, dtype, N, have_planes=True):
+        """gpg_predict's routing rule: True when it reads the fp16 planes of the cache, False when it reads Linv."""
+        code = GPG_F32 if dtype == torch.float32 else GPG_F64
+        return bool(self.lib.gpg_predict_uses_planes(self.h, code, int(N), int(bool(have_planes))))
+
+    def bcast_factor(self, theta, X, fac, root=0):
+        """Broadcast rank `root`'s factor cache (and theta, X) into the same-shaped buffers of every rank."""
+        assert theta.is_contiguous() and X.is_contiguous()
+        N, d = X.shape
+        self._check(self.lib.gpg_bcast_factor(self.h, self._dt(X), d, N, fac["ld"], _ptr(theta), _ptr(X), _ptr(fac.get("Linv")),
+                                              _ptr(fac["alpha"]), _ptr(fac.get("wsplit")), _ptr(fac.get("scales")),
+                                              _ptr(fac["info"]), int(root), self._stream()))
+        return fac
+
+    def allgather_pred(self, local, out=None):
+        """out[r] = rank r's `local` (same element count on every rank)."""
+        local = local.contiguous()
+        nranks, _ = self.comm_info()
+        if out is None:
+            out = torch.empty((nranks,) + tuple(local.shape), dtype=local.dtype, device=self.device)
+        self._check(self.lib.gpg_allgather_pred(self.h, self._dt(local), _ptr(local), local.numel(), _ptr(out), self._stream()))
+        return out
+
+    def predict_sharded(self, kernel_id, theta, X, fac, Xs_local, M_pad, root=0, gather=True, pred_local=None, pred_all=None):
+        """gpg_predict_sharded: broadcast of root's cache (pipelined) + this rank's tile + one all-gather.
+        Returns (pred_local [2, M_pad], pred_all [nranks, 2, M_pad] or None)."""
+        assert theta.is_contiguous() and X.is_contiguous()
+        Xs_local = _c(Xs_local)
+        N, d = X.shape
+        M_local = Xs_local.shape[0]
+        nranks, _ = self.comm_info()
+        if pred_local is None:
+            pred_local = torch.zeros(2, M_pad, dtype=X.dtype, device=self.device)
+        if gather and pred_all is None:
+            pred_all = torch.empty(nranks, 2, M_pad, dtype=X.dtype, device=self.device)
+        self._check(self.lib.gpg_predict_sharded(self.h, self._dt(X), kernel_id, d, _ptr(theta), _ptr(X), N,
+                                                 _ptr(fac.get("Linv")), fac["ld"], _ptr(fac["alpha"]), _ptr(fac.get("wsplit")),
+                                                 _ptr(fac.get("scales")), _ptr(fac["info"]), int(root),
+                                                 _ptr(Xs_local) if M_local else C.c_void_p(0), M_local, _ptr(pred_local),
+                                                 int(M_pad), _ptr(pred_all) if gather else C.c_void_p(0), self._stream()))
+        return pred_local, (pred_all if gather else None)
+
+    def acq_sweep_sharded(self, acq_id, mean_local, sd_local, idx_offset, k, mu_best=0.0, xi=0.01, alpha=0.0, beta=1.0,
+                          mask_local=None, want_acq=False):
+        """Global top-k of the acquisition function over a grid whose tiles live on the ranks (global flat indices)."""
+        mean_local, sd_local, mask_local = _c(mean_local), _c(sd_local), _c(mask_local)
+        M_local = mean_local.numel()
+        vals = self.empty(k, dtype=mean_local.dtype)
+        idx = torch.empty(k, dtype=torch.int64, device=self.device)
+        count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        acq = self.empty(M_local, dtype=mean_local.dtype) if want_acq else None
+        null = C.c_void_p(0)
+        self._check(self.lib.gpg_acq_sweep_sharded(self.h, self._dt(mean_local), acq_id, _ptr(mean_local) if M_local else null,
+                                                   _ptr(sd_local) if M_local else null, _ptr(mask_local), M_local,
+                                                   int(idx_offset), float(mu_best), float(xi), float(alpha), float(beta),
+                                                   int(k), _ptr(vals), _ptr(idx), _ptr(count), _ptr(acq), self._stream()))
+        return vals, idx, count, acq
 
 
 _ENGINES = {}

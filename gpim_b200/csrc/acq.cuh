@@ -18,7 +18,8 @@ template <typename T> __device__ __forceinline__ bool ranks_before(const Cand<T>
 
 template <typename T>
 __global__ void __launch_bounds__(256) acq_eval_kernel(int acq_id, const T *__restrict__ mean, const T *__restrict__ sd,
-                                                       const T *__restrict__ mask, int64_t M, double mu_best, double xi,
+                                                       const T *__restrict__ mask, int64_t M, int64_t idx_offset,
+                                                       double mu_best, double xi,
                                                        double alpha, double beta, T *__restrict__ acq_out,
                                                        Cand<T> *__restrict__ cand) {
     const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(256) acq_eval_kernel(int acq_id, const T *__re
         } else a = cdf;
     }
     Cand<T> c;
-    c.idx = j;
+    c.idx = j + idx_offset;
     if (mask) {
         a = (double)mask[j] * a;
         if (a != a) c.idx = -1;                 // masked-out entries are stripped (boptim.py:311)

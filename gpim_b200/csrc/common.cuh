@@ -37,6 +37,7 @@ struct gpg_handle_s {
     int *tc_counters = nullptr;              // pool of zeroed tile counters for the persistent GEMM
     int tc_counter_pos = 0;
     cudaStream_t fit_stream = nullptr;       // blocking stream the small-N Adam loop is captured on
+    void *comm = nullptr;                    // comm::State (comm.cuh): NCCL communicator + communication stream
     std::vector<gpg_stage_span> spans;       // recorded while opt_stage_timing != 0
     std::vector<cudaEvent_t> event_pool;
 };

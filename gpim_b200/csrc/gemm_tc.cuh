@@ -62,6 +62,7 @@ struct Params {
     int tiles_m, tiles_n, batch;
     int m_group;                 // tiles are walked in groups of m_group m-blocks (L2 residency of A); 0 = all
     int kb_mode, ke_mode, tile_mode;
+    int n_off;                   // added to the n index in the triangular k-range rules (a launch over a sub-range of n-blocks)
     // operand placement inside the matrices described by the tensor maps (elements)
     int a_row0, a_col0, a_bs;    // batch b adds a_bs to both row and column
     int b_row0, b_col0, b_bs;
@@ -167,7 +168,7 @@ __device__ __forceinline__ bool decode_tile(const Params &p, int t, Tile &o) {
     const int gsize = min(gm, p.tiles_m - grp * gm);
     o.nblk = p.tiles_n - 1 - rr / gsize;
     o.mblk = grp * gm + rr % gsize;
-    const int m0 = o.mblk * BM, n0 = o.nblk * BN;
+    const int m0 = o.mblk * BM, n0 = o.nblk * BN + p.n_off;
     if (p.tile_mode == GEMM_TILES_LOWER && n0 > m0 + BM - 1) return false;
     int kb = 0, ke = p.K;
     if (p.kb_mode == GEMM_KB_N0) kb = n0;

@@ -14,6 +14,7 @@
 #include "train.cuh"
 #include "acq.cuh"
 #include "sparse.cuh"
+#include "comm.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // errors, handle, workspace
@@ -127,6 +128,7 @@ extern "C" int gpg_create(int device, gpg_handle_t *out) {
 
 extern "C" int gpg_destroy(gpg_handle_t h) {
     if (!h) return GPG_OK;
+    gpg_comm_destroy(h);
     if (h->ws) cudaFree(h->ws);
     if (h->tc_counters) cudaFree(h->tc_counters);
     if (h->gemv_part) cudaFree(h->gemv_part);
@@ -567,10 +569,19 @@ static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T 
 
 // fp32 tensor-core path: K* tiles are generated directly as fp16 hi/lo operands, the variance
 // reduction runs in the epilogue of the tcgen05 GEMM (test points on the TMEM lanes).
+// Row blocks of the Linv planes that are still arriving (pipelined broadcast, comm.cuh): block c covers rows
+// [row_end[c-1], row_end[c]) -- boundaries are multiples of tc::BN -- and is complete once ev[c] has fired.
+struct PlaneArrival {
+    int nchunks = 0;
+    const int64_t *row_end = nullptr;
+    const cudaEvent_t *ev = nullptr;
+};
+
 template <int D>
 static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, const float *X, int64_t N,
                            const __half *Whi, const __half *Wlo, int64_t ldh, const float *scales, const float *alpha,
-                           TestPoints<float, D> tp, int64_t M, float *mean, float *sd, cudaStream_t s) {
+                           TestPoints<float, D> tp, int64_t M, float *mean, float *sd, cudaStream_t s,
+                           const PlaneArrival *arrival = nullptr) {
     int64_t chunk = h->opt_predict_chunk;
     if (chunk <= 0) {
         chunk = 16384;               // K* planes of one chunk: at most 2 GiB
@@ -607,18 +618,30 @@ static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, c
         }
         {
             StageTimer st(h, GPG_ST_PGEMM, s);
-            tc::Launch g;
-            memset(&g.p, 0, sizeof(g.p));
-            g.A.hi = Khi; g.A.lo = Klo; g.A.rows = mc; g.A.cols = N; g.A.ld = ldh;
-            g.B.hi = Whi; g.B.lo = Wlo; g.B.rows = N; g.B.cols = N; g.B.ld = ldh;
-            g.p.M = (int)mc; g.p.N = (int)N; g.p.K = (int)N; g.p.batch = 1;
-            g.p.m_group = m_group;
-            g.p.ke_mode = GEMM_KE_N;
-            g.p.epi = tc::EPI_ROWSUMSQ;
-            g.p.scale_inv = scales + 2;
-            g.p.part = part; g.p.ldpart = chunk;
-            g.p.krange = krange;
-            GPG_TRY(tc::launch(h, g, s));
+            // one launch over all n-blocks -- or, for the first tile of test points behind a pipelined broadcast,
+            // one launch per row block of Linv, each gated on that block's arrival
+            const int nlaunch = (arrival && c0 == 0) ? arrival->nchunks : 1;
+            int64_t r0 = 0;
+            for (int li = 0; li < nlaunch; ++li) {
+                const int64_t r1 = nlaunch == 1 ? N : std::min<int64_t>(N, arrival->row_end[li]);
+                if (nlaunch > 1) GPG_CUDA_CHECK(cudaStreamWaitEvent(s, arrival->ev[li], 0));
+                if (r1 > r0) {
+                    tc::Launch g;
+                    memset(&g.p, 0, sizeof(g.p));
+                    g.A.hi = Khi; g.A.lo = Klo; g.A.rows = mc; g.A.cols = N; g.A.ld = ldh;
+                    g.B.hi = Whi; g.B.lo = Wlo; g.B.rows = N; g.B.cols = N; g.B.ld = ldh;
+                    g.p.M = (int)mc; g.p.N = (int)(r1 - r0); g.p.K = (int)N; g.p.batch = 1;
+                    g.p.b_row0 = (int)r0; g.p.n_off = (int)r0;
+                    g.p.m_group = m_group;
+                    g.p.ke_mode = GEMM_KE_N;
+                    g.p.epi = tc::EPI_ROWSUMSQ;
+                    g.p.scale_inv = scales + 2;
+                    g.p.part = part + (r0 / tc::BN) * chunk; g.p.ldpart = chunk;
+                    g.p.krange = krange;
+                    GPG_TRY(tc::launch(h, g, s));
+                }
+                r0 = r1;
+            }
         }
         StageTimer st(h, GPG_ST_PFINAL, s);
         predict_finalize_kernel<float, D><<<(unsigned)((mc + 255) / 256), 256, 0, s>>>(theta, part, tiles_n, chunk, tpc, mc,
@@ -628,16 +651,21 @@ static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, c
     return GPG_OK;
 }
 
+// THE routing rule of gpg_predict: the tcgen05 kernels consume the fp16 planes, everything else the fp32 / fp64 Linv.
+// (gpg_predict_uses_planes exports it, so that whoever ships a factor cache between GPUs sends what will be read.)
+static bool predict_wants_tc(const gpg_handle_s *h, int dtype, int64_t N, bool have_planes) {
+    return dtype == GPG_F32 && have_planes && h->opt_gemm_path != 1 && (h->opt_gemm_path == 2 || N >= 1024);
+}
+
 template <typename T, int D>
 static int predict_route(gpg_handle_s *h, int kernel_id, const T *theta, const T *X, int64_t N, const T *Linv, int64_t ld,
                          const T *alpha, const void *wsplit, const float *scales, TestPoints<T, D> tp, int64_t M, T *mean,
-                         T *sd, cudaStream_t s) {
+                         T *sd, cudaStream_t s, const PlaneArrival *arrival = nullptr) {
     if constexpr (std::is_same<T, float>::value) {
-        const bool want_tc = wsplit != nullptr && h->opt_gemm_path != 1 && (h->opt_gemm_path == 2 || N >= 1024);
-        if (want_tc) {
+        if (predict_wants_tc(h, GPG_F32, N, wsplit != nullptr)) {
             const __half *whi = (const __half *)wsplit;
             return predict_core_tc<D>(h, kernel_id, theta, X, N, whi, whi + (size_t)N * ld, ld, scales, alpha, tp, M, mean,
-                                      sd, s);
+                                      sd, s, arrival);
         }
     }
     return predict_core<T, D>(h, kernel_id, theta, X, N, Linv, ld, alpha, tp, M, mean, sd, s);
@@ -647,7 +675,7 @@ template <typename T>
 static int predict_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, int64_t N, const T *Linv,
                          int64_t ld, const T *alpha, const void *wsplit, const float *scales, const T *Xs,
                          const int64_t *dims, const double *step, int64_t j0,
-                         int64_t M, T *mean, T *sd, cudaStream_t s) {
+                         int64_t M, T *mean, T *sd, cudaStream_t s, const PlaneArrival *arrival = nullptr) {
     if (M == 0) return GPG_OK;
     GPG_DISPATCH_D(d, {
         TestPoints<T, D> tp;
@@ -657,7 +685,7 @@ static int predict_entry(gpg_handle_s *h, int kernel_id, int d, const T *theta, 
             tp.dims[k] = (dims && k < D) ? dims[k] : 1;
             tp.step[k] = (step && k < D) ? (T)step[k] : T(1);
         }
-        return predict_route<T, D>(h, kernel_id, theta, X, N, Linv, ld, alpha, wsplit, scales, tp, M, mean, sd, s);
+        return predict_route<T, D>(h, kernel_id, theta, X, N, Linv, ld, alpha, wsplit, scales, tp, M, mean, sd, s, arrival);
     });
     return GPG_OK;
 }
@@ -960,37 +988,103 @@ extern "C" int gpg_fit_adam_sk(gpg_handle_t h, int dtype, int kernel_id, int d, 
     return GPG_EINVAL;
 }
 
+// vreconstructor(independent=True): T exact GPs on one X, shared lengthscale (train.cuh, MtCfg)
+template <typename T>
+static int fit_mt_entry(gpg_handle_s *h, int kernel_id, int d, int n_ls, int ntasks, const T *X, const T *Y, int64_t N,
+                        double jitter, T *u, const double *bounds, int iters, double lr, T *traj, T *theta_out,
+                        int32_t *info, cudaStream_t s) {
+    const int64_t ld = gpg_align_up((size_t)N, 64);
+    const size_t base = gpg_align_up(train_ws_bytes<T>(h, N, ld), 1024);
+    const size_t extra = bump_size({(size_t)ntasks * GPG_MAX_P * sizeof(T), (size_t)ntasks * GPG_MAX_P * sizeof(T),
+                                    (size_t)ntasks * sizeof(T), (size_t)ntasks * sizeof(double), sizeof(MtState)});
+    void *ws;
+    GPG_TRY(gpg_ws_reserve(h, base + extra, &ws));
+    TrainBufs tb = train_carve<T>(h, ws, N, ld);
+    Bump b((unsigned char *)ws + base);
+    T *theta_all = b.take<T>((size_t)ntasks * GPG_MAX_P);
+    T *grad_all = b.take<T>((size_t)ntasks * GPG_MAX_P);
+    T *nll_all = b.take<T>(ntasks);
+    double *asum = b.take<double>(ntasks);
+    MtState *st = b.take<MtState>(1);
+    MtCfg c;
+    memset(&c, 0, sizeof(c));
+    c.d = d; c.n_ls = n_ls; c.T = ntasks; c.ls_softplus = (bounds == nullptr);
+    if (bounds) for (int k = 0; k < n_ls; ++k) { c.ls_lo[k] = bounds[k]; c.ls_hi[k] = bounds[n_ls + k]; }
+    c.lr = lr; c.beta1 = 0.9; c.beta2 = 0.999; c.eps = 1e-8;
+    mt_adam_kernel<T><<<1, 32, 0, s>>>(0, c, u, st, nullptr, nullptr, nullptr, (double)N, theta_all, nullptr);
+    GPG_LAUNCH_CHECK(h);
+    GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), s));
+    for (int it = 0; it < iters; ++it) {
+        for (int t = 0; t < ntasks; ++t) {
+            const T *theta = theta_all + (size_t)t * GPG_MAX_P;
+            center_y_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, s>>>(Y + (size_t)t * N, N, theta, (T *)tb.yc);
+            GPG_LAUNCH_CHECK(h);
+            GPG_TRY(nll_grad_core<T>(h, kernel_id, d, theta, X, (const T *)tb.yc, N, jitter, tb, nll_all + t,
+                                     grad_all + (size_t)t * GPG_MAX_P, info, 0, s));
+            mt_alpha_sum_kernel<T><<<1, 256, 0, s>>>((const T *)tb.alpha, N, asum + t);
+            GPG_LAUNCH_CHECK(h);
+        }
+        mt_adam_kernel<T><<<1, 32, 0, s>>>(1, c, u, st, grad_all, nll_all, asum, (double)N, theta_all, traj);
+        GPG_LAUNCH_CHECK(h);
+    }
+    if (theta_out)
+        GPG_CUDA_CHECK(cudaMemcpy2DAsync(theta_out, (3 + d) * sizeof(T), theta_all, GPG_MAX_P * sizeof(T), (3 + d) * sizeof(T),
+                                         ntasks, cudaMemcpyDeviceToDevice, s));
+    return GPG_OK;
+}
+
+extern "C" int gpg_fit_adam_mt(gpg_handle_t h, int dtype, int kernel_id, int d, int n_ls, int ntasks, const void *X,
+                               const void *Y, int64_t N, double jitter, void *u, const double *bounds_host, int iters,
+                               double lr, void *traj_out, void *theta_out, int32_t *info, void *stream) {
+    GPG_REQUIRE(h && X && Y && u && info, "NULL argument");
+    DeviceGuard device_guard(h->device);
+    GPG_REQUIRE(N > 0 && iters >= 0, "bad size");
+    GPG_REQUIRE(d >= 1 && d <= GPG_MAX_D, "d not in 1..4");
+    GPG_REQUIRE(n_ls == 1 || n_ls == d, "n_ls must be 1 or d");
+    GPG_REQUIRE(ntasks >= 1 && ntasks <= GPG_MT_MAX_TASKS, "number of tasks not in 1..16");
+    GPG_REQUIRE(kernel_id == GPG_RBF || kernel_id == GPG_MATERN52, "gpytorch kernel book: RBF or Matern52");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == GPG_F32)
+        return fit_mt_entry<float>(h, kernel_id, d, n_ls, ntasks, (const float *)X, (const float *)Y, N, jitter, (float *)u,
+                                   bounds_host, iters, lr, (float *)traj_out, (float *)theta_out, info, s);
+    if (dtype == GPG_F64)
+        return fit_mt_entry<double>(h, kernel_id, d, n_ls, ntasks, (const double *)X, (const double *)Y, N, jitter,
+                                    (double *)u, bounds_host, iters, lr, (double *)traj_out, (double *)theta_out, info, s);
+    gpg_set_error("unknown dtype %d", dtype);
+    return GPG_EINVAL;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K6: acquisition sweep + top-k
 // ---------------------------------------------------------------------------------------------
+// Sweep + tournament: leaves the k best candidates (ranked, idx < 0 = none) in workspace memory at *best_out.
+// idx_offset is added to every flat index (a rank's tile of a sharded grid reports global indices);
+// extra_cands: room reserved behind the tournament buffers for the caller (sharded merge).
 template <typename T>
-static int acq_entry(gpg_handle_s *h, int acq_id, const T *mean, const T *sd, const T *mask, int64_t M, double mu_best,
-                     double xi, double alpha, double beta, int k, T *topk_val, int64_t *topk_idx, int32_t *count,
-                     T *acq_out, cudaStream_t s) {
+static int acq_local_topk(gpg_handle_s *h, int acq_id, const T *mean, const T *sd, const T *mask, int64_t M,
+                          int64_t idx_offset, double mu_best, double xi, double alpha, double beta, int k, T *acq_out,
+                          size_t extra_cands, Cand<T> **best_out, Cand<T> **extra_out, cudaStream_t s) {
     constexpr int CH = 2048;
-    const int64_t nblk0 = (M + CH - 1) / CH;
+    const int64_t nblk0 = std::max<int64_t>(1, (M + CH - 1) / CH);
     void *ws;
-    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)M * sizeof(Cand<T>), (size_t)(nblk0 * k + CH) * sizeof(Cand<T>),
-                                         (size_t)(nblk0 * k + CH) * sizeof(Cand<T>)}), &ws));
+    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)(M + 1) * sizeof(Cand<T>), (size_t)(nblk0 * k + CH) * sizeof(Cand<T>),
+                                         (size_t)(nblk0 * k + CH) * sizeof(Cand<T>), 2 * (extra_cands + CH) * sizeof(Cand<T>)}),
+                           &ws));
     Bump b(ws);
-    Cand<T> *cand = b.take<Cand<T>>(M);
+    Cand<T> *cand = b.take<Cand<T>>(M + 1);
     Cand<T> *bufA = b.take<Cand<T>>(nblk0 * k + CH);
     Cand<T> *bufB = b.take<Cand<T>>(nblk0 * k + CH);
-    static bool attr_set = false;
-    if (!attr_set) {
-        GPG_CUDA_CHECK(cudaFuncSetAttribute(topk_round_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            CH * (int)sizeof(Cand<T>)));
-        attr_set = true;
+    if (extra_out) *extra_out = b.take<Cand<T>>(2 * (extra_cands + CH));
+    if (M > 0) {                         // an empty tile (sharded sweep) contributes k excluded entries
+        acq_eval_kernel<T><<<(unsigned)((M + 255) / 256), 256, 0, s>>>(acq_id, mean, sd, mask, M, idx_offset, mu_best, xi,
+                                                                       alpha, beta, acq_out, cand);
+        GPG_LAUNCH_CHECK(h);
     }
-    StageTimer st(h, GPG_ST_ACQ, s);
-    acq_eval_kernel<T><<<(unsigned)((M + 255) / 256), 256, 0, s>>>(acq_id, mean, sd, mask, M, mu_best, xi, alpha, beta,
-                                                                   acq_out, cand);
-    GPG_LAUNCH_CHECK(h);
     const Cand<T> *in = cand;
     int64_t n = M;
     Cand<T> *out = bufA;
     while (true) {
-        const int64_t nblk = (n + CH - 1) / CH;
+        const int64_t nblk = std::max<int64_t>(1, (n + CH - 1) / CH);
         topk_round_kernel<T><<<(unsigned)nblk, 1024, CH * sizeof(Cand<T>), s>>>(in, n, k, out);
         GPG_LAUNCH_CHECK(h);
         if (nblk == 1) break;
@@ -998,7 +1092,18 @@ static int acq_entry(gpg_handle_s *h, int acq_id, const T *mean, const T *sd, co
         n = nblk * k;
         out = (out == bufA) ? bufB : bufA;
     }
-    topk_emit_kernel<T><<<1, 256, 0, s>>>(out, k, topk_val, topk_idx, count);
+    *best_out = out;
+    return GPG_OK;
+}
+
+template <typename T>
+static int acq_entry(gpg_handle_s *h, int acq_id, const T *mean, const T *sd, const T *mask, int64_t M, double mu_best,
+                     double xi, double alpha, double beta, int k, T *topk_val, int64_t *topk_idx, int32_t *count,
+                     T *acq_out, cudaStream_t s) {
+    StageTimer st(h, GPG_ST_ACQ, s);
+    Cand<T> *best;
+    GPG_TRY(acq_local_topk<T>(h, acq_id, mean, sd, mask, M, 0, mu_best, xi, alpha, beta, k, acq_out, 0, &best, nullptr, s));
+    topk_emit_kernel<T><<<1, 256, 0, s>>>(best, k, topk_val, topk_idx, count);
     GPG_LAUNCH_CHECK(h);
     return GPG_OK;
 }
@@ -1027,3 +1132,4 @@ extern "C" int gpg_acq_sweep(gpg_handle_t h, int dtype, int acq_id, const void *
 // workspace carving, kmat_launch and the factorisation drivers defined above.
 // ---------------------------------------------------------------------------------------------
 #include "sparse_driver.cuh"
+#include "comm_driver.cuh"

@@ -229,3 +229,120 @@ __global__ void adam_step_kernel(int mode, FitCfg c, T *__restrict__ u, FitState
         traj_row[3 + c.d] = nll[0];
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Independent multi-output GP: vreconstructor(independent=True) (gpim/gpreg/vgpr.py:320-354 over GPyTorch):
+// T exact GPs on one shared X with ONE shared lengthscale (the base kernel's parameter is created before its
+// batch_shape is overwritten, vgpr.py:346), per-task ScaleKernel outputscales, per-task ConstantMean constants and a
+// MultitaskGaussianLikelihood (rank 0): noise_t = task_noise_t + global noise, both GreaterThan(1e-4).
+//   loss = -sum_t log N(y_t; c_t, s_t K_l + noise_t I) / (N T)        (ExactMarginalLogLikelihood, vgpr.py:171-179)
+// Raw-parameter layout u: {outputscale[T] | task noise[T] | global noise | constant[T] | lengthscale[n_ls]};
+// lengthscale constraint: Interval (sigmoid) when bounds are given, else GPyTorch's default Positive (softplus).
+// ---------------------------------------------------------------------------------------------
+#define GPG_MT_MAX_TASKS 16
+#define GPG_MT_MAX_P (3 * GPG_MT_MAX_TASKS + 1 + GPG_MAX_D)
+
+struct MtCfg {
+    int d, n_ls, T, ls_softplus;
+    double ls_lo[GPG_MAX_D], ls_hi[GPG_MAX_D];
+    double lr, beta1, beta2, eps;
+};
+
+struct MtState {
+    double m[GPG_MT_MAX_P], v[GPG_MT_MAX_P];
+    double dls_du[GPG_MAX_D];
+    int step;
+};
+
+// theta_all[t] = {outputscale_t, task_noise_t + noise, constant_t, lengthscale[d]}
+template <typename T>
+__device__ void mt_constrain(const T *u, const MtCfg &c, T *theta_all, double *dls_du) {
+    const int nt = c.T;
+    T gn; double dgn;
+    softplus_fwd<T>(u[2 * nt], gn, dgn);
+    T ls[GPG_MAX_D];
+    for (int k = 0; k < c.n_ls; ++k) {
+        T val; double dv;
+        if (c.ls_softplus) softplus_fwd<T>(u[3 * nt + 1 + k], val, dv);
+        else interval_fwd<T>(u[3 * nt + 1 + k], c.ls_lo[k], c.ls_hi[k], val, dv);
+        ls[k] = val; dls_du[k] = dv;
+    }
+    for (int t = 0; t < nt; ++t) {
+        T *th = theta_all + t * GPG_MAX_P;
+        T val; double dv;
+        softplus_fwd<T>(u[t], val, dv);
+        th[0] = val;
+        softplus_fwd<T>(u[nt + t], val, dv);
+        th[1] = (val + T(1e-4)) + (gn + T(1e-4));
+        th[2] = u[2 * nt + 1 + t];
+        for (int q = 0; q < c.d; ++q) th[3 + q] = ls[c.n_ls == 1 ? 0 : q];
+    }
+}
+
+// asum[t] = sum_i alpha_i  (d nll_t / d constant_t = -asum[t]); single CTA
+template <typename T>
+__global__ void __launch_bounds__(256) mt_alpha_sum_kernel(const T *__restrict__ alpha, int64_t N, double *__restrict__ out) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += 256) s += (double)alpha[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double tot = 0.0; for (int w = 0; w < 8; ++w) tot += red[w]; *out = tot; }
+}
+
+// mode 0: fresh Adam state + theta_all = constrain(u).  mode 1: chain rule from the T per-task gradients
+// (constrained-theta layout, grad_all[t][3 + d]), one Adam step, re-constrain, record {lengthscale[d], loss}.
+template <typename T>
+__global__ void mt_adam_kernel(int mode, MtCfg c, T *__restrict__ u, MtState *__restrict__ st,
+                               const T *__restrict__ grad_all, const T *__restrict__ nll_all,
+                               const double *__restrict__ asum, double n_rows, T *__restrict__ theta_all,
+                               T *__restrict__ traj) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nt = c.T, P = 3 * nt + 1 + c.n_ls;
+    if (mode == 0) {
+        for (int p = 0; p < GPG_MT_MAX_P; ++p) { st->m[p] = 0.0; st->v[p] = 0.0; }
+        st->step = 0;
+        mt_constrain<T>(u, c, theta_all, st->dls_du);
+        return;
+    }
+    const double inv = 1.0 / (n_rows * (double)nt);
+    double g[GPG_MT_MAX_P];
+    double gnoise = 0.0, loss = 0.0;
+    double gls[GPG_MAX_D] = {0.0, 0.0, 0.0, 0.0};
+    T tmp; double dgn;
+    softplus_fwd<T>(u[2 * nt], tmp, dgn);
+    for (int t = 0; t < nt; ++t) {
+        const T *gt = grad_all + t * GPG_MAX_P;
+        double dv;
+        softplus_fwd<T>(u[t], tmp, dv);
+        g[t] = (double)gt[0] * dv * inv;
+        softplus_fwd<T>(u[nt + t], tmp, dv);
+        g[nt + t] = (double)gt[1] * dv * inv;
+        gnoise += (double)gt[1];
+        g[2 * nt + 1 + t] = -asum[t] * inv;
+        for (int q = 0; q < c.d; ++q) gls[c.n_ls == 1 ? 0 : q] += (double)gt[3 + q];
+        loss += (double)nll_all[t];
+    }
+    g[2 * nt] = gnoise * dgn * inv;
+    for (int k = 0; k < c.n_ls; ++k) g[3 * nt + 1 + k] = gls[k] * st->dls_du[k] * inv;
+    st->step += 1;
+    const double bc1 = 1.0 - pow(c.beta1, (double)st->step);
+    const double bc2 = 1.0 - pow(c.beta2, (double)st->step);
+    const double step_size = c.lr / bc1, bc2_sqrt = sqrt(bc2);
+    for (int p = 0; p < P; ++p) {
+        const T gp = (T)g[p];
+        T m = (T)st->m[p], v = (T)st->v[p];
+        m = m + (T)(1.0 - c.beta1) * (gp - m);
+        v = v * (T)c.beta2 + ((T)(1.0 - c.beta2) * gp) * gp;
+        const T denom = gpg_sqrt(v) / (T)bc2_sqrt + (T)c.eps;
+        u[p] = u[p] + ((T)(-step_size) * m) / denom;
+        st->m[p] = (double)m; st->v[p] = (double)v;
+    }
+    mt_constrain<T>(u, c, theta_all, st->dls_du);
+    if (traj) {
+        T *row = traj + (size_t)(st->step - 1) * (c.d + 1);
+        for (int q = 0; q < c.d; ++q) row[q] = theta_all[3 + q];
+        row[c.d] = (T)(loss * inv);
+    }
+}

@@ -227,7 +227,7 @@ class boptimizer:
         e = args[0]
         if self.verbose:
             print("\nExploration step {} / {}".format(e + 1, self.exploration_steps))
-        if e == 0:
+        if e == 0 and not getattr(self, "_skip_initial_training", False):
             self.surrogate_model.train()
         vals, inds = self.next_point()
         if not self.batch_update:
@@ -260,7 +260,9 @@ class boptimizer:
         # beyond the reference's four keys: the surrogate's unconstrained hyper-parameters, so that a run can
         # be resumed exactly where it stopped (the reference writes checkpoints but has no way to load them)
         results['engine_state'] = {'u': self.surrogate_model.model._u.detach().cpu().numpy().copy(),
-                                   'steps_done': len(self.gp_predictions)}
+                                   'steps_done': len(self.gp_predictions),
+                                   'trained': len(getattr(self.surrogate_model, "hyperparams", {}).get("noise", ())) > 0,
+                                   'np_random_state': np.random.get_state()}
         if hasattr(self.surrogate_model.model, "Xu"):      # sparse surrogate: the trained inducing inputs belong to the state
             results['engine_state']['Xu'] = self.surrogate_model.model.Xu.detach().cpu().numpy().copy()
         np.save(filename + ".npy", results)
@@ -287,5 +289,12 @@ class boptimizer:
             model.load_unconstrained(state['u'])
             if state.get('Xu') is not None and hasattr(model, "Xu"):
                 model.Xu = torch.as_tensor(state['Xu'])
-        self._first_step = max(1, len(self.gp_predictions))
+        # continue with the step after the last completed one; a checkpoint written before any step (or a
+        # reference-format file without predictions) starts at step 0, INCLUDING its initial training -- unless the
+        # checkpoint carries trained hyper-parameters of completed steps
+        done = int(state['steps_done']) if state is not None else len(self.gp_predictions)
+        self._first_step = done
+        self._skip_initial_training = done == 0 and state is not None and bool(state.get('trained', False))
+        if state is not None and state.get('np_random_state') is not None:
+            np.random.set_state(state['np_random_state'])   # the random fall-backs of checkvalues / update_points
         return self

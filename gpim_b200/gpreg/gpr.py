@@ -242,6 +242,7 @@ class reconstructor:
         verbose (int): 0, 1 or 2
         seed (int)
         **amplitude, **precision ('single' | 'double'), **jitter, **isotropic
+        **shard: multi-GPU prediction under torch.distributed (see _shard_group); not in the reference
     """
 
     def __init__(self, X, y, Xtest=None, kernel='RBF', lengthscale=None, sparse=False, indpoints=None,
@@ -280,6 +281,7 @@ class reconstructor:
             self.model = SparseGPModel(self.X, self.y, kern, Xu, jitter=jitter, engine=engine)
         self.learning_rate = learning_rate
         self.iterations = iterations
+        self.shard = kwargs.get("shard", "auto")
         self.indpoints_all = []
         self.lscales, self.noise_all, self.amp_all, self.loss_all = [], [], [], []
         self.hyperparams = {
@@ -343,7 +345,13 @@ class reconstructor:
             self.verbose = kwargs.get("verbose")
         if self.verbose:
             print("Calculating predictive mean and variance...", end=" ")
-        mean_d, sd_d = self.model.predict_sd(self.Xtest)
+        if self._shard_group() is not None:
+            # one process per GPU under torch.distributed (NCCL): every rank calls predict() (a collective), rank 0
+            # factorises, the rows of X_full are tiled over the ranks and every rank gets the whole (mean, sd)
+            from .. import sharded
+            mean_d, sd_d = sharded.predict_model_sharded(self.model, self.Xtest, src=0, group=self._shard_group())
+        else:
+            mean_d, sd_d = self.model.predict_sd(self.Xtest)
         self._last_pred_device = (mean_d, sd_d)
         both = torch.stack((mean_d, sd_d)).cpu().numpy()          # one device->host copy, one synchronisation
         mean, sd = both[0], both[1]
@@ -352,6 +360,20 @@ class reconstructor:
         if self.verbose:
             print("Done")
         return mean, sd
+
+    def _shard_group(self):
+        """The process group predict() shards over, or None.  ``shard=True`` / ``"auto"`` (default: auto = whenever
+        torch.distributed runs on NCCL with more than one rank), ``shard=False`` keeps every rank independent,
+        ``shard=<ProcessGroup>`` shards over that group.  Sharding makes predict() a collective call."""
+        import torch.distributed as dist
+        mode = self.shard
+        if mode is False or mode is None or not (dist.is_available() and dist.is_initialized()):
+            return None
+        if mode is True or mode == "auto":
+            if dist.get_world_size() < 2 or (mode == "auto" and dist.get_backend() != "nccl"):
+                return None
+            return dist.group.WORLD
+        return mode if dist.get_world_size(mode) > 1 else None
 
     def run(self, **kwargs):
         """train() then predict(); returns (mean, sd, hyperparams) as gpr.py:257-283."""

@@ -26,8 +26,15 @@ class KernelState:
         self.dtype = dtype
         self.amp_lo, self.amp_hi = amp
         self.ls_lo, self.ls_hi = lengthscale
-        self.isotropic = self.ls_lo.dim() == 0
+        # one lengthscale for all dimensions: scalar bounds [lo, hi], or one-element lists [[lo], [hi]] on d > 1
+        # inputs (pyro broadcasts a shape-[1] lengthscale over the input dimensions)
+        self.isotropic = self.ls_lo.dim() == 0 or (self.ls_lo.numel() == 1 and input_dim > 1)
         self.n_ls = 1 if self.isotropic else int(self.ls_lo.numel())
+        if not self.isotropic and self.n_ls != input_dim:
+            raise ValueError(f"lengthscale bounds have {self.n_ls} entries per side; expected a scalar, one entry "
+                             f"or one per input dimension ({input_dim})")
+        if self.ls_hi.numel() != self.ls_lo.numel():
+            raise ValueError("lower and upper lengthscale bounds differ in length")
         self._tf_v = transform_to(constraints.interval(self.amp_lo, self.amp_hi))
         self._tf_l = transform_to(constraints.interval(self.ls_lo, self.ls_hi))
         # unconstrained storage = transform_to(constraint).inv(value), as PyroParam does
@@ -64,7 +71,7 @@ class KernelState:
         self.u_variance = u[0].clone()
         self.u_noise = u[1].clone()
         self.u_scale_mixture = u[2].clone()
-        self.u_lengthscale = (u[3].clone() if self.isotropic else u[3:3 + self.n_ls].clone())
+        self.u_lengthscale = (u[3].clone().reshape(self.ls_lo.shape) if self.isotropic else u[3:3 + self.n_ls].clone())
 
     def pack_theta(self):
         """Constrained {variance, noise, scale_mixture, lengthscale[d]} (isotropic value repeated)."""

@@ -1,15 +1,22 @@
 """
-Tile-sharded dense-grid prediction over the GPUs of one box.
+Tile-sharded dense-grid prediction and acquisition sweep over the GPUs of one box.
 
-Test points are independent given the factor cache {Linv, alpha, theta, X}: rank 0 alone
-assembles K and factorises it, ONE broadcast ships the cache to the other ranks (NCCL over
-NVLink when the tensors live on GPUs), every rank predicts its contiguous tile of X_full rows and
-ONE all-gather returns (mean, sd).  The reference has no multi-device path at all; the
-single-device semantics being sharded are those of reconstructor.predict (gpr.py:219-255).
+Test points are independent given the factor cache {Linv, alpha, theta, X}: rank ``src`` alone assembles K
+and factorises it (training / Cholesky are replicas-only), the cache is broadcast, every rank predicts its
+contiguous tile of X_full rows and ONE all-gather returns (mean, sd).  The reference has no multi-device path
+at all; the single-device semantics being sharded are those of reconstructor.predict
+(gpr.py:219-255) and boptimizer.next_point (boptim.py:278-324).
 
-The communication plumbing is written against torch.distributed only, so the same code runs on
-the gloo backend with CPU tensors (tests/test_sharded.py drives it with a stand-in tile predictor).
+Two transports:
+
+* **native** (CUDA tensors, exact GP): ``gpg_predict_sharded`` / ``gpg_acq_sweep_sharded`` of libgpgrid.so over
+  the library's own NCCL communicator (``ensure_comm`` builds it from a ``torch.distributed`` group: the 128-byte
+  unique id travels through the group, nothing else does).  The broadcast of the fp16 planes is pipelined by row
+  blocks under the first tile's variance GEMM; (mean, sd) come back in one all-gather.
+* **generic** (any tensors, any cache -- the inducing-point cache, and the gloo / CPU test of this plumbing):
+  ``torch.distributed`` broadcasts of the cache tensors + all-gathers.
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -21,27 +28,105 @@ def tile_bounds(M, world, rank):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def broadcast_factor(fac, src=0, group=None):
-    """Broadcast the tensors of a factor cache in place (every rank passes same-shaped buffers)."""
-    # the tcgen05 predict path (f32, N >= 1024: gpg_predict's routing rule) reads only the fp16 planes of Linv;
-    # the fp32 matrix travels only when the SIMT kernels will consume it
-    planes = fac.get("wsplit")
-    if "Ui" in fac:                  # inducing-point cache (gpg_sparse_factorize): two m x m factors and a vector
-        keys = ("Ui", "Pm", "w", "split", "scales")
-    elif planes is not None and planes.shape[1] >= 1024:
-        keys = ("alpha", "wsplit", "scales")
+def tile_width(M, world):
+    """Common (padded) tile width: what every rank allocates so that one all-gather fits all tiles."""
+    return -(-int(M) // int(world))
+
+
+def _global_rank(group, group_rank):
+    """torch.distributed.broadcast takes GLOBAL ranks; callers of this module speak group ranks."""
+    if group is None or group is dist.group.WORLD:
+        return group_rank
+    return dist.get_global_rank(group, group_rank)
+
+
+# ---------------------------------------------------------------------------------------------
+# native transport
+# ---------------------------------------------------------------------------------------------
+_COMM_OF = {}          # id(engine) -> (group key, nranks, rank)
+
+
+def ensure_comm(engine, group=None):
+    """Give `engine` an NCCL communicator spanning `group` (default: the world).  Collective over the group; cached."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    key = (id(group) if group is not None else 0, world, rank)
+    if _COMM_OF.get(id(engine)) == key and engine.comm_info() == (world, rank):
+        return world, rank
+    box = [engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=_global_rank(group, 0), group=group)
+    engine.comm_init(world, rank, box[0])
+    _COMM_OF[id(engine)] = key
+    return world, rank
+
+
+def predict_exact_sharded(engine, kernel_id, theta, X, y, jitter, Xs, src=0, group=None, fac=None, tile_only=False):
+    """Exact-GP sharded predict on the native transport.  Every rank passes same-shaped theta / X / y (rank ``src``'s
+    values win: they are part of the broadcast) and the full (M, d) test rows, or -- with ``tile_only`` -- just its
+    own tile.  Returns (mean, sd, info) for all M rows on every rank (device tensors; info = src's pivot status)."""
+    world, rank = ensure_comm(engine, group)
+    N = X.shape[0]
+    if fac is None:
+        fac = engine.alloc_factor(N, X.dtype, with_L=(rank == src))
+    theta, X = theta.contiguous(), X.contiguous()
+    if rank == src:
+        engine.factorize(kernel_id, theta, X, y, jitter, out=fac)
+    if tile_only:
+        Xt = Xs
+        counts = [None] * world
+        dist.all_gather_object(counts, int(Xt.shape[0]), group=group)
+        M = sum(counts)
+        width = max(counts)
     else:
-        keys = ("Linv", "alpha", "wsplit", "scales")
-    for key in keys:
+        M = Xs.shape[0]
+        lo, hi = tile_bounds(M, world, rank)
+        Xt = Xs[lo:hi]
+        width = tile_width(M, world)
+        counts = [tile_bounds(M, world, r)[1] - tile_bounds(M, world, r)[0] for r in range(world)]
+    _, allp = engine.predict_sharded(kernel_id, theta, X, fac, Xt, max(width, 1), root=src)
+    if all(c == width for c in counts):
+        mean, sd = allp[:, 0, :].reshape(-1), allp[:, 1, :].reshape(-1)
+    else:
+        mean = torch.cat([allp[r, 0, :c] for r, c in enumerate(counts)])
+        sd = torch.cat([allp[r, 1, :c] for r, c in enumerate(counts)])
+    return mean, sd, fac["info"]
+
+
+def acq_topk_sharded(engine, acq_id, mean_local, sd_local, idx_offset, k, group=None, **kw):
+    """Global top-k of the acquisition sweep over tiles that live on the ranks (native transport)."""
+    ensure_comm(engine, group)
+    return engine.acq_sweep_sharded(acq_id, mean_local, sd_local, idx_offset, k, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# generic transport (torch.distributed)
+# ---------------------------------------------------------------------------------------------
+def factor_keys(fac, engine=None):
+    """Which tensors of a factor cache have to travel.  The exact-GP cache carries Linv twice (fp32 / fp64 matrix and
+    its fp16 planes); gpg_predict reads one of them -- the engine's own routing rule (gpg_predict_uses_planes) says
+    which.  Without an engine to ask, everything present is sent."""
+    if "Ui" in fac:                  # inducing-point cache (gpg_sparse_factorize): two m x m factors and a vector
+        return ("Ui", "Pm", "w", "split", "scales", "info")
+    planes = fac.get("wsplit")
+    if planes is not None and engine is not None and hasattr(engine, "predict_uses_planes") and \
+            engine.predict_uses_planes(fac["alpha"].dtype, fac["alpha"].shape[0], True):
+        return ("alpha", "wsplit", "scales", "info")
+    return ("Linv", "alpha", "wsplit", "scales", "info")
+
+
+def broadcast_factor(fac, src=0, group=None, engine=None):
+    """Broadcast the tensors of a factor cache in place (every rank passes same-shaped buffers).  ``src`` is a rank
+    of ``group``."""
+    gsrc = _global_rank(group, src)
+    for key in factor_keys(fac, engine):
         if fac.get(key) is not None:
-            dist.broadcast(fac[key], src=src, group=group)
+            dist.broadcast(fac[key], src=gsrc, group=group)
     return fac
 
 
 def gather_tiles(local, M, group=None):
     """All-gather the per-rank tiles of a length-M vector (tiles as produced by tile_bounds)."""
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
     base, extra = divmod(int(M), world)
     if extra == 0:
         out = torch.empty(M, dtype=local.dtype, device=local.device)
@@ -56,13 +141,20 @@ def gather_tiles(local, M, group=None):
     for r in range(world):
         lo, hi = tile_bounds(M, world, r)
         parts.append(out[r * width: r * width + (hi - lo)])
-    del rank
     return torch.cat(parts)
 
 
-def predict_sharded(factorize_fn, alloc_fn, predict_tile_fn, Xs, group=None):
+def _raise_not_pd(info):
+    raise torch.linalg.LinAlgError(
+        f"linalg.cholesky: The factorization could not be completed because the input is not "
+        f"positive-definite (the leading minor of order {info} is not positive-definite).")
+
+
+def predict_sharded(factorize_fn, alloc_fn, predict_tile_fn, Xs, group=None, src=0, engine=None):
     """
-    factorize_fn() -> fac      run on rank 0 only (K assembly + Cholesky + inverse + solves)
+    factorize_fn() -> fac      run on rank ``src`` only (K assembly + Cholesky + inverse + solves); it must NOT raise on
+                               a failed factorisation (the other ranks are already waiting in the broadcast): the pivot
+                               status travels in fac["info"] and every rank raises together after the collective
     alloc_fn() -> fac          empty same-shaped buffers on the other ranks
     predict_tile_fn(fac, Xs_tile) -> (mean_tile, sd_tile)
     Xs: (M, d) test rows, identical on every rank (each rank only reads its tile).
@@ -71,9 +163,12 @@ def predict_sharded(factorize_fn, alloc_fn, predict_tile_fn, Xs, group=None):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     M = Xs.shape[0]
-    fac = factorize_fn() if rank == 0 else alloc_fn()
+    fac = factorize_fn() if rank == src else alloc_fn()
     if world > 1:
-        broadcast_factor(fac, 0, group)
+        broadcast_factor(fac, src, group, engine)
+    info = int(fac["info"].item()) if fac.get("info") is not None else 0
+    if info != 0:
+        _raise_not_pd(info)                             # on every rank: nobody is left behind in a collective
     lo, hi = tile_bounds(M, world, rank)
     mean_t, sd_t = predict_tile_fn(fac, Xs[lo:hi])
     if world == 1:
@@ -81,25 +176,54 @@ def predict_sharded(factorize_fn, alloc_fn, predict_tile_fn, Xs, group=None):
     return gather_tiles(mean_t, M, group), gather_tiles(sd_t, M, group)
 
 
+def topk_merge_generic(vals_local, idx_local, k, group=None):
+    """Merge per-rank candidate lists (values, global flat indices; already the local top-k) into the global top-k in
+    the reference's order -- descending value, NaN first, ties by larger flat index (boptim.py:304-306).  Host-side:
+    the generic transport's counterpart of gpg_acq_sweep_sharded."""
+    world = dist.get_world_size(group)
+    box = [None] * world
+    dist.all_gather_object(box, (np.asarray(vals_local, dtype=np.float64), np.asarray(idx_local, dtype=np.int64)),
+                           group=group)
+    vals = np.concatenate([b[0] for b in box])
+    idx = np.concatenate([b[1] for b in box])
+    keep = idx >= 0
+    vals, idx = vals[keep], idx[keep]
+    nan = np.isnan(vals)
+    order = np.lexsort((-idx, -np.where(nan, np.inf, vals), ~nan))     # last key first: NaN group, value, index
+    order = order[:k]
+    return vals[order], idx[order]
+
+
 def predict_model_sharded(model, Xs, src=0, group=None):
     """Tile-sharded ``model.predict_sd`` for the model object of a reconstructor / skreconstructor (ExactGPModel,
-    SparseGPModel, SKExactGPModel): rank ``src``'s hyper-parameters (and inducing inputs) are broadcast first --
-    training is replicas-only, so the ranks may hold different values -- then rank ``src`` factorises, the cache
-    is broadcast, every rank predicts its tile of ``Xs`` and the tiles are all-gathered.  Every rank passes a model
-    built on the same (X, y); returns (mean, sd) for all of ``Xs`` on every rank."""
+    SparseGPModel, SKExactGPModel): rank ``src``'s hyper-parameters (and inducing inputs) win -- training is
+    replicas-only, so the ranks may hold different values -- rank ``src`` factorises, the cache is broadcast, every rank
+    predicts its tile of ``Xs`` and the tiles are all-gathered.  Every rank passes a model built on the same (X, y);
+    returns (mean, sd) for all of ``Xs`` on every rank.  A failed factorisation raises LinAlgError on EVERY rank."""
     eng = model.engine
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     Xs = Xs.to(eng.device, model.kernel.dtype).contiguous()
     sparse = hasattr(model, "Xu")
-    if world > 1:
-        dist.broadcast(model._theta, src=src, group=group)
-        if sparse:
-            dist.broadcast(model._Xu, src=src, group=group)
-        model._factor = None
     kid = model.kernel.kernel_id
+    shift = getattr(model, "mean_shift", None)          # constant mean of the GPyTorch-semantics model
+    native = world > 1 and not sparse and Xs.is_cuda and hasattr(eng, "predict_sharded") and shift is None
+    if native:
+        model._factor = None
+        y = model._y
+        mean, sd, info = predict_exact_sharded(eng, kid, model._theta, model._X, y, model.jitter, Xs, src=src, group=group)
+        info = int(info.item())
+        if info != 0:
+            _raise_not_pd(info)
+        return mean, sd
+    if world > 1:
+        gsrc = _global_rank(group, src)
+        dist.broadcast(model._theta, src=gsrc, group=group)
+        if sparse:
+            dist.broadcast(model._Xu, src=gsrc, group=group)
+        model._factor = None
 
     def factorize():
-        fac, _ = model.factor(check=True)
+        fac, _ = model.factor(check=False)              # never raise before the collective (see predict_sharded)
         return fac
 
     if sparse:
@@ -108,6 +232,5 @@ def predict_model_sharded(model, Xs, src=0, group=None):
     else:
         alloc = lambda: eng.alloc_factor(model._X.shape[0], model.kernel.dtype, with_L=False)
         tile = lambda fac, X: eng.predict(kid, model._theta, model._X, fac, X)
-    mean, sd = predict_sharded(factorize, alloc, tile, Xs, group)
-    shift = getattr(model, "mean_shift", None)          # constant mean of the GPyTorch-semantics model
+    mean, sd = predict_sharded(factorize, alloc, tile, Xs, group, src=src, engine=eng)
     return (mean + shift() if shift is not None else mean), sd

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GPG_VERSION 110
+#define GPG_VERSION 120
 
 enum { GPG_OK = 0, GPG_EINVAL = 1, GPG_ENOTPD = 2, GPG_ECUDA = 3 };
 enum { GPG_F32 = 0, GPG_F64 = 1 };
@@ -189,6 +189,23 @@ int gpg_fit_adam_sk(gpg_handle_t h, int dtype, int kernel_id, int d, int n_ls,
                     void *u, const double *bounds_host, int iters, double lr,
                     void *traj_out, void *theta_out, int32_t *info, void *stream);
 
+/* gpg_fit_adam for vreconstructor(independent=True) -- gpim/gpreg/vgpr.py:320-354 (ivgprmodel) trained as at
+ * vgpr.py:157-179: `ntasks` exact GPs on one shared X with ONE shared lengthscale (the base kernel's parameter exists
+ * before its batch_shape is overwritten, vgpr.py:346), per-task ScaleKernel outputscales and ConstantMean constants,
+ * MultitaskGaussianLikelihood noise_t = task_noise_t + global noise (both softplus + 1e-4);
+ * loss = -sum_t log N(y_t; c_t, s_t K_l + noise_t I) / (N ntasks), torch.optim.Adam on the raw parameters.
+ *   Y        dtype[ntasks * N], task-major (row t = observations of output t at the N training rows)
+ *   u        dtype[3 ntasks + 1 + n_ls] in/out raw {outputscale[ntasks] | task noise[ntasks] | global noise |
+ *            constant[ntasks] | lengthscale[n_ls]} (GPyTorch initialises all of them to 0)
+ *   bounds_host  double[2 n_ls] {ls_lo[n_ls], ls_hi[n_ls]} (gpytorch.constraints.Interval), or NULL for GPyTorch's
+ *            default Positive constraint (softplus) -- the reference's lengthscale=None
+ *   traj_out dtype[iters * (d + 1)]: per iteration {lengthscale[d], loss}
+ *   theta_out dtype[ntasks * (3 + d)]: per task {outputscale, total noise, constant, lengthscale[d]} after the last
+ *            step -- the theta gpg_factorize / gpg_predict take for that task (on y_t - constant). */
+int gpg_fit_adam_mt(gpg_handle_t h, int dtype, int kernel_id, int d, int n_ls, int ntasks, const void *X,
+                    const void *Y, int64_t N, double jitter, void *u, const double *bounds_host, int iters, double lr,
+                    void *traj_out, void *theta_out, int32_t *info, void *stream);
+
 /* K6 -- acquisition sweep + top-k (acqfunc.py:11-92, boptim.py:303-315).
  *   acq_id CB: alpha*mean + beta*sd;  EI: imp*Phi(z) + sd*phi(z), imp = mean - mu_best - xi,
  *   z = imp/sd;  POI: Phi(z).   mask (nullable, dtype[M]): multiplied in, NaN entries excluded.
@@ -245,6 +262,57 @@ int gpg_sparse_predict(gpg_handle_t h, int dtype, int kernel_id, int d, const vo
                        const void *Xu, int64_t m, const void *Ui, const void *Pm, int64_t ld, const void *w,
                        const void *split, const float *scales,
                        const void *Xs, int64_t M, void *mean_out, void *sd_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU of one box, one NCCL communicator per handle.  The reference has no
+ * multi-device path (gpr.py:136-140 moves the one model to the one GPU); what is sharded is reconstructor.predict
+ * (gpr.py:219-255): test points are independent given the factor cache, so rank `root` alone factorises (training /
+ * Cholesky stay replicas-only), the cache is broadcast over NVLink, every rank predicts its contiguous tile of
+ * X_full rows and one all-gather returns (mean, sd).  NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy
+ * the process already has loaded, else the system one); without it these entry points return GPG_ECUDA and
+ * everything else keeps working.  Collective calls: every rank of the communicator must make the same call.
+ * --------------------------------------------------------------------------------------------- */
+
+/* Rank 0 draws the 128-byte NCCL unique id (host memory) and hands it to the other ranks by any out-of-band means
+ * (torch.distributed object broadcast, MPI_Bcast, a file); every rank then calls gpg_comm_init with it. */
+int gpg_comm_unique_id(void *id_host);
+int gpg_comm_init(gpg_handle_t h, int nranks, int rank, const void *id_host);
+int gpg_comm_destroy(gpg_handle_t h);
+/* nranks / rank of the handle's communicator; 0 / -1 when there is none */
+int gpg_comm_info(gpg_handle_t h, int *nranks_out, int *rank_out);
+
+/* 1 when gpg_predict would read the fp16 planes (wsplit) of a cache for this dtype / N under the handle's options,
+ * 0 when it would read Linv: what a factor cache has to carry to another GPU. */
+int gpg_predict_uses_planes(gpg_handle_t h, int dtype, int64_t N, int have_planes);
+
+/* Broadcast of the factor cache of gpg_factorize from rank `root`, in place on every rank, stream-ordered on
+ * `stream`: {theta[3 + d], X[N x d], alpha[N], scales[16], info} as one fused NCCL launch, then the N x N part --
+ * the fp16 planes when gpg_predict_uses_planes(), otherwise Linv (wsplit / scales may be NULL then). */
+int gpg_bcast_factor(gpg_handle_t h, int dtype, int d, int64_t N, int64_t ld, void *theta, void *X, void *Linv,
+                     void *alpha, void *wsplit, float *scales, int32_t *info, int root, void *stream);
+
+/* One all-gather: pred_all[r * count + i] = rank r's pred_local[i]  (dtype elements; count equal on all ranks). */
+int gpg_allgather_pred(gpg_handle_t h, int dtype, const void *pred_local, int64_t count, void *pred_all, void *stream);
+
+/* The sharded predict in one call: gpg_bcast_factor from `root` + gpg_predict of this rank's M_local rows +
+ * gpg_allgather_pred.  On the tcgen05 route the broadcast of the planes is pipelined by row blocks on the handle's
+ * communication stream and the variance GEMM of the first tile of test points starts on the n-blocks of Linv that
+ * have landed while the rest is in flight (the n-blocks are independent: block b needs rows [256 b, 256 b + 256)).
+ *   pred_local  dtype[2 * M_pad]: mean at [0, M_local), sd at [M_pad, M_pad + M_local)
+ *   pred_all    dtype[nranks * 2 * M_pad] or NULL (no gather): rank r's pred_local at offset r * 2 * M_pad
+ * M_pad (>= M_local) must be the same on all ranks.  *info on every rank receives root's factorisation status. */
+int gpg_predict_sharded(gpg_handle_t h, int dtype, int kernel_id, int d, void *theta, void *X, int64_t N,
+                        void *Linv, int64_t ld, void *alpha, void *wsplit, float *scales, int32_t *info, int root,
+                        const void *Xs_local, int64_t M_local, void *pred_local, int64_t M_pad, void *pred_all,
+                        void *stream);
+
+/* K6 over a sharded grid (boptim.py:303-315 is what it replaces): gpg_acq_sweep on this rank's tile with global flat
+ * indices idx_offset + j, a k * nranks-element all-gather, and the merge -- every rank ends with the global top-k
+ * in the reference's order.  mean_local / sd_local / mask_local / acq_out_local: this rank's M_local entries. */
+int gpg_acq_sweep_sharded(gpg_handle_t h, int dtype, int acq_id, const void *mean_local, const void *sd_local,
+                          const void *mask_local, int64_t M_local, int64_t idx_offset, double mu_best, double xi,
+                          double alpha, double beta, int k, void *topk_val, int64_t *topk_idx, int32_t *count_out,
+                          void *acq_out_local, void *stream);
 
 #ifdef __cplusplus
 }

@@ -330,31 +330,37 @@ def bo_run(X_seed, y_seed, X_full, target, acquisition="cb", exploration_steps=1
 # fixed-theta predict used as the CPU baseline timer (bench.py cpu_baseline / --impl reference)
 # --------------------------------------------------------------------------------------
 def predict_fixed_theta(kernel, X, y, Xs, variance, lengthscale, noise, jitter=1e-5,
-                        dtype=torch.float64, scale_mixture=1.0):
+                        dtype=torch.float64, scale_mixture=1.0, device=None, to_numpy=True):
     """One reference-style predict() with given constrained theta: K, cholesky, K*, trsm, reduce.
-    X (N,d), y (N,), Xs (M,d) numpy.  Returns (mean, sd, seconds_by_stage)."""
-    X = torch.as_tensor(X, dtype=dtype)
-    y = torch.as_tensor(y, dtype=dtype)
-    Xs = torch.as_tensor(Xs, dtype=dtype)
-    ls = torch.as_tensor(lengthscale, dtype=dtype)
+    X (N,d), y (N,), Xs (M,d) numpy (or tensors).  Returns (mean, sd, seconds_by_stage).
+    device="cuda" runs the same torch ops on the GPU (what the reference's use_gpu=True dispatches to:
+    cuSOLVER potrf, cuBLAS trsm) -- bench.py's torch_cuda_baseline leg; stages are then synchronised."""
+    dev = torch.device(device) if device is not None else torch.device("cpu")
+    sync = (lambda: torch.cuda.synchronize(dev)) if dev.type == "cuda" else (lambda: None)
+    X = torch.as_tensor(X, dtype=dtype, device=dev)
+    y = torch.as_tensor(y, dtype=dtype, device=dev)
+    Xs = torch.as_tensor(Xs, dtype=dtype, device=dev)
+    ls = torch.as_tensor(lengthscale, dtype=dtype, device=dev)
     t = {}
-    t0 = time.perf_counter()
+    sync(); t0 = time.perf_counter()
     K = kernel_matrix(kernel, X, X, variance, ls, scale_mixture)
     K.view(-1)[:: X.shape[0] + 1] += jitter + noise
-    t["kmat"] = time.perf_counter() - t0
+    sync(); t["kmat"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     L = torch.linalg.cholesky(K)
-    t["cholesky"] = time.perf_counter() - t0
+    sync(); t["cholesky"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     Kfs = kernel_matrix(kernel, X, Xs, variance, ls, scale_mixture)
-    t["kcross"] = time.perf_counter() - t0
+    sync(); t["kcross"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     sol = torch.linalg.solve_triangular(L, torch.cat((y.unsqueeze(1), Kfs), dim=1), upper=False)
-    t["trsm"] = time.perf_counter() - t0
+    sync(); t["trsm"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     vhat, W = sol[:, :1], sol[:, 1:].t()
     mean = W.matmul(vhat).squeeze(-1)
     var = (variance - W.pow(2).sum(-1)).clamp(min=0) + noise
     sd = var.sqrt()
-    t["reduce"] = time.perf_counter() - t0
-    return mean.numpy(), sd.numpy(), t
+    sync(); t["reduce"] = time.perf_counter() - t0
+    if to_numpy:
+        return mean.cpu().numpy(), sd.cpu().numpy(), t
+    return mean, sd, t

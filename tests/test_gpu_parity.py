@@ -373,6 +373,72 @@ def test_full_size_properties_c2(eng):
     assert relinf(sd[pick].cpu(), s64.cpu()) < 1e-3
 
 
+def _engine_predict_full(eng, name, rows):
+    """fp32 default route (tcgen05) of `eng` on workload `name` at FULL training-set size, at grid rows `rows`."""
+    from gpim_b200._lib import KERNEL_IDS
+    wl = W.make_workload(name)
+    X, y = O.training_rows(O.sparse_grid(wl["R"]), wl["R"])
+    Xs = W.rows_of(wl["Xfull"])[rows]
+    kid = KERNEL_IDS[wl["kernel"]]
+    th = torch.tensor(wl["theta"], dtype=torch.float32).cuda()
+    Xd, yd = torch.tensor(X, dtype=torch.float32).cuda(), torch.tensor(y, dtype=torch.float32).cuda()
+    fac = eng.factorize(kid, th, Xd, yd, wl["jitter"])
+    assert int(fac["info"].item()) == 0
+    mean, sd = eng.predict(kid, th, Xd, fac, torch.tensor(Xs, dtype=torch.float32).cuda())
+    return wl, X, y, Xs, mean.cpu().numpy(), sd.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "h512"])
+def test_full_size_configs_against_fp64_oracle_vectors(eng, name, golden_dir):
+    """BASELINE.json configs[1] (C2, N = 7 688), configs[2] (C3, Matern52, d = 3, N = 19 744) and the 512 x 512 headline
+    (N = 15 377) at FULL size: the fp32 tcgen05 path against the fp64 oracle on 1 024 rows of the dense grid
+    (tests/golden/oracle_full_*.npz, generated by make_fullsize_vectors.py).  north_star tolerance: mean 1e-4, sd 1e-3."""
+    import os
+    g = np.load(os.path.join(golden_dir, f"oracle_full_{name}.npz"))
+    wl, X, y, Xs, mean, sd = _engine_predict_full(eng, name, g["sel"])
+    assert X.shape[0] == int(g["N"]) and W.rows_of(wl["Xfull"]).shape[0] == int(g["M"])
+    np.testing.assert_allclose(np.array(wl["theta"]), g["theta"])
+    em, es = relinf(mean, g["mean"]), relinf(sd, g["sd"])
+    print(f"{name}: N={X.shape[0]} mean relinf {em:.2e} sd relinf {es:.2e}")
+    assert em < 1e-4 and es < 1e-3
+
+
+def test_full_size_c2_against_live_oracle(eng):
+    """C2 at full size against the oracle run HERE in fp64 (K + Cholesky at N = 7 688, 1 024 grid rows offset from the
+    fixture's), so that the committed vectors are not the only witness."""
+    M = 256 * 256
+    rows = (W.sample_rows(M, 1024) + 17) % M
+    wl, X, y, Xs, mean, sd = _engine_predict_full(eng, "c2", rows)
+    th = wl["theta"]
+    om, osd, _ = O.predict_fixed_theta(wl["kernel"], X, y, Xs, th[0], th[3:], th[1], jitter=wl["jitter"],
+                                       dtype=torch.float64, scale_mixture=th[2])
+    assert relinf(mean, om) < 1e-4 and relinf(sd, osd) < 1e-3
+
+
+def test_c4_trimmed_bo_picks_match_oracle(tmp_path):
+    """BASELINE.json configs[3] trimmed (128 x 128 grid, EI, 100 seed pixels, 5 exploration steps x 200 Adam
+    iterations, fp64): the measured points, in order, and the final hyper-parameters equal the oracle's bo_run."""
+    import gpim
+    n = 128
+    f = W.bo_trial_func(n)
+    np.random.seed(0)
+    idx = np.random.randint(0, n, size=(100, 2))
+    Zs = np.full((n, n), np.nan)
+    for i, j in idx:
+        Zs[i, j] = f((i, j))
+    X_full, X_sparse = gpim.utils.get_full_grid(Zs), gpim.utils.get_sparse_grid(Zs)
+    ref = O.bo_run(X_sparse, Zs, X_full, f, acquisition="ei", exploration_steps=5, gp_iterations=200)
+    bo = gpim.boptimizer(X_sparse, Zs, X_full, f, acquisition_function="ei", exploration_steps=5, gp_iterations=200,
+                         verbose=0, filename=str(tmp_path / "bo"))
+    bo.run()
+    assert [list(map(int, p)) for p in bo.indices_all] == [list(map(int, p)) for p in ref["indices_all"]]
+    np.testing.assert_allclose(bo.target_func_vals[-1], ref["target_func_vals"][-1])
+    np.testing.assert_allclose(bo.vals_all, ref["vals_all"], rtol=1e-5)
+    np.testing.assert_allclose(bo.surrogate_model.hyperparams["noise"][-1], ref["gp"].noise_all[-1], rtol=1e-5)
+    np.testing.assert_allclose(bo.surrogate_model.hyperparams["lengthscale"][-1], ref["gp"].lscales[-1], rtol=1e-5)
+    assert relinf(bo.gp_predictions[-1][0], ref["gp_predictions"][-1][0]) < 1e-6
+
+
 # ---------------------------------------------------------------------------------------------
 def _torch_nll(kernel, X, y, theta, jitter):
     v, n, a, l = theta[0], theta[1], theta[2], theta[3:]

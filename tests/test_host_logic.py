@@ -229,3 +229,29 @@ def test_checkpoint_carries_the_inducing_inputs_of_a_sparse_surrogate(tmp_path):
     np.testing.assert_allclose(second.surrogate_model.model._u.numpy(), [0.1, -0.2, 0.0, 0.3, 0.4])
     assert second.indices_all == [[1, 2]] and second._first_step == 1
     assert tuple(second.surrogate_model.model.X.shape) == (2, 2)                     # the two measured pixels
+
+
+def test_resume_from_a_checkpoint_written_before_any_step_starts_at_step_zero(tmp_path):
+    """a checkpoint with no completed step must not skip step 0 (and its initial training); one-element
+    lengthscale bounds on d > 1 inputs pack as ONE shared lengthscale."""
+    import types
+    import torch
+    from gpim_b200.kernels import gp_kernels
+    trained = []
+    model = types.SimpleNamespace(_u=torch.zeros(5, dtype=torch.float64), X=None, y=None)
+    model.load_unconstrained = lambda u: setattr(model, "_u", torch.as_tensor(np.asarray(u)))
+    sur = types.SimpleNamespace(model=model, train=lambda **kw: trained.append(1), hyperparams={"noise": []})
+    y = np.full((4, 4), np.nan)
+    y[1, 2] = 0.5
+    common = dict(filename=str(tmp_path / "bo0"), extent=None, precision="double", exploration_steps=3,
+                  gp_predictions=[], target_func_vals=[y.copy()], indices_all=[], vals_all=[], surrogate_model=sur)
+    first = _bare_boptimizer(**common)
+    first.save_results()
+    second = _bare_boptimizer(**common)
+    second.resume()
+    assert second._first_step == 0 and not second._skip_initial_training
+    k = gp_kernels.get_kernel("RBF", 3, [[1.0], [5.0]])
+    assert k.isotropic and k.n_ls == 1 and k.pack_theta().numel() == 3 + 3 and k.pack_u().numel() == 3 + 1
+    assert len(k.bounds()) == 2 + 2
+    with pytest.raises(ValueError):
+        gp_kernels.get_kernel("RBF", 3, [[1.0, 1.0], [5.0, 5.0]])

@@ -91,6 +91,41 @@ def bo_trial_func(n=128):
     return f
 
 
+def make_workload(name, dense=1):
+    """BASELINE.json configs by name -> dict(R, kernel, theta(list), d, label, Xfull, jitter).
+    `dense` multiplies the number of X_full rows (weak scaling of the dense grid).
+    c2 / h512 / c5: 256 / 512 / 1024 spiral scans (RBF); c3: 64x64x16 hyperspectral (Matern52, d = 3);
+    c1k: a 128 x 128 spiral (N ~ 3.4 k) for quick checks."""
+    ft = FIXED_THETA
+    if name in ("c2", "h512", "c5", "c1k"):
+        n = {"c2": 256, "h512": 512, "c5": 1024, "c1k": 128}[name]
+        R = spiral_scan(n)
+        theta = [ft["variance"], ft["noise"], 1.0, ft["lengthscale"], ft["lengthscale"]]
+        kern = "RBF"
+        label = f"2D {n}x{n} sparse spiral scan, RBF, fixed theta"
+    elif name == "c3":
+        R = hyperspectral((64, 64, 16))
+        theta = [ft["variance"], ft["noise"], 1.0, ft["lengthscale"], ft["lengthscale"], ft["lengthscale_z"]]
+        kern = "Matern52"
+        label = "3D 64x64x16 hyperspectral, Matern52, fixed theta"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    sl = [slice(0, R.shape[0], 1.0 / dense)] + [slice(0, e, 1.0) for e in R.shape[1:]]
+    Xfull = np.array(np.mgrid[tuple(sl)])                     # gprutils.get_full_grid layout (c, *dims)
+    return {"name": name, "R": R, "kernel": kern, "theta": theta, "d": R.ndim, "label": label,
+            "Xfull": Xfull, "jitter": ft["jitter"]}
+
+
+def rows_of(Xgrid):
+    """(c, *dims) -> (prod(dims), c): the row layout of gprutils.prepare_test_data (gprutils.py:82)."""
+    return Xgrid.reshape(Xgrid.shape[0], -1).T
+
+
+def sample_rows(M, m):
+    """The m grid rows (evenly spread over the M of X_full) the bounded CPU legs and the full-size fixtures use."""
+    return np.linspace(0, M - 1, m).astype(np.int64)
+
+
 if __name__ == "__main__":
     for n in (128, 256, 512, 1024):
         print(n, int(spiral_mask(n).sum()))
