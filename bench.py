@@ -337,6 +337,7 @@ def measure_predict(eng, wl, steps, warmup, world=1, rank=0, keep_outputs=True):
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - launches0
     stages = eng.stage_times()
+    macs = eng.variance_gemm_macs()                          # what the variance GEMM executed on THIS rank, all steps
     eng.set_option(_lib.OPT_STAGE_TIMING, 0)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -365,7 +366,8 @@ def measure_predict(eng, wl, steps, warmup, world=1, rank=0, keep_outputs=True):
         torch.cuda.synchronize()
         ms_cached = e2.elapsed_time(e3) / max(1, steps // 2)
     out = {"N": N, "M": M, "d": d, "m_local": hi - lo, "ms_per_step": ms / steps, "value": M / (ms / steps * 1e-3),
-           "launches": launches, "stages": stages, "steps": steps, "wall": (wall0, wall1), "ms_cached": ms_cached}
+           "launches": launches, "stages": stages, "steps": steps, "wall": (wall0, wall1), "ms_cached": ms_cached,
+           "pgemm_macs": macs}
     if world > 1 and rank == 0:
         # sharded == unsharded: the same kernels on the same inputs, tile by tile -> must be bit-identical
         m1, s1 = eng.predict(kid, th, Xd, fac, torch.tensor(Xs, dtype=dt, device=dev))
@@ -392,20 +394,29 @@ def roofline_blocks(res, wl, steps, peaks, timed_region_s):
         "fallback of B200_PROFILING.md (no MEASURED_PEAKS.json)"
     hbm = peaks.get("hbm_gbs") or 6650.0
     pg_ms, pg_n = stages["pgemm"]
-    flops_per_step = float(N) * float(N) * float(m_local)    # N^2 FLOP per predicted point
-    achieved = flops_per_step * steps / (pg_ms * 1e-3) / 1e12 if pg_ms > 0 else 0.0
+    dense_flops_per_step = float(N) * float(N) * float(m_local)    # N^2 FLOP per predicted point (dense product)
+    # ALGORITHMIC work of the launch = what the product has to do once K* entries below fp32 resolution are left out
+    # (GPG_OPT_COMPACT_SUPPORT, the default): counted by the kernel itself at tile granularity, 2 FLOP per MAC
+    flops_total = 2.0 * res["pgemm_macs"] if res.get("pgemm_macs") else dense_flops_per_step * steps
+    achieved = flops_total / (pg_ms * 1e-3) / 1e12 if pg_ms > 0 else 0.0
+    dense_equiv = dense_flops_per_step * steps / (pg_ms * 1e-3) / 1e12 if pg_ms > 0 else 0.0
     traffic, traffic_src = ncu_traffic(wl["name"])
     pts_per_launch = min(PREDICT_CHUNK, m_local)
     roof = {"kernel": "gemm_tc_kernel as the predict GEMM: Linv x K* + column-sum-of-squares epilogue (stage pgemm)",
             "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
             "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": 4.0 * pts_per_launch * N + 2.0 * N * N,
-            "algorithmic_bytes_note": "4 B x (points per launch x N) K* planes + 2 N^2 B lower-triangle planes of Linv",
+            "algorithmic_bytes_note": "4 B x (points per launch x N) K* planes + 2 N^2 B lower-triangle planes of Linv "
+                                      "(upper bound: the compact-support ranges read less)",
             "launches": pg_n, "avg_launch_ms": pg_ms / max(pg_n, 1),
-            "algorithmic_flops_per_launch": flops_per_step * steps / max(pg_n, 1),
+            "algorithmic_flops_per_launch": flops_total / max(pg_n, 1),
+            "executed_fraction_of_dense": flops_total / (dense_flops_per_step * steps) if dense_flops_per_step else None,
+            "dense_equivalent_tflops": dense_equiv,
+            "dense_equivalent_note": "N^2 FLOP per point / time: what a dense product would have to sustain for the same "
+                                     "points/s; not a hardware rate (the skipped K* entries are below fp32 resolution)",
             "peak_source": peak_src,
             "note": "fp32-faithful split-fp16 product: 3 tcgen05 MMAs per algorithmic MAC, so the tensor pipe "
-                    "executes 3 x achieved",
+                    "executes 3 x achieved; achieved counts the MACs the kernel executed (128 x 256 x 32 per k-block)",
             "tensor_pipe_tflops": 3.0 * achieved, "tensor_pipe_frac": 3.0 * achieved / peak_tf}
     ch_ms, ch_n = stages["cholesky"]
     ch_tf = (N ** 3 / 3.0) * ch_n / (ch_ms * 1e-3) / 1e12 if ch_ms > 0 else 0.0
@@ -694,19 +705,21 @@ def measure_sparse(eng, name, iters, steps):
     return out
 
 
-def measure_compact(eng, name, steps, warmup):
-    """GPG_OPT_COMPACT_SUPPORT = 1 (opt-in, NOT the headline): the variance GEMM of each 128-row tile of test points
-    only visits the training rows whose covariance with the tile exceeds 1e-14 x variance."""
+def measure_dense(eng, name, steps, warmup, peaks):
+    """GPG_OPT_COMPACT_SUPPORT = 0: the variance GEMM over ALL training rows for every tile of test points -- what the
+    default degenerates to when nothing of K* is negligible (long lengthscales, unordered training rows)."""
     from gpim_b200 import _lib
-    eng.set_option(_lib.OPT_COMPACT_SUPPORT, 1)
+    eng.set_option(_lib.OPT_COMPACT_SUPPORT, 0)
     try:
-        res = measure_predict(eng, make_workload(name), steps, warmup, keep_outputs=False)
+        wl = make_workload(name)
+        res = measure_predict(eng, wl, steps, warmup, keep_outputs=False)
     finally:
-        eng.set_option(_lib.OPT_COMPACT_SUPPORT, 0)
+        eng.set_option(_lib.OPT_COMPACT_SUPPORT, 1)
+    roof, _, _ = roofline_blocks(res, wl, steps, peaks, res["ms_per_step"] * steps * 1e-3)
     return {"ms_per_step": res["ms_per_step"], "value": res["value"], "unit": UNIT, "factor_cached_ms": res["ms_cached"],
-            "note": "variance GEMM restricted per tile to the training rows with covariance > 1e-14 x variance; outputs "
-                    "equal the dense ones to fp32 rounding (tests/test_gpu_parity.py::"
-                    "test_predict_compact_support_option_is_exact); speed depends on the hyper-parameters"}
+            "roofline": {k: roof[k] for k in ("achieved", "peak", "frac", "unit", "tensor_pipe_frac", "avg_launch_ms")},
+            "note": "dense variance GEMM (GPG_OPT_COMPACT_SUPPORT = 0); outputs equal the default's to fp32 rounding "
+                    "(tests/test_gpu_parity.py::test_predict_compact_support_option_is_exact)"}
 
 
 def run_cuda(args):
@@ -810,8 +823,8 @@ def run_cuda(args):
             wls["c4"] = measure_c4(eng, peaks, steps=args.c4_steps)
         line["workloads"] = wls
         line["extra_workloads"] = {"train_c2": measure_training(eng, "c2", 10),
-                                   "c2_compact_support": measure_compact(eng, "c2", max(3, args.steps // 2), 2),
-                                   "h512_compact_support": measure_compact(eng, "h512", max(3, args.steps // 4), 2),
+                                   "c2_dense": measure_dense(eng, "c2", max(3, args.steps // 2), 2, peaks),
+                                   "h512_dense": measure_dense(eng, "h512", max(3, args.steps // 4), 2, peaks),
                                    "sparse_c2": measure_sparse(eng, "c2", 10, max(2, args.steps // 2))}
     print(json.dumps(line), flush=True)
     if world > 1:

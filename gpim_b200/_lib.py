@@ -18,6 +18,7 @@ KERNEL_IDS = {"RBF": 0, "Matern52": 1, "RationalQuadratic": 2}
 ACQ_IDS = {"cb": 0, "ei": 1, "poi": 2}
 OPT_GEMM_PATH, OPT_PREDICT_CHUNK, OPT_STAGE_TIMING = 1, 2, 3
 OPT_PANEL_REFINE, OPT_SYRK_CHUNK, OPT_FACTOR_ALGO, OPT_FIT_GRAPH, OPT_PANEL_MODE, OPT_OUTER_PANEL, OPT_COMPACT_SUPPORT = 4, 5, 6, 7, 8, 9, 10
+OPT_INNER_LEFT, OPT_LOOKAHEAD, OPT_PANEL_WORKERS = 11, 12, 13
 STAGES = ("kmat", "cholesky", "trtri", "solve", "kcross", "pgemm", "pfinal", "grad", "acq")
 
 _vp, _i32, _i64, _f64 = C.c_void_p, C.c_int, C.c_int64, C.c_double
@@ -31,6 +32,7 @@ SIGNATURES = {
     "gpg_set_option": ([_vp, _i32, C.c_longlong], C.c_int),
     "gpg_launch_count": ([_vp], C.c_longlong),
     "gpg_workspace_bytes": ([_vp], C.c_size_t),
+    "gpg_variance_gemm_macs": ([_vp, C.POINTER(_f64)], C.c_int),
     "gpg_stage_times": ([_vp, C.POINTER(_f64), C.POINTER(C.c_longlong)], C.c_int),
     "gpg_gemm_nt_f32": ([_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _f64, _f64, _f64, _f64, _vp], C.c_int),
     "gpg_kmat": ([_vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _f64, _i32, _vp, _i64, _vp], C.c_int),
@@ -182,6 +184,12 @@ class Engine:
         n = (C.c_longlong * len(STAGES))()
         self._check(self.lib.gpg_stage_times(self.h, ms, n))
         return {name: (ms[i], int(n[i])) for i, name in enumerate(STAGES)}
+
+    def variance_gemm_macs(self):
+        """MACs the variance GEMM executed under stage timing since the last call (tile granularity)."""
+        v = _f64(0.0)
+        self._check(self.lib.gpg_variance_gemm_macs(self.h, C.byref(v)))
+        return float(v.value)
 
     def empty(self, *shape, dtype):
         return torch.empty(*shape, dtype=dtype, device=self.device)

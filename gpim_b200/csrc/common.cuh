@@ -24,19 +24,26 @@ struct gpg_handle_s {
     int opt_stage_timing = 0;
     int opt_factor_algo = 0;
     int opt_fit_graph = 1;
-    int opt_panel_mode = 1;
+    int opt_panel_mode = 3;
     int opt_outer_panel = 512;
-    int opt_compact_support = 0;
+    int opt_compact_support = 1;
     int opt_inner_left = 1;
     int opt_panel_refine = 1;
     int opt_syrk_chunk = 0;
+    int opt_lookahead = 1;
+    int opt_panel_workers = 0;
     void *ws = nullptr;          // grow-only device workspace
     size_t ws_bytes = 0;
     double *gemv_part = nullptr;             // partial sums of the transposed triangular GEMV (grow-only)
     size_t gemv_part_elems = 0;
     int *tc_counters = nullptr;              // pool of zeroed tile counters for the persistent GEMM
     int tc_counter_pos = 0;
+    int *tc_counters_side = nullptr;         // the same for launches on side_stream
+    int tc_counter_pos_side = 0;
     cudaStream_t fit_stream = nullptr;       // blocking stream the small-N Adam loop is captured on
+    cudaStream_t side_stream = nullptr;      // look-ahead of the blocked Cholesky: trailing updates beyond the next panel
+    cudaEvent_t ev_fork = nullptr, ev_side = nullptr;
+    unsigned long long *work_counter = nullptr;   // device: k-blocks executed by the variance GEMM while stage timing is on
     void *comm = nullptr;                    // comm::State (comm.cuh): NCCL communicator + communication stream
     std::vector<gpg_stage_span> spans;       // recorded while opt_stage_timing != 0
     std::vector<cudaEvent_t> event_pool;
@@ -65,6 +72,8 @@ struct StageTimer {
 void gpg_set_error(const char *fmt, ...);
 // next zeroed tile counter of the handle's pool (re-zeroed stream-ordered when it wraps)
 int gpg_tc_counter(gpg_handle_s *h, cudaStream_t stream, int **out);
+// n consecutive zeroed ints of the same pool (flags of the cooperative panel kernel)
+int gpg_tc_counters(gpg_handle_s *h, cudaStream_t stream, int n, int **out);
 // returns pointer into the handle workspace, growing it if needed (synchronises on growth)
 int gpg_ws_reserve(gpg_handle_s *h, size_t bytes, void **out);
 // scratch for gemv_tri_T: at least `elems` doubles (synchronises on growth)

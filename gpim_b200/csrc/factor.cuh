@@ -174,11 +174,12 @@ __device__ __forceinline__ void invert_tri32(const T *__restrict__ S, T *__restr
 __device__ __forceinline__ float gpg_rsqrt(float x) { return rsqrtf(x); }
 __device__ __forceinline__ double gpg_rsqrt(double x) { return 1.0 / sqrt(x); }
 
-// Cholesky of the 32 x 32 block at S[c0.., c0..] in registers (lane = row).  Per pivot: the pivot
-// travels by one warp shuffle, the scaled column goes through a 32-entry shared buffer and comes back
-// as broadcast 128-bit loads (fewer shared-pipe instructions than one shuffle per column, and no
-// divergent code between the collectives).  Returns 0 or 1 + the local index of the first
-// non-positive pivot among the first `valid` columns.
+// Cholesky of the 32 x 32 block at S[c0.., c0..] in registers (lane = row).  The serial chain of a pivot is kept as
+// short as the data flow allows: the NEXT pivot's diagonal entry only needs the owning lane's own l_ij, so it is
+// updated, broadcast (one shuffle) and sent through rsqrt BEFORE the scaled column is exchanged; the exchange goes
+// through a double-buffered 32-entry shared array (one __syncwarp per pivot) and comes back as broadcast 128-bit
+// loads for the rank-1 update of the rest of the row.  Returns 0 or 1 + the local index of the first non-positive
+// pivot among the first `valid` columns.  colbuf: 64 entries.
 template <typename T>
 __device__ __forceinline__ int factor_tri32(T *__restrict__ S, int lds, int c0, int lane, int valid,
                                             T *__restrict__ colbuf, T *__restrict__ rdiag) {
@@ -186,34 +187,43 @@ __device__ __forceinline__ int factor_tri32(T *__restrict__ S, int lds, int c0, 
     T row[32];
 #pragma unroll
     for (int k = 0; k < 32; ++k) row[k] = S[(c0 + lane) * lds + c0 + k];
-    int bad = 0;
+    T djj = __shfl_sync(FULL, row[0], 0);
+    int bad = (!(djj > T(0)) && 0 < valid) ? 1 : 0;
+    T rs = gpg_rsqrt(djj);
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        const T djj = __shfl_sync(FULL, row[j], j);
-        bad = (bad == 0 && !(djj > T(0)) && j < valid) ? j + 1 : bad;
-        const T rs = gpg_rsqrt(djj);
-        T lij = row[j] * rs;                          // lane j: djj / sqrt(djj) = l_jj
+        const T lij = row[j] * rs;                    // lane j: djj / sqrt(djj) = l_jj
         row[j] = lij;
         if (lane == j) rdiag[j] = rs;                 // 1 / l_jj for the panel solve
         if (j < 31) {
-            colbuf[lane] = lij;
+            T *cb = colbuf + (j & 1) * 32;
+            cb[lane] = lij;
+            if (lane == j + 1) row[j + 1] = fma(-lij, lij, row[j + 1]);
+            const T dn = __shfl_sync(FULL, row[j + 1], j + 1);
+            bad = (bad == 0 && !(dn > T(0)) && j + 1 < valid) ? j + 2 : bad;
+            const T rsn = gpg_rsqrt(dn);
             __syncwarp();
 #pragma unroll
             for (int k4 = ((j + 1) / 4) * 4; k4 < 32; k4 += 4) {
                 T c[4];
                 if (sizeof(T) == 4) {
-                    const float4 v = *reinterpret_cast<const float4 *>(colbuf + k4);
+                    const float4 v = *reinterpret_cast<const float4 *>(cb + k4);
                     c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
                 } else {
-                    const double2 a = *reinterpret_cast<const double2 *>(colbuf + k4);
-                    const double2 b = *reinterpret_cast<const double2 *>(colbuf + k4 + 2);
+                    const double2 a = *reinterpret_cast<const double2 *>(cb + k4);
+                    const double2 b = *reinterpret_cast<const double2 *>(cb + k4 + 2);
                     c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
                 }
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (k4 + e > j) row[k4 + e] -= lij * c[e];     // meaningful for lane >= k only
+                for (int e = 0; e < 4; ++e) {
+                    if (k4 + e == j + 1) {
+                        if (lane != j + 1) row[j + 1] = fma(-lij, c[e], row[j + 1]);   // the owner has done its own already
+                    } else if (k4 + e > j + 1) {
+                        row[k4 + e] = fma(-lij, c[e], row[k4 + e]);     // meaningful for lane >= k only
+                    }
+                }
             }
-            __syncwarp();
+            rs = rsn;
         }
     }
 #pragma unroll
@@ -222,84 +232,89 @@ __device__ __forceinline__ int factor_tri32(T *__restrict__ S, int lds, int c0, 
     return bad;
 }
 
+// Trailing update of the blocked factorisation inside a diagonal block: the lower triangle of
+// S[base.., base..] (R = 16 TI rows) -= P P^T with P = S[base.., c0 .. c0 + 32).  256 threads as a 16 x 16 grid, each
+// TI x TI outputs (rows ty + 16 i, columns tx + 16 j); tiles strictly above the diagonal (j > i) are not computed.
+template <typename T, int TI>
+__device__ __forceinline__ void trailing_lower32(T *__restrict__ S, int lds, int base, int c0, int ty, int tx) {
+    T acc[TI][TI];
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TI; ++j) acc[i][j] = T(0);
+    const T *P = S + base * lds + c0;
+#pragma unroll 2
+    for (int k = 0; k < 32; k += 4) {
+        V4<T> a[TI], b[TI];
+#pragma unroll
+        for (int i = 0; i < TI; ++i) a[i] = ld4(P + (ty + 16 * i) * lds + k);
+#pragma unroll
+        for (int j = 0; j < TI; ++j) b[j] = ld4(P + (tx + 16 * j) * lds + k);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int i = 0; i < TI; ++i)
+#pragma unroll
+                for (int j = 0; j < TI; ++j)
+                    if (j <= i) acc[i][j] = fma(a[i].v[e], b[j].v[e], acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < TI; ++i)
+#pragma unroll
+        for (int j = 0; j < TI; ++j) {
+            const int gi = base + ty + 16 * i, gk = base + tx + 16 * j;
+            if (j <= i && gk <= gi) S[gi * lds + gk] -= acc[i][j];
+        }
+}
+
+// Blocked Cholesky of the NB x NB block held in shared memory (S: NB x (NB + 4), lower triangle; the strict upper
+// triangle must be zero).  256 threads.  Right-looking over 32-column panels: (1) warp 0 factors the 32 x 32 diagonal
+// sub-block in registers, (2) one thread per row below solves X L11^T = A21 by forward substitution, (3) all threads
+// apply the rank-32 update to the trailing lower triangle in 32 x 32 chunks.  nb: valid rows of a ragged last block.
 template <typename T, int NB>
-__global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int64_t ld, int64_t N, int64_t j0_first,
-                                                         int do_factor, T *__restrict__ inv_out, int64_t ld_inv,
-                                                         int64_t inv_block_stride, int dense_out,
-                                                         int32_t *__restrict__ info, DiagEmit em) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int LDS = NB + 4;                       // 16-byte aligned rows, 4 banks of skew per row
+__device__ __forceinline__ void diag_factor_smem(T *__restrict__ S, T *__restrict__ colbuf, T *__restrict__ rdiag, int nb,
+                                                 int64_t j0, int32_t *__restrict__ info) {
+    constexpr int LDS = NB + 4;
     constexpr int NSUB = NB / 32;
-    T *S = reinterpret_cast<T *>(smem_raw);
-    T *W = S + NB * LDS;
-    __shared__ __align__(16) T colbuf[32];
-    __shared__ __align__(16) T rdiag[32];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int tx = t & 15, ty = t >> 4;
-    const int64_t j0 = j0_first + (int64_t)blockIdx.x * NB;
-    const int nb = (int)min((int64_t)NB, N - j0);
-    T *Ab = A + j0 * ld + j0;
-    pdl_trigger();
-    pdl_wait();
-    for (int idx = t; idx < NB * NB; idx += 256) {
-        const int i = idx / NB, k = idx % NB;
-        T v = (i == k) ? T(1) : T(0);                 // identity padding of a ragged last block
-        if (i < nb && k <= i) v = Ab[(int64_t)i * ld + k];
-        S[i * LDS + k] = v;
-        W[i * LDS + k] = T(0);
-    }
-    GPG_PHASE(0);
-    __syncthreads();
-    GPG_PHASE(1);
-    if (do_factor) {
-        // right-looking over 32-column panels: (1) warp 0 factors the 32 x 32 diagonal sub-block in registers,
-        // (2) one thread per row below solves X L11^T = A21 by forward substitution, (3) all threads apply the
-        // rank-32 update to the trailing lower triangle in 32 x 32 chunks
-        for (int p = 0; p < NSUB; ++p) {
-            const int c0 = p * 32;
-            if (warp == 0) {
-                GPG_PHASE(2 + 5 * p);
-                const int bad = factor_tri32<T>(S, LDS, c0, lane, nb - c0, colbuf, rdiag);
-                if (lane == 0 && bad) atomicCAS(info, 0, (int32_t)(j0 + c0 + bad));
-                GPG_PHASE(3 + 5 * p);
-            }
-            __syncthreads();
-            const int base = c0 + 32;
-            if (base < NB) {
-                const int R = NB - base;
-                if (t < R) panel_solve32<T>(S, LDS, c0, base + t, rdiag);
-                __syncthreads();
-                GPG_PHASE(5 + 5 * p);
-                // trailing lower triangle: S[i][k] -= sum_m S[i][c0+m] S[k][c0+m]; chunk (ib, kb), kb <= ib,
-                // 32 x 32 outputs = 2 x 2 per thread.  Chunks are independent: walk them without barriers.
-                const int nchunk = R / 32;
-                for (int ib = 0; ib < nchunk; ++ib)
-                    for (int kb = 0; kb <= ib; ++kb) {
-                        T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
-                        mm_kk<T, 2, 2>(S + (base + 32 * ib) * LDS + c0, S + (base + 32 * kb) * LDS + c0, LDS, 32, acc, ty, tx);
-#pragma unroll
-                        for (int i = 0; i < 2; ++i)
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const int gi = base + 32 * ib + ty + 16 * i, gk = base + 32 * kb + tx + 16 * j;
-                                if (gk <= gi) S[gi * LDS + gk] -= acc[i][j];
-                            }
-                    }
-                __syncthreads();
-                GPG_PHASE(6 + 5 * p);
-            }
+    for (int p = 0; p < NSUB; ++p) {
+        const int c0 = p * 32;
+        if (warp == 0) {
+            GPG_PHASE(2 + 5 * p);
+            const int bad = factor_tri32<T>(S, LDS, c0, lane, nb - c0, colbuf, rdiag);
+            if (lane == 0 && bad && info) atomicCAS(info, 0, (int32_t)(j0 + c0 + bad));
+            GPG_PHASE(3 + 5 * p);
         }
-        GPG_PHASE(22);
+        __syncthreads();
+        const int base = c0 + 32;
+        if (base < NB) {
+            const int R = NB - base;
+            if (t < R) panel_solve32<T>(S, LDS, c0, base + t, rdiag);
+            __syncthreads();
+            GPG_PHASE(5 + 5 * p);
+            // trailing lower triangle: S[i][k] -= sum_m S[i][c0+m] S[k][c0+m], register tiles of R / 16 squared
+            if (R == 96) trailing_lower32<T, 6>(S, LDS, base, c0, ty, tx);
+            else if (R == 64) trailing_lower32<T, 4>(S, LDS, base, c0, ty, tx);
+            else trailing_lower32<T, 2>(S, LDS, base, c0, ty, tx);
+            __syncthreads();
+            GPG_PHASE(6 + 5 * p);
+        }
     }
-    // the inverse is computed only when somebody consumes it (the blocked Cholesky solves its panels against
-    // the factor itself and leaves all inverses to the batched trtri that follows)
-    const bool need_inv = (inv_out != nullptr) || (em.Wh != nullptr) || (em.WTh != nullptr);
-    // inverses of the NSUB diagonal 32 x 32 sub-blocks, one warp each
-    if (need_inv && warp < NSUB) invert_tri32<T>(S, W, LDS, warp * 32, lane);
+}
+
+// W = S^-1 for the lower-triangular factor in S (W must be zero on entry; both NB x (NB + 4)).  256 threads.
+// The 32 x 32 diagonal sub-blocks by forward substitution, one warp each, then recursive doubling
+// W21 = -W22 (L21 W11); the upper triangles of S and W are zero, so the products are plain dense ones.
+template <typename T, int NB>
+__device__ __forceinline__ void diag_invert_smem(const T *__restrict__ S, T *__restrict__ W) {
+    constexpr int LDS = NB + 4;
+    constexpr int NSUB = NB / 32;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int tx = t & 15, ty = t >> 4;
+    if (warp < NSUB) invert_tri32<T>(S, W, LDS, warp * 32, lane);
     __syncthreads();
-    // recursive doubling inside the block: W21 = -W22 (L21 W11); the upper triangles of S and W are zero,
-    // so the products are plain dense ones
-    if (need_inv && NB >= 64) {
+    if (NB >= 64) {
         for (int s0 = 0; s0 < NB; s0 += 64) {        // hb = 32: out(ty + 16 i, 2 tx + j)
             T acc[2][2] = {{T(0), T(0)}, {T(0), T(0)}};
             mm_kn<T, 2, 2>(S + (s0 + 32) * LDS + s0, W + s0 * LDS + s0, LDS, 32, acc, ty, tx);
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
         }
     }
     GPG_PHASE(23);
-    if (need_inv && NB >= 128) {                      // hb = 64: out(ty + 16 i, 4 tx + j)
+    if (NB >= 128) {                                  // hb = 64: out(ty + 16 i, 4 tx + j)
         T acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -345,6 +360,44 @@ __global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int6
             for (int j = 0; j < 4; ++j) W[(64 + ty + 16 * i) * LDS + 4 * tx + j] = -acc[i][j];
         __syncthreads();
     }
+}
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(256) diag_block_kernel(T *__restrict__ A, int64_t ld, int64_t N, int64_t j0_first,
+                                                         int do_factor, T *__restrict__ inv_out, int64_t ld_inv,
+                                                         int64_t inv_block_stride, int dense_out,
+                                                         int32_t *__restrict__ info, DiagEmit em) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int LDS = NB + 4;                       // 16-byte aligned rows, 4 banks of skew per row
+    T *S = reinterpret_cast<T *>(smem_raw);
+    T *W = S + NB * LDS;
+    __shared__ __align__(16) T colbuf[64];
+    __shared__ __align__(16) T rdiag[32];
+    const int t = threadIdx.x;
+    const int64_t j0 = j0_first + (int64_t)blockIdx.x * NB;
+    const int nb = (int)min((int64_t)NB, N - j0);
+    T *Ab = A + j0 * ld + j0;
+    pdl_trigger();
+    pdl_wait();
+    for (int idx = t; idx < NB * NB; idx += 256) {
+        const int i = idx / NB, k = idx % NB;
+        T v = (i == k) ? T(1) : T(0);                 // identity padding of a ragged last block
+        if (i < nb && k <= i) v = Ab[(int64_t)i * ld + k];
+        S[i * LDS + k] = v;
+        W[i * LDS + k] = T(0);
+    }
+    GPG_PHASE(0);
+    __syncthreads();
+    GPG_PHASE(1);
+    if (do_factor) {
+        diag_factor_smem<T, NB>(S, colbuf, rdiag, nb, j0, info);
+        GPG_PHASE(22);
+    }
+    // the inverse is computed only when somebody consumes it (the blocked Cholesky solves its panels against
+    // the factor itself and leaves all inverses to the batched trtri that follows)
+    const bool need_inv = (inv_out != nullptr) || (em.Wh != nullptr) || (em.WTh != nullptr);
+    if (need_inv) diag_invert_smem<T, NB>(S, W);
+    else __syncthreads();
     GPG_PHASE(24);
     static_assert(NB == 64 || NB == 128, "diag_block_kernel handles NB = 64 or 128");
     // Outputs, four consecutive columns per thread: factor block (fp32 + fp16 hi/lo), inverse block (fp32 +

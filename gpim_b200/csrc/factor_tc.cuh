@@ -122,7 +122,6 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
                                float *dinv, TcPlanes Ls, const float *scales, cudaStream_t stream,
                                TcPlanes As = TcPlanes(), TcPlanes Ws = TcPlanes()) {
     constexpr int NB = 128;
-    const int64_t NB2 = h->opt_outer_panel;
     static bool attr_set = false;
     if (!attr_set) {
         GPG_CUDA_CHECK(cudaFuncSetAttribute(diag_block_kernel<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -130,13 +129,21 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
         GPG_CUDA_CHECK(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_trsm_smem()));
         attr_set = true;
     }
-    const int panel_mode = h->opt_panel_mode == 1 && !(As.hi && Ws.hi) ? 2 : h->opt_panel_mode;
+    int panel_mode = h->opt_panel_mode;
+    // mode 3 needs the W planes, 16-byte aligned fp32 rows and a device on which the cooperative grid fits
+    if (panel_mode == 3 && !(Ws.hi && (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && h->sm_count >= 4))
+        panel_mode = 1;
+    if (panel_mode == 1 && !(As.hi && Ws.hi)) panel_mode = 2;
+    // the cooperative panel keeps the update sums of one row block in the 512 TMEM columns: at most 4 block columns
+    const int64_t NB2 = panel_mode == 3 ? std::min<int64_t>(h->opt_outer_panel, 512) : h->opt_outer_panel;
     if (reset_info) GPG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
-    auto syrk = [&](int64_t row0, int64_t col0, int64_t k0, int64_t rows, int64_t cols, int64_t kk) -> int {
+    auto syrk = [&](int64_t row0, int64_t col0, int64_t k0, int64_t rows, int64_t cols, int64_t kk,
+                    cudaStream_t on = nullptr, int max_ctas = 0) -> int {
         // A[row0.., col0..] -= L[row0.., k0..k0+kk) L[col0.., k0..k0+kk)^T on the tiles that touch row >= col
         if (rows <= 0 || cols <= 0) return GPG_OK;
         tc::Launch g;
         tc_params_clear(g);
+        g.max_ctas = max_ctas;
         g.A.hi = Ls.hi; g.A.lo = Ls.lo; g.A.rows = N; g.A.cols = N; g.A.ld = ld;
         g.B = g.A;
         g.p.M = (int)rows; g.p.N = (int)cols; g.p.K = (int)kk; g.p.batch = 1;
@@ -152,10 +159,75 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
             g.p.s_ncols = NB;
             g.p.scale_out = scales + SC_A;
         }
-        return tc::launch(h, g, stream);
+        return tc::launch(h, g, on ? on : stream);
     };
+    bool side_pending = false;
     for (int64_t J0 = 0; J0 < N; J0 += NB2) {
         const int64_t Jend = std::min<int64_t>(N, J0 + NB2);
+        if (panel_mode == 3) {
+            // the whole column panel (diagonal blocks, panel products, updates inside the panel) in ONE cooperative
+            // kernel with a device-side dependency chain (chol_panel.cuh); then the K = panel-width update of the rest
+            const int64_t nbp = (Jend - J0 + NB - 1) / NB;
+            const int64_t rows_blk = (N - J0 + NB - 1) / NB;                  // row blocks including the diagonal one
+            if (rows_blk <= 1) {                                              // a lone last block: nothing below it
+                DiagEmit em;
+                em.Lh = Ls.hi; em.Ll = Ls.lo; em.lds = ld; em.scale_L = scales + SC_L;
+                diag_block_kernel<float, NB><<<1, 256, diag_block_smem<float, NB>(), stream>>>(
+                    A, ld, N, J0, 1, (float *)nullptr, (int64_t)NB, (int64_t)0, 1, info, em);
+                GPG_LAUNCH_CHECK(h);
+                break;
+            }
+            cpanel::Args pa;
+            pa.A = A; pa.ld = ld; pa.N = N; pa.J0 = J0; pa.nbp = (int)std::min<int64_t>(nbp, 4);
+            pa.Ls_hi = Ls.hi; pa.Ls_lo = Ls.lo; pa.Ws_hi = Ws.hi; pa.Ws_lo = Ws.lo;
+            pa.scales = scales; pa.sc_A = SC_A; pa.sc_W = SC_W; pa.sc_L = SC_L; pa.sc_inv_AW = SC_INV_AW; pa.sc_inv_LL = SC_INV_LL;
+            pa.info = info;
+            GPG_TRY(gpg_tc_counters(h, stream, cpanel::NFLAGS, &pa.flags));
+            CUtensorMap mLhi, mLlo, mWhi, mWlo;
+            GPG_TRY(tc::make_tensor_map(&mLhi, Ls.hi, N, N, ld, NB));
+            GPG_TRY(tc::make_tensor_map(&mLlo, Ls.lo, N, N, ld, NB));
+            GPG_TRY(tc::make_tensor_map(&mWhi, Ws.hi, N, N, ld, NB));
+            GPG_TRY(tc::make_tensor_map(&mWlo, Ws.lo, N, N, ld, NB));
+            // chain + workers.  With look-ahead the rest of the trailing update of the PREVIOUS panel runs next to this
+            // kernel on the side stream, so the workers are capped at half the SMs (a worker then owns several row blocks)
+            // Look-ahead pays where the chain dominates, i.e. once one worker per row block leaves at least half of the
+            // SMs to the side stream; further up the matrix the trailing update is the bulk of the work, wants every
+            // SM, and runs in stream order.
+            const int64_t rest = N - Jend - NB2;                              // trailing columns beyond the next panel
+            const bool small = rows_blk - 1 <= h->sm_count / 2;
+            const bool ahead = h->opt_lookahead && small && rest > 0;
+            int wcap = h->opt_panel_workers > 0 ? h->opt_panel_workers : h->sm_count - 1;
+            wcap = std::max(3, std::min(wcap, h->sm_count - 1));
+            const int grid = 1 + (int)std::min<int64_t>(rows_blk - 1, wcap);
+            void *kargs[] = {&mLhi, &mLlo, &mWhi, &mWlo, &pa};
+            GPG_CUDA_CHECK(cudaLaunchCooperativeKernel((const void *)cpanel::chol_panel_kernel, dim3(grid), dim3(cpanel::NUM_THREADS),
+                                                       kargs, (size_t)cpanel::SMEM_BYTES, stream));
+            GPG_LAUNCH_CHECK(h);
+            if (!ahead && !side_pending) {
+                GPG_TRY(syrk(Jend, Jend, J0, N - Jend, N - Jend, Jend - J0));
+                continue;
+            }
+            if (!h->side_stream) {
+                GPG_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+                GPG_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+                GPG_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
+            }
+            if (ahead) {           // the rest, K = panel width, on the side stream as soon as this panel is done ...
+                GPG_CUDA_CHECK(cudaEventRecord(h->ev_fork, stream));
+                GPG_CUDA_CHECK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+            }
+            // ... the next panel's columns here -- after the previous panel's rest, which writes the same tiles
+            if (side_pending) GPG_CUDA_CHECK(cudaStreamWaitEvent(stream, h->ev_side, 0));
+            GPG_TRY(syrk(Jend, Jend, J0, N - Jend, std::min<int64_t>(NB2, N - Jend), Jend - J0));
+            if (ahead) {
+                // next to it runs the NEXT panel's kernel: chain + one worker per row block below Jend
+                const int next_grid = 1 + (int)std::min<int64_t>((N - Jend + NB - 1) / NB - 1, wcap);
+                GPG_TRY(syrk(Jend + NB2, Jend + NB2, J0, rest, rest, Jend - J0, h->side_stream, std::max(16, h->sm_count - next_grid)));
+                GPG_CUDA_CHECK(cudaEventRecord(h->ev_side, h->side_stream));
+                side_pending = true;
+            }
+            continue;
+        }
         // inner update after the panel of block column j0.  Right-looking (opt_inner_left == 0): all remaining
         // columns of the outer panel, K = nb.  Left-looking (default): only the NEXT block column, but with the
         // contributions of every inner panel so far (K = j0 + nb - J0) -- half the epilogue per step and a third
@@ -219,6 +291,7 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
         // outer update: everything right of the panel, K = panel width
         GPG_TRY(syrk(Jend, Jend, J0, N - Jend, N - Jend, Jend - J0));
     }
+    if (side_pending) GPG_CUDA_CHECK(cudaStreamWaitEvent(stream, h->ev_side, 0));
     return GPG_OK;
 }
 

@@ -81,6 +81,7 @@ struct Params {
     const float *scale_out;      // device scalar multiplied into the emitted splits
     int *tile_counter;           // zero before launch
     const int *krange;           // optional: per m-tile [lo, hi) of the k indices where operand A is non-negligible
+    unsigned long long *work_counter;   // optional: += number of (tile, k-block) pairs executed (one atomic per CTA)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -237,6 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
             int stage = 0; uint32_t phase = 0;
             int slot = 0; uint32_t sphase = 0;
+            unsigned long long kblocks = 0;
             while (true) {
                 mbar_wait(BAR(BAR_SEMPTY + slot), sphase ^ 1);
                 const int t = atomicAdd(p.tile_counter, 1);
@@ -250,6 +252,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 const int acol = p.a_col0 + ti.batch * (p.a_bs + p.a_kbs);
                 const int brow = p.b_row0 + ti.batch * p.b_bs + ti.nblk * BN;
                 const int bcol = p.b_col0 + ti.batch * (p.b_bs + p.b_kbs);
+                kblocks += (unsigned long long)(ti.ke_blk - ti.kb_blk);
                 for (int kb = ti.kb_blk; kb < ti.ke_blk; ++kb) {
                     mbar_wait(BAR(BAR_EMPTY + stage), phase ^ 1);
                     const uint32_t sbase = tiles + (uint32_t)stage * STAGE_BYTES;
@@ -261,6 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+            if (p.work_counter && kblocks) atomicAdd(p.work_counter, kblocks);
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -532,6 +536,7 @@ struct SplitMat {
 struct Launch {
     SplitMat A, B;
     Params p;
+    int max_ctas = 0;            // > 0: cap of the persistent grid (leave SMs to a kernel running next to this one)
 };
 
 inline int launch(gpg_handle_s *h, Launch &L, cudaStream_t stream) {
@@ -552,7 +557,7 @@ inline int launch(gpg_handle_s *h, Launch &L, cudaStream_t stream) {
     GPG_TRY(make_tensor_map(&mBlo, L.B.lo, L.B.rows, L.B.cols, L.B.ld, BN));
     GPG_TRY(gpg_tc_counter(h, stream, &p.tile_counter));
     const long long total = (long long)p.tiles_m * p.tiles_n * p.batch;
-    const int grid = (int)std::min<long long>(total, h->sm_count);
+    const int grid = (int)std::min<long long>(total, L.max_ctas > 0 ? std::min(L.max_ctas, h->sm_count) : h->sm_count);
     GPG_CUDA_CHECK(launch_pdl(gemm_tc_kernel, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, mAhi, mAlo, mBhi, mBlo, p));
     GPG_LAUNCH_CHECK(h);
     return GPG_OK;

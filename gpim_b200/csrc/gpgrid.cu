@@ -10,6 +10,7 @@
 #include "gemm_tc.cuh"
 #include "kmat.cuh"
 #include "factor.cuh"
+#include "chol_panel.cuh"
 #include "factor_tc.cuh"
 #include "train.cuh"
 #include "acq.cuh"
@@ -56,19 +57,26 @@ int gpg_gemv_part_reserve(gpg_handle_s *h, size_t elems, double **out) {
     return GPG_OK;
 }
 
-int gpg_tc_counter(gpg_handle_s *h, cudaStream_t stream, int **out) {
+int gpg_tc_counters(gpg_handle_s *h, cudaStream_t stream, int n, int **out) {
     constexpr int POOL = 8192;
-    if (!h->tc_counters) {
-        GPG_CUDA_CHECK(cudaMalloc(&h->tc_counters, POOL * sizeof(int)));
-        h->tc_counter_pos = POOL;
+    // one pool per stream the library launches on: the pool is re-zeroed stream-ordered when it wraps, which is only
+    // ordered against launches of the SAME stream
+    const int which = (h->side_stream != nullptr && stream == h->side_stream) ? 1 : 0;
+    int *&pool = which ? h->tc_counters_side : h->tc_counters;
+    int &pos = which ? h->tc_counter_pos_side : h->tc_counter_pos;
+    if (!pool) {
+        GPG_CUDA_CHECK(cudaMalloc(&pool, POOL * sizeof(int)));
+        pos = POOL;
     }
-    if (h->tc_counter_pos >= POOL) {
-        GPG_CUDA_CHECK(cudaMemsetAsync(h->tc_counters, 0, POOL * sizeof(int), stream));
-        h->tc_counter_pos = 0;
+    if (pos + n > POOL) {
+        GPG_CUDA_CHECK(cudaMemsetAsync(pool, 0, POOL * sizeof(int), stream));
+        pos = 0;
     }
-    *out = h->tc_counters + h->tc_counter_pos++;
+    *out = pool + pos;
+    pos += n;
     return GPG_OK;
 }
+int gpg_tc_counter(gpg_handle_s *h, cudaStream_t stream, int **out) { return gpg_tc_counters(h, stream, 1, out); }
 
 struct Bump {            // carve a reserved workspace into aligned pieces
     unsigned char *base;
@@ -99,6 +107,7 @@ static int set_function_attributes() {
                                         diag_block_smem<double, 64>()));
     GPG_CUDA_CHECK(cudaFuncSetAttribute(panel_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, panel_trsm_smem()));
     GPG_CUDA_CHECK(cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+    GPG_CUDA_CHECK(cudaFuncSetAttribute(cpanel::chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cpanel::SMEM_BYTES));
     GPG_CUDA_CHECK(cudaFuncSetAttribute(topk_round_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         2048 * (int)sizeof(Cand<float>)));
     GPG_CUDA_CHECK(cudaFuncSetAttribute(topk_round_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -131,8 +140,13 @@ extern "C" int gpg_destroy(gpg_handle_t h) {
     gpg_comm_destroy(h);
     if (h->ws) cudaFree(h->ws);
     if (h->tc_counters) cudaFree(h->tc_counters);
+    if (h->tc_counters_side) cudaFree(h->tc_counters_side);
+    if (h->work_counter) cudaFree(h->work_counter);
     if (h->gemv_part) cudaFree(h->gemv_part);
     if (h->fit_stream) cudaStreamDestroy(h->fit_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_side) cudaEventDestroy(h->ev_side);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.beg); cudaEventDestroy(sp.end); }
     for (auto &e : h->event_pool) cudaEventDestroy(e);
     delete h;
@@ -149,9 +163,11 @@ extern "C" int gpg_set_option(gpg_handle_t h, int key, long long value) {
         case GPG_OPT_INNER_LEFT: h->opt_inner_left = value != 0; break;
         case GPG_OPT_COMPACT_SUPPORT: h->opt_compact_support = value != 0; break;
         case GPG_OPT_OUTER_PANEL: GPG_REQUIRE(value >= 128 && value % 128 == 0, "outer panel: a multiple of 128"); h->opt_outer_panel = (int)value; break;
-        case GPG_OPT_PANEL_MODE: GPG_REQUIRE(value >= 0 && value <= 2, "panel mode 0..2"); h->opt_panel_mode = (int)value; break;
+        case GPG_OPT_PANEL_MODE: GPG_REQUIRE(value >= 0 && value <= 3, "panel mode 0..3"); h->opt_panel_mode = (int)value; break;
         case GPG_OPT_FACTOR_ALGO: GPG_REQUIRE(value == 0 || value == 1, "factor algorithm 0..1"); h->opt_factor_algo = (int)value; break;
         case GPG_OPT_PANEL_REFINE: h->opt_panel_refine = value != 0; break;
+        case GPG_OPT_LOOKAHEAD: h->opt_lookahead = value != 0; break;
+        case GPG_OPT_PANEL_WORKERS: GPG_REQUIRE(value >= 0, "panel workers >= 0"); h->opt_panel_workers = (int)value; break;
         case GPG_OPT_SYRK_CHUNK: GPG_REQUIRE(value >= 0 && value % 64 == 0, "chunk must be a multiple of 64"); h->opt_syrk_chunk = (int)value; break;
         default: gpg_set_error("unknown option %d", key); return GPG_EINVAL;
     }
@@ -177,6 +193,19 @@ extern "C" int gpg_stage_times(gpg_handle_t h, double *ms_host, long long *spans
 }
 
 extern "C" long long gpg_launch_count(gpg_handle_t h) { return h ? h->launches : -1; }
+
+extern "C" int gpg_variance_gemm_macs(gpg_handle_t h, double *macs_host) {
+    GPG_REQUIRE(h && macs_host, "NULL argument");
+    DeviceGuard device_guard(h->device);
+    *macs_host = 0.0;
+    if (!h->work_counter) return GPG_OK;
+    GPG_CUDA_CHECK(cudaDeviceSynchronize());
+    unsigned long long kb = 0;
+    GPG_CUDA_CHECK(cudaMemcpy(&kb, h->work_counter, sizeof(kb), cudaMemcpyDeviceToHost));
+    GPG_CUDA_CHECK(cudaMemset(h->work_counter, 0, sizeof(kb)));
+    *macs_host = (double)kb * (double)tc::BM * (double)tc::BN * (double)tc::BK;
+    return GPG_OK;
+}
 extern "C" size_t gpg_workspace_bytes(gpg_handle_t h) { return h ? h->ws_bytes : 0; }
 
 // ---------------------------------------------------------------------------------------------
@@ -638,6 +667,13 @@ static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, c
                     g.p.scale_inv = scales + 2;
                     g.p.part = part + (r0 / tc::BN) * chunk; g.p.ldpart = chunk;
                     g.p.krange = krange;
+                    if (h->opt_stage_timing) {
+                        if (!h->work_counter) {
+                            GPG_CUDA_CHECK(cudaMalloc(&h->work_counter, sizeof(unsigned long long)));
+                            GPG_CUDA_CHECK(cudaMemsetAsync(h->work_counter, 0, sizeof(unsigned long long), s));
+                        }
+                        g.p.work_counter = h->work_counter;
+                    }
                     GPG_TRY(tc::launch(h, g, s));
                 }
                 r0 = r1;

@@ -51,16 +51,25 @@ enum {
                                      batched triangular inverse; 1 recursive Cholesky + inverse */
     GPG_OPT_FIT_GRAPH = 7,        /* gpg_fit_adam on small problems (SIMT path): replay one captured iteration as a CUDA
                                      graph (default 1) */
-    GPG_OPT_PANEL_MODE = 8,       /* blocked Cholesky panel: 0 forward substitution against the diagonal factor, 1 (default)
-                                     tcgen05 GEMM through the block inverse, 2 SIMT GEMM through the block inverse */
+    GPG_OPT_PANEL_MODE = 8,       /* blocked Cholesky panel: 0 forward substitution against the diagonal factor, 1 tcgen05
+                                     GEMM through the block inverse, 2 SIMT GEMM through the block inverse, 3 (default) the
+                                     whole 512-column panel as one cooperative kernel with a device-side dependency
+                                     chain: diagonal blocks on one CTA, panel products and updates of every row block on
+                                     tcgen05 with the update sums held in tensor memory (chol_panel.cuh) */
     GPG_OPT_OUTER_PANEL = 9,      /* blocked Cholesky: width of the outer panel (multiple of 128; default 512 -- wider is a
                                      few per cent faster at N > 15 000 but doubles the TMEM accumulation bias of the update) */
-    GPG_OPT_COMPACT_SUPPORT = 10, /* gpg_predict, tcgen05 path (default 0 = dense): per 128-row tile of test points, restrict
-                                     the variance GEMM to the contiguous range of training rows whose covariance with the
-                                     tile exceeds 1e-14 x variance (what lies outside contributes below fp32 resolution);
-                                     pays off for lengthscales much shorter than the grid with row-major training rows */
-    GPG_OPT_INNER_LEFT = 11       /* blocked Cholesky, update inside the outer panel: 1 (default) left-looking (next block
+    GPG_OPT_COMPACT_SUPPORT = 10, /* gpg_predict, tcgen05 path (default 1; 0 = always dense): per 128-row tile of test points,
+                                     restrict the variance GEMM to the contiguous range of training rows whose covariance
+                                     with the tile exceeds 1e-14 x variance (what lies outside contributes below fp32
+                                     resolution, whatever theta is: |L^-1_ij| <= (noise + jitter)^-1/2).  The range is found
+                                     on the device while K* is assembled, so the policy is automatic: a tile whose support
+                                     is everything (long lengthscales, unordered training rows) runs the dense product */
+    GPG_OPT_INNER_LEFT = 11,      /* blocked Cholesky, update inside the outer panel: 1 (default) left-looking (next block
                                      column only, all inner panels so far), 0 right-looking (all remaining columns) */
+    GPG_OPT_LOOKAHEAD = 12,       /* blocked Cholesky with the cooperative panel (panel mode 3): 1 (default) the trailing
+                                     update of an outer panel is split -- the next panel's columns first, on the caller's
+                                     stream; the rest on a side stream with a capped grid, UNDER the next panel's chain */
+    GPG_OPT_PANEL_WORKERS = 13    /* cooperative panel: cap on the number of worker CTAs (0 = auto) */
 };
 /* stages reported by gpg_stage_times */
 enum {
@@ -85,6 +94,11 @@ int gpg_destroy(gpg_handle_t h);
 int gpg_set_option(gpg_handle_t h, int key, long long value);
 /* number of kernel launches this handle has enqueued since creation (bench.py gpu_launches) */
 long long gpg_launch_count(gpg_handle_t h);
+/* Multiply-accumulates (at tile granularity: 128 x 256 x 32 per executed k-block, algorithmic MACs -- the tensor
+ * pipe executes three fp16 MMAs for each) the variance GEMM of gpg_predict has executed while GPG_OPT_STAGE_TIMING
+ * was on, since the last call; synchronises the device and clears the count.  With GPG_OPT_COMPACT_SUPPORT this is
+ * what the kernel really did, as opposed to the dense N^2 / 2 per test point. */
+int gpg_variance_gemm_macs(gpg_handle_t h, double *macs_host);
 /* bytes of device workspace currently owned by the handle */
 size_t gpg_workspace_bytes(gpg_handle_t h);
 /* Synchronises the device, then adds up the CUDA-event spans recorded since the last call:

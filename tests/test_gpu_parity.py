@@ -181,11 +181,12 @@ def test_predict_3d_matern(eng):
     assert relinf(m.cpu(), ref_mean) < 1e-4 and relinf(s.cpu(), ref_sd) < 1e-3
 
 
-@pytest.mark.parametrize("n", [64, 128, 129, 257, 700, 1024, 1111, 2500])
-@pytest.mark.parametrize("algo", [0, 1, 2, 3])
+@pytest.mark.parametrize("n", [64, 128, 129, 257, 511, 513, 700, 1024, 1111, 2500, 5000])
+@pytest.mark.parametrize("algo", [0, 1, 2, 3, 4])
 def test_factorize_tensor_core(eng, n, algo):
     """gpg_factorize on the forced tcgen05 path (algo 0: two-level blocked Cholesky + batched inverse, tcgen05
-    panel; 1: recursive Cholesky + inverse; 2 / 3: blocked with the forward-substitution / SIMT panel):
+    panel; 1: recursive Cholesky + inverse; 2 / 3: blocked with the forward-substitution / SIMT panel; 4: the
+    DEFAULT -- the cooperative panel kernel with its device-side dependency chain, chol_panel.cuh):
     L, L^-1, its fp16 hi/lo planes, alpha and logdet against numpy fp64 on ragged sizes."""
     from gpim_b200._lib import KERNEL_IDS, OPT_GEMM_PATH
     X = rand_points(n, 2, n, scale=40.0)
@@ -198,20 +199,20 @@ def test_factorize_tensor_core(eng, n, algo):
     th = torch.tensor([v, noise, 1.0, *ls], dtype=torch.float32).cuda()
     eng.set_option(OPT_GEMM_PATH, 2)
     eng.set_option(6, 1 if algo == 1 else 0)      # GPG_OPT_FACTOR_ALGO: 0 blocked, 1 recursive
-    eng.set_option(8, {0: 1, 1: 1, 2: 0, 3: 2}[algo])   # GPG_OPT_PANEL_MODE of the blocked algorithm: tcgen05 / trsm / SIMT
+    eng.set_option(8, {0: 1, 1: 1, 2: 0, 3: 2, 4: 3}[algo])   # GPG_OPT_PANEL_MODE: tcgen05 / trsm / SIMT / cooperative panel
     try:
         fac = eng.factorize(KERNEL_IDS["RBF"], th, torch.tensor(X, dtype=torch.float32).cuda(),
                             torch.tensor(y, dtype=torch.float32).cuda(), jitter)
     finally:
         eng.set_option(OPT_GEMM_PATH, 0)
         eng.set_option(6, 0)
-        eng.set_option(8, 1)
+        eng.set_option(8, 3)
     assert int(fac["info"].item()) == 0
     L = torch.tril(fac["L"][:, :n]).cpu().double().numpy()
     Li = fac["Linv"][:, :n].cpu().double().numpy()
     assert relinf(L, Lref) < 1e-4          # panels go through explicit inverses of the leading blocks
     assert np.abs(np.triu(Li, 1)).max() == 0.0
-    assert np.abs(Li @ Lref - np.eye(n)).max() < 2e-4
+    assert np.abs(Li @ Lref - np.eye(n)).max() < (2e-4 if algo != 1 else 5e-4)   # the recursive variant is the less accurate
     sc = fac["scales"].cpu().numpy()
     planes = fac["wsplit"][:, :, :n].cpu().double().numpy()
     Ws = (planes[0] + planes[1]) / sc[1]
@@ -272,8 +273,8 @@ def test_predict_4d_inputs(eng, kernel, n):
 
 @pytest.mark.parametrize("kernel,ls", [("RBF", 3.0), ("RBF", 40.0), ("Matern52", 2.0)])
 def test_predict_compact_support_option_is_exact(eng, kernel, ls):
-    """GPG_OPT_COMPACT_SUPPORT restricts the variance GEMM of each 128-row tile of test points to the training
-    rows whose covariance with the tile exceeds 1e-14 x variance: same mean (bit-identical, the mean does not go
+    """GPG_OPT_COMPACT_SUPPORT (default on) restricts the variance GEMM of each 128-row tile of test points to the
+    training rows whose covariance with the tile exceeds 1e-14 x variance; against the dense product (option 0): same mean (bit-identical, the mean does not go
     through the GEMM) and the same sd to fp32 rounding, for a short lengthscale (most of K* negligible), a long
     one (nothing negligible) and a slowly decaying kernel."""
     from gpim_b200._lib import KERNEL_IDS, OPT_COMPACT_SUPPORT
@@ -285,13 +286,13 @@ def test_predict_compact_support_option_is_exact(eng, kernel, ls):
     assert int(fac["info"].item()) == 0
     Xf = torch.tensor(O.to_rows(O.full_grid(R)), dtype=torch.float32).cuda()
     Xf[77, 0] = float("nan")
-    m0, s0 = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, Xf)
-    eng.set_option(OPT_COMPACT_SUPPORT, 1)
+    eng.set_option(OPT_COMPACT_SUPPORT, 0)                                        # the dense product
     try:
-        m1, s1 = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, Xf)
-        m2, s2 = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, Xf[:1000])          # ragged last tile
+        m0, s0 = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, Xf)
     finally:
-        eng.set_option(OPT_COMPACT_SUPPORT, 0)
+        eng.set_option(OPT_COMPACT_SUPPORT, 1)                                    # the default
+    m1, s1 = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, Xf)
+    m2, s2 = eng.predict(KERNEL_IDS[kernel], th, Xd, fac, Xf[:1000])              # ragged last tile
     ok = ~torch.isnan(m0)
     assert bool(torch.isnan(s1[~ok]).all()) and torch.equal(m0[ok], m1[ok])
     assert relinf(s1[ok].cpu(), s0[ok].cpu()) < 2e-6
