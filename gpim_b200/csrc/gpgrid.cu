@@ -620,29 +620,34 @@ static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, c
     const int tiles_n = (int)((N + tc::BN - 1) / tc::BN);
     void *ws;
     const int mtiles = (int)(chunk / tc::BM);
+    const int nblk32 = (int)((N + 31) / 32);
     GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)chunk * ldh * 2, (size_t)chunk * ldh * 2,
-                                         (size_t)tiles_n * chunk * sizeof(float), 2 * (size_t)mtiles * sizeof(int)}), &ws));
+                                         (size_t)tiles_n * chunk * sizeof(float), 2 * (size_t)mtiles * sizeof(int),
+                                         (size_t)nblk32 * 2 * D * sizeof(float)}), &ws));
     Bump b(ws);
     __half *Khi = b.take<__half>((size_t)chunk * ldh);
     __half *Klo = b.take<__half>((size_t)chunk * ldh);
     float *part = b.take<float>((size_t)tiles_n * chunk);
     int *krange = h->opt_compact_support ? b.take<int>(2 * (size_t)mtiles) : nullptr;
+    float *bbox = h->opt_compact_support ? b.take<float>((size_t)nblk32 * 2 * D) : nullptr;
+    if (bbox) {                      // boxes of 32-row blocks of X: what the K* kernel derives the support ranges from
+        StageTimer st(h, GPG_ST_KCROSS, s);
+        block_bbox_kernel<float, D><<<(unsigned)((nblk32 + 7) / 8), 256, 0, s>>>(X, N, bbox);
+        GPG_LAUNCH_CHECK(h);
+    }
     // A-operand groups sized to stay L2-resident while the n-blocks sweep over them
     const int m_group = (int)std::max<int64_t>(1, ((int64_t)64 << 20) / (tc::BM * ldh * 4));
     for (int64_t c0 = 0; c0 < M; c0 += chunk) {
         const int64_t mc = std::min<int64_t>(chunk, M - c0);
         TestPoints<float, D> tpc = tp;
         if (tpc.Xs) tpc.Xs += c0 * D; else tpc.j0 += c0;
-        if (krange) {                // tiles outside every support range are skipped: their partial sums must read zero
-            krange_init_kernel<<<(mtiles + 255) / 256, 256, 0, s>>>(krange, mtiles);
-            GPG_LAUNCH_CHECK(h);
+        if (krange)                  // n-blocks outside a tile's support range are skipped: their partial sums must read zero
             GPG_CUDA_CHECK(cudaMemsetAsync(part, 0, (size_t)tiles_n * chunk * sizeof(float), s));
-        }
         {
             StageTimer st(h, GPG_ST_KCROSS, s);
             GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<float, KID, D, true><<<(unsigned)((mc + 7) / 8), 256, 0, s>>>(
                                             theta, X, N, tpc, mc, alpha, nullptr, 0, Khi, Klo, ldh, scales, mean + c0,
-                                            nullptr, 0.f, krange, 1e-14f));
+                                            nullptr, 0.f, krange, 1e-14f, bbox, nblk32));
             GPG_LAUNCH_CHECK(h);
         }
         {

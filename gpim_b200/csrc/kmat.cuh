@@ -104,6 +104,51 @@ __global__ void __launch_bounds__(256) kmat_kernel(const T *__restrict__ theta, 
     }
 }
 
+// Squared lengthscale-scaled distance beyond which k(r2) < rel * variance (compact support of K* at fp32 resolution).
+template <typename T, int KID>
+__device__ __forceinline__ float support_r2(const Theta<T> &th, float rel) {
+    const float lt = -logf(rel);                         // > 0
+    if (KID == GPG_RBF) return 2.0f * lt;
+    if (KID == GPG_MATERN52) {                           // (1 + s + s^2 / 3) exp(-s) = rel, s = sqrt(5) r: Newton on the log
+        float s = lt + 8.0f;
+#pragma unroll
+        for (int it = 0; it < 6; ++it) {
+            const float q = 1.0f + s + s * s * (1.0f / 3.0f);
+            const float f = logf(q) - s + lt, df = (1.0f + s * (2.0f / 3.0f)) / q - 1.0f;
+            s -= f / df;
+        }
+        return s * s * 0.2f;
+    }
+    const float a = (float)th.alpha;                     // (1 + r2 / (2 a))^-a = rel
+    const float e = lt / a;
+    return e > 80.0f ? 3.0e38f : 2.0f * a * (expf(e) - 1.0f);
+}
+
+// Bounding boxes of the training rows in blocks of 32 consecutive rows: bbox[b][0..D) = min, [D..2D) = max.
+template <typename T, int D>
+__global__ void __launch_bounds__(256) block_bbox_kernel(const T *__restrict__ X, int64_t N, float *__restrict__ bbox) {
+    const int lane = threadIdx.x & 31;
+    const int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (b * 32 >= N) return;
+    const int64_t i = b * 32 + lane;
+    float lo[D], hi[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        const float v = i < N ? (float)X[i * D + k] : 0.f;
+        lo[k] = i < N ? v : 3.0e38f;
+        hi[k] = i < N ? v : -3.0e38f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) { bbox[b * 2 * D + k] = lo[k]; bbox[b * 2 * D + D + k] = hi[k]; }
+    }
+}
+
 // K2: rows of the cross-kernel for test points j in [0, mc): Ks[j*ldk + i] = k(Xs_j, X_i), and
 // mean[j] = sum_i Ks[j][i] * alpha[i].  One warp per test point, lanes sweep i four at a time.
 // Test points with a NaN coordinate get a zero row (so the variance GEMM stays finite) and
@@ -118,7 +163,8 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                                                           __half *__restrict__ Khi, __half *__restrict__ Klo, int64_t ldh,
                                                           const float *__restrict__ scale_ptr, T *__restrict__ mean,
                                                           const T *__restrict__ y_resid = nullptr, T jitter = T(0),
-                                                          int *__restrict__ krange = nullptr, float support_rel = 0.f) {
+                                                          int *__restrict__ krange = nullptr, float support_rel = 0.f,
+                                                          const float *__restrict__ bbox = nullptr, int nblk32 = 0) {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (j >= mc) return;
@@ -133,12 +179,64 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
     double accd = 0.0;
     float acc_s = 0.f, acc_c = 0.f;
     const float scale = SPLIT ? *scale_ptr : 1.0f;
-    // compact support (optional): per 128-row tile of test points, the range [lo, hi) of training indices whose
-    // covariance exceeds support_rel * variance; everything outside contributes below fp32 resolution
-    const float support_thr = support_rel * (float)th.variance;
-    int sup_lo = 0x7fffffff, sup_hi = 0;
     // row padding [N, ldk) (and [N, ldh)) is zero-filled so K-tiles may over-read it
     const int64_t width = SPLIT ? ldh : (Ks ? ldk : N);
+    // Compact support (optional, SPLIT only): the contiguous range of training rows that can have a covariance above
+    // support_rel * variance with ANY of the 128 test points of this row's tile -- found geometrically, from the
+    // tile's bounding box against the boxes of 32-row blocks of X (conservative: box distance <= point distance).
+    // Everything outside contributes below fp32 resolution; it is neither evaluated nor written nor read by the
+    // variance GEMM (krange), and the warps of a tile all derive the same range.
+    int64_t c_lo = 0, c_hi = width;
+    if (SPLIT && krange) {
+        const int64_t tile0 = (j / 128) * 128;
+        float blo[D], bhi[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) { blo[k] = 3.0e38f; bhi[k] = -3.0e38f; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t jj = tile0 + lane + 32 * q;
+            if (jj < mc) {
+                T zz[D];
+                tp.load(jj, zz);
+                bool nanp = false;
+#pragma unroll
+                for (int k = 0; k < D; ++k) nanp |= (zz[k] != zz[k]);
+                if (!nanp) {
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { blo[k] = fminf(blo[k], (float)zz[k]); bhi[k] = fmaxf(bhi[k], (float)zz[k]); }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                blo[k] = fminf(blo[k], __shfl_xor_sync(0xffffffffu, blo[k], o));
+                bhi[k] = fmaxf(bhi[k], __shfl_xor_sync(0xffffffffu, bhi[k], o));
+            }
+        const float r2max = 1.02f * support_r2<T, KID>(th, support_rel);
+        int first = 0x7fffffff, last = 0;
+        for (int b = lane; b < nblk32; b += 32) {
+            float d2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float gap = fmaxf(0.f, fmaxf(bbox[b * 2 * D + k] - bhi[k], blo[k] - bbox[b * 2 * D + D + k])) * (float)th.inv_ls[k];
+                d2 += gap * gap;
+            }
+            if (d2 < r2max) { first = min(first, b); last = max(last, b + 1); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        }
+        if (last <= first) { c_lo = 0; c_hi = 0; }
+        else {
+            c_lo = ((int64_t)first * 32 / 128) * 128;
+            c_hi = min(width, (((int64_t)last * 32 + 127) / 128) * 128);
+        }
+        if (lane == 0) { krange[2 * (j / 128)] = (int)c_lo; krange[2 * (j / 128) + 1] = (int)min(c_hi, N); }
+    }
     __half *__restrict__ hrow = SPLIT ? Khi + j * ldh : nullptr;
     __half *__restrict__ lrow = SPLIT ? Klo + j * ldh : nullptr;
     T *__restrict__ krow = (!SPLIT && Ks) ? Ks + j * ldk : nullptr;
@@ -146,7 +244,7 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                           (reinterpret_cast<uintptr_t>(alpha) & 7) == 0 && !bad);
     // lane owns the column pairs i0 + 2 lane + {0, 1} and i0 + 64 + 2 lane + {0, 1}: coordinates, alpha and the
     // fp16 planes are all touched with unit stride across the warp (128-bit / 64-bit / 32-bit per lane)
-    for (int64_t i0 = 0; i0 < width; i0 += 128) {
+    for (int64_t i0 = c_lo; i0 < c_hi; i0 += 128) {
         T v[4];
         if (fast_ok && i0 + 128 <= N) {
 #pragma unroll
@@ -189,16 +287,6 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                 v[c] = val;
             }
         }
-        if (SPLIT && krange) {
-#pragma unroll
-            for (int hblk = 0; hblk < 2; ++hblk) {
-                const int i = (int)(i0 + 64 * hblk + 2 * lane);
-                if (fabsf((float)v[2 * hblk]) > support_thr || fabsf((float)v[2 * hblk + 1]) > support_thr) {
-                    sup_lo = min(sup_lo, i);
-                    sup_hi = max(sup_hi, i + 2);
-                }
-            }
-        }
         if (SPLIT) {
 #pragma unroll
             for (int hblk = 0; hblk < 2; ++hblk) {
@@ -220,17 +308,6 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
             }
         }
     }
-    if (SPLIT && krange) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sup_lo = min(sup_lo, __shfl_xor_sync(0xffffffffu, sup_lo, o));
-            sup_hi = max(sup_hi, __shfl_xor_sync(0xffffffffu, sup_hi, o));
-        }
-        if (lane == 0 && sup_hi > 0) {
-            atomicMin(krange + 2 * (j / 128), sup_lo);
-            atomicMax(krange + 2 * (j / 128) + 1, sup_hi);
-        }
-    }
     if (sizeof(T) == 4) acc_c = -acc_c;               // Kahan keeps the NEGATIVE of the running error
     double acc = (sizeof(T) == 4) ? (double)acc_s + (double)acc_c : accd;
     acc = warp_sum(acc);
@@ -240,11 +317,6 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
     }
 }
 
-// resets the per-tile support ranges to empty
-__global__ void krange_init_kernel(int *__restrict__ krange, int ntiles) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < ntiles) { krange[2 * t] = 0x7fffffff; krange[2 * t + 1] = 0; }
-}
 
 // K5: sd = sqrt(max(v - sum_tiles part[t][j], 0) + noise); NaN coordinates -> NaN.
 template <typename T, int D>

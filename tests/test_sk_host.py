@@ -101,3 +101,26 @@ def test_sk_oracle_reproduces_its_committed_training_vectors(kernel, golden_dir)
     np.testing.assert_allclose(np.array(ora.losses), g["loss"], rtol=1e-9)
     np.testing.assert_allclose(mean, g["mean"], rtol=0, atol=1e-9 * np.abs(g["mean"]).max())
     np.testing.assert_allclose(sd, g["sd"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "Matern52"])
+def test_sk_oracle_loss_and_prediction_by_the_dense_route(kernel):
+    """Nothing reference-held pins the GPyTorch-semantics oracle, so it is verified by an ALGEBRAICALLY INDEPENDENT
+    route: the marginal likelihood from torch.distributions.MultivariateNormal on the dense covariance
+    (no hand-rolled Cholesky / log-determinant), the prediction from torch.linalg.solve on the full system."""
+    R = W.dummy_blob(14, 60) + 0.3
+    Xs, Xf = O.sparse_grid(R), O.full_grid(R)
+    g = SKOracleGP(Xs, R, Xf, kernel=kernel, lengthscale=[[1.0, 1.0], [10.0, 10.0]], learning_rate=0.1, iterations=5).train()
+    with torch.no_grad():
+        v, noise, c, ls = g.theta()
+        N = g.X.shape[0]
+        A = v * sk_kernel_matrix(kernel, g.X, g.X, ls) + noise * torch.eye(N, dtype=torch.float64)
+        mvn = torch.distributions.MultivariateNormal(c.expand(N), covariance_matrix=A)
+        assert float(g.loss()) == pytest.approx(float(-mvn.log_prob(g.y) / N), rel=1e-10)
+        Xt = g.Xtest[::5]
+        Ks = v * sk_kernel_matrix(kernel, g.X, Xt, ls)
+        mean = c + Ks.t() @ torch.linalg.solve(A, g.y - c)
+        var = v - (Ks * torch.linalg.solve(A, Ks)).sum(0) + noise
+    m0, s0 = g.predict()
+    np.testing.assert_allclose(m0.reshape(-1)[::5], mean.numpy(), rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(s0.reshape(-1)[::5], var.sqrt().numpy(), rtol=1e-8)

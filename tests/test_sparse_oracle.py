@@ -151,3 +151,37 @@ def test_closed_form_gradient_of_the_vfe_bound_matches_autograd(kernel):
     if kernel == "RationalQuadratic":
         assert abs(float(al2.grad) - float(al.grad)) < 1e-8 * abs(float(al.grad))
     assert float((Guu - Guu.T).abs().max()) < 1e-9 * float(Guu.abs().max())       # the kernel's factor 2 on dF/dXu relies on it
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "Matern52", "RationalQuadratic"])
+def test_vfe_objective_and_prediction_by_the_dense_route(kernel):
+    """No reference test or golden pins sparse=True, so the restatement is verified by an ALGEBRAICALLY INDEPENDENT
+    route: the N x N covariance Qff + noise I of the Nystrom model built explicitly (torch.linalg.solve, no Woodbury /
+    matrix-determinant lemma), its log-density from torch.distributions, the trace term from the dense Kff - Qff, and
+    Titsias' predictive equations with the m x m matrix Sigma = (Kuu + Kuf Kfu / noise)^-1 -- none of the
+    low-rank factorisations the oracle (and the CUDA path) go through."""
+    from oracle.gp_oracle import kernel_matrix
+    from oracle.sparse_oracle import vfe_loss, vfe_predict
+    R, Xs, Xf = _problem()
+    g = SparseOracleGP(Xs, R, Xf, kernel=kernel, indpoints=17, seed=2, learning_rate=0.1, iterations=4).train()
+    with torch.no_grad():
+        v, ls, noise, a = g._theta()
+        X, y, Xu = g.X, g.y, g.Xu.detach()
+        N, m = X.shape[0], Xu.shape[0]
+        Kuu = kernel_matrix(kernel, Xu, Xu, v, ls, a) + g.jitter * torch.eye(m, dtype=torch.float64)
+        Kuf = kernel_matrix(kernel, Xu, X, v, ls, a)
+        Qff = Kuf.t() @ torch.linalg.solve(Kuu, Kuf)
+        mvn = torch.distributions.MultivariateNormal(torch.zeros(N, dtype=torch.float64),
+                                                     covariance_matrix=Qff + noise * torch.eye(N, dtype=torch.float64))
+        Kff_diag = kernel_matrix(kernel, X, X, v, ls, a).diagonal()
+        dense = -mvn.log_prob(y) + 0.5 * torch.clamp((Kff_diag - Qff.diagonal()).sum() / noise, min=0)
+        got = vfe_loss(kernel, X, y, Xu, v, ls, noise, a, g.jitter)
+        np.testing.assert_allclose(float(got), float(dense), rtol=1e-9)
+        Xt = g.Xtest[::7]
+        Kus = kernel_matrix(kernel, Xu, Xt, v, ls, a)
+        Sigma = torch.linalg.inv(Kuu + Kuf @ Kuf.t() / noise)
+        mean = Kus.t() @ Sigma @ (Kuf @ y) / noise
+        var = v + noise - (Kus * torch.linalg.solve(Kuu, Kus)).sum(0) + (Kus * (Sigma @ Kus)).sum(0)
+        loc, var0 = vfe_predict(kernel, X, y, Xu, Xt, v, ls, noise, a, g.jitter)
+        np.testing.assert_allclose(loc.numpy(), mean.numpy(), rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(var0.numpy(), var.numpy(), rtol=1e-7)
