@@ -28,6 +28,15 @@
 
 namespace cpanel {
 
+// development aid (tools/panel_bench.cu): timestamps of the chain (CTA 0) and of the worker on the critical path
+#ifdef GPG_PANEL_PROFILE
+__device__ long long g_panel_clk[512];
+__device__ __forceinline__ long long panel_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PANEL_CLK(slot) do { if (threadIdx.x == 0) { g_panel_clk[slot] = clock64(); g_panel_clk[256 + (slot)] = panel_now(); } } while (0)
+#else
+#define PANEL_CLK(slot)
+#endif
+
 constexpr int NB = 128;
 constexpr int KBLK = 32;                                   // halves per swizzled k-block (64-byte swizzle, as gemm_tc)
 constexpr int TILE_BYTES = NB * KBLK * 2;                  // 8 KB: [128 rows][32 halves]
@@ -69,7 +78,7 @@ __device__ __noinline__ bool spin_until_set(const int *flag, int *abort_flag) {
             if (ld_acquire(abort_flag) != 0) return false;
             if (clock64() - start > (1LL << 32)) { atomicExch(abort_flag, 1); return false; }
         }
-        __nanosleep(40);
+        if (it > 4096) __nanosleep(64);                   // poll tightly at first: the hand-overs of the chain are short
     }
     return true;
 }
@@ -131,7 +140,14 @@ __device__ __forceinline__ void split8(const float *v, float s, uint4 &hi, uint4
 // ---------------------------------------------------------------------------------------------
 // the chain (CTA 0)
 // ---------------------------------------------------------------------------------------------
-__device__ void chain_role(const Args &p, unsigned char *smem, int *s_flag) {
+// separate functions: each gets a register allocation of its own (inlined into the role they spill)
+__device__ __noinline__ void chain_factor(float *S, float *colbuf, float *rdiag, int nb, long long j0, int32_t *info) {
+    diag_factor_smem<float, NB>(S, colbuf, rdiag, nb, j0, info);
+}
+__device__ __noinline__ void chain_invert(const float *S, float *W) { diag_invert_smem<float, NB>(S, W); }
+
+
+__device__ __noinline__ void chain_role(const Args &p, unsigned char *smem, int *s_flag) {
     constexpr int LDS = NB + 4;
     float *S = reinterpret_cast<float *>(smem);
     float *W = S + NB * LDS;
@@ -144,71 +160,82 @@ __device__ void chain_role(const Args &p, unsigned char *smem, int *s_flag) {
         const long long j0 = p.J0 + (long long)NB * j;
         const int nb = (int)min((long long)NB, p.N - j0);
         const bool rows_below = j0 + NB < p.N;
+        PANEL_CLK(16 * j + 0);
         if (j > 0) {                                   // the owner of row block j has applied the updates of columns < j
             if (t == 0) *s_flag = spin_until_set(p.flags + F_DIAG_READY + j, abort_flag) ? 1 : 0;
             __syncthreads();
         }
         const float *Ab = p.A + j0 * p.ld + j0;
-        for (int idx = t; idx < NB * NB / 4; idx += NUM_THREADS) {
-            const int i = idx / (NB / 4), k4 = (idx % (NB / 4)) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < nb && k4 <= i) v = __ldcg(reinterpret_cast<const float4 *>(Ab + (long long)i * p.ld + k4));
-            float e[4] = {v.x, v.y, v.z, v.w};
+        PANEL_CLK(16 * j + 1);
+        // global -> shared by cp.async (no registers in between: all 16 copies of a thread are in flight at once;
+        // .cg = through L2, where the worker's release made the block visible); then the strict upper triangle of the
+        // diagonal-crossing groups is cleared and a ragged last block is padded with the identity
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int k = k4 + q;
-                if (k > i || i >= nb || k >= nb) e[q] = (i == k) ? 1.f : 0.f;      // identity padding of a ragged block
-            }
-            *reinterpret_cast<float4 *>(S + i * LDS + k4) = make_float4(e[0], e[1], e[2], e[3]);
+        for (int q = 0; q < NB * NB / 4 / NUM_THREADS; ++q) {
+            const int idx = t + q * NUM_THREADS;
+            const int i = idx >> 5, k4 = (idx & 31) << 2;
+            float *sdst = S + i * LDS + k4;
+            if (i < nb && k4 <= i)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(sdst)), "l"(Ab + (long long)i * p.ld + k4) : "memory");
+            else
+                *reinterpret_cast<float4 *>(sdst) = make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4 *>(W + i * LDS + k4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        diag_factor_smem<float, NB>(S, colbuf, rdiag, nb, j0, p.info);
+        if (t < NB) {
+            const int i = t;
+            if (i < nb) {
+                const int k4 = (i >> 2) << 2;
+#pragma unroll
+                for (int c = 1; c < 4; ++c)
+                    if (k4 + c > i) S[i * LDS + k4 + c] = 0.f;
+            } else {
+                S[i * LDS + i] = 1.f;
+            }
+        }
+        __syncthreads();
+        PANEL_CLK(16 * j + 2);
+        chain_factor(S, colbuf, rdiag, nb, j0, p.info);
+        PANEL_CLK(16 * j + 3);
         if (rows_below) {
-            diag_invert_smem<float, NB>(S, W);
+            chain_invert(S, W);
+            PANEL_CLK(16 * j + 4);
             // critical output first: the planes of W_jj (B operand of every worker's panel product)
-            for (int q = t; q < NB * NB / 4; q += NUM_THREADS) {
-                const int i = q / (NB / 4), k4 = (q % (NB / 4)) * 4;
-                const float4 w4 = *reinterpret_cast<const float4 *>(W + i * LDS + k4);
-                const float a0 = w4.x * sW, a1 = w4.y * sW, a2 = w4.z * sW, a3 = w4.w * sW;
-                const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
-                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
-                const long long off = (j0 + i) * p.ld + j0 + k4;
-                *reinterpret_cast<uint2 *>(p.Ws_hi + off) = make_uint2(*reinterpret_cast<const unsigned *>(&h01), *reinterpret_cast<const unsigned *>(&h23));
-                *reinterpret_cast<uint2 *>(p.Ws_lo + off) = make_uint2(*reinterpret_cast<const unsigned *>(&l01), *reinterpret_cast<const unsigned *>(&l23));
+#pragma unroll 2
+            for (int q = t; q < NB * NB / 8; q += NUM_THREADS) {
+                const int i = q >> 4, k8 = (q & 15) << 3;
+                const float4 wa = *reinterpret_cast<const float4 *>(W + i * LDS + k8);
+                const float4 wb = *reinterpret_cast<const float4 *>(W + i * LDS + k8 + 4);
+                const float v8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+                uint4 hi, lo;
+                split8(v8, sW, hi, lo);
+                const long long off = (j0 + i) * p.ld + j0 + k8;
+                *reinterpret_cast<uint4 *>(p.Ws_hi + off) = hi;
+                *reinterpret_cast<uint4 *>(p.Ws_lo + off) = lo;
             }
             __threadfence();
         }
         __syncthreads();
         if (t == 0) st_release(p.flags + F_DIAG_DONE + j, 1);
-        // off the critical path: the factor block itself, fp32 in place + planes (zero right of the diagonal)
+        PANEL_CLK(16 * j + 5);
+        // off the critical path: the factor block itself, fp32 in place.  (Its fp16 planes are never an operand: the
+        // trailing updates, the panel products and the triangular inverse only read off-diagonal blocks of Ls.)
+#pragma unroll 4
         for (int q = t; q < NB * NB / 4; q += NUM_THREADS) {
-            const int i = q / (NB / 4), k4 = (q % (NB / 4)) * 4;
-            if (i >= nb || k4 >= nb) continue;
+            const int i = q >> 5, k4 = (q & 31) << 2;
+            if (i >= nb || k4 > i) continue;
             const float4 s4 = *reinterpret_cast<const float4 *>(S + i * LDS + k4);
-            const float e[4] = {s4.x, s4.y, s4.z, s4.w};
-            const int nvalid = min(4, nb - k4);
             float *dst = const_cast<float *>(Ab) + (long long)i * p.ld + k4;
-            if (k4 + 3 <= i && nvalid == 4) *reinterpret_cast<float4 *>(dst) = s4;
-            else for (int q2 = 0; q2 < nvalid; ++q2) if (k4 + q2 <= i) dst[q2] = e[q2];
-            float a[4];
-#pragma unroll
-            for (int q2 = 0; q2 < 4; ++q2) a[q2] = (k4 + q2 <= i) ? e[q2] * sL : 0.f;
-            const __half2 h01 = __floats2half2_rn(a[0], a[1]), h23 = __floats2half2_rn(a[2], a[3]);
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            const __half2 l01 = __floats2half2_rn(a[0] - f01.x, a[1] - f01.y), l23 = __floats2half2_rn(a[2] - f23.x, a[3] - f23.y);
-            const long long off = (j0 + i) * p.ld + j0 + k4;
-            if (nvalid == 4) {
-                *reinterpret_cast<uint2 *>(p.Ls_hi + off) = make_uint2(*reinterpret_cast<const unsigned *>(&h01), *reinterpret_cast<const unsigned *>(&h23));
-                *reinterpret_cast<uint2 *>(p.Ls_lo + off) = make_uint2(*reinterpret_cast<const unsigned *>(&l01), *reinterpret_cast<const unsigned *>(&l23));
-            } else {
-                const __half hh[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
-                const __half ll[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
-                for (int q2 = 0; q2 < nvalid; ++q2) { p.Ls_hi[off + q2] = hh[q2]; p.Ls_lo[off + q2] = ll[q2]; }
+            if (k4 + 3 <= i) *reinterpret_cast<float4 *>(dst) = s4;
+            else {
+                const float e[4] = {s4.x, s4.y, s4.z, s4.w};
+                for (int c = 0; c < 4; ++c) if (k4 + c <= i) dst[c] = e[c];
             }
         }
         __syncthreads();                                // S / W are reused by the next diagonal block
+        PANEL_CLK(16 * j + 6);
     }
     if (t == 0 && ld_acquire(abort_flag) != 0) atomicCAS(p.info, 0, -1);
 }
@@ -250,7 +277,7 @@ __device__ __forceinline__ void emit_L(const Args &p, uint32_t tlane, unsigned c
 // ---------------------------------------------------------------------------------------------
 // a worker (CTAs 1..)
 // ---------------------------------------------------------------------------------------------
-__device__ void worker_role(const Args &p, const CUtensorMap *mLhi, const CUtensorMap *mLlo, const CUtensorMap *mWhi,
+__device__ __noinline__ void worker_role(const Args &p, const CUtensorMap *mLhi, const CUtensorMap *mLlo, const CUtensorMap *mWhi,
                             const CUtensorMap *mWlo, unsigned char *smem, uint64_t *bars, uint32_t *tmem_slot) {
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int quarter = warp & 3, half = warp >> 2;           // TMEM lanes 32 q .., columns 64 h .. of a 128-column block
@@ -296,6 +323,10 @@ __device__ void worker_role(const Args &p, const CUtensorMap *mLhi, const CUtens
         for (int j = 0; j < ncol; ++j) {
             const long long col0 = p.J0 + (long long)NB * j;
             // (1) X = A[rb][j] - U_j  -> fp16 hi/lo, swizzled, into XA (does not need the chain: done before the wait)
+#ifdef GPG_PANEL_PROFILE
+            const bool prof = rb < p.nbp && j == (int)rb - 1;
+            if (prof) PANEL_CLK(128 + 16 * (int)rb + 0);
+#endif
             {
                 float *arow = p.A + gr * p.ld + col0 + 64 * half;
 #pragma unroll 1
@@ -332,13 +363,22 @@ __device__ void worker_role(const Args &p, const CUtensorMap *mLhi, const CUtens
             tc::tcgen05_fence_before();
             __syncthreads();
             // (2) W_jj planes -> B0 as soon as the chain has published them; (3) scratch = X W_jj^T
+#ifdef GPG_PANEL_PROFILE
+            if (prof) PANEL_CLK(128 + 16 * (int)rb + 1);
+#endif
             if (t == 0) {
                 live = live && spin_until_set(p.flags + F_DIAG_DONE + j, abort_flag);
+#ifdef GPG_PANEL_PROFILE
+                if (prof) PANEL_CLK(128 + 16 * (int)rb + 2);
+#endif
                 tc::tcgen05_fence_after();
                 if (live) {
                     fence_proxy_async();
                     load_operand(b0, mWhi, mWlo, BAR_TMA0, (int)col0, (int)col0);
                     tc::mbar_wait(BAR_TMA0, ph_tma0); ph_tma0 ^= 1;
+#ifdef GPG_PANEL_PROFILE
+                    if (prof) PANEL_CLK(128 + 16 * (int)rb + 3);
+#endif
                     tc::tcgen05_fence_after();
                     issue_product(tmem_base, xa, b0, 0);
                 }
@@ -346,11 +386,15 @@ __device__ void worker_role(const Args &p, const CUtensorMap *mLhi, const CUtens
             }
             tc::mbar_wait(BAR_MMA, ph_mma); ph_mma ^= 1;
             tc::tcgen05_fence_after();
+#ifdef GPG_PANEL_PROFILE
+            if (prof) PANEL_CLK(128 + 16 * (int)rb + 4);
+#endif
             // (4) L[rb][j]: fp32 in place, planes to global, planes into XA (operand of the updates)
             const bool final_near = near_blk && j == (int)rb - 1;
             if (final_near) {
-                // the chain waits for THIS row block: first the operand planes (smem only) and the one update that is
-                // left -- the own diagonal block, both operands L[rb][j] --, the global copies of L[rb][j] under the MMA
+                // The chain waits for THIS row block.  Critical order: operand planes (smem only) -> the one update that
+                // is left, the own diagonal block (both operands L[rb][j]) -> A[rb][rb] - U_rb to global -> flag.  The
+                // global copies of L[rb][j] (fp32 + planes) follow afterwards.
                 emit_L<true, false>(p, tlane, xa_gen, r, half, gr, col0, valid, inv_AW, sL);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 tc::tcgen05_fence_before();
@@ -360,9 +404,62 @@ __device__ void worker_role(const Args &p, const CUtensorMap *mLhi, const CUtens
                     if (live) issue_product(tmem_base + (uint32_t)(NB * (int)rb), xa, xa, j > 0 ? 1u : 0u);
                     tc::tcgen05_commit(BAR_MMA);
                 }
-                emit_L<false, true>(p, tlane, xa_gen, r, half, gr, col0, valid, inv_AW, sL);
                 tc::mbar_wait(BAR_MMA, ph_mma); ph_mma ^= 1;
                 tc::tcgen05_fence_after();
+#ifdef GPG_PANEL_PROFILE
+                PANEL_CLK(128 + 16 * (int)rb + 5);
+#endif
+                // U_rb: TMEM (one row per thread) -> fp32 tile in XA (16-byte chunks XOR-swizzled by the row, conflict
+                // free both ways) -> coalesced read-modify-write of the lower part of the diagonal block
+                float *stg = reinterpret_cast<float *>(xa_gen);
+#pragma unroll 1
+                for (int cc = 0; cc < 64; cc += 32) {
+                    uint32_t u[32];
+                    tc::tmem_ld32(tlane + (uint32_t)(NB * (int)rb + 64 * half + cc), u);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int c4 = (64 * half + cc) / 4 + q;
+                        *reinterpret_cast<float4 *>(stg + r * NB + ((c4 ^ (r & 31)) << 2)) =
+                            make_float4(__uint_as_float(u[4 * q]) * inv_LL, __uint_as_float(u[4 * q + 1]) * inv_LL,
+                                        __uint_as_float(u[4 * q + 2]) * inv_LL, __uint_as_float(u[4 * q + 3]) * inv_LL);
+                    }
+                }
+                tc::tcgen05_fence_before();
+                __syncthreads();
+                {
+                    float *dblk = p.A + row0 * p.ld + row0;
+                    const int nrows = (int)min((long long)NB, p.N - row0);
+                    float4 a4[NB * NB / 4 / NUM_THREADS];
+#pragma unroll
+                    for (int q = 0; q < NB * NB / 4 / NUM_THREADS; ++q) {
+                        const int idx = t + q * NUM_THREADS, i = idx >> 5, c4 = idx & 31;
+                        if (i < nrows && 4 * c4 <= i) a4[q] = *reinterpret_cast<const float4 *>(dblk + (long long)i * p.ld + 4 * c4);
+                    }
+#pragma unroll
+                    for (int q = 0; q < NB * NB / 4 / NUM_THREADS; ++q) {
+                        const int idx = t + q * NUM_THREADS, i = idx >> 5, c4 = idx & 31;
+                        if (i < nrows && 4 * c4 <= i) {
+                            const float4 u4 = *reinterpret_cast<const float4 *>(stg + i * NB + ((c4 ^ (i & 31)) << 2));
+                            *reinterpret_cast<float4 *>(dblk + (long long)i * p.ld + 4 * c4) =
+                                make_float4(a4[q].x - u4.x, a4[q].y - u4.y, a4[q].z - u4.z, a4[q].w - u4.w);
+                        }
+                    }
+                }
+                __threadfence();
+                __syncthreads();
+                if (t == 0) st_release(p.flags + F_DIAG_READY + (int)rb, 1);
+#ifdef GPG_PANEL_PROFILE
+                PANEL_CLK(128 + 16 * (int)rb + 6);
+#endif
+                emit_L<false, true>(p, tlane, xa_gen, r, half, gr, col0, valid, inv_AW, sL);
+                __threadfence();
+                tc::tcgen05_fence_before();
+                __syncthreads();
+                if (t == 0) st_release(p.flags + F_ROW_DONE + 4 * (int)rb + j, 1);
+#ifdef GPG_PANEL_PROFILE
+                PANEL_CLK(128 + 16 * (int)rb + 7);
+#endif
             } else {
                 emit_L<true, true>(p, tlane, xa_gen, r, half, gr, col0, valid, inv_AW, sL);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -404,32 +501,6 @@ __device__ void worker_role(const Args &p, const CUtensorMap *mLhi, const CUtens
                 }
                 tc::mbar_wait(BAR_MMA, ph_mma); ph_mma ^= 1;
                 tc::tcgen05_fence_after();
-            }
-            // (6) the row block that owns diagonal block rb hands it to the chain once column rb - 1 is in
-            if (near_blk && j == (int)rb - 1) {
-                float *drow = p.A + gr * p.ld + (p.J0 + rb * NB) + 64 * half;
-#pragma unroll 1
-                for (int cc = 0; cc < 64; cc += 32) {
-                    uint32_t u[32];
-                    tc::tmem_ld32(tlane + (uint32_t)(NB * (int)rb + 64 * half + cc), u);
-                    tc::tmem_ld_wait();
-                    if (valid) {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float4 a4 = *reinterpret_cast<const float4 *>(drow + cc + 4 * q);
-                            a4.x -= __uint_as_float(u[4 * q]) * inv_LL; a4.y -= __uint_as_float(u[4 * q + 1]) * inv_LL;
-                            a4.z -= __uint_as_float(u[4 * q + 2]) * inv_LL; a4.w -= __uint_as_float(u[4 * q + 3]) * inv_LL;
-                            *reinterpret_cast<float4 *>(drow + cc + 4 * q) = a4;
-                        }
-                    }
-                }
-                __threadfence();
-                tc::tcgen05_fence_before();
-                __syncthreads();
-                if (t == 0) {
-                    st_release(p.flags + F_DIAG_READY + (int)rb, 1);
-                    st_release(p.flags + F_ROW_DONE + 4 * (int)rb + j, 1);
-                }
             }
             tc::tcgen05_fence_before();
             __syncthreads();                                   // XA / TMEM scratch are rewritten by the next step

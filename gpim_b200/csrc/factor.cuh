@@ -171,7 +171,11 @@ __device__ __forceinline__ void invert_tri32(const T *__restrict__ S, T *__restr
     for (int i = 0; i < 32; ++i) W[(b0 + i) * lds + b0 + lane] = x[i];
 }
 
-__device__ __forceinline__ float gpg_rsqrt(float x) { return rsqrtf(x); }
+__device__ __forceinline__ float gpg_rsqrt(float x) {          // the bare MUFU.RSQ (2 ulp): it sits on the pivot chain
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ double gpg_rsqrt(double x) { return 1.0 / sqrt(x); }
 
 // Cholesky of the 32 x 32 block at S[c0.., c0..] in registers (lane = row).  The serial chain of a pivot is kept as
@@ -679,7 +683,29 @@ __global__ void __launch_bounds__(256) gemv_tri_kernel(const T *__restrict__ Mx,
         const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
         if (i >= N) return;
         double acc = 0.0;
-        for (int64_t k = lane; k <= i; k += 32) acc += (double)Mx[i * ld + k] * (double)x[k];
+        if (sizeof(T) == 4 && (ld & 3) == 0 && ((reinterpret_cast<uintptr_t>(Mx) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
+            // 128-bit loads, four rows of loads in flight per lane; the tail group of the row is masked
+            const float *row = reinterpret_cast<const float *>(Mx) + i * ld;
+            const float *xf = reinterpret_cast<const float *>(x);
+            double a0 = 0.0, a1 = 0.0;
+            int64_t k = 4 * lane;
+            for (; k + 128 + 3 <= i; k += 256) {
+                const float4 m0 = *reinterpret_cast<const float4 *>(row + k), m1 = *reinterpret_cast<const float4 *>(row + k + 128);
+                const float4 x0 = *reinterpret_cast<const float4 *>(xf + k), x1 = *reinterpret_cast<const float4 *>(xf + k + 128);
+                a0 += (double)m0.x * x0.x + (double)m0.y * x0.y + (double)m0.z * x0.z + (double)m0.w * x0.w;
+                a1 += (double)m1.x * x1.x + (double)m1.y * x1.y + (double)m1.z * x1.z + (double)m1.w * x1.w;
+            }
+            for (; k <= i; k += 128) {
+                const float4 m0 = *reinterpret_cast<const float4 *>(row + k);        // k + 3 < ld: ld is a multiple of 4
+                const float mm[4] = {m0.x, m0.y, m0.z, m0.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (k + e <= i) a0 += (double)mm[e] * (double)xf[k + e];
+            }
+            acc = a0 + a1;
+        } else {
+            for (int64_t k = lane; k <= i; k += 32) acc += (double)Mx[i * ld + k] * (double)x[k];
+        }
         acc = warp_sum(acc);
         if (lane == 0) out[i] = (T)((double)alpha * acc + (yin ? (double)beta * (double)yin[i] : 0.0));
     } else {
@@ -773,13 +799,14 @@ static int gemv_tri_T(gpg_handle_s *h, const T *Mx, int64_t ld, int64_t N, const
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) solve_scalars_kernel(const T *__restrict__ L, int64_t ld, int64_t N,
-                                                            const T *__restrict__ vhat, T *__restrict__ scalars,
-                                                            const T *__restrict__ y = nullptr,
-                                                            const T *__restrict__ alpha = nullptr) {
-    __shared__ double r0[8], r1[8];
+__global__ void __launch_bounds__(1024) solve_scalars_kernel(const T *__restrict__ L, int64_t ld, int64_t N,
+                                                             const T *__restrict__ vhat, T *__restrict__ scalars,
+                                                             const T *__restrict__ y = nullptr,
+                                                             const T *__restrict__ alpha = nullptr) {
+    // one CTA; the diagonal gathers are latency-bound (one sector each), so as many threads as a CTA can hold
+    __shared__ double r0[32], r1[32];
     double q = 0.0, ld_sum = 0.0;
-    for (int64_t i = threadIdx.x; i < N; i += 256) {
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
         if (y) q += (double)y[i] * (double)alpha[i];
         else { const double v = (double)vhat[i]; q += v * v; }
         ld_sum += log((double)L[i * ld + i]);
@@ -790,7 +817,7 @@ __global__ void __launch_bounds__(256) solve_scalars_kernel(const T *__restrict_
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0, b = 0;
-        for (int w = 0; w < 8; ++w) { a += r0[w]; b += r1[w]; }
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += r0[w]; b += r1[w]; }
         scalars[0] = (T)(0.5 * a);
         scalars[1] = (T)b;
     }
@@ -849,7 +876,7 @@ static int solve_vec_refined(gpg_handle_s *h, const T *L, const T *Linv, int64_t
         GPG_CUDA_CHECK(cudaMemcpyAsync(alpha, dx, N * sizeof(T), cudaMemcpyDeviceToDevice, stream));
     }
     if (scalars) {
-        solve_scalars_kernel<T><<<1, 256, 0, stream>>>(L, ld, N, vhat, scalars);
+        solve_scalars_kernel<T><<<1, (N >= 1024 ? 1024 : 256), 0, stream>>>(L, ld, N, vhat, scalars);
         GPG_LAUNCH_CHECK(h);
     }
     return GPG_OK;

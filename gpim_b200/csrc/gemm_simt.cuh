@@ -31,6 +31,10 @@ template <typename T> struct GemmArgs {
     __half *split_hi = nullptr, *split_lo = nullptr;
     int64_t ld_split = 0;
     const float *split_scale = nullptr;
+    // optional compact support of operand B (K* rows of the predict product): krange[2 t], krange[2 t + 1] = the k range
+    // [lo, hi) outside of which the B rows of the 128-row group t = n / 128 are negligible (and not even stored);
+    // lo is a multiple of 128
+    const int *krange = nullptr;
 };
 
 template <typename T> struct GemmCfg;
@@ -61,6 +65,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs<T> g) {
     else if (g.kb_mode == GEMM_KB_MAXMN) kb = max(m0, n0);
     if (g.ke_mode == GEMM_KE_M) ke = min(g.K, m0 + BM);
     else if (g.ke_mode == GEMM_KE_N) ke = min(g.K, n0 + BN);
+    if (g.krange) {
+        static_assert(128 % BN == 0, "a column tile must not straddle two support groups");
+        kb = max(kb, __ldg(g.krange + 2 * (n0 / 128)));
+        ke = min(ke, __ldg(g.krange + 2 * (n0 / 128) + 1));
+    }
     kb = (kb / BK) * BK;
 
     const int t = threadIdx.x;

@@ -383,6 +383,7 @@ extern "C" int gpg_solve_vec(gpg_handle_t h, int dtype, const void *L, const voi
 template <typename T> struct FactorWs {
     T *tmp = nullptr, *dinv = nullptr, *vs = nullptr;       // vs: 4 N vector scratch
     double *best = nullptr;
+    float *bbox = nullptr;            // boxes of 32-row blocks of X (support ranges of the residual kernel), f32 only
     void *planes = nullptr;           // Ls | WTs | TTs | As (2 N ld halves each) | Rf (N ld floats): tensor-core path
 };
 
@@ -394,7 +395,8 @@ template <typename T> static size_t factor_ws_bytes(const gpg_handle_s *h, int64
     constexpr int NB = GemmCfg<T>::BN;
     const bool tcp = std::is_same<T, float>::value && tc_factor_wanted(h, N, ld, wsplit);
     const size_t big = tcp ? 5 * (size_t)N * ld * 4 : (size_t)N * ld * sizeof(T);
-    return bump_size({big, NB * NB * sizeof(T), 4 * (size_t)N * sizeof(T), sizeof(double)});
+    return bump_size({big, NB * NB * sizeof(T), 4 * (size_t)N * sizeof(T), sizeof(double),
+                      (size_t)((N + 31) / 32) * 2 * GPG_MAX_D * sizeof(float)});
 }
 
 template <typename T> static FactorWs<T> factor_ws_carve(const gpg_handle_s *h, Bump &b, int64_t N, int64_t ld, const void *wsplit) {
@@ -406,6 +408,7 @@ template <typename T> static FactorWs<T> factor_ws_carve(const gpg_handle_s *h, 
     w.dinv = b.take<T>(NB * NB);
     w.vs = b.take<T>(4 * N);
     w.best = b.take<double>(1);
+    w.bbox = b.take<float>((size_t)((N + 31) / 32) * 2 * GPG_MAX_D);
     return w;
 }
 
@@ -419,16 +422,22 @@ __global__ void set_double_kernel(double *p, double v) { if (threadIdx.x == 0 &&
 template <typename T>
 static int refine_alpha_against_K(gpg_handle_s *h, int kernel_id, int d, const T *theta, const T *X, const T *y,
                                   int64_t N, double jitter, const T *Linv, int64_t ld, T *alpha, T *scratch,
-                                  double *best, int rounds, cudaStream_t s) {
+                                  double *best, int rounds, cudaStream_t s, float *bbox = nullptr) {
     T *r = scratch, *t = scratch + N, *an = scratch + 2 * N, *rn = scratch + 3 * N;
     const unsigned gk = (unsigned)((N + 7) / 8), gN = gk;
+    const int nblk32 = (int)((N + 31) / 32);
+    if (bbox && !h->opt_compact_support) bbox = nullptr;
+    if (bbox) {                      // the residual only visits the training rows inside each point's support
+        GPG_DISPATCH_D(d, block_bbox_kernel<T, D><<<(unsigned)((nblk32 + 7) / 8), 256, 0, s>>>(X, N, bbox));
+        GPG_LAUNCH_CHECK(h);
+    }
     auto resid = [&](const T *a, T *out) -> int {
         GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, {
             TestPoints<T, D> tp;
             tp.Xs = X; tp.j0 = 0;
             for (int k = 0; k < GPG_MAX_D; ++k) { tp.dims[k] = 1; tp.step[k] = T(1); }
             kcross_mean_kernel<T, KID, D, false><<<gk, 256, 0, s>>>(theta, X, N, tp, N, a, nullptr, 0, nullptr, nullptr, 0,
-                                                                     nullptr, out, y, (T)jitter);
+                                                                     nullptr, out, y, (T)jitter, nullptr, 1e-14f, bbox, nblk32);
         }));
         GPG_LAUNCH_CHECK(h);
         return GPG_OK;
@@ -505,9 +514,14 @@ static int factorize_core(gpg_handle_s *h, int kernel_id, int d, const T *theta,
     {
         StageTimer st(h, GPG_ST_SOLVE, s);
         GPG_TRY(solve_vec_refined<T>(h, L, Linv, N, ld, y, vhat, alpha, nullptr, w.vs, s, 0));
-        GPG_TRY(refine_alpha_against_K<T>(h, kernel_id, d, theta, X, y, N, jitter, Linv, ld, alpha, w.vs, w.best, 2, s));
+        // The refinement against K removes the backward error of the fp32 factorisation (split-fp16 contractions,
+        // panels through explicit inverses).  In fp64 the factor cache is accurate to ~cond(L) eps already and the
+        // small-N regime of the Bayesian-optimisation loop is bound by the NUMBER of dependent launches per Adam
+        // iteration: there the 13 launches of the two refinement rounds are left out.
+        if (sizeof(T) == 4)
+            GPG_TRY(refine_alpha_against_K<T>(h, kernel_id, d, theta, X, y, N, jitter, Linv, ld, alpha, w.vs, w.best, 2, s, w.bbox));
         if (scalars) {               // 0.5 y^T K^-1 y from the refined alpha, log-determinant from diag L
-            solve_scalars_kernel<T><<<1, 256, 0, s>>>(L, ld, N, vhat, scalars, y, alpha);
+            solve_scalars_kernel<T><<<1, (N >= 1024 ? 1024 : 256), 0, s>>>(L, ld, N, vhat, scalars, y, alpha);
             GPG_LAUNCH_CHECK(h);
         }
     }
@@ -564,11 +578,24 @@ static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T 
     }
     chunk = std::min<int64_t>(chunk, gpg_align_up((size_t)M, 128));
     const int tiles_m = (int)((N + C::BM - 1) / C::BM);
+    const int nblk32 = (int)((N + 31) / 32);
+    const int groups = (int)((chunk + 127) / 128);
     void *ws;
-    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)chunk * ldk * sizeof(T), (size_t)tiles_m * chunk * sizeof(T)}), &ws));
+    GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)chunk * ldk * sizeof(T), (size_t)tiles_m * chunk * sizeof(T),
+                                         2 * (size_t)groups * sizeof(int), (size_t)nblk32 * 2 * D * sizeof(float)}), &ws));
     Bump b(ws);
     T *Ks = b.take<T>((size_t)chunk * ldk);
     T *part = b.take<T>((size_t)tiles_m * chunk);
+    // compact support of K* (GPG_OPT_COMPACT_SUPPORT): per group of 128 test points the range of training rows that
+    // can matter at the resolution of T -- found geometrically by the K* kernel, honoured by the product
+    int *krange = h->opt_compact_support ? b.take<int>(2 * (size_t)groups) : nullptr;
+    float *bbox = h->opt_compact_support ? b.take<float>((size_t)nblk32 * 2 * D) : nullptr;
+    const float support_rel = sizeof(T) == 4 ? 1e-14f : 1e-30f;
+    if (bbox) {
+        StageTimer st(h, GPG_ST_KCROSS, s);
+        block_bbox_kernel<T, D><<<(unsigned)((nblk32 + 7) / 8), 256, 0, s>>>(X, N, bbox);
+        GPG_LAUNCH_CHECK(h);
+    }
     for (int64_t c0 = 0; c0 < M; c0 += chunk) {
         const int64_t mc = std::min<int64_t>(chunk, M - c0);
         TestPoints<T, D> tpc = tp;
@@ -577,7 +604,8 @@ static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T 
         {
             StageTimer st(h, GPG_ST_KCROSS, s);
             GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<T, KID, D, false><<<gk, 256, 0, s>>>(
-                                            theta, X, N, tpc, mc, alpha, Ks, ldk, nullptr, nullptr, 0, nullptr, mean + c0));
+                                            theta, X, N, tpc, mc, alpha, Ks, ldk, nullptr, nullptr, 0, nullptr, mean + c0,
+                                            nullptr, T(0), krange, support_rel, bbox, nblk32));
             GPG_LAUNCH_CHECK(h);
         }
         GemmArgs<T> g;           // colsum((Linv Ks^T)^2): C[i][j] = sum_k Linv[i][k] Ks[j][k], k <= i
@@ -587,6 +615,7 @@ static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T 
         g.ke_mode = GEMM_KE_M;
         g.epi = GEMM_EPI_COLSUMSQ;
         g.part = part; g.ldpart = chunk;
+        g.krange = krange;
         { StageTimer st(h, GPG_ST_PGEMM, s); GPG_TRY(gemm_simt<T>(h, g, s)); }
         StageTimer st(h, GPG_ST_PFINAL, s);
         predict_finalize_kernel<T, D><<<(unsigned)((mc + 255) / 256), 256, 0, s>>>(theta, part, tiles_m, chunk, tpc, mc,
@@ -781,6 +810,7 @@ extern "C" int gpg_predict_grid(gpg_handle_t h, int dtype, int kernel_id, int d,
 // ---------------------------------------------------------------------------------------------
 struct TrainBufs {
     void *L, *Linv, *Kinv, *dinv, *vs, *vhat, *alpha, *scalars, *grad, *nll, *theta, *yc;
+    float *bbox;
     void *planes;            // tensor-core path: Ls | WTs | TTs | As (Kinv aliases TTs, which is dead by then)
     void *wsplit;            // tensor-core path: Ws
     float *scales;
@@ -802,7 +832,8 @@ template <typename T> static size_t train_ws_bytes(const gpg_handle_s *h, int64_
     // L, Linv + (SIMT: Kinv | TC: 4 plane pairs + Rf + Ws)
     return bump_size({nn, nn, tcp ? 6 * nn : nn, NB * NB * sizeof(T), 4 * (size_t)N * sizeof(T) + 64, (size_t)N * sizeof(T),
                       (size_t)N * sizeof(T), 2 * sizeof(T), GPG_MAX_P * sizeof(T), sizeof(T), GPG_MAX_P * sizeof(T),
-                      SC_COUNT * sizeof(float), nb * GPG_MAX_P * sizeof(double), sizeof(FitState), (size_t)N * sizeof(T)});
+                      SC_COUNT * sizeof(float), nb * GPG_MAX_P * sizeof(double), sizeof(FitState), (size_t)N * sizeof(T),
+                      (size_t)((N + 31) / 32) * 2 * GPG_MAX_D * sizeof(float)});
 }
 
 template <typename T> static TrainBufs train_carve(const gpg_handle_s *h, void *ws, int64_t N, int64_t ld) {
@@ -836,6 +867,7 @@ template <typename T> static TrainBufs train_carve(const gpg_handle_s *h, void *
     t.partial = b.take<double>((size_t)t.nblocks * GPG_MAX_P);
     t.st = b.take<FitState>(1);
     t.yc = b.take<T>(N);
+    t.bbox = b.take<float>((size_t)((N + 31) / 32) * 2 * GPG_MAX_D);
     return t;
 }
 
@@ -851,6 +883,7 @@ static int nll_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, 
     w.dinv = (T *)tb.dinv;
     w.vs = (T *)tb.vs;
     w.best = reinterpret_cast<double *>((T *)tb.vs + 4 * N);       // 16 N or 32 N bytes past a 1 KB boundary: aligned
+    w.bbox = tb.bbox;
     GPG_TRY(factorize_core<T>(h, kernel_id, d, theta, X, y, N, jitter, L, Linv, tb.ld, (T *)tb.vhat, (T *)tb.alpha,
                               (T *)tb.scalars, info, reset_info, w, tb.wsplit, tb.scales, s));
     StageTimer st(h, GPG_ST_GRAD, s);

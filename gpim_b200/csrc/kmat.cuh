@@ -187,7 +187,29 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
     // Everything outside contributes below fp32 resolution; it is neither evaluated nor written nor read by the
     // variance GEMM (krange), and the warps of a tile all derive the same range.
     int64_t c_lo = 0, c_hi = width;
-    if (SPLIT && krange) {
+    if (!SPLIT && bbox != nullptr && sizeof(T) == 4 && !bad) {
+        // no tile to agree with (nothing is stored for a GEMM): the range of THIS point, box = the point itself
+        const float r2max = 1.02f * support_r2<T, KID>(th, support_rel);
+        int first = 0x7fffffff, last = 0;
+        for (int b = lane; b < nblk32; b += 32) {
+            float d2 = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float zk = (float)z[k];
+                const float gap = fmaxf(0.f, fmaxf(bbox[b * 2 * D + k] - zk, zk - bbox[b * 2 * D + D + k])) * (float)th.inv_ls[k];
+                d2 += gap * gap;
+            }
+            if (d2 < r2max) { first = min(first, b); last = max(last, b + 1); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        }
+        if (last <= first) { c_lo = 0; c_hi = 0; }
+        else { c_lo = ((int64_t)first * 32 / 128) * 128; c_hi = min(width, (((int64_t)last * 32 + 127) / 128) * 128); }
+    }
+    if (krange && bbox) {
         const int64_t tile0 = (j / 128) * 128;
         float blo[D], bhi[D];
 #pragma unroll
