@@ -25,17 +25,9 @@
 #pragma once
 #include "factor.cuh"
 #include "gemm_tc.cuh"
+#include "chol_chain.cuh"
 
 namespace cpanel {
-
-// development aid (tools/panel_bench.cu): timestamps of the chain (CTA 0) and of the worker on the critical path
-#ifdef GPG_PANEL_PROFILE
-__device__ long long g_panel_clk[512];
-__device__ __forceinline__ long long panel_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define PANEL_CLK(slot) do { if (threadIdx.x == 0) { g_panel_clk[slot] = clock64(); g_panel_clk[256 + (slot)] = panel_now(); } } while (0)
-#else
-#define PANEL_CLK(slot)
-#endif
 
 constexpr int NB = 128;
 constexpr int KBLK = 32;                                   // halves per swizzled k-block (64-byte swizzle, as gemm_tc)
@@ -43,7 +35,7 @@ constexpr int TILE_BYTES = NB * KBLK * 2;                  // 8 KB: [128 rows][3
 constexpr int PLANE_BYTES = (NB / KBLK) * TILE_BYTES;      // 32 KB: one plane of a 128 x 128 operand
 constexpr int OPND_BYTES = 2 * PLANE_BYTES;                // hi + lo
 constexpr int SMEM_WORKER = 3 * OPND_BYTES;                // XA, B0, B1
-constexpr int SMEM_CHAIN = 2 * NB * (NB + 4) * 4;
+constexpr int SMEM_CHAIN = cchain::SMEM_BYTES;
 constexpr int SMEM_BYTES = (SMEM_WORKER > SMEM_CHAIN ? SMEM_WORKER : SMEM_CHAIN) + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int NUM_THREADS = 256;
 constexpr int NFLAGS = 32;
@@ -140,22 +132,19 @@ __device__ __forceinline__ void split8(const float *v, float s, uint4 &hi, uint4
 // ---------------------------------------------------------------------------------------------
 // the chain (CTA 0)
 // ---------------------------------------------------------------------------------------------
-// separate functions: each gets a register allocation of its own (inlined into the role they spill)
-__device__ __noinline__ void chain_factor(float *S, float *colbuf, float *rdiag, int nb, long long j0, int32_t *info) {
-    diag_factor_smem<float, NB>(S, colbuf, rdiag, nb, j0, info);
-}
-__device__ __noinline__ void chain_invert(const float *S, float *W) { diag_invert_smem<float, NB>(S, W); }
-
-
 __device__ __noinline__ void chain_role(const Args &p, unsigned char *smem, int *s_flag) {
-    constexpr int LDS = NB + 4;
+    constexpr int LDS = cchain::LDS;
     float *S = reinterpret_cast<float *>(smem);
     float *W = S + NB * LDS;
-    __shared__ __align__(16) float colbuf[64];
-    __shared__ __align__(16) float rdiag[32];
+    float *Q = W + NB * LDS;
+    float *ring = Q + 96 * cchain::LDQ;
     const int t = threadIdx.x;
     int *abort_flag = p.flags + F_ABORT;
-    const float sL = p.scales[p.sc_L], sW = p.scales[p.sc_W];
+    cchain::Scales sc;
+    sc.sA = p.scales[p.sc_A]; sc.sL = p.scales[p.sc_L]; sc.sW = p.scales[p.sc_W];
+    sc.sQ = sc.sL * sc.sW * (1.0f / (16384.0f * 32.0f));        // |Q| = |L_rr W_rc| <= 32 max|L| max|W|
+    sc.iAW = p.scales[p.sc_inv_AW]; sc.iLL = p.scales[p.sc_inv_LL];
+    sc.iLW = 1.0f / (sc.sL * sc.sW); sc.iWQ = 1.0f / (sc.sW * sc.sQ);
     for (int j = 0; j < p.nbp; ++j) {
         const long long j0 = p.J0 + (long long)NB * j;
         const int nb = (int)min((long long)NB, p.N - j0);
@@ -179,7 +168,6 @@ __device__ __noinline__ void chain_role(const Args &p, unsigned char *smem, int 
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(sdst)), "l"(Ab + (long long)i * p.ld + k4) : "memory");
             else
                 *reinterpret_cast<float4 *>(sdst) = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4 *>(W + i * LDS + k4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -197,26 +185,11 @@ __device__ __noinline__ void chain_role(const Args &p, unsigned char *smem, int 
         }
         __syncthreads();
         PANEL_CLK(16 * j + 2);
-        chain_factor(S, colbuf, rdiag, nb, j0, p.info);
+        // Cholesky + inverse of the block; the planes of W_jj (B operand of every worker's panel product) go to
+        // global memory row block by row block while the factorisation is still running (chol_chain.cuh)
+        cchain::factor_invert_block(S, W, Q, ring, nb, j0, p.info, rows_below, p.Ws_hi, p.Ws_lo, p.ld, sc);
         PANEL_CLK(16 * j + 3);
-        if (rows_below) {
-            chain_invert(S, W);
-            PANEL_CLK(16 * j + 4);
-            // critical output first: the planes of W_jj (B operand of every worker's panel product)
-#pragma unroll 2
-            for (int q = t; q < NB * NB / 8; q += NUM_THREADS) {
-                const int i = q >> 4, k8 = (q & 15) << 3;
-                const float4 wa = *reinterpret_cast<const float4 *>(W + i * LDS + k8);
-                const float4 wb = *reinterpret_cast<const float4 *>(W + i * LDS + k8 + 4);
-                const float v8[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-                uint4 hi, lo;
-                split8(v8, sW, hi, lo);
-                const long long off = (j0 + i) * p.ld + j0 + k8;
-                *reinterpret_cast<uint4 *>(p.Ws_hi + off) = hi;
-                *reinterpret_cast<uint4 *>(p.Ws_lo + off) = lo;
-            }
-            __threadfence();
-        }
+        PANEL_CLK(16 * j + 4);
         __syncthreads();
         if (t == 0) st_release(p.flags + F_DIAG_DONE + j, 1);
         PANEL_CLK(16 * j + 5);

@@ -18,6 +18,7 @@ template <> int gemm_dispatch<double>(gpg_handle_s *, const GemmArgs<double> &, 
 int main(int argc, char **argv) {
     const long long N = argc > 1 ? atoll(argv[1]) : 2048, ld = (N + 63) / 64 * 64;
     const int nbp = (int)std::min<long long>(4, (N + 127) / 128);
+    if (N < 128 * nbp && N % 128 == 0) return 1;
     std::vector<float> A((size_t)N * ld, 0.f);
     // K = 0.5 exp(-d^2 / 2 l^2) on a line + nugget: SPD, well conditioned
     for (long long i = 0; i < N; ++i)
@@ -28,7 +29,7 @@ int main(int argc, char **argv) {
     // reference: double Cholesky of the leading 128 nbp columns (panel only)
     std::vector<double> Lr((size_t)N * 128 * nbp, 0.0);
     const int W = 128 * nbp;
-    for (int j = 0; j < W; ++j) {
+    for (int j = 0; j < W && j < N; ++j) {
         double d = A[(size_t)j * ld + j];
         for (int k = 0; k < j; ++k) d -= Lr[(size_t)j * W + k] * Lr[(size_t)j * W + k];
         const double ljj = sqrt(d);
@@ -73,7 +74,7 @@ int main(int argc, char **argv) {
     }
 #ifdef GPG_PANEL_PROFILE
     long long clk[512]; cudaMemcpyFromSymbol(clk, cpanel::g_panel_clk, sizeof(clk));
-    const char *cn[7] = {"", "wait diag_ready", "load", "factor", "invert", "W out + flag", "L out"};
+    const char *cn[7] = {"", "wait diag_ready", "load", "factor + inverse + planes", "-", "sync + flag", "L out"};
     for (int j = 0; j < nbp; ++j) {
         printf("chain block %d (cycles):", j);
         for (int k = 1; k <= 6; ++k) printf("  %s %lld", cn[k], clk[16 * j + k] - clk[16 * j + k - 1]);
@@ -88,7 +89,22 @@ int main(int argc, char **argv) {
                clk[256 + 128 + 16 * rb + 6] - clk[256 + 128 + 16 * rb + 2]);
     }
 #endif
-#ifdef GPG_DIAG_PROFILE
+#ifdef GPG_PANEL_PROFILE
+    {   // inside factor_invert_block of the LAST diagonal block the chain handled (thread 0 = lane 0 of the pivot warp)
+        const long long *c = clk + 64;
+        printf("last chain block, inside (cycles):");
+        for (int p4 = 0; p4 < 4; ++p4) {
+            printf("  p%d: pivot32 %lld, wait for the others %lld", p4, c[4 * p4 + 1] - c[4 * p4], c[4 * p4 + 2] - c[4 * p4 + 1]);
+            if (p4 < 3) printf(", rows below %lld, next-panel update + sync %lld |", c[4 * p4 + 3] - c[4 * p4 + 2], c[4 * p4 + 4] - c[4 * p4 + 3]);
+        }
+        printf("\n   warp 6 (shadow jobs of sub-step k, cycles):");
+        for (int k = 0; k < 3; ++k) printf("  k%d: starts %lld after the pivot, stage 1 %lld, group barrier %lld, stage 2 %lld, planes %lld |", k, clk[96 + 4 * k] - c[4 * (k + 1)],
+                                           clk[96 + 4 * k + 1] - clk[96 + 4 * k], clk[96 + 4 * k + 2] - clk[96 + 4 * k + 1], clk[96 + 4 * k + 3] - clk[96 + 4 * k + 2], clk[96 + 12 + k] - clk[96 + 4 * k + 3]);
+        printf("\n");
+        printf("  | last sync %lld  tail product %lld  planes of the last 32 rows %lld\n", c[16] - c[14], c[17] - c[16], c[18] - c[17]);
+    }
+#endif
+#ifdef GPG_DIAG_PROFILE_OLD
     {   // phases inside diag_factor_smem / diag_invert_smem of the LAST diagonal block the chain handled
         long long d[64]; cudaMemcpyFromSymbol(d, g_diag_clk, sizeof(d));
         printf("last chain block, inside: ");
@@ -104,7 +120,7 @@ int main(int argc, char **argv) {
     int hinfo; cudaMemcpy(&hinfo, info, 4, cudaMemcpyDeviceToHost);
     double err = 0, mx = 0;
     for (long long i = 0; i < N; ++i)
-        for (int j = 0; j < W && j <= i; ++j) { err = fmax(err, fabs(L[i * ld + j] - Lr[(size_t)i * W + j])); mx = fmax(mx, fabs(Lr[(size_t)i * W + j])); }
+        for (int j = 0; j < W && j <= i; ++j) { const double e = fabs(L[i * ld + j] - Lr[(size_t)i * W + j]); err = (e > err || e != e) ? e : err; mx = fmax(mx, fabs(Lr[(size_t)i * W + j])); }
     printf("info %d   max |L - Lref| / max |Lref| over the panel = %.2e\n", hinfo, err / mx);
     return 0;
 }
