@@ -413,11 +413,16 @@ __device__ __forceinline__ void factor_invert_block(float *__restrict__ S, float
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     float *rsv = ring + 32 * 32;
     int *progress = reinterpret_cast<int *>(rsv + 32);
-    // warp 0: pivots; warp 5: inverse follower (another scheduler than warp 0's); warp 4 (warp 0's scheduler) rests
-    // while the pivots run; shadow group: warps 1, 2, 3, 6, 7
+    // warp 0: pivots; warp 5: inverse follower (another scheduler than warp 0's); shadow group: the other six
+#ifdef GPG_CHAIN_G5
     constexpr int G = 5;
     const int g = warp <= 3 ? warp - 1 : warp - 3;
     const bool shadow = warp != 0 && warp != 4 && warp != 5;
+#else
+    constexpr int G = 6;
+    const int g = warp <= 4 ? warp - 1 : warp - 2;
+    const bool shadow = warp != 0 && warp != 5;
+#endif
     for (int p = 0; p < 4; ++p) {
         const int c0 = 32 * p;
         if (t == 0) st_flag(progress, 0);

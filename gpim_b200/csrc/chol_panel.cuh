@@ -335,6 +335,21 @@ __device__ __noinline__ void worker_role(const Args &p, const CUtensorMap *mLhi,
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic smem writes -> visible to the MMA
             tc::tcgen05_fence_before();
             __syncthreads();
+            // the row block the chain waits for: its diagonal block A[rb][rb] is fetched now (cp.async into the idle B1
+            // buffer, same XOR-swizzled fp32 layout as the staging tile below), off the hand-over path
+            const bool final_near = near_blk && j == (int)rb - 1;
+            if (final_near) {
+                const float *dblk = p.A + row0 * p.ld + row0;
+                const int nrows = (int)min((long long)NB, p.N - row0);
+#pragma unroll
+                for (int q = 0; q < NB * NB / 4 / NUM_THREADS; ++q) {
+                    const int idx = t + q * NUM_THREADS, i = idx >> 5, c4 = idx & 31;
+                    if (i < nrows && 4 * c4 <= i)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(b1 + (uint32_t)(i * NB + ((c4 ^ (i & 31)) << 2)) * 4u),
+                                     "l"(dblk + (long long)i * p.ld + 4 * c4) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
             // (2) W_jj planes -> B0 as soon as the chain has published them; (3) scratch = X W_jj^T
 #ifdef GPG_PANEL_PROFILE
             if (prof) PANEL_CLK(128 + 16 * (int)rb + 1);
@@ -363,7 +378,6 @@ __device__ __noinline__ void worker_role(const Args &p, const CUtensorMap *mLhi,
             if (prof) PANEL_CLK(128 + 16 * (int)rb + 4);
 #endif
             // (4) L[rb][j]: fp32 in place, planes to global, planes into XA (operand of the updates)
-            const bool final_near = near_blk && j == (int)rb - 1;
             if (final_near) {
                 // The chain waits for THIS row block.  Critical order: operand planes (smem only) -> the one update that
                 // is left, the own diagonal block (both operands L[rb][j]) -> A[rb][rb] - U_rb to global -> flag.  The
@@ -398,35 +412,32 @@ __device__ __noinline__ void worker_role(const Args &p, const CUtensorMap *mLhi,
                                         __uint_as_float(u[4 * q + 2]) * inv_LL, __uint_as_float(u[4 * q + 3]) * inv_LL);
                     }
                 }
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
                 tc::tcgen05_fence_before();
                 __syncthreads();
                 {
                     float *dblk = p.A + row0 * p.ld + row0;
                     const int nrows = (int)min((long long)NB, p.N - row0);
-                    float4 a4[NB * NB / 4 / NUM_THREADS];
-#pragma unroll
-                    for (int q = 0; q < NB * NB / 4 / NUM_THREADS; ++q) {
-                        const int idx = t + q * NUM_THREADS, i = idx >> 5, c4 = idx & 31;
-                        if (i < nrows && 4 * c4 <= i) a4[q] = *reinterpret_cast<const float4 *>(dblk + (long long)i * p.ld + 4 * c4);
-                    }
+                    const float *pre = reinterpret_cast<const float *>(xa_gen + 2 * OPND_BYTES);      // B1: the prefetched block
 #pragma unroll
                     for (int q = 0; q < NB * NB / 4 / NUM_THREADS; ++q) {
                         const int idx = t + q * NUM_THREADS, i = idx >> 5, c4 = idx & 31;
                         if (i < nrows && 4 * c4 <= i) {
-                            const float4 u4 = *reinterpret_cast<const float4 *>(stg + i * NB + ((c4 ^ (i & 31)) << 2));
+                            const int so = i * NB + ((c4 ^ (i & 31)) << 2);
+                            const float4 a4 = *reinterpret_cast<const float4 *>(pre + so);
+                            const float4 u4 = *reinterpret_cast<const float4 *>(stg + so);
                             *reinterpret_cast<float4 *>(dblk + (long long)i * p.ld + 4 * c4) =
-                                make_float4(a4[q].x - u4.x, a4[q].y - u4.y, a4[q].z - u4.z, a4[q].w - u4.w);
+                                make_float4(a4.x - u4.x, a4.y - u4.y, a4.z - u4.z, a4.w - u4.w);
                         }
                     }
                 }
-                __threadfence();
+                // no per-thread fence: the CTA barrier orders these stores before thread 0's release at gpu scope
                 __syncthreads();
                 if (t == 0) st_release(p.flags + F_DIAG_READY + (int)rb, 1);
 #ifdef GPG_PANEL_PROFILE
                 PANEL_CLK(128 + 16 * (int)rb + 6);
 #endif
                 emit_L<false, true>(p, tlane, xa_gen, r, half, gr, col0, valid, inv_AW, sL);
-                __threadfence();
                 tc::tcgen05_fence_before();
                 __syncthreads();
                 if (t == 0) st_release(p.flags + F_ROW_DONE + 4 * (int)rb + j, 1);
@@ -436,7 +447,6 @@ __device__ __noinline__ void worker_role(const Args &p, const CUtensorMap *mLhi,
             } else {
                 emit_L<true, true>(p, tlane, xa_gen, r, half, gr, col0, valid, inv_AW, sL);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                if (near_blk) __threadfence();                // the planes just written are another CTA's TMA source
                 tc::tcgen05_fence_before();
                 __syncthreads();
                 if (near_blk && t == 0) st_release(p.flags + F_ROW_DONE + 4 * (int)rb + j, 1);
