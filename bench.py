@@ -284,7 +284,7 @@ def bench_config(wl, gpus, N, M):
                          "K* tiles; no explicit flush"}
 
 
-def measure_predict(eng, wl, steps, warmup, world=1, rank=0, keep_outputs=True):
+def measure_predict(eng, wl, steps, warmup, world=1, rank=0, keep_outputs=True, dtype_name="f32"):
     """`steps` timed passes (factorise + predict) with device-resident inputs, CUDA events, stage clocks.
     world > 1: gpg_predict_sharded (rank 0 factorises).  Returns a dict; on rank 0 it carries the gathered outputs."""
     import torch
@@ -295,7 +295,7 @@ def measure_predict(eng, wl, steps, warmup, world=1, rank=0, keep_outputs=True):
     Xs = rows_of(wl["Xfull"])
     N, M, d = X.shape[0], Xs.shape[0], X.shape[1]
     kid = KERNEL_IDS[wl["kernel"]]
-    dev, dt = eng.device, torch.float32
+    dev, dt = eng.device, (torch.float32 if dtype_name == "f32" else torch.float64)
     th = torch.tensor(wl["theta"], dtype=dt, device=dev)
     Xd = torch.tensor(X, dtype=dt, device=dev)
     yd = torch.tensor(y, dtype=dt, device=dev)
@@ -722,6 +722,27 @@ def measure_dense(eng, name, steps, warmup, peaks):
                     "(tests/test_gpu_parity.py::test_predict_compact_support_option_is_exact)"}
 
 
+def measure_f64(eng, name, steps, warmup):
+    """The reference's default precision (gpr.py:92, precision='double'): the same step in fp64 -- blocked SIMT Cholesky,
+    variance product on DMMA tiles (mma.sync.m8n8k4.f64), compact support at fp64 resolution."""
+    wl = make_workload(name)
+    res = measure_predict(eng, wl, steps, warmup, keep_outputs=False, dtype_name="f64")
+    N, M = res["N"], res["M"]
+    st = {k: v[0] / steps for k, v in res["stages"].items() if v[1]}
+    out = {"workload": wl["label"], "dtype": "f64", "ms_per_step": res["ms_per_step"],
+           "value": res["value"], "unit": UNIT, "factor_cached_ms": res["ms_cached"], "stages_ms_per_step": st,
+           "round_1": "307 ms per step (SIMT product, dense)"}
+    if st.get("pgemm"):
+        out["variance_product"] = {"kernel": "gemm_dmma_kernel (COLSUMSQ epilogue)", "ms_per_step": st["pgemm"],
+                                   "dense_equivalent_tflops": N * N * M / (st["pgemm"] * 1e-3) / 1e12,
+                                   "peak": 40.0, "peak_source": "B200 data sheet fp64 (tensor = vector = 40 TFLOP/s); "
+                                   "no measured fp64 figure in MEASURED_PEAKS.json",
+                                   "note": "dense-equivalent rate: N^2 FLOP per point / time; the compact support of K* "
+                                           "at fp64 resolution skips about half of it, so the executed rate is about "
+                                           "half the figure"}
+    return out
+
+
 def run_cuda(args):
     import torch
     import torch.distributed as dist
@@ -823,6 +844,7 @@ def run_cuda(args):
             wls["c4"] = measure_c4(eng, peaks, steps=args.c4_steps)
         line["workloads"] = wls
         line["extra_workloads"] = {"train_c2": measure_training(eng, "c2", 10),
+                                   "c2_f64": measure_f64(eng, "c2", 3, 1),
                                    "c2_dense": measure_dense(eng, "c2", max(3, args.steps // 2), 2, peaks),
                                    "h512_dense": measure_dense(eng, "h512", max(3, args.steps // 4), 2, peaks),
                                    "sparse_c2": measure_sparse(eng, "c2", 10, max(2, args.steps // 2))}

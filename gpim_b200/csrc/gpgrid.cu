@@ -212,6 +212,7 @@ extern "C" size_t gpg_workspace_bytes(gpg_handle_t h) { return h ? h->ws_bytes :
 // GEMM dispatch: tcgen05 split-fp16 path for large fp32 problems, SIMT otherwise
 // ---------------------------------------------------------------------------------------------
 template <> int gemm_dispatch<double>(gpg_handle_s *h, const GemmArgs<double> &g, cudaStream_t stream) {
+    if (g.epi == GEMM_EPI_STORE && gemm_f64_uses_dmma(g) && h->opt_gemm_path != 1) return gemm_dmma(h, g, stream);
     return gemm_simt<double>(h, g, stream);
 }
 template <> int gemm_dispatch<float>(gpg_handle_s *h, const GemmArgs<float> &g, cudaStream_t stream) {
@@ -577,7 +578,11 @@ static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T 
         while (chunk > 512 && chunk * ldk * (int64_t)sizeof(T) > (int64_t)768 << 20) chunk /= 2;
     }
     chunk = std::min<int64_t>(chunk, gpg_align_up((size_t)M, 128));
-    const int tiles_m = (int)((N + C::BM - 1) / C::BM);
+    // fp64: the variance product runs on DMMA tiles of 128 rows when the problem fills them (GPG_OPT_GEMM_PATH = 1 keeps SIMT)
+    bool dmma = false;
+    if constexpr (std::is_same<T, double>::value) dmma = N >= 256 && h->opt_gemm_path != 1;
+    const int bm = dmma ? 128 : C::BM;
+    const int tiles_m = (int)((N + bm - 1) / bm);
     const int nblk32 = (int)((N + 31) / 32);
     const int groups = (int)((chunk + 127) / 128);
     void *ws;
@@ -616,7 +621,15 @@ static int predict_core(gpg_handle_s *h, int kernel_id, const T *theta, const T 
         g.epi = GEMM_EPI_COLSUMSQ;
         g.part = part; g.ldpart = chunk;
         g.krange = krange;
-        { StageTimer st(h, GPG_ST_PGEMM, s); GPG_TRY(gemm_simt<T>(h, g, s)); }
+        {
+            StageTimer st(h, GPG_ST_PGEMM, s);
+            if constexpr (std::is_same<T, double>::value) {
+                if (dmma) GPG_TRY(gemm_dmma(h, g, s));
+                else GPG_TRY(gemm_simt<T>(h, g, s));
+            } else {
+                GPG_TRY(gemm_simt<T>(h, g, s));
+            }
+        }
         StageTimer st(h, GPG_ST_PFINAL, s);
         predict_finalize_kernel<T, D><<<(unsigned)((mc + 255) / 256), 256, 0, s>>>(theta, part, tiles_m, chunk, tpc, mc,
                                                                                    T(1), sd + c0);

@@ -41,7 +41,7 @@ enum { GPG_RBF = 0, GPG_MATERN52 = 1, GPG_RATQUAD = 2 };
 enum { GPG_ACQ_CB = 0, GPG_ACQ_EI = 1, GPG_ACQ_POI = 2 };
 /* gpg_set_option keys.  Every default is the fastest correct setting; the alternatives exist for A/B measurements. */
 enum {
-    GPG_OPT_GEMM_PATH = 1,        /* 0 auto (tcgen05 for f32 when N >= 1024), 1 SIMT only, 2 force tcgen05 */
+    GPG_OPT_GEMM_PATH = 1,        /* 0 auto (f32: tcgen05 when N >= 1024; f64: DMMA tiles when N >= 256), 1 SIMT only, 2 force tcgen05 */
     GPG_OPT_PREDICT_CHUNK = 2,    /* test points per internal tile of gpg_predict (0 = auto: 16384) */
     GPG_OPT_STAGE_TIMING = 3,     /* != 0: bracket every stage with CUDA events, read by gpg_stage_times */
     GPG_OPT_PANEL_REFINE = 4,     /* recursive factorisation: refine every panel solve against L11 (default 1) */
