@@ -28,9 +28,12 @@ each with its own `value`, `e2e`, `roofline` and `cpu_baseline`.
 * `torch_cuda_baseline`: the oracle's torch ops on device="cuda" -- what the reference's use_gpu=True dispatches to
              on the same box (cuSOLVER potrf, cuBLAS trsm; gpr.py:136-140,248).  A baseline leg, not the product.
 
-N > 1 (torchrun, one rank per GPU): weak scaling on the headline workload -- the dense grid gets N times more rows
--- through gpg_predict_sharded (rank 0 factorises, pipelined NCCL broadcast of the cache, every rank predicts its
-row tile, one all-gather); `shard_parity_max_rel` compares the gathered result with an unsharded predict on rank 0;
+N > 1 (torchrun, one rank per GPU): weak scaling on the headline workload -- the dense grid gets N times more rows.
+Every rank factorises (the same deterministic kernels on the same inputs: bit-identical caches; the ranks would idle
+during a single rank's factorisation anyway, and the 2 N ld-byte broadcast of the cache leaves the step), predicts
+its row tile, ONE all-gather of (mean, sd) through gpg_allgather_pred.  `broadcast_mode` carries the same step with
+rank 0 factorising alone and the cache travelling by the pipelined NCCL broadcast of gpg_predict_sharded;
+`shard_parity_max_rel` compares the gathered result with an unsharded predict on rank 0;
 `strong_c5` is BASELINE.json configs[4] as configured (1024 x 1024, M fixed at 1 048 576, tiles of M / N rows).
 """
 import argparse
@@ -278,15 +281,18 @@ def bench_config(wl, gpus, N, M):
     return {"workload": wl["label"], "name": wl["name"], "N_train": N, "M_grid": M, "kernel": wl["kernel"],
             "theta": {"variance": wl["theta"][0], "noise": wl["theta"][1], "lengthscale": wl["theta"][3:],
                       "jitter": wl["jitter"]},
-            "sharding": "1 GPU" if gpus == 1 else f"X_full row tiles over {gpus} GPUs: pipelined NCCL broadcast of the "
-                                                  f"factor cache from rank 0 + 1 all-gather of (mean, sd)",
+            "sharding": "1 GPU" if gpus == 1 else f"128-row groups of X_full dealt round-robin over {gpus} GPUs, every rank factorises (replicated, "
+                                                  f"bit-identical caches), 1 all-gather of (mean, sd)",
             "l2_policy": "inputs larger than L2: every step rewrites and rereads K/L/Linv (N x N fp32 each) and the "
                          "K* tiles; no explicit flush"}
 
 
-def measure_predict(eng, wl, steps, warmup, world=1, rank=0, keep_outputs=True, dtype_name="f32"):
+def measure_predict(eng, wl, steps, warmup, world=1, rank=0, keep_outputs=True, dtype_name="f32", factor_mode="replicate"):
     """`steps` timed passes (factorise + predict) with device-resident inputs, CUDA events, stage clocks.
-    world > 1: gpg_predict_sharded (rank 0 factorises).  Returns a dict; on rank 0 it carries the gathered outputs."""
+    world > 1, factor_mode "replicate": every rank factorises (identical kernels on identical inputs: bit-identical caches,
+    no factor broadcast), predicts its tile, ONE all-gather of (mean, sd) through gpg_allgather_pred;
+    factor_mode "broadcast": gpg_predict_sharded (rank 0 factorises, pipelined NCCL broadcast of the cache).
+    Returns a dict; on rank 0 it carries the gathered outputs."""
     import torch
     import torch.distributed as dist
     from gpim_b200 import _lib, sharded
@@ -299,18 +305,28 @@ def measure_predict(eng, wl, steps, warmup, world=1, rank=0, keep_outputs=True, 
     th = torch.tensor(wl["theta"], dtype=dt, device=dev)
     Xd = torch.tensor(X, dtype=dt, device=dev)
     yd = torch.tensor(y, dtype=dt, device=dev)
-    lo, hi = sharded.tile_bounds(M, world, rank)
-    Xsd = torch.tensor(Xs[lo:hi], dtype=dt, device=dev)
-    fac = eng.alloc_factor(N, dt, with_L=(rank == 0))
+    # the engine's 128-row groups of X_full are dealt round-robin to the ranks (sharded.cyclic_rows): equal mix of
+    # cheap and expensive groups on every GPU
+    rows = sharded.cyclic_rows(M, world, rank).numpy() if world > 1 else np.arange(M)
+    lo, hi = 0, len(rows)
+    Xsd = torch.tensor(Xs[rows], dtype=dt, device=dev)
+    replicate = factor_mode == "replicate"
+    fac = eng.alloc_factor(N, dt, with_L=(rank == 0 or replicate))
     width = sharded.tile_width(M, world)
     pred_local = torch.zeros(2, width, dtype=dt, device=dev)
     pred_all = torch.empty(world, 2, width, dtype=dt, device=dev) if world > 1 else None
 
+    m_loc = hi - lo
+
     def step():
-        if rank == 0:
+        if rank == 0 or replicate:
             eng.factorize(kid, th, Xd, yd, wl["jitter"], out=fac)
-        if world > 1:
+        if world > 1 and not replicate:
             eng.predict_sharded(kid, th, Xd, fac, Xsd, width, root=0, pred_local=pred_local, pred_all=pred_all)
+        elif world > 1:
+            if m_loc:
+                eng.predict(kid, th, Xd, fac, Xsd, mean=pred_local[0, :m_loc], sd=pred_local[1, :m_loc])
+            eng.allgather_pred(pred_local, out=pred_all)
         else:
             eng.predict(kid, th, Xd, fac, Xsd, mean=pred_local[0], sd=pred_local[1])
 
@@ -349,9 +365,8 @@ def measure_predict(eng, wl, steps, warmup, world=1, rank=0, keep_outputs=True, 
     info = int(fac["info"].item())
     assert info == 0, f"factorisation failed at pivot {info}"
     if world > 1:
-        counts = [sharded.tile_bounds(M, world, r)[1] - sharded.tile_bounds(M, world, r)[0] for r in range(world)]
-        mean = torch.cat([pred_all[r, 0, :c] for r, c in enumerate(counts)])
-        sd = torch.cat([pred_all[r, 1, :c] for r, c in enumerate(counts)])
+        both = sharded.cyclic_merge(pred_all, M, world)
+        mean, sd = both[0].contiguous(), both[1].contiguous()
     else:
         mean, sd = pred_local[0, :M], pred_local[1, :M]
     assert bool(torch.isfinite(mean).all()) and bool(torch.isfinite(sd).all()), "non-finite prediction"
@@ -782,7 +797,13 @@ def run_cuda(args):
     e2e = run_e2e(wl, args.steps) if world == 1 else run_e2e_sharded(wl, max(2, args.steps // 2), world, rank)
 
     strong = None
+    bmode = None
     if world > 1 and not args.no_extra:
+        rb = measure_predict(eng, wl, max(3, args.steps // 2), 3, world, rank, keep_outputs=False, factor_mode="broadcast")
+        bmode = {"ms_per_step": rb["ms_per_step"], "value": rb["value"], "unit": UNIT,
+                 "shard_parity_max_rel": rb.get("shard_parity_max_rel"),
+                 "what": "rank 0 factorises alone; gpg_predict_sharded broadcasts its cache in row blocks under the "
+                         "first K* tiles"}
         # BASELINE.json configs[4] as configured: M fixed at 1024 x 1024, N = 30 757, tiles of M / world rows
         c5 = make_workload("c5")
         r5 = measure_predict(eng, c5, max(2, args.steps // 4), 2, world, rank, keep_outputs=False)
@@ -793,8 +814,8 @@ def run_cuda(args):
                       "unit": UNIT, "ms_per_step": r5["ms_per_step"], "steps": r5["steps"], "rows_per_gpu": r5["m_local"],
                       "stages_ms_per_step_rank0": st5,
                       "serial_ms_rank0": serial, "serial_fraction_of_step": serial / r5["ms_per_step"],
-                      "serial_note": "K assembly + Cholesky + inverse + solves run on rank 0 only (training / factorisation "
-                                     "are replicas-only); the other ranks wait for the first row block of the broadcast",
+                      "serial_note": "K assembly + Cholesky + inverse + solves do not shard (replicas-only): every rank runs "
+                                     "them on the same inputs; they are the serial fraction of the strong-scaling step",
                       "shard_parity_max_rel": r5.get("shard_parity_max_rel"), "gpu_launches": r5["launches"]}
 
     if rank != 0:
@@ -820,6 +841,8 @@ def run_cuda(args):
         line["shard_parity_max_rel"] = res["shard_parity_max_rel"]
     if strong is not None:
         line["strong_c5"] = strong
+    if bmode is not None:
+        line["broadcast_mode"] = bmode
     if world == 1 and not args.no_cpu_baseline:
         # the parity reference of north_star is the fp64 oracle; the f32 sample is the timing baseline of the fp32 config
         cb = cpu_baseline_block(wl, args.cpu_sample, args.cpu_dtype, cuda_out=None)

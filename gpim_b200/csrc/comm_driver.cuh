@@ -212,7 +212,7 @@ static int acq_sharded_entry(gpg_handle_s *h, comm::State *st, int acq_id, const
     Cand<T> *out = merged;
     while (true) {                                   // k * nranks <= 1024 * nranks: one or two rounds
         const int64_t nblk = (n + CH - 1) / CH;
-        topk_round_kernel<T><<<(unsigned)nblk, 1024, CH * sizeof(Cand<T>), s>>>(in, n, k, out);
+        topk_round_kernel<T><<<(unsigned)nblk, 1024, CH * sizeof(Cand<T>), s>>>(in, n, k, out, nullptr, nullptr);
         GPG_LAUNCH_CHECK(h);
         if (nblk == 1) break;
         in = out;

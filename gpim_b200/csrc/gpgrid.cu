@@ -1153,31 +1153,57 @@ static int acq_local_topk(gpg_handle_s *h, int acq_id, const T *mean, const T *s
                           size_t extra_cands, Cand<T> **best_out, Cand<T> **extra_out, cudaStream_t s) {
     constexpr int CH = 2048;
     const int64_t nblk0 = std::max<int64_t>(1, (M + CH - 1) / CH);
+    // large grids: a two-level key histogram keeps the k best plus one fine bin's worth of candidates out of M before
+    // anything is sorted (acq.cuh); the tournament then runs on the survivors with its counts on the device
+    const bool prefilter = M >= 65536 && M < ((int64_t)1 << 31);
+    const size_t aux_bytes = (2 * TOPK_BINS + 8) * sizeof(unsigned);
     void *ws;
     GPG_TRY(gpg_ws_reserve(h, bump_size({(size_t)(M + 1) * sizeof(Cand<T>), (size_t)(nblk0 * k + CH) * sizeof(Cand<T>),
-                                         (size_t)(nblk0 * k + CH) * sizeof(Cand<T>), 2 * (extra_cands + CH) * sizeof(Cand<T>)}),
+                                         (size_t)(nblk0 * k + CH) * sizeof(Cand<T>), 2 * (extra_cands + CH) * sizeof(Cand<T>),
+                                         prefilter ? (size_t)(M + 1) * sizeof(Cand<T>) : 0, aux_bytes}),
                            &ws));
     Bump b(ws);
     Cand<T> *cand = b.take<Cand<T>>(M + 1);
     Cand<T> *bufA = b.take<Cand<T>>(nblk0 * k + CH);
     Cand<T> *bufB = b.take<Cand<T>>(nblk0 * k + CH);
     if (extra_out) *extra_out = b.take<Cand<T>>(2 * (extra_cands + CH));
+    Cand<T> *surv = prefilter ? b.take<Cand<T>>(M + 1) : nullptr;
+    unsigned *hist1 = b.take<unsigned>(2 * TOPK_BINS + 8), *hist2 = hist1 + TOPK_BINS;
+    int *sel = reinterpret_cast<int *>(hist2 + TOPK_BINS), *ncnt = sel + 4;
+    const unsigned gsweep = (unsigned)std::min<int64_t>((M + 255) / 256, (int64_t)h->sm_count * 8);
+    if (prefilter) GPG_CUDA_CHECK(cudaMemsetAsync(hist1, 0, aux_bytes, s));
     if (M > 0) {                         // an empty tile (sharded sweep) contributes k excluded entries
-        acq_eval_kernel<T><<<(unsigned)((M + 255) / 256), 256, 0, s>>>(acq_id, mean, sd, mask, M, idx_offset, mu_best, xi,
-                                                                       alpha, beta, acq_out, cand);
+        acq_eval_kernel<T><<<std::max(1u, gsweep), 256, 0, s>>>(acq_id, mean, sd, mask, M, idx_offset, mu_best, xi,
+                                                                 alpha, beta, acq_out, cand, prefilter ? hist1 : nullptr);
         GPG_LAUNCH_CHECK(h);
     }
     const Cand<T> *in = cand;
     int64_t n = M;
+    if (prefilter) {
+        topk_level1_kernel<<<1, 1024, 0, s>>>(hist1, k, sel);
+        GPG_LAUNCH_CHECK(h);
+        topk_hist2_kernel<T><<<gsweep, 256, 0, s>>>(cand, M, sel, hist2);
+        GPG_LAUNCH_CHECK(h);
+        topk_level2_kernel<<<1, 1024, 0, s>>>(hist2, k, sel, ncnt);
+        GPG_LAUNCH_CHECK(h);
+        topk_compact_kernel<T><<<gsweep, 256, 0, s>>>(cand, M, sel, surv, ncnt);
+        GPG_LAUNCH_CHECK(h);
+        in = surv;
+    }
     Cand<T> *out = bufA;
+    int round = 0;
     while (true) {
         const int64_t nblk = std::max<int64_t>(1, (n + CH - 1) / CH);
-        topk_round_kernel<T><<<(unsigned)nblk, 1024, CH * sizeof(Cand<T>), s>>>(in, n, k, out);
+        // with the pre-filter the grid is sized for the worst case (nothing filtered out: all values equal) and the
+        // blocks past the survivors return at once
+        topk_round_kernel<T><<<(unsigned)nblk, 1024, CH * sizeof(Cand<T>), s>>>(in, n, k, out, prefilter ? ncnt + (round & 1) : nullptr,
+                                                                                prefilter ? ncnt + ((round + 1) & 1) : nullptr);
         GPG_LAUNCH_CHECK(h);
         if (nblk == 1) break;
         in = out;
         n = nblk * k;
         out = (out == bufA) ? bufB : bufA;
+        ++round;
     }
     *best_out = out;
     return GPG_OK;

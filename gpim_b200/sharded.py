@@ -21,16 +21,43 @@ import torch
 import torch.distributed as dist
 
 
+TILE_ALIGN = 128        # rows: the engine groups test points by 128 (support ranges of K*, GEMM tiles)
+
+
 def tile_bounds(M, world, rank):
-    """Contiguous row tile [lo, hi) of rank `rank`; the first M % world ranks get one extra row."""
-    base, extra = divmod(int(M), int(world))
-    lo = rank * base + min(rank, extra)
-    return lo, lo + base + (1 if rank < extra else 0)
+    """Contiguous row tile [lo, hi) of rank `rank`.  Tile edges fall on multiples of 128 rows (the last tile takes the
+    ragged rest, trailing tiles may be empty): the engine's 128-row groups of test points -- the unit of the compact
+    support of K* -- are then the same groups as in an unsharded call, which is what makes sharded == unsharded hold
+    bit for bit."""
+    per = tile_width(M, world)
+    lo = min(int(M), rank * per)
+    return lo, min(int(M), lo + per)
 
 
 def tile_width(M, world):
     """Common (padded) tile width: what every rank allocates so that one all-gather fits all tiles."""
-    return -(-int(M) // int(world))
+    groups = -(-int(M) // TILE_ALIGN)
+    return -(-groups // int(world)) * TILE_ALIGN
+
+
+def cyclic_rows(M, world, rank, device=None):
+    """Row indices of rank `rank` under the CYCLIC distribution of the engine's 128-row groups (group g goes to rank
+    g % world).  The cost of a group depends on where its points lie (its K* support range against the triangular
+    factor), so contiguous tiles are unevenly loaded; dealing the groups round-robin gives every rank the same mix."""
+    M, world = int(M), int(world)
+    groups = -(-M // TILE_ALIGN)
+    if rank >= groups:
+        return torch.zeros(0, dtype=torch.int64, device=device)
+    g = torch.arange(rank, groups, world, device=device)
+    idx = (g[:, None] * TILE_ALIGN + torch.arange(TILE_ALIGN, device=device)[None, :]).reshape(-1)
+    return idx[idx < M]
+
+
+def cyclic_merge(allp, M, world):
+    """allp [world, C, tile_width(M, world)] (rank r's rows in cyclic_rows order, zero padded) -> [C, M] in row order."""
+    C = allp.shape[1]
+    gr = allp.shape[2] // TILE_ALIGN
+    return allp.reshape(world, C, gr, TILE_ALIGN).permute(1, 2, 0, 3).reshape(C, gr * world * TILE_ALIGN)[:, :int(M)]
 
 
 def _global_rank(group, group_rank):
@@ -60,17 +87,36 @@ def ensure_comm(engine, group=None):
     return world, rank
 
 
-def predict_exact_sharded(engine, kernel_id, theta, X, y, jitter, Xs, src=0, group=None, fac=None, tile_only=False):
+def predict_exact_sharded(engine, kernel_id, theta, X, y, jitter, Xs, src=0, group=None, fac=None, tile_only=False,
+                          factor="replicate", synced=False, layout="cyclic"):
     """Exact-GP sharded predict on the native transport.  Every rank passes same-shaped theta / X / y (rank ``src``'s
-    values win: they are part of the broadcast) and the full (M, d) test rows, or -- with ``tile_only`` -- just its
-    own tile.  Returns (mean, sd, info) for all M rows on every rank (device tensors; info = src's pivot status)."""
+    values win) and the full (M, d) test rows, or -- with ``tile_only`` -- just its own tile.  Returns (mean, sd, info)
+    for all M rows on every rank (device tensors; info = the pivot status of the factorisation).
+
+    factor="replicate" (default): rank ``src``'s theta / X / y are broadcast (a few KB; skipped with ``synced=True``
+    when the caller knows they are equal already) and EVERY rank factorises -- the same deterministic kernels on the same
+    inputs give bit-identical caches, the other ranks would idle during rank ``src``'s factorisation anyway, and the
+    2 N ld-byte plane broadcast (238 MB at N = 7 688) disappears from the step: the only collective left is the
+    all-gather of (mean, sd).  factor="broadcast": rank ``src`` alone factorises and its cache travels in row blocks
+    (gpg_predict_sharded); the choice when the other GPUs have something else to do meanwhile.
+
+    layout="cyclic" (default): the 128-row groups of the test rows are dealt round-robin to the ranks (cyclic_rows), which
+    balances the position-dependent cost of the groups; layout="tiles": contiguous tiles (tile_bounds)."""
     world, rank = ensure_comm(engine, group)
     N = X.shape[0]
+    replicate = factor == "replicate"
     if fac is None:
-        fac = engine.alloc_factor(N, X.dtype, with_L=(rank == src))
+        fac = engine.alloc_factor(N, X.dtype, with_L=(replicate or rank == src))
     theta, X = theta.contiguous(), X.contiguous()
-    if rank == src:
+    if replicate:
+        if world > 1 and not synced:
+            gsrc = _global_rank(group, src)
+            for t in (theta, X, y):
+                dist.broadcast(t, src=gsrc, group=group)
         engine.factorize(kernel_id, theta, X, y, jitter, out=fac)
+    elif rank == src:
+        engine.factorize(kernel_id, theta, X, y, jitter, out=fac)
+    cyclic = False
     if tile_only:
         Xt = Xs
         counts = [None] * world
@@ -79,12 +125,25 @@ def predict_exact_sharded(engine, kernel_id, theta, X, y, jitter, Xs, src=0, gro
         width = max(counts)
     else:
         M = Xs.shape[0]
-        lo, hi = tile_bounds(M, world, rank)
-        Xt = Xs[lo:hi]
+        cyclic = layout == "cyclic" and world > 1
         width = tile_width(M, world)
-        counts = [tile_bounds(M, world, r)[1] - tile_bounds(M, world, r)[0] for r in range(world)]
-    _, allp = engine.predict_sharded(kernel_id, theta, X, fac, Xt, max(width, 1), root=src)
-    if all(c == width for c in counts):
+        if cyclic:
+            Xt = Xs.index_select(0, cyclic_rows(M, world, rank, Xs.device))
+        else:
+            lo, hi = tile_bounds(M, world, rank)
+            Xt = Xs[lo:hi]
+            counts = [tile_bounds(M, world, r)[1] - tile_bounds(M, world, r)[0] for r in range(world)]
+    if replicate:
+        local = torch.zeros(2, max(width, 1), dtype=X.dtype, device=X.device)
+        if Xt.shape[0]:
+            engine.predict(kernel_id, theta, X, fac, Xt, mean=local[0, :Xt.shape[0]], sd=local[1, :Xt.shape[0]])
+        allp = engine.allgather_pred(local)
+    else:
+        _, allp = engine.predict_sharded(kernel_id, theta, X, fac, Xt, max(width, 1), root=src)
+    if cyclic:
+        both = cyclic_merge(allp, M, world)
+        mean, sd = both[0].contiguous(), both[1].contiguous()
+    elif all(c == width for c in counts):
         mean, sd = allp[:, 0, :].reshape(-1), allp[:, 1, :].reshape(-1)
     else:
         mean = torch.cat([allp[r, 0, :c] for r, c in enumerate(counts)])
@@ -127,21 +186,16 @@ def broadcast_factor(fac, src=0, group=None, engine=None):
 def gather_tiles(local, M, group=None):
     """All-gather the per-rank tiles of a length-M vector (tiles as produced by tile_bounds)."""
     world = dist.get_world_size(group)
-    base, extra = divmod(int(M), world)
-    if extra == 0:
+    width = tile_width(M, world)
+    if width * world == M:
         out = torch.empty(M, dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         return out
-    width = base + 1                                    # pad ragged tiles to a common width
-    buf = torch.zeros(width, dtype=local.dtype, device=local.device)
+    buf = torch.zeros(width, dtype=local.dtype, device=local.device)      # pad ragged / empty tiles to the common width
     buf[: local.numel()] = local
     out = torch.empty(world * width, dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, buf, group=group)
-    parts = []
-    for r in range(world):
-        lo, hi = tile_bounds(M, world, r)
-        parts.append(out[r * width: r * width + (hi - lo)])
-    return torch.cat(parts)
+    return out[:M].clone()                              # tiles are back to back: tile r starts at r * width
 
 
 def _raise_not_pd(info):
@@ -197,8 +251,10 @@ def topk_merge_generic(vals_local, idx_local, k, group=None):
 def predict_model_sharded(model, Xs, src=0, group=None):
     """Tile-sharded ``model.predict_sd`` for the model object of a reconstructor / skreconstructor (ExactGPModel,
     SparseGPModel, SKExactGPModel): rank ``src``'s hyper-parameters (and inducing inputs) win -- training is
-    replicas-only, so the ranks may hold different values -- rank ``src`` factorises, the cache is broadcast, every rank
-    predicts its tile of ``Xs`` and the tiles are all-gathered.  Every rank passes a model built on the same (X, y);
+    replicas-only, so the ranks may hold different values.  Exact GP on the native transport: the few KB of
+    (theta, X, y) are broadcast and every rank factorises (predict_exact_sharded, factor="replicate"); the other models:
+    rank ``src`` factorises and its cache is broadcast.  Every rank predicts its tile of ``Xs`` and the tiles are
+    all-gathered.  Every rank passes a model built on the same (X, y);
     returns (mean, sd) for all of ``Xs`` on every rank.  A failed factorisation raises LinAlgError on EVERY rank."""
     eng = model.engine
     world = dist.get_world_size(group) if dist.is_initialized() else 1

@@ -12,12 +12,34 @@ from gpim_b200 import sharded
 
 
 def test_tile_bounds_partition_exactly():
-    for M in (0, 1, 7, 64, 65537):
+    for M in (0, 1, 7, 64, 300, 65537, 128 * 128 - 37):
         for world in (1, 2, 3, 8):
             edges = [sharded.tile_bounds(M, world, r) for r in range(world)]
+            width = sharded.tile_width(M, world)
             assert edges[0][0] == 0 and edges[-1][1] == M
+            for r, (a, b) in enumerate(edges):
+                assert 0 <= b - a <= width and a == min(M, r * width)      # back to back, common padded width
+                assert a % 128 == 0 or a == M                              # edges on the engine's 128-row groups
             for (a, b), (c, d) in zip(edges, edges[1:]):
-                assert b == c and b - a >= d - c >= 0 and (b - a) - (d - c) <= 1
+                assert b == c
+
+
+def test_cyclic_rows_partition_and_merge():
+    for M in (1, 127, 128, 129, 1000, 128 * 128 - 37, 65536):
+        for world in (1, 2, 3, 8):
+            w = sharded.tile_width(M, world)
+            allp = torch.zeros(world, 2, max(w, 1))
+            seen = torch.zeros(M)
+            for r in range(world):
+                idx = sharded.cyclic_rows(M, world, r)
+                assert len(idx) <= w
+                assert all(int(i) // 128 % world == r for i in idx[::128])      # whole 128-row groups, dealt round-robin
+                allp[r, 0, :len(idx)] = idx.double().float()
+                allp[r, 1, :len(idx)] = -idx.double().float()
+                seen[idx] += 1
+            assert bool((seen == 1).all())
+            m = sharded.cyclic_merge(allp, M, world)
+            assert torch.equal(m[0], torch.arange(M).float()) and torch.equal(m[1], -torch.arange(M).float())
 
 
 def _worker(rank, world, port, M, out_dir):
@@ -208,13 +230,17 @@ def _nccl_worker(rank, world, port, out_dir):
         if rank != 0:
             th = th * 0 + 1.0                                              # the source's theta must win
         Xd, yd, Xsd = (torch.tensor(a, dtype=dtype).cuda() for a in (X, y, Xs))
-        mean, sd, info = sharded.predict_exact_sharded(eng, kid, th, Xd, yd, wl["jitter"], Xsd, src=0)
-        assert int(info.item()) == 0
         th0 = torch.tensor(wl["theta"], dtype=dtype).cuda()
         fac = eng.factorize(kid, th0, Xd, yd, wl["jitter"])
         m1, s1 = eng.predict(kid, th0, Xd, fac, Xsd)
         tag = "f32" if dtype == torch.float32 else "f64"
-        res[tag] = (bool(torch.equal(mean, m1)), bool(torch.equal(sd, s1)))
+        ok = []
+        for mode in ("replicate", "broadcast"):                                # every rank factorises / rank 0's cache travels
+            thm = th.clone()
+            mean, sd, info = sharded.predict_exact_sharded(eng, kid, thm, Xd, yd, wl["jitter"], Xsd, src=0, factor=mode)
+            assert int(info.item()) == 0
+            ok += [bool(torch.equal(mean, m1)), bool(torch.equal(sd, s1))]
+        res[tag] = (all(ok[0::2]), all(ok[1::2]))
         # sharded acquisition sweep == single-device sweep over the whole grid
         lo, hi = sharded.tile_bounds(Xs.shape[0], world, rank)
         v0, i0, c0, _ = eng.acq_sweep(ACQ_IDS["ei"], m1, s1, 100, mu_best=float(m1.max()), xi=0.01)
