@@ -689,7 +689,7 @@ static int predict_core_tc(gpg_handle_s *h, int kernel_id, const float *theta, c
             StageTimer st(h, GPG_ST_KCROSS, s);
             GPG_DISPATCH_KID(kernel_id, kcross_mean_kernel<float, KID, D, true><<<(unsigned)((mc + 7) / 8), 256, 0, s>>>(
                                             theta, X, N, tpc, mc, alpha, nullptr, 0, Khi, Klo, ldh, scales, mean + c0,
-                                            nullptr, 0.f, krange, 1e-14f, bbox, nblk32));
+                                            nullptr, 0.f, krange, 1e-14f, bbox, nblk32, 2e-7f));
             GPG_LAUNCH_CHECK(h);
         }
         {

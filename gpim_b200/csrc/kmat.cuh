@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                                                           const float *__restrict__ scale_ptr, T *__restrict__ mean,
                                                           const T *__restrict__ y_resid = nullptr, T jitter = T(0),
                                                           int *__restrict__ krange = nullptr, float support_rel = 0.f,
-                                                          const float *__restrict__ bbox = nullptr, int nblk32 = 0) {
+                                                          const float *__restrict__ bbox = nullptr, int nblk32 = 0,
+                                                          float var_target = 0.f) {
     const int lane = threadIdx.x & 31;
     const int64_t j = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (j >= mc) return;
@@ -186,7 +187,12 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
     // tile's bounding box against the boxes of 32-row blocks of X (conservative: box distance <= point distance).
     // Everything outside contributes below fp32 resolution; it is neither evaluated nor written nor read by the
     // variance GEMM (krange), and the warps of a tile all derive the same range.
-    int64_t c_lo = 0, c_hi = width;
+    // Two ranges (SPLIT): [m_lo, m_hi) for the MEAN (linear in K*, weights alpha ~ y / noise: threshold support_rel) and
+    // the narrower [c_lo, c_hi) for the planes the VARIANCE product reads.  Dropping entries below eps x variance changes
+    // q = L^-1 k* by at most ||L^-1||_2 eps v sqrt(N) and sum q^2 <= v by at most 2 sqrt(v) ||dq||, i.e. the variance by
+    // at most 2 eps sqrt(v N / noise) relative to v: eps = var_target / (2 sqrt(v N / noise)) keeps it below var_target
+    // (2e-7, the rounding of the fp32 result itself) whatever the data.
+    int64_t c_lo = 0, c_hi = width, m_lo = 0, m_hi = width;
     if (!SPLIT && bbox != nullptr && sizeof(T) == 4 && !bad) {
         // no tile to agree with (nothing is stored for a GEMM): the range of THIS point, box = the point itself
         const float r2max = 1.02f * support_r2<T, KID>(th, support_rel);
@@ -208,6 +214,7 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
         }
         if (last <= first) { c_lo = 0; c_hi = 0; }
         else { c_lo = ((int64_t)first * 32 / 128) * 128; c_hi = min(width, (((int64_t)last * 32 + 127) / 128) * 128); }
+        m_lo = c_lo; m_hi = c_hi;
     }
     if (krange && bbox) {
         const int64_t tile0 = (j / 128) * 128;
@@ -237,7 +244,12 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                 bhi[k] = fmaxf(bhi[k], __shfl_xor_sync(0xffffffffu, bhi[k], o));
             }
         const float r2max = 1.02f * support_r2<T, KID>(th, support_rel);
-        int first = 0x7fffffff, last = 0;
+        float rel_var = support_rel;
+        if (var_target > 0.f)
+            rel_var = fminf(1e-6f, fmaxf(support_rel, var_target / (2.0f * sqrtf(fmaxf((float)th.variance, 1e-30f) * (float)N /
+                                                                                    fmaxf((float)th.noise, 1e-30f)))));
+        const float r2var = 1.02f * support_r2<T, KID>(th, rel_var);
+        int first = 0x7fffffff, last = 0, vfirst = 0x7fffffff, vlast = 0;
         for (int b = lane; b < nblk32; b += 32) {
             float d2 = 0.f;
 #pragma unroll
@@ -246,16 +258,24 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                 d2 += gap * gap;
             }
             if (d2 < r2max) { first = min(first, b); last = max(last, b + 1); }
+            if (d2 < r2var) { vfirst = min(vfirst, b); vlast = max(vlast, b + 1); }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
             last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+            vfirst = min(vfirst, __shfl_xor_sync(0xffffffffu, vfirst, o));
+            vlast = max(vlast, __shfl_xor_sync(0xffffffffu, vlast, o));
         }
-        if (last <= first) { c_lo = 0; c_hi = 0; }
+        if (last <= first) { m_lo = 0; m_hi = 0; }
         else {
-            c_lo = ((int64_t)first * 32 / 128) * 128;
-            c_hi = min(width, (((int64_t)last * 32 + 127) / 128) * 128);
+            m_lo = ((int64_t)first * 32 / 128) * 128;
+            m_hi = min(width, (((int64_t)last * 32 + 127) / 128) * 128);
+        }
+        if (vlast <= vfirst) { c_lo = 0; c_hi = 0; }
+        else {
+            c_lo = ((int64_t)vfirst * 32 / 128) * 128;
+            c_hi = min(width, (((int64_t)vlast * 32 + 127) / 128) * 128);
         }
         if (lane == 0) { krange[2 * (j / 128)] = (int)c_lo; krange[2 * (j / 128) + 1] = (int)min(c_hi, N); }
     }
@@ -266,7 +286,7 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                           (reinterpret_cast<uintptr_t>(alpha) & 7) == 0 && !bad);
     // lane owns the column pairs i0 + 2 lane + {0, 1} and i0 + 64 + 2 lane + {0, 1}: coordinates, alpha and the
     // fp16 planes are all touched with unit stride across the warp (128-bit / 64-bit / 32-bit per lane)
-    for (int64_t i0 = c_lo; i0 < c_hi; i0 += 128) {
+    for (int64_t i0 = m_lo; i0 < m_hi; i0 += 128) {
         T v[4];
         if (fast_ok && i0 + 128 <= N) {
 #pragma unroll
@@ -309,7 +329,7 @@ __global__ void __launch_bounds__(256) kcross_mean_kernel(const T *__restrict__ 
                 v[c] = val;
             }
         }
-        if (SPLIT) {
+        if (SPLIT && i0 >= c_lo && i0 < c_hi) {
 #pragma unroll
             for (int hblk = 0; hblk < 2; ++hblk) {
                 const int64_t i = i0 + 64 * hblk + 2 * lane;

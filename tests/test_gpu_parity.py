@@ -274,8 +274,9 @@ def test_predict_4d_inputs(eng, kernel, n):
 @pytest.mark.parametrize("kernel,ls", [("RBF", 3.0), ("RBF", 40.0), ("Matern52", 2.0)])
 def test_predict_compact_support_option_is_exact(eng, kernel, ls):
     """GPG_OPT_COMPACT_SUPPORT (default on) restricts the variance GEMM of each 128-row tile of test points to the
-    training rows whose covariance with the tile exceeds 1e-14 x variance; against the dense product (option 0): same mean (bit-identical, the mean does not go
-    through the GEMM) and the same sd to fp32 rounding, for a short lengthscale (most of K* negligible), a long
+    training rows whose covariance with the tile exceeds eps x variance (eps chosen from a bound on the change of the
+    variance, 2e-7 relative; the mean keeps the wider 1e-14 range); against the dense product (option 0): same mean
+    (the mean does not go through the GEMM) and the same sd to fp32 rounding, for a short lengthscale (most of K* negligible), a long
     one (nothing negligible) and a slowly decaying kernel."""
     from gpim_b200._lib import KERNEL_IDS, OPT_COMPACT_SUPPORT
     n = 128
