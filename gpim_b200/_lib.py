@@ -53,6 +53,8 @@ SIGNATURES = {
                          _vp, _vp, _vp, _vp], C.c_int),
     "gpg_acq_sweep": ([_vp, _i32, _i32, _vp, _vp, _vp, _i64, _f64, _f64, _f64, _f64, _i32, _vp, _vp, _vp, _vp, _vp],
                       C.c_int),
+    "gpg_acq_select": ([_vp, _i32, _vp, _vp, _vp, _i32, _i32, C.POINTER(_i64), _vp, _i32, _i32, _f64, _f64, _i32, _f64,
+                        _i32, _vp, _vp], C.c_int),
     "gpg_sparse_loss_grad": ([_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _i64, _f64, _vp, _vp, _vp, _vp, _vp],
                              C.c_int),
     "gpg_sparse_fit_adam": ([_vp, _i32, _i32, _i32, _i32, _vp, _vp, _i64, _vp, _i64, _f64, _vp, C.POINTER(_f64), _i32,
@@ -358,6 +360,20 @@ class Engine:
                                            float(mu_best), float(xi), float(alpha), float(beta), k, _ptr(vals),
                                            _ptr(idx), _ptr(count), _ptr(acq), self._stream()))
         return vals, idx, count, acq
+
+    def acq_select(self, vals, idx, count, dims, visited_flat, memory=10, dscale=0.0, gamma=0.8, batch=False,
+                   batch_dscale=0.0, batch_out_max=10):
+        """gpg_acq_select on the device-resident output of acq_sweep -> (first, start, picks list, nan_seen) on the host."""
+        k = int(vals.numel())
+        dims_c = (_i64 * len(dims))(*[int(v) for v in dims])
+        nv = len(visited_flat)
+        vis = torch.as_tensor(np.asarray(visited_flat, dtype=np.int64), device=self.device) if nv else None
+        sel = torch.zeros(4 + max(int(batch_out_max), 0), dtype=torch.int32, device=self.device)
+        self._check(self.lib.gpg_acq_select(self.h, self._dt(vals), _ptr(vals), _ptr(idx), _ptr(count), k, len(dims), dims_c,
+                                            _ptr(vis), nv, int(memory), float(dscale), float(gamma), int(bool(batch)),
+                                            float(batch_dscale), int(batch_out_max), _ptr(sel), self._stream()))
+        out = sel.cpu().numpy()
+        return int(out[0]), int(out[1]), [int(v) for v in out[4:4 + int(out[2])]], bool(out[3])
 
     # -- inducing-point GP (sparse=True) ----------------------------------------------------
     def sparse_loss_grad(self, kernel_id, theta, X, y, Xu, jitter):

@@ -238,3 +238,88 @@ __global__ void topk_emit_kernel(const Cand<T> *__restrict__ in, int k, T *__res
     __syncthreads();
     if (threadIdx.x == 0) *count = cnt;
 }
+
+// ---------------------------------------------------------------------------------------------
+// The point filters of the BO loop on the ranked candidate list (boptim.py:326-429; the reference walks Python
+// lists and a cKDTree).  One CTA, one thread per candidate (k <= 1024).
+//   admissible(t): candidate t was not measured before and keeps the distance dscale * gamma^q from the q-th most
+//                  recent measured point (q < memory)                                     -- checkvalues
+//   first        = the first admissible candidate, -1 when the list is exhausted (the caller applies the
+//                  reference's exit strategy, which draws from numpy's generator)
+//   batch mode   : the list is cut at the first candidate whose VALUE equals that of `first`
+//                  (np.where(vals == val)[0][0]); greedy ball suppression from there: take the best candidate
+//                  left (= the earliest: the list is ranked), drop everything within batch_dscale of it (closed
+//                  ball, as cKDTree.query_ball_point), until batch_out_max picks or nothing is left -- update_points
+// Coordinates are the grid indices of the flat index (row-major over dims), distances exact in integers.
+// sel_out int32[4 + batch_out_max]: {first, start, npicks, nan_seen, picks...} (positions in the candidate list).
+// ---------------------------------------------------------------------------------------------
+struct SelectArgs {
+    int ndim;
+    long long dims[4];
+    int n_visited, memory, do_batch, batch_out_max;
+    double dscale, gamma, batch_dscale;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024) acq_select_kernel(const T *__restrict__ val, const int64_t *__restrict__ idx,
+                                                          const int32_t *__restrict__ count, int kmax,
+                                                          const int64_t *__restrict__ visited, SelectArgs a,
+                                                          int32_t *__restrict__ sel_out) {
+    __shared__ int s_first, s_start, s_next, s_nan;
+    __shared__ long long s_pick[4];
+    const int t = threadIdx.x;
+    const int n = min(*count, kmax);
+    if (t == 0) { s_first = 0x7fffffff; s_start = 0x7fffffff; s_nan = 0; }
+    __syncthreads();
+    long long c[4] = {0, 0, 0, 0};
+    bool ok = false;
+    T v = T(0);
+    if (t < n) {
+        v = val[t];
+        if (v != v) atomicOr(&s_nan, 1);
+        long long f = idx[t];
+        for (int q = a.ndim - 1; q >= 0; --q) { c[q] = f % a.dims[q]; f /= a.dims[q]; }
+        ok = true;
+        for (int q = 0; q < a.n_visited && ok; ++q) ok = visited[q] != idx[t];
+        double lim = a.dscale;
+        for (int q = 0; q < a.memory && q < a.n_visited && ok; ++q) {     // q-th most recent measured point
+            long long f2 = visited[a.n_visited - 1 - q], d2 = 0;
+            for (int e = a.ndim - 1; e >= 0; --e) { const long long ce = f2 % a.dims[e]; f2 /= a.dims[e]; d2 += (c[e] - ce) * (c[e] - ce); }
+            ok = sqrt((double)d2) > lim;
+            lim *= a.gamma;
+        }
+        if (ok) atomicMin(&s_first, t);
+    }
+    __syncthreads();
+    const int first = s_first == 0x7fffffff ? -1 : s_first;
+    int npicks = 0;
+    if (a.do_batch && first >= 0) {
+        const T v0 = val[first];
+        if (t < n && v == v0) atomicMin(&s_start, t);
+        __syncthreads();
+        const int start = s_start;
+        bool alive = t < n && t >= start;
+        const double r2 = a.batch_dscale * a.batch_dscale;
+        while (npicks < a.batch_out_max) {
+            if (t == 0) s_next = 0x7fffffff;
+            __syncthreads();
+            if (alive) atomicMin(&s_next, t);
+            __syncthreads();
+            const int b = s_next;
+            if (b == 0x7fffffff) break;
+            if (t == b) {
+                for (int e = 0; e < 4; ++e) s_pick[e] = c[e];
+                sel_out[4 + npicks] = b;
+            }
+            __syncthreads();
+            if (alive) {
+                long long d2 = 0;
+                for (int e = 0; e < a.ndim; ++e) d2 += (c[e] - s_pick[e]) * (c[e] - s_pick[e]);
+                if ((double)d2 <= r2) alive = false;
+            }
+            ++npicks;
+            __syncthreads();
+        }
+    }
+    if (t == 0) { sel_out[0] = first; sel_out[1] = a.do_batch && first >= 0 ? s_start : -1; sel_out[2] = npicks; sel_out[3] = s_nan; }
+}

@@ -1240,6 +1240,31 @@ extern "C" int gpg_acq_sweep(gpg_handle_t h, int dtype, int acq_id, const void *
     return GPG_EINVAL;
 }
 
+extern "C" int gpg_acq_select(gpg_handle_t h, int dtype, const void *topk_val, const int64_t *topk_idx,
+                              const int32_t *count, int k, int ndim, const int64_t *dims_host, const int64_t *visited,
+                              int n_visited, int memory, double dscale, double gamma, int do_batch, double batch_dscale,
+                              int batch_out_max, int32_t *sel_out, void *stream) {
+    GPG_REQUIRE(h && topk_val && topk_idx && count && dims_host && sel_out, "NULL argument");
+    GPG_REQUIRE(k >= 1 && k <= 1024, "k must be in 1..1024");
+    GPG_REQUIRE(ndim >= 1 && ndim <= 4, "ndim not in 1..4");
+    GPG_REQUIRE(n_visited >= 0 && (n_visited == 0 || visited != nullptr), "visited list missing");
+    GPG_REQUIRE(batch_out_max >= 0 && batch_out_max <= 1024 && memory >= 0, "bad batch_out_max / memory");
+    DeviceGuard device_guard(h->device);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    SelectArgs a;
+    a.ndim = ndim;
+    for (int q = 0; q < 4; ++q) a.dims[q] = q < ndim ? dims_host[q] : 1;
+    a.n_visited = n_visited; a.memory = memory; a.do_batch = do_batch; a.batch_out_max = batch_out_max;
+    a.dscale = dscale; a.gamma = gamma; a.batch_dscale = batch_dscale;
+    if (dtype == GPG_F32)
+        acq_select_kernel<float><<<1, 1024, 0, s>>>((const float *)topk_val, topk_idx, count, k, visited, a, sel_out);
+    else if (dtype == GPG_F64)
+        acq_select_kernel<double><<<1, 1024, 0, s>>>((const double *)topk_val, topk_idx, count, k, visited, a, sel_out);
+    else { gpg_set_error("unknown dtype %d", dtype); return GPG_EINVAL; }
+    GPG_LAUNCH_CHECK(h);
+    return GPG_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Inducing-point GP (sparse=True): drivers and gpg_sparse_* entry points.  Same translation unit: they use the
 // workspace carving, kmat_launch and the factorisation drivers defined above.

@@ -118,13 +118,31 @@ class boptimizer:
         k = min(self.batch_size, mean_d.numel(), 1024)
         vals, idx, count, _ = sm.model.engine.acq_sweep(ACQ_IDS[name], mean_d, sd_d, k, mu_best=mu_best, xi=self.xi,
                                                         alpha=self.alpha, beta=self.beta, mask=mask_d)
+        # the point filters (checkvalues / update_points) on the ranked list while it is still on the device
+        sel = None
+        if self.verbose != 2 and mean.ndim <= 4:
+            visited = [int(np.ravel_multi_index(tuple(int(c) for c in p), mean.shape)) for p in self.indices_all]
+            if self.batch_update:
+                bd = (sm.model.kernel.lengthscale.mean().item() if self.batch_dscale is None else self.batch_dscale)
+            else:
+                bd = 0.0
+            sel = sm.model.engine.acq_select(vals, idx, count, mean.shape, visited, memory=self.points_mem,
+                                             dscale=0.0 if self.dscale is None else self.dscale, gamma=self.gamma,
+                                             batch=self.batch_update, batch_dscale=bd,
+                                             batch_out_max=self.batch_out_max if self.batch_update else 0)
         n = int(count.item())
         vals = vals[:n].cpu().numpy().astype(np.float64)
         flat = idx[:n].cpu().numpy()
         indices = np.stack(np.unravel_index(flat, mean.shape), axis=1)
-        return vals.tolist(), indices.tolist(), (mean, sd)
+        vals_l, idx_l = vals.tolist(), indices.tolist()
+        # only trusted for exactly these lists, and never when a NaN ranks in them (the reference's loops then end
+        # through NaN comparisons) or when the list is exhausted (its exit strategies draw from numpy's generator)
+        self._sel = None if (sel is None or sel[3] or sel[0] < 0) else {"vals": vals_l, "idx": idx_l, "first": sel[0],
+                                                                          "start": sel[1], "picks": sel[2]}
+        return vals_l, idx_l, (mean, sd)
 
     def _host_candidates(self, acq, shape_like):
+        self._sel = None
         """Custom acquisition functions (and batch sizes beyond the device top-k): the reference's
         full argsort, boptim.py:303-315."""
         if self.mask is not None:
@@ -168,6 +186,21 @@ class boptimizer:
         """Greedy ball suppression: repeatedly take the best remaining candidate and discard every
         candidate within `dscale` of it (cKDTree), then pad with random candidates up to
         batch_out_max; boptim.py:326-376."""
+        sel = getattr(self, "_sel", None)
+        if sel is not None and sel["idx"] is indices and sel["vals"] is acqfunc_values and sel["start"] >= 0:
+            # gpg_acq_select did the cut and the greedy suppression on the device (same picks, tests/test_gpu_parity.py)
+            start = sel["start"]
+            vals = np.array(acqfunc_values, dtype=float)[start:]
+            pts = np.vstack(indices)[start:]
+            chosen_ids = [q - start for q in sel["picks"]]
+            chosen_vals = [float(vals[q]) for q in chosen_ids]
+            out_idx = pts[chosen_ids].tolist()
+            short = self.batch_out_max - len(out_idx)
+            if short > 0:
+                extra = np.random.randint(0, len(vals), short)
+                out_idx.extend(pts[extra].tolist())
+                chosen_vals.extend(vals[extra].tolist())
+            return chosen_vals, out_idx
         _, val0 = self.checkvalues(indices, acqfunc_values)
         start = int(np.where(np.array(acqfunc_values) == val0)[0][0])
         vals = np.array(acqfunc_values, dtype=float)[start:]
@@ -196,6 +229,9 @@ class boptimizer:
     def checkvalues(self, idx_list, val_list):
         """First candidate that was not measured before and that keeps the distance
         dscale * gamma**k from the k-th most recent pick (k < memory); boptim.py:378-429."""
+        sel = getattr(self, "_sel", None)
+        if sel is not None and sel["idx"] is idx_list and sel["vals"] is val_list:
+            return idx_list[sel["first"]], val_list[sel["first"]]
         dscale_ = 0 if self.dscale is None else self.dscale
 
         def too_close(idx):

@@ -230,6 +230,22 @@ int gpg_acq_sweep(gpg_handle_t h, int dtype, int acq_id, const void *mean, const
                   const void *mask, int64_t M, double mu_best, double xi, double alpha, double beta,
                   int k, void *topk_val, int64_t *topk_idx, int32_t *count_out, void *acq_out, void *stream);
 
+/* K6, the point filters on the ranked list (boptim.py:378-429 checkvalues, boptim.py:326-376 update_points; Python lists
+ * and a scipy cKDTree in the reference).  topk_val / topk_idx / count: the output of gpg_acq_sweep, still on the device.
+ *   dims_host int64[ndim]: shape of the dense grid (flat indices are row-major over it);
+ *   visited int64[n_visited] (device): flat indices of every point measured so far, oldest first;
+ *   a candidate is admissible when it is not in `visited` and farther than dscale * gamma^q from the q-th most recent
+ *   visited point, q < memory (dscale 0 = the reference's dscale=None);
+ *   do_batch: greedy ball suppression of radius batch_dscale (closed ball) from the first candidate whose value equals
+ *   the first admissible one's, at most batch_out_max picks.
+ *   sel_out int32[4 + batch_out_max] (device): {first admissible position or -1, start position of the cut list or -1,
+ *   number of picks, 1 if a NaN value was seen, pick positions...}.  The exit strategies and the random padding of the
+ *   reference draw from numpy's generator and stay with the caller. */
+int gpg_acq_select(gpg_handle_t h, int dtype, const void *topk_val, const int64_t *topk_idx, const int32_t *count,
+                   int k, int ndim, const int64_t *dims_host, const int64_t *visited, int n_visited, int memory,
+                   double dscale, double gamma, int do_batch, double batch_dscale, int batch_out_max, int32_t *sel_out,
+                   void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Inducing-point GP: reconstructor(sparse=True), gpim/gpreg/gpr.py:145-155,198-199 over pyro's
  * SparseGPRegression with its default VFE approximation.  Xu: m x d inducing inputs

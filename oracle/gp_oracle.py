@@ -291,11 +291,43 @@ def pick_unvisited(idx_list, val_list, visited, dscale=None, gamma=0.8, memory=1
     return idx_list[j], val_list[j]
 
 
+def suppress_batch(val_list, idx_list, visited, batch_dscale, batch_out_max=10, dscale=None, gamma=0.8, memory=10,
+                   exit_strategy=1):
+    """boptim.py:326-376 restated (batch_update=True).  The list is cut at the first admissible candidate
+    (pick_unvisited), then: take the largest remaining value, drop every candidate within batch_dscale of it
+    (closed ball, Euclidean distance between index vectors), repeat until nothing is left; keep the first
+    batch_out_max picks; if fewer were found, pad with uniformly random candidates of the cut list (np.random)."""
+    _, val0 = pick_unvisited(idx_list, val_list, visited, dscale, gamma, memory, exit_strategy)
+    start = int(np.where(np.array(val_list) == val0)[0][0])
+    vals = np.array(val_list, dtype=float)[start:]
+    pts = np.vstack(idx_list)[start:].astype(float)
+    orig = vals.copy()
+    dead = vals.min() - 1
+    picks = []
+    while True:
+        b = int(np.argmax(vals))
+        if not vals[b] > dead:
+            break
+        picks.append(b)
+        vals[np.linalg.norm(pts - pts[b], axis=1) <= batch_dscale] = dead
+    picks = picks[:batch_out_max]
+    out_vals = [float(orig[b]) for b in picks]
+    out_idx = [[int(c) for c in pts[b]] for b in picks]
+    short = batch_out_max - len(picks)
+    if short > 0:
+        extra = np.random.randint(0, len(vals), short)
+        out_idx.extend([[int(c) for c in pts[b]] for b in extra])
+        out_vals.extend(orig[extra].tolist())
+    return out_vals, out_idx
+
+
 def bo_run(X_seed, y_seed, X_full, target, acquisition="cb", exploration_steps=10, batch_size=100,
            kernel="RBF", lengthscale=None, gp_iterations=1000, seed=0, learning_rate=5e-2,
            jitter=1e-6, precision="double", isotropic=False, mask=None, dscale=None,
-           on_train=None, **acq_kw):
-    """boptimizer.run restated for batch_update=False (boptim.py:431-470).
+           on_train=None, batch_update=False, batch_dscale=None, batch_out_max=10, gamma=0.8, memory=10,
+           **acq_kw):
+    """boptimizer.run restated (boptim.py:431-470), single-point steps and batch_update=True (every step measures the
+    batch_out_max points suppress_batch returns; batch_dscale defaults to the mean kernel lengthscale, boptim.py:318-322).
     Returns dict(target_func_vals, gp_predictions, indices_all, vals_all, gp)."""
     gp = OracleGP(X_seed, y_seed, X_full, kernel, lengthscale, learning_rate, gp_iterations, seed,
                   precision=precision, jitter=jitter, isotropic=isotropic)
@@ -312,16 +344,26 @@ def bo_run(X_seed, y_seed, X_full, target, acquisition="cb", exploration_steps=1
         acq, pred = acq_fn(gp, X_full, X_sparse, **acq_kw)
         preds.append(pred)
         vals, idxs = rank_points(acq, batch_size, mask)
-        ind, val = pick_unvisited(idxs, vals, picked, dscale)
-        y_sparse[tuple(ind)] = target(tuple(ind))
+        if batch_update:
+            bd = float(torch.as_tensor(gp.theta()[1]).detach().double().mean()) if batch_dscale is None else batch_dscale
+            bvals, binds = suppress_batch(vals, idxs, picked, bd, batch_out_max, dscale, gamma, memory)
+            for ind in binds:
+                y_sparse[tuple(ind)] = target(tuple(ind))
+        else:
+            ind, val = pick_unvisited(idxs, vals, picked, dscale, gamma, memory)
+            y_sparse[tuple(ind)] = target(tuple(ind))
         X_sparse = sparse_grid(y_sparse)
         vals_hist.append(y_sparse.copy())
         gp.set_data(X_sparse, y_sparse)
         gp.train()
         if on_train:
             on_train(gp)
-        picked.append(ind)
-        picked_vals.append(val)
+        if batch_update:
+            picked.extend(binds)
+            picked_vals.extend(bvals)
+        else:
+            picked.append(ind)
+            picked_vals.append(val)
     return {"target_func_vals": vals_hist, "gp_predictions": preds, "indices_all": picked,
             "vals_all": picked_vals, "gp": gp}
 

@@ -678,6 +678,70 @@ def test_boptimizer_batch_update_and_distance_filter(tmp_path):
     assert {"gp_pred", "func_val", "inds_all", "vals_all"} <= set(saved)
 
 
+def test_acq_select_matches_the_host_filters(eng):
+    """gpg_acq_select (the dscale / visited filter and the greedy ball suppression on the device-resident ranked list)
+    against the host restatement of boptim.py:326-429 on random lists: first admissible candidate, start of the cut
+    list, picks."""
+    from test_host_logic import _bare_boptimizer, _random_ranked_list
+    rng = np.random.default_rng(11)
+    for trial in range(30):
+        shape = (17, 23) if trial % 2 == 0 else (7, 9, 5)
+        n = int(rng.integers(5, 80))
+        vals, idx = _random_ranked_list(rng, n, shape)
+        nvis = int(rng.integers(0, 5))
+        visited = [idx[int(q)] for q in rng.choice(n, size=min(nvis, n - 1), replace=False)]
+        radius = float(rng.choice([1.0, 2.0, 2.5, 4.0, 6.3]))
+        ds = None if trial % 3 == 0 else float(rng.choice([1.0, 3.0]))
+        dtype = torch.float64 if trial % 2 else torch.float32
+        v_d = torch.tensor(vals, dtype=dtype).cuda()
+        i_d = torch.tensor(np.ravel_multi_index(np.array(idx).T, shape), dtype=torch.int64).cuda()
+        c_d = torch.tensor([n], dtype=torch.int32).cuda()
+        vis_flat = [int(np.ravel_multi_index(tuple(p), shape)) for p in visited]
+        first, start, picks, nan_seen = eng.acq_select(v_d, i_d, c_d, shape, vis_flat, memory=10, dscale=ds or 0.0, gamma=0.8,
+                                                       batch=True, batch_dscale=radius, batch_out_max=7)
+        assert not nan_seen
+        bo = _bare_boptimizer(indices_all=[list(p) for p in visited], dscale=ds, batch_out_max=7, exit_strategy=0)
+
+        def admissible(pt):
+            if pt in visited:
+                return False
+            for q, old in enumerate(visited[-10:][::-1]):
+                if not (np.linalg.norm(np.array(pt, dtype=float) - np.array(old, dtype=float)) > (ds or 0.0) * 0.8 ** q):
+                    return False
+            return True
+
+        ok = [admissible(pt) for pt in idx]
+        if first < 0:
+            assert not any(ok)                           # nothing admissible: the host walks off the list too
+            continue
+        assert first == ok.index(True)
+        hi, hv = bo.checkvalues([list(p) for p in idx], list(vals))
+        assert idx[first] == hi and vals[first] == hv
+        assert start == vals.index(hv)
+        np.random.seed(0)
+        bv, bi = bo.update_points(list(vals), [list(p) for p in idx], radius)
+        greedy = [idx[q] for q in picks]
+        assert bi[:len(greedy)] == greedy and (len(greedy) == 7 or len(bi) == 7)
+
+
+def test_boptimizer_batch_update_matches_the_oracle(tmp_path):
+    """batch_update=True end to end in fp64 (the device-side filters in the loop) against oracle.bo_run restating
+    boptim.py:326-376,431-470: identical picks and measured values.  batch_size / radius are chosen so that every step
+    finds batch_out_max points by suppression alone (no draw from numpy's generator)."""
+    import gpim_b200 as gpim
+    f, Z = _boptim_setup()
+    X_full, X_sparse = gpim.utils.get_full_grid(Z), gpim.utils.get_sparse_grid(Z)
+    kw = dict(batch_dscale=3.0, batch_out_max=3)
+    bo = gpim.boptimizer(X_sparse, Z.copy(), X_full, f, acquisition_function="ei", exploration_steps=3, batch_update=True,
+                         gp_iterations=40, verbose=0, filename=str(tmp_path / "bo"), **kw)
+    bo.run()
+    ref = O.bo_run(X_sparse, Z.copy(), X_full, f, acquisition="ei", exploration_steps=3, gp_iterations=40,
+                   batch_update=True, **kw)
+    assert bo.indices_all == [list(p) for p in ref["indices_all"]] and len(bo.indices_all) == 9
+    np.testing.assert_allclose(bo.target_func_vals[-1], ref["target_func_vals"][-1], equal_nan=True)
+    np.testing.assert_allclose(bo.vals_all, ref["vals_all"], rtol=1e-6)
+
+
 def test_boptimizer_resume_continues_the_same_run(tmp_path):
     """save_results() + resume(): 3 steps, checkpoint, a NEW optimizer resumed from the file and run
     for 3 more steps reproduces the picks and measured values of an uninterrupted 6-step run."""

@@ -255,3 +255,47 @@ def test_resume_from_a_checkpoint_written_before_any_step_starts_at_step_zero(tm
     assert len(k.bounds()) == 2 + 2
     with pytest.raises(ValueError):
         gp_kernels.get_kernel("RBF", 3, [[1.0, 1.0], [5.0, 5.0]])
+
+
+def _random_ranked_list(rng, n, shape):
+    """n distinct grid points with descending values (a few ties), as next_point returns them"""
+    flat = rng.choice(int(np.prod(shape)), size=n, replace=False)
+    idx = np.stack(np.unravel_index(flat, shape), axis=1).tolist()
+    vals = np.sort(rng.integers(0, max(3, n // 2), size=n).astype(float) / 7.0)[::-1].tolist()
+    return vals, idx
+
+
+def test_oracle_batch_suppression_against_an_independent_kdtree_route():
+    """oracle.suppress_batch (the restatement of boptim.py:326-376) against a second implementation built on
+    scipy's cKDTree ball queries, and the product's host path against both, on random ranked lists."""
+    from scipy import spatial
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(5)
+    for trial in range(40):
+        shape = (17, 23) if trial % 2 == 0 else (7, 9, 5)
+        n = int(rng.integers(5, 60))
+        vals, idx = _random_ranked_list(rng, n, shape)
+        visited = [idx[int(q)] for q in rng.choice(n, size=int(rng.integers(0, 4)), replace=False)]
+        radius = float(rng.choice([1.0, 2.0, 2.5, 4.0, 6.3]))
+        ds = None if trial % 3 == 0 else float(rng.choice([1.0, 3.0]))
+        bmax = int(rng.choice([3, 200]))                 # 200: every greedy pick is kept, the rest is random padding
+        np.random.seed(trial)
+        ov, oi = O.suppress_batch(list(vals), [list(p) for p in idx], visited, radius, bmax, dscale=ds)
+        # independent route: cut at the first admissible value, greedy over a KD-tree
+        _, v0 = O.pick_unvisited(idx, vals, visited, ds)
+        start = vals.index(v0)
+        pts = np.array(idx[start:], dtype=float)
+        tree = spatial.cKDTree(pts)
+        alive = np.ones(len(pts), dtype=bool)
+        want = []
+        for q in range(len(pts)):
+            if alive[q]:
+                want.append(idx[start + q])
+                alive[tree.query_ball_point(pts[q], radius)] = False
+        want = want[:bmax]
+        assert len(oi) == bmax and oi[:len(want)] == want
+        assert ov[:len(want)] == [vals[start + idx[start:].index(p)] for p in want]
+        bo = _bare_boptimizer(indices_all=[list(p) for p in visited], dscale=ds, batch_out_max=bmax)
+        np.random.seed(trial)                            # same draws for the random padding
+        hv, hi = bo.update_points(list(vals), [list(p) for p in idx], radius)
+        assert hi == oi and hv == ov
