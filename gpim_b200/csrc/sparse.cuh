@@ -181,15 +181,18 @@ __global__ void __launch_bounds__(256) sgp_form_phi_kernel(const T *__restrict__
 }
 
 // sum_ij G_ij d k(A_i, Z_j) / d{variance, scale_mixture, lengthscale_k, A_i}, G_ij = gscale * (Gm[i][j] - w_i rho_j)
-// with gscale = host_scale * (inv_noise ? 1 / theta[1] : 1).  One warp per row i: partial[block][3 + D] in double
-// (entry 1, the noise, stays zero) and gA[i][k] (= xu_factor * sum_j ..., or += when accumulate).
+// with gscale = host_scale * (inv_noise ? 1 / theta[1] : 1).  One warp per (row i, column chunk blockIdx.y): the
+// columns are split over gridDim.y chunks so that a 769 x 7 688 sensitivity matrix keeps 776 CTAs busy instead of 97
+// (one chunk: 12.5 % of the warp slots, 2.3 % of the HBM roofline).  partial[chunk][block][3 + D] in double (entry 1,
+// the noise, stays zero); row sums for the inducing inputs either straight into gA[i][k] (= xu_factor * sum_j ..., or +=
+// when accumulate; gridDim.y == 1 only) or, chunked, as doubles into gAp[chunk][i][k] for sgp_gxu_reduce_kernel.
 template <typename T, int KID, int D>
 __global__ void __launch_bounds__(256) sgp_kgrad_kernel(const T *__restrict__ theta, const T *__restrict__ A, int64_t P,
                                                         const T *__restrict__ Z, int64_t Q, const T *__restrict__ Gm,
                                                         int64_t ld, const T *__restrict__ w, const T *__restrict__ rho,
                                                         double host_scale, int inv_noise, double xu_factor,
                                                         int accumulate, double *__restrict__ partial,
-                                                        T *__restrict__ gA) {
+                                                        T *__restrict__ gA, double *__restrict__ gAp = nullptr) {
     constexpr int NP = 3 + D;
     __shared__ double red[8][NP];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
@@ -206,7 +209,9 @@ __global__ void __launch_bounds__(256) sgp_kgrad_kernel(const T *__restrict__ th
 #pragma unroll
         for (int k = 0; k < D; ++k) x[k] = A[i * D + k];
         const double wi = w ? (double)w[i] : 0.0;
-        for (int64_t j = lane; j < Q; j += 32) {
+        const int64_t qc = (((Q + gridDim.y - 1) / gridDim.y + 31) / 32) * 32;     // columns per chunk
+        const int64_t j_end = min(Q, (int64_t)(blockIdx.y + 1) * qc);
+        for (int64_t j = (int64_t)blockIdx.y * qc + lane; j < j_end; j += 32) {
             double G = (double)Gm[i * ld + j];
             if (w) G -= wi * (double)rho[j];
             G *= gscale;
@@ -253,14 +258,28 @@ __global__ void __launch_bounds__(256) sgp_kgrad_kernel(const T *__restrict__ th
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         const double s = warp_sum(gx[k]) * xu_factor;
-        if (lane == 0 && i < P && gA) gA[i * D + k] = (T)(s + (accumulate ? (double)gA[i * D + k] : 0.0));
+        if (lane == 0 && i < P) {
+            if (gAp) gAp[((int64_t)blockIdx.y * P + i) * D + k] = s;
+            else if (gA) gA[i * D + k] = (T)(s + (accumulate ? (double)gA[i * D + k] : 0.0));
+        }
     }
     __syncthreads();
     if (threadIdx.x < NP) {
         double s = 0.0;
         for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
-        partial[(int64_t)blockIdx.x * NP + threadIdx.x] = s;
+        partial[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * NP + threadIdx.x] = s;
     }
+}
+
+// gA[i][k] = sum over the chunk rows of gAp (already scaled by their xu_factor): nrows chunks of P x D doubles
+template <typename T>
+__global__ void __launch_bounds__(256) sgp_gxu_reduce_kernel(const double *__restrict__ gAp, int nrows, int64_t PD,
+                                                             T *__restrict__ gA) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= PD) return;
+    double s = 0.0;
+    for (int r = 0; r < nrows; ++r) s += gAp[(int64_t)r * PD + e];
+    gA[e] = (T)s;
 }
 
 // the scalar reductions of one evaluation (single CTA, double): see SGP_SC_*

@@ -4,7 +4,10 @@
 // algebra.  The m x m factorisations run on the blocked SIMT drivers of factor.cuh; the m x m x N and m^3 products on the
 // SIMT GEMM (fp64, small problems) or the tcgen05 split-fp16 GEMM (fp32, m >= 512 and N >= 2048).
 #pragma once
+constexpr int SGP_KGRAD_CHUNKS = 16;     // most column chunks of the m x N kernel-derivative reduction
+
 template <typename T> struct SgpBufs {
+    double *gxup = nullptr;      // double partials of the inducing-input gradient: [1 + SGP_KGRAD_CHUNKS][m][d]
     int64_t m = 0, N = 0, ldm = 0, ldn = 0;
     int nz = 1;                  // SIMT route: split-K factor of S = B B^T; ldn = nz * kchunk (columns [N, ldn) of B are kept zero)
     int64_t kchunk = 0;
@@ -63,7 +66,8 @@ template <typename T> static size_t sgp_ws_bytes(const gpg_handle_s *h, int64_t 
     return bump_size({(size_t)nz * mm, mm, mm, mm, mn, mn, mm, mm, mm, mm, mm, mm, mm, mm, mm, mm,
                       mv, mv, mv, mv, mv, (size_t)N * sizeof(T), NB * NB * sizeof(T), GPG_MAX_P * sizeof(T),
                       mv * d, GPG_MAX_P * sizeof(T), sizeof(T), GPG_MAX_P * sizeof(T), mv * d, mv * d,
-                      SGP_SC_COUNT * sizeof(double), nb * GPG_MAX_P * sizeof(double), nb * GPG_MAX_P * sizeof(double),
+                      SGP_SC_COUNT * sizeof(double), nb * GPG_MAX_P * sizeof(double),
+                      SGP_KGRAD_CHUNKS * nb * GPG_MAX_P * sizeof(double), (size_t)(1 + SGP_KGRAD_CHUNKS) * m * d * sizeof(double),
                       sizeof(FitState)}) + tc_bytes;
 }
 
@@ -90,7 +94,8 @@ template <typename T> static SgpBufs<T> sgp_carve(const gpg_handle_s *h, void *w
     s.sc = b.take<double>(SGP_SC_COUNT);
     s.nb = (int)((m + 7) / 8);
     s.partA = b.take<double>((size_t)s.nb * GPG_MAX_P);
-    s.partB = b.take<double>((size_t)s.nb * GPG_MAX_P);
+    s.partB = b.take<double>((size_t)SGP_KGRAD_CHUNKS * s.nb * GPG_MAX_P);
+    s.gxup = b.take<double>((size_t)(1 + SGP_KGRAD_CHUNKS) * m * d);
     s.st = b.take<FitState>(1);
     s.tc = sgp_uses_tc<T>(h, m, N);
     s.ldk = gpg_align_up((size_t)m, 64);
@@ -354,15 +359,21 @@ static int sgp_loss_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *th
         GPG_TRY(gemm_simt<T>(h, g, s));
     }
     T *gxu = gxu_out ? gxu_out : b.gxu;
+    const int kchunks = (int)std::max<int64_t>(1, std::min<int64_t>(SGP_KGRAD_CHUNKS, (N + 1023) / 1024));
     GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, {
+        // row sums for the inducing inputs go through double partials: [0] the m x m term (factor 2), [1..] the chunks of
+        // the m x N term; one small kernel adds them up (deterministic, no atomics)
         sgp_kgrad_kernel<T, KID, D><<<b.nb, 256, 0, s>>>(theta, Xu, m, Xu, m, b.Guu, ldm, nullptr, nullptr, 1.0, 0, 2.0, 0,
-                                                        b.partA, gxu);
-        sgp_kgrad_kernel<T, KID, D><<<b.nb, 256, 0, s>>>(theta, Xu, m, X, N, b.Kuf, ldn, b.w, b.rho, 1.0, 1, 1.0, 1,
-                                                        b.partB, gxu);
+                                                        b.partA, nullptr, b.gxup);
+        sgp_kgrad_kernel<T, KID, D><<<dim3(b.nb, kchunks), 256, 0, s>>>(theta, Xu, m, X, N, b.Kuf, ldn, b.w, b.rho, 1.0, 1, 1.0,
+                                                                       0, b.partB, nullptr, b.gxup + (size_t)m * D);
     }));
     GPG_LAUNCH_CHECK(h);
     h->launches++;
-    sgp_finish_kernel<T><<<1, 256, 0, s>>>(b.partA, b.nb, b.partB, b.nb, 3 + d, b.sc, theta, N, m, grad_out, loss_out);
+    if (sizeof(T) == 4) sgp_gxu_reduce_kernel<float><<<(unsigned)((m * d + 255) / 256), 256, 0, s>>>(b.gxup, 1 + kchunks, m * d, (float *)gxu);
+    else sgp_gxu_reduce_kernel<double><<<(unsigned)((m * d + 255) / 256), 256, 0, s>>>(b.gxup, 1 + kchunks, m * d, (double *)gxu);
+    GPG_LAUNCH_CHECK(h);
+    sgp_finish_kernel<T><<<1, 256, 0, s>>>(b.partA, b.nb, b.partB, b.nb * kchunks, 3 + d, b.sc, theta, N, m, grad_out, loss_out);
     GPG_LAUNCH_CHECK(h);
     return GPG_OK;
 }
