@@ -85,6 +85,38 @@ __global__ void __launch_bounds__(256) scales_from_diag_kernel(const float *__re
     }
 }
 
+// For an SPD matrix with a known lower bound lam_min on its spectrum (Kuu + jitter I: jitter; A' = I + B B^T / s2: 1):
+//   |a_ij| <= max_i A_ii =: D,  |L_ij| <= sqrt(D),  |(L^-1)_ij| <= lam_min^-1/2,  |(L21 W11)_ij| <= sqrt(N D / lam_min).
+// Fills every slot the cooperative panel Cholesky and trtri_tc read.
+__global__ void __launch_bounds__(256) scales_from_diag_bound_kernel(const float *__restrict__ A, int64_t ld, int64_t N,
+                                                                     float lam_min, float *__restrict__ scales) {
+    __shared__ float red[8];
+    float m = 0.f;
+    for (int64_t i = threadIdx.x; i < N; i += 256) m = fmaxf(m, fabsf(A[i * ld + i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        m = fmaxf(m, 1e-30f);
+        const float lm = fmaxf(lam_min, 1e-30f);
+        const int el = pow2_exp_below(16384.0f / sqrtf(m));
+        const int ea = pow2_exp_below(16384.0f / m);
+        const int ew = pow2_exp_below(16384.0f * sqrtf(lm));
+        const int et = pow2_exp_below(16384.0f * sqrtf(lm) / sqrtf((float)N * m));
+        for (int i = 0; i < SC_COUNT; ++i) scales[i] = 0.f;
+        scales[SC_L] = exp2f((float)el);
+        scales[SC_INV_LL] = exp2f((float)(-2 * el));
+        scales[SC_A] = exp2f((float)ea);
+        scales[SC_W] = exp2f((float)ew);
+        scales[SC_INV_AW] = exp2f((float)(-ea - ew));
+        scales[SC_T] = exp2f((float)et);
+        scales[SC_INV_LW] = exp2f((float)(-el - ew));
+        scales[SC_INV_WT] = exp2f((float)(-ew - et));
+        scales[SC_INV_WW] = exp2f((float)(-2 * ew));
+    }
+}
+
 template <typename E>
 __global__ void __launch_bounds__(256) zero_band_kernel(E *__restrict__ p, int64_t ld, int64_t N, int64_t lo_off,
                                                         int64_t hi_off) {

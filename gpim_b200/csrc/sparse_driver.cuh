@@ -8,6 +8,9 @@ constexpr int SGP_KGRAD_CHUNKS = 16;     // most column chunks of the m x N kern
 
 template <typename T> struct SgpBufs {
     double *gxup = nullptr;      // double partials of the inducing-input gradient: [1 + SGP_KGRAD_CHUNKS][m][d]
+    // tcgen05 route of the two m x m factorisations (cooperative panel Cholesky + trtri_tc): four plane pairs and scales
+    unsigned char *fplanes = nullptr;
+    float *fscales = nullptr;
     int64_t m = 0, N = 0, ldm = 0, ldn = 0;
     int nz = 1;                  // SIMT route: split-K factor of S = B B^T; ldn = nz * kchunk (columns [N, ldn) of B are kept zero)
     int64_t kchunk = 0;
@@ -59,7 +62,8 @@ template <typename T> static size_t sgp_ws_bytes(const gpg_handle_s *h, int64_t 
                                              (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4, SGP_S_COUNT * sizeof(float),
                                              (size_t)m * (size_t)(nz * kchunk) * 4, nzt_ * m * ldm_ * 4,
                                              (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4, (size_t)m * ldm_ * 4,
-                                             SGP_AMAX_BLOCKS * sizeof(float)}) : 0;
+                                             SGP_AMAX_BLOCKS * sizeof(float), 4 * (size_t)m * ldm_ * 4,
+                                             SC_COUNT * sizeof(float)}) : 0;
     const int64_t ldm = gpg_align_up((size_t)m, 64), ldn = nz * kchunk;
     const size_t mm = (size_t)m * ldm * sizeof(T), mn = (size_t)m * ldn * sizeof(T), mv = (size_t)m * sizeof(T);
     const size_t nb = (size_t)((m + 7) / 8);
@@ -113,8 +117,27 @@ template <typename T> static SgpBufs<T> sgp_carve(const gpg_handle_s *h, void *w
         s.P2 = b.take<__half>(2 * (size_t)m * s.ldm);
         s.P3 = b.take<__half>(2 * (size_t)m * s.ldm);
         s.amax = b.take<float>(SGP_AMAX_BLOCKS);
+        s.fplanes = b.take<unsigned char>(4 * (size_t)m * s.ldm * 4);
+        s.fscales = b.take<float>(SC_COUNT);
     }
     return s;
+}
+
+// Cholesky (in place) + inverse of an m x m SPD matrix whose spectrum is bounded below by lam_min, on the tensor-core
+// drivers of the exact path: the cooperative panel kernel (chol_panel.cuh) and trtri_tc.  For m of a few hundred the SIMT
+// drivers are a chain of ~80 us steps per 128 columns; here a 512-column panel is one ~125 us launch.
+static bool sgp_factor_uses_tc(const gpg_handle_s *h, int64_t m, int64_t ldm) {
+    return m >= 384 && (ldm % 8) == 0 && h->opt_panel_mode == 3 && h->sm_count >= 4 && h->opt_gemm_path != 1;
+}
+static int sgp_factor_inverse_tc(gpg_handle_s *h, float *A, int64_t m, int64_t ldm, float *Ainv, float lam_min,
+                                 int32_t *info, float *dinv, unsigned char *planes, float *scales, cudaStream_t s) {
+    const size_t pl = (size_t)m * ldm * 4;
+    TcPlanes Ls(planes, m, ldm), Ws(planes + pl, m, ldm), WTs(planes + 2 * pl, m, ldm), TTs(planes + 3 * pl, m, ldm);
+    scales_from_diag_bound_kernel<<<1, 256, 0, s>>>(A, ldm, m, lam_min, scales);
+    GPG_LAUNCH_CHECK(h);
+    { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked_tc(h, A, m, ldm, info, 0, dinv, Ls, scales, s, TcPlanes(), Ws)); }
+    { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_tc(h, A, m, ldm, Ainv, Ls, Ws, WTs, TTs, scales, s)); }
+    return GPG_OK;
 }
 
 // C (m x N, fp32, leading dimension ldc) = A (m x m, fp16 planes As) * Bt^T with Bt (N x m, fp16 planes) on tcgen05;
@@ -206,8 +229,17 @@ static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *thet
           }
       }
       if (!b.tc) GPG_TRY(kmat_launch<T>(h, kernel_id, d, theta, Xu, m, X, N, 0.0, 0, b.Kuf, ldn, s)); }
-    { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.Luu, m, ldm, info, 0, b.dinv, s)); }
-    { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.Luu, m, ldm, b.Ui, ldm, b.tmp, s)); }
+    bool fdone = false;
+    if constexpr (std::is_same<T, float>::value) {
+        if (b.tc && sgp_factor_uses_tc(h, m, ldm)) {     // Kuu + jitter I >= jitter
+            GPG_TRY(sgp_factor_inverse_tc(h, b.Luu, m, ldm, b.Ui, (float)jitter, info, b.dinv, b.fplanes, b.fscales, s));
+            fdone = true;
+        }
+    }
+    if (!fdone) {
+        { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.Luu, m, ldm, info, 0, b.dinv, s)); }
+        { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.Luu, m, ldm, b.Ui, ldm, b.tmp, s)); }
+    }
     {
         StageTimer stg(h, GPG_ST_PGEMM, s);      // B = Ui Kuf (booked under the predict GEMM's stage; S = B B^T under PFINAL)
         if (ldn > N)                 // the split-K batches of S = B B^T read B up to column ldn
@@ -268,8 +300,17 @@ static int sgp_lowrank_core(gpg_handle_s *h, int kernel_id, int d, const T *thet
             GPG_LAUNCH_CHECK(h);
         }
     }
-    { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.LA, m, ldm, info, 0, b.dinv, s)); }
-    { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.LA, m, ldm, b.LAi, ldm, b.tmp, s)); }
+    fdone = false;
+    if constexpr (std::is_same<T, float>::value) {
+        if (b.tc && sgp_factor_uses_tc(h, m, ldm)) {     // A' = I + B B^T / s2 >= I
+            GPG_TRY(sgp_factor_inverse_tc(h, b.LA, m, ldm, b.LAi, 1.0f, info, b.dinv, b.fplanes, b.fscales, s));
+            fdone = true;
+        }
+    }
+    if (!fdone) {
+        { StageTimer st(h, GPG_ST_CHOLESKY, s); GPG_TRY(cholesky_blocked<T>(h, b.LA, m, ldm, info, 0, b.dinv, s)); }
+        { StageTimer st(h, GPG_ST_TRTRI, s); GPG_TRY(trtri_blocked<T>(h, b.LA, m, ldm, b.LAi, ldm, b.tmp, s)); }
+    }
     StageTimer st(h, GPG_ST_SOLVE, s);
     const unsigned gm8 = (unsigned)((m + 7) / 8), gm256 = (unsigned)((m + 255) / 256);
     gemv_rect_kernel<T><<<gm8, 256, 0, s>>>(b.B, ldn, m, N, y, b.beta);                              // beta = B y
