@@ -335,6 +335,7 @@ static int cholesky_blocked_tc(gpg_handle_s *h, float *A, int64_t N, int64_t ld,
 static int trtri_tc(gpg_handle_s *h, const float *L, int64_t N, int64_t ld, float *Linv, TcPlanes Ls, TcPlanes Ws,
                     TcPlanes WTs, TcPlanes TTs, const float *scales, cudaStream_t stream) {
     constexpr int NB = 128;
+    cudaStream_t stream_main = stream;
     static bool attr_set = false;
     if (!attr_set) {
         GPG_CUDA_CHECK(cudaFuncSetAttribute(diag_block_kernel<float, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -367,11 +368,24 @@ static int trtri_tc(gpg_handle_s *h, const float *L, int64_t N, int64_t ld, floa
         const int64_t npairs_full = N / (2 * b);                   // pairs whose second block is complete
         const int64_t rem_start = npairs_full * 2 * b;
         const int64_t rem_rows = (N - rem_start > b) ? (N - rem_start - b) : 0;   // ragged last pair
+        // the ragged last pair is independent of the full pairs of its level: its two (small, latency-bound) GEMMs run
+        // on the side stream next to them
+        const bool fork = npairs_full > 0 && rem_rows > 0;
+        if (fork) {
+            if (!h->side_stream) {
+                GPG_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+                GPG_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+                GPG_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
+            }
+            GPG_CUDA_CHECK(cudaEventRecord(h->ev_fork, stream_main));
+            GPG_CUDA_CHECK(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        }
         for (int pass = 0; pass < 2; ++pass) {
             const int64_t s0 = pass == 0 ? 0 : rem_start;
             const int64_t rows = pass == 0 ? b : rem_rows;
             const int64_t batch = pass == 0 ? npairs_full : (rem_rows > 0 ? 1 : 0);
             if (batch == 0 || rows == 0) continue;
+            cudaStream_t stream = (fork && pass == 1) ? h->side_stream : stream_main;
             const long long bs = 2 * b * (ld + 1);
             tc::Launch g1;                   // T = L21 W11, emitted transposed into TTs
             tc_params_clear(g1);
@@ -406,6 +420,10 @@ static int trtri_tc(gpg_handle_s *h, const float *L, int64_t N, int64_t ld, floa
             g2.p.ldt = ld; g2.p.t_bs = bs;
             g2.p.scale_out = scales + SC_W;
             GPG_TRY(tc::launch(h, g2, stream));
+        }
+        if (fork) {
+            GPG_CUDA_CHECK(cudaEventRecord(h->ev_side, h->side_stream));
+            GPG_CUDA_CHECK(cudaStreamWaitEvent(stream_main, h->ev_side, 0));
         }
     }
     return GPG_OK;
