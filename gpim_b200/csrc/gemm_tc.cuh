@@ -380,19 +380,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                 // Cholesky).  Same data flow as the general loop below without its per-chunk option branches: the general
                 // body is ~1 k instructions per chunk and the four epilogue warps were fetch-bound on it (ncu: 21 % of all
                 // samples in no_inst, 19 us of epilogue per tile against 6 us of MMA).
-                if (rd && !C2b && !Sh && !Th && ti.mblk * BM + BM <= p.M && n0 + BN <= p.N) {
-                    const float beta = p.beta;
+                if (Cb && c_vec && (rd || p.beta == 0.f) && !C2b && !Sh && !Th && ti.mblk * BM + BM <= p.M && n0 + BN <= p.N) {
+                    const float beta = rd ? p.beta : 0.f;
                     const float *crow = Cb + (long long)(m_base + sub_r) * p.ldc + n0 + sub_c;
                     const long long rstep = 4 * (long long)p.ldc;
                     float4 cur[8];
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) cur[it] = *reinterpret_cast<const float4 *>(crow + it * rstep);
+                    for (int it = 0; it < 8; ++it)
+                        cur[it] = rd ? *reinterpret_cast<const float4 *>(crow + it * rstep) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
                     for (int c = 0; c < BN; c += 32) {
                         uint32_t r[32];
                         tmem_ld32(taddr + c, r);
                         float4 nx[8];
-                        if (c + 32 < BN) {
+                        if (rd && c + 32 < BN) {
 #pragma unroll
                             for (int it = 0; it < 8; ++it) nx[it] = *reinterpret_cast<const float4 *>(crow + it * rstep + c + 32);
                         }
@@ -411,10 +412,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                             *reinterpret_cast<float4 *>(const_cast<float *>(crow) + it * rstep + c) = x;
                         }
                         __syncwarp();
-                        if (c + 32 < BN) {
+                        if (rd && c + 32 < BN) {
 #pragma unroll
                             for (int it = 0; it < 8; ++it) cur[it] = nx[it];
                         }
+                    }
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(BAR(BAR_TEMPTY + buf));
+                    if (++buf == 2) { buf = 0; bphase ^= 1; }
+                    continue;
+                }
+                // Second fast path: interior tile that is stored three ways and not read -- C, its fp16 planes and the
+                // transposed planes (the W21 = -W22 T products of the triangular inverse; same fetch-bound general body).
+                if (Cb && !rd && p.beta == 0.f && c_vec && s_vec && Sh && Th && !C2b && p.s_ncols == 0 &&
+                    ti.mblk * BM + BM <= p.M && n0 + BN <= p.N) {
+                    float *crow = Cb + (long long)(m_base + sub_r) * p.ldc + n0 + sub_c;
+                    __half *shrow = Sh + (long long)(m_base + sub_r) * p.lds + n0 + sub_c;
+                    __half *slrow = Sl + (long long)(m_base + sub_r) * p.lds + n0 + sub_c;
+                    const long long rstep = 4 * (long long)p.ldc, sstep = 4 * (long long)p.lds;
+#pragma unroll 1
+                    for (int c = 0; c < BN; c += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + c, r);
+                        tmem_ld_wait();
+                        __half *th = Th + (long long)(n0 + c) * p.ldt + m, *tl = Tl + (long long)(n0 + c) * p.ldt + m;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float vi = a_eff * __uint_as_float(r[i]);
+                            r[i] = __float_as_uint(vi);
+                            __half hi, lo;
+                            split_fp16(vi * sout, hi, lo);
+                            th[(long long)i * p.ldt] = hi;
+                            tl[(long long)i * p.ldt] = lo;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4 *>(stg + lane * EPI_LD + 4 * q) =
+                                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                            __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                        __syncwarp();
+#pragma unroll
+                        for (int it = 0; it < 8; ++it) {
+                            const float4 x = *reinterpret_cast<const float4 *>(stg + (it * 4 + sub_r) * EPI_LD + sub_c);
+                            *reinterpret_cast<float4 *>(crow + it * rstep + c) = x;
+                            __align__(8) __half h4[4], l4[4];
+                            split_fp16(x.x * sout, h4[0], l4[0]);
+                            split_fp16(x.y * sout, h4[1], l4[1]);
+                            split_fp16(x.z * sout, h4[2], l4[2]);
+                            split_fp16(x.w * sout, h4[3], l4[3]);
+                            *reinterpret_cast<uint2 *>(shrow + it * sstep + c) = *reinterpret_cast<const uint2 *>(h4);
+                            *reinterpret_cast<uint2 *>(slrow + it * sstep + c) = *reinterpret_cast<const uint2 *>(l4);
+                        }
+                        __syncwarp();
                     }
                     tcgen05_fence_before();
                     __syncwarp();
