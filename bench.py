@@ -215,15 +215,23 @@ def run_reference(args):
     steps = max(1, min(args.steps, args.cpu_full_steps))
     a = torch.randn(2048, 2048)
     (a @ a).sum().item()
+    # the whole grid up to args.cpu_max_rows rows (C2: all 65 536, ~46 s per step); beyond that (--gpus N makes the grid N
+    # times denser: minutes per step) the FIRST cpu_max_rows rows -- a contiguous piece of the same workload run in full
+    # (factorisation included), its throughput reported as measured, nothing scaled
+    rows = None if M <= args.cpu_max_rows else np.arange(args.cpu_max_rows)
+    m_run = M if rows is None else len(rows)
     walls, stages = [], None
     for _ in range(steps):
-        _, _, st, wall = cpu_predict(wl, None, args.cpu_dtype)
+        _, _, st, wall = cpu_predict(wl, rows, args.cpu_dtype)
         walls.append(wall); stages = st
     sec = float(np.mean(walls))
-    value = M / sec
-    sample = (f"whole workload, nothing extrapolated: K + Cholesky at N = {N} and K* / TRSM / reduce on all {M} grid rows, "
-              f"{steps} timed step(s) (requested {args.steps}; capped: one step is {sec:.0f} s), thread-pool warm-up only; "
-              f"torch {torch.__version__} CPU {args.cpu_dtype}")
+    value = m_run / sec
+    what = (f"whole workload, nothing extrapolated: K + Cholesky at N = {N} and K* / TRSM / reduce on all {M} grid rows"
+            if rows is None else
+            f"bounded sample, nothing extrapolated: K + Cholesky at N = {N} and K* / TRSM / reduce on the first {m_run} of "
+            f"{M} grid rows; value = {m_run} rows / measured seconds")
+    sample = (f"{what}, {steps} timed step(s) (requested {args.steps}; capped: one step is {sec:.0f} s), thread-pool "
+              f"warm-up only; torch {torch.__version__} CPU {args.cpu_dtype}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "steps_requested": args.steps, "warmup": 0, "warmup_requested": args.warmup,
             "ms_per_step": 1e3 * sec, "higher_is_better": True,
@@ -888,6 +896,8 @@ def main():
     ap.add_argument("--cpu-full-steps", type=int, default=1, dest="cpu_full_steps",
                     help="--impl reference: cap on the number of full-workload steps timed (max 2)")
     ap.add_argument("--cpu-dtype", default="f32", choices=["f32", "f64"], dest="cpu_dtype")
+    ap.add_argument("--cpu-max-rows", type=int, default=131072, dest="cpu_max_rows",
+                    help="--impl reference: most grid rows of one CPU step (the whole grid when it has no more)")
     ap.add_argument("--c4-steps", type=int, default=50, dest="c4_steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="headline workload only")
