@@ -678,6 +678,29 @@ def test_boptimizer_batch_update_and_distance_filter(tmp_path):
     assert {"gp_pred", "func_val", "inds_all", "vals_all"} <= set(saved)
 
 
+def test_factorize_is_bitwise_reproducible(eng):
+    """The cooperative panel kernel synchronises its CTAs and the warps of the chain CTA through flags (global memory,
+    a shared-memory ring) instead of barriers; a missed hand-over would show up as run-to-run differences.  Twelve
+    factorisations of the same matrix (N = 3 860: eight panels, ragged last block; fresh output buffers every time):
+    alpha, L and L^-1 must agree bit for bit."""
+    from gpim_b200._lib import KERNEL_IDS
+    wl = W.make_workload("c1k")
+    X, y = O.training_rows(O.sparse_grid(wl["R"]), wl["R"])
+    N = len(y)
+    th = torch.tensor(wl["theta"], dtype=torch.float32).cuda()
+    Xd, yd = torch.tensor(X, dtype=torch.float32).cuda(), torch.tensor(y, dtype=torch.float32).cuda()
+    ref, keep = None, []
+    for _ in range(12):
+        fac = eng.factorize(KERNEL_IDS[wl["kernel"]], th, Xd, yd, wl["jitter"])
+        assert int(fac["info"].item()) == 0
+        cur = (fac["alpha"].clone(), torch.tril(fac["L"][:N, :N]), torch.tril(fac["Linv"][:N, :N]))
+        keep.append(fac)                                  # different buffers (and different garbage in their padding) per run
+        if ref is None:
+            ref = cur
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(ref, cur))
+
+
 def test_acq_select_matches_the_host_filters(eng):
     """gpg_acq_select (the dscale / visited filter and the greedy ball suppression on the device-resident ranked list)
     against the host restatement of boptim.py:326-429 on random lists: first admissible candidate, start of the cut
