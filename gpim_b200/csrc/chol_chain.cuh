@@ -8,7 +8,7 @@
 //       warp 5, the INVERSE FOLLOWER, consumes the ring column by column: the forward substitution x_j <- x_j / l_jj,
 //       x_k <- x_k - x_j l_kj started from the identity gives L11^-T, so lane i ends up with column i of the inverse
 //       W_pp of the sub-block IN LOCKSTEP with the factorisation.  No separate triangular inversion is left.
-//       warps 1, 2, 3, 6, 7 meanwhile run the SHADOW tiles of sub-step k = p - 1:
+//       the other six warps meanwhile run the SHADOW tiles of sub-step k = p - 1:
 //         (a) the part of the rank-32 trailing update the next sub-step does not need,
 //         (b) row block k of the inverse:   W[k][0:k] = -W_kk Q[k][0:k],
 //         (c) the running products          Q[r][0:k+1] += L[r][k] W[k][0:k+1],  r > k,
@@ -19,7 +19,7 @@
 // All block products are 16 x 32 x 32 tiles on mma.sync (fp16 hi/lo split, three products: mma_tile below).
 //
 // Shared memory: S (the block / its factor) and W (its inverse), 128 x 136 floats each; Q, 96 x 104; the ring.
-// Measured on B200 (tools/panel_bench.cu, 512-column panel = 4 blocks): 166 -> 136 us.
+// Measured on B200 (tools/panel_bench.cu, 512-column panel = 4 blocks): 166 -> 123 us.
 #pragma once
 #include "factor.cuh"
 
