@@ -845,7 +845,7 @@ template <typename T> static size_t train_ws_bytes(const gpg_handle_s *h, int64_
     // L, Linv + (SIMT: Kinv | TC: 4 plane pairs + Rf + Ws)
     return bump_size({nn, nn, tcp ? 6 * nn : nn, NB * NB * sizeof(T), 4 * (size_t)N * sizeof(T) + 64, (size_t)N * sizeof(T),
                       (size_t)N * sizeof(T), 2 * sizeof(T), GPG_MAX_P * sizeof(T), sizeof(T), GPG_MAX_P * sizeof(T),
-                      SC_COUNT * sizeof(float), nb * GPG_MAX_P * sizeof(double), sizeof(FitState), (size_t)N * sizeof(T),
+                      SC_COUNT * sizeof(float), GRAD_CHUNKS_MAX * nb * GPG_MAX_P * sizeof(double), sizeof(FitState), (size_t)N * sizeof(T),
                       (size_t)((N + 31) / 32) * 2 * GPG_MAX_D * sizeof(float)});
 }
 
@@ -877,7 +877,7 @@ template <typename T> static TrainBufs train_carve(const gpg_handle_s *h, void *
     t.theta = b.take<T>(GPG_MAX_P);
     t.scales = b.take<float>(SC_COUNT);
     t.nblocks = (int)((N + 7) / 8);
-    t.partial = b.take<double>((size_t)t.nblocks * GPG_MAX_P);
+    t.partial = b.take<double>((size_t)GRAD_CHUNKS_MAX * t.nblocks * GPG_MAX_P);
     t.st = b.take<FitState>(1);
     t.yc = b.take<T>(N);
     t.bbox = b.take<float>((size_t)((N + 31) / 32) * 2 * GPG_MAX_D);
@@ -918,11 +918,13 @@ static int nll_grad_core(gpg_handle_s *h, int kernel_id, int d, const T *theta, 
         g.tile_mode = GEMM_TILES_LOWER;
         GPG_TRY(gemm_dispatch<T>(h, g, s));
     }
-    GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, grad_partial_kernel<T, KID, D><<<tb.nblocks, 256, 0, s>>>(
+    // rows split over column chunks for large N (one warp per row keeps too few loads in flight: 11 % of the HBM roofline)
+    const int gchunks = (int)std::max<int64_t>(1, std::min<int64_t>(GRAD_CHUNKS_MAX, N / 1024));
+    GPG_DISPATCH_KID(kernel_id, GPG_DISPATCH_D(d, grad_partial_kernel<T, KID, D><<<dim3(tb.nblocks, gchunks), 256, 0, s>>>(
                                                        theta, X, (const T *)tb.alpha, Kinv, tb.ld, N, tb.partial)));
     GPG_LAUNCH_CHECK(h);
     const double hl = 0.5 * (double)N * 1.8378770664093454835606594728112;   // N/2 log(2 pi)
-    grad_finish_kernel<T><<<1, 256, 0, s>>>(tb.partial, tb.nblocks, 3 + d, (const T *)tb.scalars, hl, grad_out, nll_out);
+    grad_finish_kernel<T><<<1, 256, 0, s>>>(tb.partial, tb.nblocks * gchunks, 3 + d, (const T *)tb.scalars, hl, grad_out, nll_out);
     GPG_LAUNCH_CHECK(h);
     return GPG_OK;
 }

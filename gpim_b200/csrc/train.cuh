@@ -69,7 +69,8 @@ __device__ void constrain_params(const T *u, const FitCfg &c, T *theta, double *
 }
 
 // 0.5 * sum_ij G_ij dA_ij/dtheta_p over the lower triangle, G = Kinv - alpha alpha^T.
-// One warp per row i; partial[block][3+D] in double.  Reads Kinv's lower triangle once.
+// One warp per (row i, column chunk blockIdx.y); partial[chunk][block][3+D] in double.  Reads Kinv's lower triangle once.
+constexpr int GRAD_CHUNKS_MAX = 8;
 template <typename T, int KID, int D>
 __global__ void __launch_bounds__(256) grad_partial_kernel(const T *__restrict__ theta, const T *__restrict__ X,
                                                            const T *__restrict__ alpha, const T *__restrict__ Kinv,
@@ -87,7 +88,9 @@ __global__ void __launch_bounds__(256) grad_partial_kernel(const T *__restrict__
 #pragma unroll
         for (int k = 0; k < D; ++k) x[k] = X[i * D + k];
         const T ai = alpha[i];
-        for (int64_t j = lane; j <= i; j += 32) {
+        const int64_t qc = (((N + gridDim.y - 1) / gridDim.y + 31) / 32) * 32;          // columns per chunk
+        const int64_t j_end = min(i + 1, (int64_t)(blockIdx.y + 1) * qc);
+        for (int64_t j = (int64_t)blockIdx.y * qc + lane; j < j_end; j += 32) {
             const double G = (double)Kinv[i * ld + j] - (double)ai * (double)alpha[j];
             const double wgt = (j < i) ? 1.0 : 0.5;
             T q[D];
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256) grad_partial_kernel(const T *__restrict__
     if (threadIdx.x < P) {
         double s = 0.0;
         for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
-        partial[(int64_t)blockIdx.x * P + threadIdx.x] = s;
+        partial[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * P + threadIdx.x] = s;
     }
 }
 
