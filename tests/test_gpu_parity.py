@@ -578,6 +578,46 @@ def test_acq_sweep_and_topk(eng, acq, dtype, M, k):
     np.testing.assert_array_equal(vals.cpu().double().numpy(), out[order])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("k", [1, 100, 1024])
+def test_acq_sweep_large_grid_prefilter(eng, dtype, k):
+    """M >= 65 536 goes through the two-level key-histogram pre-filter (acq.cuh: topk_hist2 / topk_compact) before the
+    tournament: same ranking as the reversed stable arg-sort with NaN predictions (they rank first), exact ties across
+    a plateau, negative zeros, and a mask that leaves fewer than k valid points."""
+    from gpim_b200._lib import ACQ_IDS
+    rng = np.random.RandomState(k)
+    M = 70001
+    mean, sd = rng.randn(M), np.abs(rng.randn(M)) + 0.1
+    mean[1000:9000] = 2.5                                  # a plateau of exact ties near the top
+    sd[1000:9000] = 0.5
+    mean[::501] = np.nan                                   # NaN predictions rank first (boptim.py:304-306)
+    mean[7::1013] = -0.0
+    sd[7::1013] = 0.0                                      # CB = -0 + 0: zeros of both signs tie
+    md, sdd = torch.tensor(mean, dtype=dtype).cuda(), torch.tensor(sd, dtype=dtype).cuda()
+    vals, idx, count, out = eng.acq_sweep(ACQ_IDS["cb"], md, sdd, k, alpha=1.0, beta=1.0, want_acq=True)
+    out = out.cpu().double().numpy()
+    order = np.argsort(out, kind="stable")[::-1][:k]
+    assert int(count.item()) == k
+    np.testing.assert_array_equal(idx.cpu().numpy(), order)
+    # fewer valid points than k: everything valid comes back, ranked
+    mask = np.full(M, np.nan)
+    keep = rng.choice(M, size=37, replace=False)
+    mask[keep] = 1.0
+    vals, idx, count, _ = eng.acq_sweep(ACQ_IDS["cb"], md, sdd, max(k, 64), alpha=1.0, beta=1.0,
+                                        mask=torch.tensor(mask, dtype=dtype).cuda())
+    acq = mask * out
+    o2 = np.argsort(acq, kind="stable")
+    valid = o2[~np.isnan(mask[o2])]                        # masked-out entries are stripped, NaN predictions stay
+    n = int(count.item())
+    nan_valid = [i for i in keep if np.isnan(out[i])]
+    assert n == len(keep) - len(nan_valid) or n == len(keep)
+    got = idx.cpu().numpy()[:n]
+    assert set(got.tolist()) <= set(keep.tolist())
+    finite = [i for i in got if not np.isnan(out[i])]
+    ref_finite = [i for i in valid[::-1] if not np.isnan(out[i])]
+    assert finite == ref_finite[:len(finite)]
+
+
 def test_acq_sweep_mask(eng):
     from gpim_b200._lib import ACQ_IDS
     rng = np.random.RandomState(0)
